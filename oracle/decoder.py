@@ -1,0 +1,113 @@
+"""Oracle SDF auto-decoder: fp32 (or fp64) torch-CPU restatement and the
+low-precision-emulating variant the tensor-core kernel is gated against.
+
+Reference: none (`/root/reference/README.md:1`); follows SURVEY.md section 8(a)
+rows A2/A3.  Test infrastructure only - never imported by the product path.
+
+Network (DeepSDF-style):  in = concat(z[256], xyz[3]) = 259
+    h0 = relu(L0 in)            259 -> 512
+    h1 = relu(L1 h0)            512 -> 512
+    h2 = relu(L2 h1)            512 -> 512
+    h3 = relu(L3 h2)            512 -> 253
+    h4 = relu(L4 concat(h3, in))  512 -> 512      (skip connection)
+    h5..h7 = relu(L5..L7 .)     512 -> 512
+    sdf = tanh(L8 h7)           512 -> 1
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .grid import grid_points
+from .weights import DEC_LATENT, DEC_SKIP_OUT, decoder_weights
+
+
+def _as_t(a, dtype):
+    return torch.as_tensor(np.asarray(a), dtype=dtype)
+
+
+def decoder_forward(latent, xyz, params=None, dtype=torch.float32, chunk: int = 1 << 16):
+    """Decoder(latent, xyz) -> sdf.  latent [256] (one shape) or [M,256]; xyz [M,3].
+
+    Plain dense evaluation exactly as written in the module docstring, in
+    ``dtype`` (float32 = the oracle; float64 = its self-check).
+    Returns a float32/float64 numpy array [M].
+    """
+    params = decoder_weights() if params is None else params
+    W = [_as_t(w, dtype) for w, _ in params]
+    B = [_as_t(b, dtype) for _, b in params]
+    xyz_t = _as_t(xyz, dtype).reshape(-1, 3)
+    lat = _as_t(latent, dtype)
+    M = xyz_t.shape[0]
+    out = torch.empty(M, dtype=dtype)
+    with torch.no_grad():
+        for s in range(0, M, chunk):
+            e = min(M, s + chunk)
+            x = xyz_t[s:e]
+            z = lat.expand(e - s, DEC_LATENT) if lat.ndim == 1 else lat[s:e]
+            inp = torch.cat([z, x], dim=1)
+            h = torch.relu(inp @ W[0].T + B[0])
+            h = torch.relu(h @ W[1].T + B[1])
+            h = torch.relu(h @ W[2].T + B[2])
+            h = torch.relu(h @ W[3].T + B[3])
+            h = torch.relu(torch.cat([h, inp], dim=1) @ W[4].T + B[4])
+            h = torch.relu(h @ W[5].T + B[5])
+            h = torch.relu(h @ W[6].T + B[6])
+            h = torch.relu(h @ W[7].T + B[7])
+            out[s:e] = torch.tanh(h @ W[8].T + B[8]).squeeze(1)
+    return out.numpy()
+
+
+def decode_grid(latent, res: int, z0: int = 0, z1: int | None = None, params=None,
+                dtype=torch.float32):
+    """decode_grid(z, res) -> sdf[z1-z0, res, res] (C-contiguous [z,y,x])."""
+    z1 = res if z1 is None else z1
+    sdf = decoder_forward(latent, grid_points(res, z0, z1), params=params, dtype=dtype)
+    return sdf.reshape(z1 - z0, res, res)
+
+
+def _round_to(t: torch.Tensor, lowp: torch.dtype) -> torch.Tensor:
+    return t.to(lowp).to(torch.float32)
+
+
+def decoder_forward_lowp(latent, xyz, params=None, lowp=torch.bfloat16, chunk: int = 1 << 16):
+    """The arithmetic the tensor-core kernel performs, emulated on the CPU.
+
+    * per-shape constants are folded in fp32: bias0' = b0 + W0[:, :256] z and
+      bias4' = b4 + W4[:, 253:509] z;
+    * the xyz columns of L0 and L4 stay fp32 (the kernel feeds them to the
+      tensor core as exact 3-way bf16 splits of both operands);
+    * every other weight is rounded to ``lowp``; activations h0..h6 are rounded
+      to ``lowp`` after the ReLU; products accumulate in fp32;
+    * h7 stays fp32 and the 512 -> 1 head and tanh are evaluated in fp32.
+    Only a single shared latent ([256]) is supported, as in the kernel.
+    """
+    params = decoder_weights() if params is None else params
+    f32 = torch.float32
+    W = [_as_t(w, f32) for w, _ in params]
+    B = [_as_t(b, f32) for _, b in params]
+    z = _as_t(latent, f32).reshape(DEC_LATENT)
+    xyz_t = _as_t(xyz, f32).reshape(-1, 3)
+    L, S = DEC_LATENT, DEC_SKIP_OUT
+    bias0 = B[0] + W[0][:, :L] @ z
+    bias4 = B[4] + W[4][:, S:S + L] @ z
+    W0x = W[0][:, L:L + 3]
+    W4x = W[4][:, S + L:S + L + 3]
+    W4h = _round_to(W[4][:, :S], lowp)
+    Wq = {i: _round_to(W[i], lowp) for i in (1, 2, 3, 5, 6, 7)}
+    M = xyz_t.shape[0]
+    out = torch.empty(M, dtype=f32)
+    with torch.no_grad():
+        for s in range(0, M, chunk):
+            e = min(M, s + chunk)
+            x = xyz_t[s:e]
+            h = _round_to(torch.relu(x @ W0x.T + bias0), lowp)
+            h = _round_to(torch.relu(h @ Wq[1].T + B[1]), lowp)
+            h = _round_to(torch.relu(h @ Wq[2].T + B[2]), lowp)
+            h = _round_to(torch.relu(h @ Wq[3].T + B[3]), lowp)
+            h = _round_to(torch.relu(h @ W4h.T + x @ W4x.T + bias4), lowp)
+            h = _round_to(torch.relu(h @ Wq[5].T + B[5]), lowp)
+            h = _round_to(torch.relu(h @ Wq[6].T + B[6]), lowp)
+            h = torch.relu(h @ Wq[7].T + B[7])
+            out[s:e] = torch.tanh(h @ W[8].T + B[8]).squeeze(1)
+    return out.numpy()

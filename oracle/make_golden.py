@@ -1,0 +1,111 @@
+"""Generate the committed fixtures under tests/golden/ from the CPU oracle.
+
+    python -m oracle.make_golden            # rewrite tests/golden/oracle_golden.{npz,json}
+    python -m oracle.make_golden --calibrate  # print the head bias that puts 25% of 64^3 inside
+
+There is no upstream reference to generate vectors from
+(`/root/reference/README.md:1` is a title), so these fixtures pin the oracle to
+itself: "frozen" becomes enforceable, and the GPU box (which has no
+/root/reference either) checks the CUDA path against the same numbers.
+Test infrastructure only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import (axis_coords, grid_points, sign_change_mask, decoder_weights, ddpm_weights,
+               default_latent, weights_sha256, decode_grid, decoder_forward,
+               decoder_forward_lowp, sample_latents)
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+DDPM_NOISE_SEED = 2
+DDPM_GOLDEN_N = 8
+
+
+def ddpm_golden_inputs(n: int = DDPM_GOLDEN_N, steps: int = 1000):
+    """x_T [n,256] and noise [steps,n,256] of the golden DDPM run (RandomState(2))."""
+    rs = np.random.RandomState(DDPM_NOISE_SEED)
+    x_T = rs.standard_normal((n, 256)).astype(np.float32)
+    noise = rs.standard_normal((steps, n, 256)).astype(np.float32)
+    return x_T, noise
+
+
+def calibrate():
+    params = [(w.copy(), b.copy()) for w, b in decoder_weights()]
+    params[8] = (params[8][0], np.zeros(1, np.float32))
+    sdf0 = decode_grid(default_latent(), 64, params=params)
+    pre = np.arctanh(np.clip(sdf0.astype(np.float64), -0.999999, 0.999999))
+    print("DEC_HEAD_BIAS =", repr(np.float32(-np.quantile(pre, 0.25))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--calibrate", action="store_true")
+    args = ap.parse_args()
+    if args.calibrate:
+        return calibrate()
+    torch.set_num_threads(os.cpu_count() or 1)
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    z = default_latent()
+    arrays, meta = {}, {}
+    meta["decoder_sha256"] = weights_sha256(decoder_weights())
+    meta["ddpm_sha256"] = weights_sha256(ddpm_weights())
+    meta["latent_sha256"] = __import__("hashlib").sha256(z.tobytes()).hexdigest()
+    for res in (64, 128, 256, 512):
+        arrays[f"coords_{res}"] = axis_coords(res)
+
+    sdf64 = decode_grid(z, 64)
+    mask64 = sign_change_mask(sdf64)
+    meta["sdf64_inside"] = int((sdf64 < 0).sum())
+    meta["sdf64_active_cells"] = int(mask64.sum())
+    meta["sdf64_min"] = float(sdf64.min())
+    meta["sdf64_max"] = float(sdf64.max())
+    arrays["mask64_bits"] = np.packbits(mask64.ravel())
+    rs = np.random.RandomState(7)
+    idx = np.sort(rs.choice(64 ** 3, 512, replace=False)).astype(np.int64)
+    pts64 = grid_points(64)
+    arrays["sdf64_idx"] = idx
+    arrays["sdf64_fp32"] = sdf64.ravel()[idx]
+    arrays["sdf64_bf16"] = decoder_forward_lowp(z, pts64[idx], lowp=torch.bfloat16)
+    arrays["sdf64_fp16"] = decoder_forward_lowp(z, pts64[idx], lowp=torch.float16)
+    # a z-slab the multi-GPU tests decode on their own: planes [16, 24) of 64^3
+    arrays["sdf64_slab_16_24"] = sdf64[16:24].copy()
+    # sparse samples of the big grids (the full 256^3 / 512^3 oracle is minutes of CPU)
+    for res in (256, 512):
+        c = axis_coords(res)
+        q = np.sort(rs.choice(res ** 3, 256, replace=False)).astype(np.int64)
+        ix, iy, iz = q % res, (q // res) % res, q // (res * res)
+        pts = np.stack([c[ix], c[iy], c[iz]], axis=1)
+        arrays[f"sdf{res}_idx"] = q
+        arrays[f"sdf{res}_fp32"] = decoder_forward(z, pts)
+        arrays[f"sdf{res}_bf16"] = decoder_forward_lowp(z, pts, lowp=torch.bfloat16)
+    # a second latent, arbitrary (off-grid) points: the Decoder(latent, xyz) entry
+    z1 = default_latent(1)
+    pts = (rs.uniform(-1, 1, size=(256, 3))).astype(np.float32)
+    arrays["points_xyz"] = pts
+    arrays["points_fp32"] = decoder_forward(z1, pts)
+    arrays["points_bf16"] = decoder_forward_lowp(z1, pts, lowp=torch.bfloat16)
+
+    x_T, noise = ddpm_golden_inputs()
+    arrays["ddpm_fp32"] = sample_latents(DDPM_GOLDEN_N, x_T, noise)
+    arrays["ddpm_bf16"] = sample_latents(DDPM_GOLDEN_N, x_T, noise, lowp=torch.bfloat16)
+    x64 = sample_latents(DDPM_GOLDEN_N, x_T, noise, dtype=torch.float64)
+    meta["ddpm_fp32_vs_fp64_maxabs"] = float(np.abs(arrays["ddpm_fp32"] - x64).max())
+    sdf64_f64 = decode_grid(z, 64, dtype=torch.float64)
+    meta["sdf64_fp32_vs_fp64_maxabs"] = float(np.abs(sdf64 - sdf64_f64).max())
+    meta["torch"] = torch.__version__
+    meta["numpy"] = np.__version__
+
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "oracle_golden.npz"), **arrays)
+    with open(os.path.join(GOLDEN_DIR, "oracle_golden.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+    print(json.dumps(meta, indent=1, sort_keys=True))
+
+
+if __name__ == "__main__":
+    main()

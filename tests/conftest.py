@@ -1,0 +1,25 @@
+"""pytest configuration: registers the ``gpu`` marker and shared fixtures."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    arrays = dict(np.load(os.path.join(GOLDEN_DIR, "oracle_golden.npz")))
+    with open(os.path.join(GOLDEN_DIR, "oracle_golden.json")) as f:
+        meta = json.load(f)
+    return arrays, meta

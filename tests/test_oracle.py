@@ -1,0 +1,129 @@
+"""CPU tests: the oracle against its committed golden fixtures and its own fp64
+re-evaluation (there are no upstream vectors: /root/reference/README.md:1 is a title)."""
+import hashlib
+
+import numpy as np
+import torch
+
+import oracle
+from oracle.make_golden import ddpm_golden_inputs
+
+
+def test_weights_are_frozen(golden):
+    _, meta = golden
+    assert oracle.weights_sha256(oracle.decoder_weights()) == meta["decoder_sha256"]
+    assert oracle.weights_sha256(oracle.ddpm_weights()) == meta["ddpm_sha256"]
+    assert hashlib.sha256(oracle.default_latent().tobytes()).hexdigest() == meta["latent_sha256"]
+    flat = oracle.flatten_params(oracle.decoder_weights())
+    assert flat.size == 1_835_520 + 3_838
+
+
+def test_axis_coords_bit_exact(golden):
+    arrays, _ = golden
+    for res in (64, 128, 256, 512):
+        c = oracle.axis_coords(res)
+        assert c.dtype == np.float32
+        assert np.array_equal(c.view(np.uint32), arrays[f"coords_{res}"].view(np.uint32))
+        assert c[0] == -1.0 and c[-1] == 1.0
+        # antisymmetric by construction
+        assert np.array_equal(c, -c[::-1])
+
+
+def test_grid_points_order():
+    p = oracle.grid_points(4)
+    c = oracle.axis_coords(4)
+    assert p.shape == (64, 3)
+    q = (2 * 4 + 1) * 4 + 3          # iz=2, iy=1, ix=3
+    assert tuple(p[q]) == (c[3], c[1], c[2])
+    slab = oracle.grid_points(4, 1, 3)
+    assert np.array_equal(slab, p[16:48])
+
+
+def test_mask_definition():
+    s = np.ones((3, 3, 3), np.float32)
+    assert oracle.sign_change_mask(s).sum() == 0
+    s[1, 1, 1] = -1.0                       # centre node touches all 8 cells
+    assert oracle.sign_change_mask(s).sum() == 8
+    s[:] = -1.0
+    assert oracle.sign_change_mask(s).sum() == 0
+    s = np.ones((2, 2, 2), np.float32)
+    s[0, 0, 0] = -0.0                       # -0 is outside
+    assert oracle.sign_change_mask(s).sum() == 0
+    s[0, 0, 0] = np.nan                     # NaN is outside
+    assert oracle.sign_change_mask(s).sum() == 0
+
+
+def test_decoder_golden_64(golden):
+    arrays, meta = golden
+    torch.set_num_threads(8)
+    sdf = oracle.decode_grid(oracle.default_latent(), 64)
+    assert sdf.shape == (64, 64, 64) and sdf.dtype == np.float32
+    np.testing.assert_allclose(sdf.ravel()[arrays["sdf64_idx"]], arrays["sdf64_fp32"], atol=2e-6, rtol=0)
+    # non-degenerate field: a real surface inside the cube
+    assert abs(int((sdf < 0).sum()) - meta["sdf64_inside"]) <= 8
+    mask = oracle.sign_change_mask(sdf)
+    golden_mask = np.unpackbits(arrays["mask64_bits"])[:63 ** 3].reshape(63, 63, 63)
+    assert (mask != golden_mask).sum() <= 16     # sgemm summation order may flip |sdf|<1e-6 nodes
+    assert meta["sdf64_active_cells"] > 5000
+    np.testing.assert_allclose(sdf[16:24], arrays["sdf64_slab_16_24"], atol=2e-6, rtol=0)
+
+
+def test_decoder_fp32_vs_fp64_noise_floor(golden):
+    arrays, _ = golden
+    z = oracle.default_latent()
+    pts = oracle.grid_points(64)[arrays["sdf64_idx"]]
+    f32 = oracle.decoder_forward(z, pts)
+    f64 = oracle.decoder_forward(z, pts, dtype=torch.float64)
+    assert np.abs(f32 - f64).max() < 5e-6       # the 1e-5 fp32 criterion sits above this floor
+
+
+def test_decoder_lowp_golden_and_distance(golden):
+    arrays, _ = golden
+    z = oracle.default_latent()
+    pts = oracle.grid_points(64)[arrays["sdf64_idx"]]
+    bf = oracle.decoder_forward_lowp(z, pts, lowp=torch.bfloat16)
+    np.testing.assert_allclose(bf, arrays["sdf64_bf16"], atol=5e-4, rtol=0)
+    fh = oracle.decoder_forward_lowp(z, pts, lowp=torch.float16)
+    np.testing.assert_allclose(fh, arrays["sdf64_fp16"], atol=1e-4, rtol=0)
+    ref = arrays["sdf64_fp32"]
+    # measured distances to the fp32 oracle: bf16 misses 2e-3, fp16 meets it
+    assert 2e-3 < np.abs(bf - ref).max() < 2e-2
+    assert np.abs(fh - ref).max() < 2e-3
+    m = np.abs(ref) > 2e-3
+    assert ((bf < 0) == (ref < 0))[m].mean() >= 0.999
+
+
+def test_decoder_batched_latents_and_points(golden):
+    arrays, _ = golden
+    z1 = oracle.default_latent(1)
+    out = oracle.decoder_forward(z1, arrays["points_xyz"])
+    np.testing.assert_allclose(out, arrays["points_fp32"], atol=2e-6, rtol=0)
+    zz = np.stack([z1] * 4)
+    out_b = oracle.decoder_forward(zz, arrays["points_xyz"][:4])
+    np.testing.assert_allclose(out_b, arrays["points_fp32"][:4], atol=2e-6, rtol=0)
+
+
+def test_ddpm_schedule_and_embedding():
+    s = oracle.ddpm_schedule()
+    assert all(v.shape == (1000,) and v.dtype == np.float32 for v in s.values())
+    assert s["sigma"][0] == 0.0 and s["c2"][0] == 0.0
+    np.testing.assert_allclose(s["c1"][0], 1.0, rtol=1e-6)
+    te = oracle.time_embedding([0, 999])
+    assert te.shape == (2, 256)
+    assert np.all(te[0, :128] == 0) and np.all(te[0, 128:] == 1)
+
+
+def test_ddpm_golden(golden):
+    arrays, meta = golden
+    x_T, noise = ddpm_golden_inputs()
+    x = oracle.sample_latents(8, x_T, noise)
+    np.testing.assert_allclose(x, arrays["ddpm_fp32"], atol=2e-5, rtol=0)
+    assert meta["ddpm_fp32_vs_fp64_maxabs"] < 2e-5       # contractive sampler: 1e-4 is meaningful
+    assert np.abs(x).max() <= 1.0 + 1e-6                 # t=0 step returns the clipped x0
+
+
+def test_ddpm_short_run_lowp_tracks_fp32():
+    x_T, noise = ddpm_golden_inputs(n=4, steps=50)
+    a = oracle.sample_latents(4, x_T, noise, steps=50)
+    b = oracle.sample_latents(4, x_T, noise, steps=50, lowp=torch.bfloat16)
+    assert np.abs(a - b).max() < 5e-2
