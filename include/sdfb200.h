@@ -1,0 +1,131 @@
+/* sdfb200.h - C ABI of libsdfb200.so: the B200-native shape-SDF decoder and
+ * latent-DDPM sampler hot path.
+ *
+ * Reference interface replaced: there is none to cite beyond the title line
+ * /root/reference/README.md:1 (the mounted reference has no source).  The
+ * entry points below are the C-level boundary underneath the Python API that
+ * BASELINE.json's north_star names - Decoder(latent, xyz) -> sdf,
+ * decode_grid(z, res), sample_latents(n) - and that SURVEY.md section 8(b)
+ * proposes.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative SDFB_E_* code on
+ *    failure; sdfb_last_error() gives a thread-local human-readable message.
+ *    Nothing throws across the boundary.
+ *  - pointers named *_dev are device pointers on the context's device,
+ *    *_host are host pointers.  `stream` is a cudaStream_t passed as void*
+ *    (NULL = the legacy default stream).  Calls are asynchronous on `stream`
+ *    unless the name ends in _host.
+ *  - a context belongs to one device; calls on one context must be issued
+ *    from one thread at a time and on one stream at a time (the per-latent
+ *    constant block lives in the context).
+ *  - no CPU fallback exists: without a CUDA device of compute capability
+ *    10.x the create calls fail with SDFB_E_DEVICE.
+ */
+#ifndef SDFB200_H_
+#define SDFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDFB_OK 0
+#define SDFB_E_INVALID (-1)   /* bad argument / unsupported shape            */
+#define SDFB_E_DEVICE (-2)    /* no usable sm_100 device                     */
+#define SDFB_E_CUDA (-3)      /* a CUDA runtime call failed                  */
+#define SDFB_E_KERNEL (-4)    /* in-kernel watchdog or self-check tripped    */
+#define SDFB_E_NOMEM (-5)
+
+/* arithmetic of the matrix products */
+#define SDFB_PREC_FP32 0 /* FFMA SIMT kernels: carries the 1e-5 / 1e-4 criteria          */
+#define SDFB_PREC_BF16 1 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM    */
+#define SDFB_PREC_FP16 2 /* same kernel, fp16 operands (meets the 2e-3 bound vs fp32)    */
+
+/* decoder parameter blob: W0,b0,W1,b1,...,W8,b8 (row-major W[out][in], fp32) */
+#define SDFB_DECODER_PARAM_FLOATS 1839358
+/* denoiser parameter blob: W0,b0,...,W4,b4                                   */
+#define SDFB_DDPM_PARAM_FLOATS 3936512
+#define SDFB_LATENT_DIM 256
+#define SDFB_DDPM_STEPS 1000
+
+typedef struct sdfb_decoder sdfb_decoder;
+typedef struct sdfb_ddpm sdfb_ddpm;
+
+int sdfb_version(void);
+const char* sdfb_last_error(void);
+
+/* ---- SDF auto-decoder -------------------------- */
+
+/* Copies the fp32 parameters to `device`, packs the bf16 and fp16 tensor-core
+ * weight streams and allocates the context workspace. */
+int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, sdfb_decoder** out);
+int sdfb_decoder_destroy(sdfb_decoder* dec);
+
+/* decode_grid(z, res) restricted to planes [z0, z1): writes
+ * sdf_dev[(z1-z0)*res*res] (C order z,y,x).  Node (iz,iy,ix) sits at
+ * c_i = float(2i-(res-1))/float(res-1) on each axis (bit-exact rule A1).
+ * If mask_dev != NULL the sign-change mask (A4) of the cell layers
+ * [z0, min(z1,res-1)) is written as uint8 [(layers)*(res-1)*(res-1)]; when
+ * z1 < res this needs the halo plane z1, which is then decoded too and stored
+ * after the slab, so sdf_dev must hold (z1-z0+1)*res*res floats in that case. */
+int sdfb_decode_grid(sdfb_decoder* dec, const float* latent_dev, int res, int z0, int z1,
+                     float* sdf_dev, uint8_t* mask_dev, int precision, void* stream);
+
+/* Decoder(latent, xyz) -> sdf for M arbitrary points, xyz_dev [M][3]. */
+int sdfb_decode_points(sdfb_decoder* dec, const float* latent_dev, const float* xyz_dev, int64_t M,
+                       float* sdf_dev, int precision, void* stream);
+
+/* Host-buffer forms (what a plugin caller with CPU arrays uses): stage through
+ * pinned memory owned by the context, run, copy back, synchronise. */
+int sdfb_decode_grid_host(sdfb_decoder* dec, const float* latent_host, int res, int z0, int z1,
+                          float* sdf_host, uint8_t* mask_host, int precision);
+int sdfb_decode_points_host(sdfb_decoder* dec, const float* latent_host, const float* xyz_host,
+                            int64_t M, float* sdf_host, int precision);
+
+/* xyz of planes [z0,z1) of the res^3 grid -> xyz_dev [(z1-z0)*res*res][3] */
+int sdfb_grid_points(int res, int z0, int z1, float* xyz_dev, void* stream);
+/* A4 on an arbitrary [nz][ny][nx] field -> uint8 [(nz-1)(ny-1)(nx-1)] */
+int sdfb_sign_change_mask(const float* sdf_dev, int nz, int ny, int nx, uint8_t* mask_dev,
+                          void* stream);
+
+/* Debug/diagnostic: pre-activation (accumulator + bias, before ReLU) of
+ * tensor-core pass `pass` (0..12) for the first 128 queries of a grid decode,
+ * 128 x 256 floats.  Used by the parity tests to localise a failing layer. */
+int sdfb_decode_debug_pass(sdfb_decoder* dec, const float* latent_dev, int res, int pass,
+                           float* dump_dev, int precision, void* stream);
+/* Elapsed device time of the last fused-decoder launch on this context, in
+ * milliseconds, measured with CUDA events on the launching stream (blocks
+ * until that launch has finished). */
+int sdfb_decoder_last_kernel_ms(sdfb_decoder* dec, float* ms);
+
+/* ---- latent DDPM ------------------------------- */
+
+int sdfb_ddpm_create(const float* params_host, size_t n_floats, int device, sdfb_ddpm** out);
+int sdfb_ddpm_destroy(sdfb_ddpm* ddpm);
+
+/* sample_latents(n): x_dev [n][256] holds x_T on entry and x_0 on return.
+ * noise_dev [steps][n][256] is the explicit noise stream (noise[t] is consumed
+ * at step t, noise[0] is ignored).  Runs t = steps-1 .. 0 of the 1000-step
+ * linear-beta schedule with the x0-clipped posterior-mean update. */
+int sdfb_ddpm_sample(sdfb_ddpm* ddpm, float* x_dev, const float* noise_dev, int n, int steps,
+                     int precision, void* stream);
+/* one denoiser evaluation eps_hat(x, t) -> eps_dev [n][256] */
+int sdfb_ddpm_denoise(sdfb_ddpm* ddpm, const float* x_dev, int t, int n, float* eps_dev,
+                      int precision, void* stream);
+int sdfb_ddpm_sample_host(sdfb_ddpm* ddpm, float* x_host, const float* noise_host, int n, int steps,
+                          int precision);
+
+/* ---- unit-test hook for the UMMA plumbing -------------------------------- */
+/* D[128][256] (fp32) = A[128][64] * B[256][64]^T with A and B given as
+ * row-major 16-bit arrays on the device (bf16 or fp16 per `precision`); the
+ * kernel stages them into the 128B-swizzled smem layout itself. */
+int sdfb_umma_selftest(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int precision,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFB200_H_ */

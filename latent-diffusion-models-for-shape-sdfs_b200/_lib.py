@@ -1,0 +1,69 @@
+"""ctypes binding of libsdfb200.so (the C ABI in include/sdfb200.h).
+
+There is no fallback: if the shared library is missing or fails to load, importing the
+product API raises.  The oracle under ``oracle/`` is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB
+
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
+
+DECODER_PARAM_FLOATS = 1839358
+DDPM_PARAM_FLOATS = 3936512
+
+_vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/sdfb200.h declares
+SIGNATURES = {
+    "sdfb_version": (_i, []),
+    "sdfb_last_error": (C.c_char_p, []),
+    "sdfb_decoder_create": (_i, [_vp, _sz, _i, C.POINTER(_vp)]),
+    "sdfb_decoder_destroy": (_i, [_vp]),
+    "sdfb_decode_grid": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "sdfb_decode_points": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _vp]),
+    "sdfb_decode_grid_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i]),
+    "sdfb_decode_points_host": (_i, [_vp, _vp, _vp, _i64, _vp, _i]),
+    "sdfb_grid_points": (_i, [_i, _i, _i, _vp, _vp]),
+    "sdfb_sign_change_mask": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "sdfb_decode_debug_pass": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
+    "sdfb_decoder_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
+    "sdfb_ddpm_create": (_i, [_vp, _sz, _i, C.POINTER(_vp)]),
+    "sdfb_ddpm_destroy": (_i, [_vp]),
+    "sdfb_ddpm_sample": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "sdfb_ddpm_denoise": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
+    "sdfb_ddpm_sample_host": (_i, [_vp, _vp, _vp, _i, _i, _i]),
+    "sdfb_umma_selftest": (_i, [_vp, _vp, _vp, _i, _vp]),
+}
+
+_lib = None
+
+
+class SdfbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsdfb200 error {code}: {msg}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    """Load libsdfb200.so (must have been built: ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        raise ImportError(f"{LIB} is missing - run __graft_entry__.build(); there is no CPU fallback")
+    lib = C.CDLL(LIB)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise SdfbError(rc, load().sdfb_last_error().decode("utf-8", "replace"))

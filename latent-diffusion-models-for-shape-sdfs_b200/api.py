@@ -1,0 +1,286 @@
+"""Host-side API: thin, validating wrappers that hand device pointers to the C ABI.
+
+Names and argument meaning follow the oracle modules (oracle/decoder.py, oracle/ddpm.py),
+which restate the method in SURVEY.md section 8(a); results are torch CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PRECISIONS, check
+
+LATENT = 256
+DDPM_STEPS = 1000
+
+
+def _flat_params(params, expect: int) -> np.ndarray:
+    """Accepts the flat blob (numpy / torch) or a list of (W[out,in], b[out]) pairs."""
+    if isinstance(params, (list, tuple)):
+        parts = []
+        for w, b in params:
+            parts.append(np.asarray(w, dtype=np.float32).ravel())
+            parts.append(np.asarray(b, dtype=np.float32).ravel())
+        flat = np.concatenate(parts)
+    elif isinstance(params, torch.Tensor):
+        flat = params.detach().cpu().numpy().astype(np.float32, copy=False).ravel()
+    else:
+        flat = np.asarray(params, dtype=np.float32).ravel()
+    if flat.size != expect:
+        raise ValueError(f"parameter blob has {flat.size} floats, expected {expect}")
+    return np.ascontiguousarray(flat)
+
+
+def _device_index(device) -> int:
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise ValueError("libsdfb200 runs on CUDA devices only (no CPU fallback)")
+    return torch.cuda.current_device() if dev.index is None else dev.index
+
+
+def _prec(precision: str) -> int:
+    try:
+        return PRECISIONS[precision]
+    except KeyError:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}") from None
+
+
+def _stream_ptr(device_index: int) -> int:
+    return torch.cuda.current_stream(device_index).cuda_stream
+
+
+def _as_dev_f32(t, device: torch.device, shape=None) -> torch.Tensor:
+    t = torch.as_tensor(np.asarray(t) if not isinstance(t, torch.Tensor) else t)
+    t = t.to(device=device, dtype=torch.float32).contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t
+
+
+class Decoder:
+    """DeepSDF-style auto-decoder (259 -> 512x3 -> 253 (+259 skip) -> 512x4 -> 1, tanh).
+
+    ``Decoder(latent, xyz) -> sdf``; ``decode_grid(z, res)``.  ``precision``: "bf16" / "fp16"
+    run the fused tcgen05 kernel, "fp32" the FFMA kernels.
+    """
+
+    def __init__(self, params, device="cuda:0", precision: str = "bf16"):
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", _device_index(device))
+        self.precision = precision
+        _prec(precision)
+        flat = _flat_params(params, _lib.DECODER_PARAM_FLOATS)
+        handle = C.c_void_p()
+        check(self._lib.sdfb_decoder_create(flat.ctypes.data, flat.size, self.device.index, C.byref(handle)))
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sdfb_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- Decoder(latent, xyz) -> sdf ------------------------------------------------
+    def __call__(self, latent, xyz, precision: str | None = None) -> torch.Tensor:
+        prec = _prec(precision or self.precision)
+        lat = _as_dev_f32(latent, self.device)
+        pts = _as_dev_f32(xyz, self.device)
+        if lat.ndim == 1:
+            if lat.shape[0] != LATENT or pts.ndim != 2 or pts.shape[1] != 3:
+                raise ValueError("expected latent [256] and xyz [M,3]")
+            return self._points(lat, pts, prec)
+        # batch of shapes: latent [B,256], xyz [B,M,3] -> sdf [B,M]
+        if lat.ndim != 2 or lat.shape[1] != LATENT or pts.ndim != 3 or pts.shape[0] != lat.shape[0] or pts.shape[2] != 3:
+            raise ValueError("expected latent [B,256] and xyz [B,M,3]")
+        out = torch.empty(pts.shape[:2], dtype=torch.float32, device=self.device)
+        for b in range(lat.shape[0]):
+            out[b] = self._points(lat[b], pts[b], prec)
+        return out
+
+    def _points(self, lat, pts, prec) -> torch.Tensor:
+        M = pts.shape[0]
+        out = torch.empty(M, dtype=torch.float32, device=self.device)
+        check(self._lib.sdfb_decode_points(self._h, lat.data_ptr(), pts.data_ptr() if M else None, M,
+                                           out.data_ptr() if M else None, prec, _stream_ptr(self.device.index)))
+        return out
+
+    # ---- decode_grid(z, res) -> sdf[z,y,x] (+ mask) -------------------------------------
+    def decode_grid(self, latent, res: int, z0: int = 0, z1: int | None = None, mask: bool = False,
+                    precision: str | None = None, out: torch.Tensor | None = None):
+        """sdf [z1-z0, res, res] float32 of planes [z0, z1); with ``mask=True`` also the uint8
+        sign-change mask of cell layers [z0, min(z1, res-1)) as [layers, res-1, res-1].
+
+        ``out`` (optional) is a preallocated float32 buffer; with ``mask`` and z1 < res it must
+        hold one extra (halo) plane, which is decoded locally instead of being exchanged."""
+        prec = _prec(precision or self.precision)
+        z1 = res if z1 is None else z1
+        if not (0 <= z0 <= z1 <= res) or res < 2:
+            raise ValueError(f"bad plane range [{z0}, {z1}) for res {res}")
+        lat = _as_dev_f32(latent, self.device, (LATENT,))
+        halo = 1 if (mask and z1 < res and z1 > z0) else 0
+        planes = z1 - z0 + halo
+        if out is None:
+            buf = torch.empty((planes, res, res), dtype=torch.float32, device=self.device)
+        else:
+            if out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous() or out.numel() < planes * res * res:
+                raise ValueError("out must be a contiguous float32 CUDA tensor with room for the slab (+ halo plane)")
+            buf = out
+        layers = (z1 if halo else min(z1, res - 1)) - z0
+        m = None
+        if mask:
+            m = torch.empty((max(layers, 0), res - 1, res - 1), dtype=torch.uint8, device=self.device)
+        check(self._lib.sdfb_decode_grid(self._h, lat.data_ptr(), res, z0, z1, buf.data_ptr(),
+                                         m.data_ptr() if (m is not None and m.numel()) else None, prec,
+                                         _stream_ptr(self.device.index)))
+        sdf = buf.view(-1)[: (z1 - z0) * res * res].view(z1 - z0, res, res)
+        return (sdf, m) if mask else sdf
+
+    def decode_grid_host(self, latent: np.ndarray, res: int, z0: int = 0, z1: int | None = None,
+                         mask: bool = False, precision: str | None = None):
+        """Same result as ``decode_grid`` but through the host-buffer entry point: numpy in,
+        numpy out, host<->device copies inside the call (the plugin-style call bench.py times)."""
+        prec = _prec(precision or self.precision)
+        z1 = res if z1 is None else z1
+        lat = np.ascontiguousarray(np.asarray(latent, dtype=np.float32).reshape(LATENT))
+        sdf = np.empty((z1 - z0, res, res), dtype=np.float32)
+        halo = mask and z1 < res and z1 > z0
+        layers = (z1 if halo else min(z1, res - 1)) - z0
+        m = np.empty((max(layers, 0), res - 1, res - 1), dtype=np.uint8) if mask else None
+        check(self._lib.sdfb_decode_grid_host(self._h, lat.ctypes.data, res, z0, z1, sdf.ctypes.data,
+                                              m.ctypes.data if (m is not None and m.size) else None, prec))
+        return (sdf, m) if mask else sdf
+
+    def decode_points_host(self, latent: np.ndarray, xyz: np.ndarray, precision: str | None = None) -> np.ndarray:
+        prec = _prec(precision or self.precision)
+        lat = np.ascontiguousarray(np.asarray(latent, dtype=np.float32).reshape(LATENT))
+        pts = np.ascontiguousarray(np.asarray(xyz, dtype=np.float32).reshape(-1, 3))
+        out = np.empty(pts.shape[0], dtype=np.float32)
+        check(self._lib.sdfb_decode_points_host(self._h, lat.ctypes.data, pts.ctypes.data, pts.shape[0],
+                                                out.ctypes.data, prec))
+        return out
+
+    # ---- diagnostics -----------------------------------------------------------------------
+    def debug_pass(self, latent, res: int, pass_index: int, precision: str | None = None) -> torch.Tensor:
+        """[128,256] pre-activations (accumulator + bias) of tensor-core pass ``pass_index`` for the
+        first 128 grid queries."""
+        prec = _prec(precision or self.precision)
+        lat = _as_dev_f32(latent, self.device, (LATENT,))
+        dump = torch.zeros((128, 256), dtype=torch.float32, device=self.device)
+        check(self._lib.sdfb_decode_debug_pass(self._h, lat.data_ptr(), res, pass_index, dump.data_ptr(), prec,
+                                               _stream_ptr(self.device.index)))
+        return dump
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(self._lib.sdfb_decoder_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+
+class LatentDDPM:
+    """Latent-space DDPM sampler: MLP denoiser 512 -> 1024x4 -> 256 (epsilon prediction,
+    linear beta schedule, 1000 steps, x0-clipped posterior-mean update)."""
+
+    def __init__(self, params, device="cuda:0", precision: str = "fp32"):
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", _device_index(device))
+        self.precision = precision
+        _prec(precision)
+        flat = _flat_params(params, _lib.DDPM_PARAM_FLOATS)
+        handle = C.c_void_p()
+        check(self._lib.sdfb_ddpm_create(flat.ctypes.data, flat.size, self.device.index, C.byref(handle)))
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sdfb_ddpm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def denoise(self, x, t: int, precision: str | None = None) -> torch.Tensor:
+        prec = _prec(precision or self.precision)
+        xt = _as_dev_f32(x, self.device)
+        if xt.ndim != 2 or xt.shape[1] != LATENT:
+            raise ValueError("x must be [n,256]")
+        eps = torch.empty_like(xt)
+        check(self._lib.sdfb_ddpm_denoise(self._h, xt.data_ptr(), int(t), xt.shape[0], eps.data_ptr(), prec,
+                                          _stream_ptr(self.device.index)))
+        return eps
+
+    def sample_latents(self, n: int, x_T=None, noise=None, steps: int = DDPM_STEPS, seed: int = 0,
+                       precision: str | None = None) -> torch.Tensor:
+        """x_0 [n,256].  ``x_T`` [n,256] and ``noise`` [steps,n,256] make the run reproducible
+        against the oracle ("identical noise stream"); when omitted they are drawn on the device
+        from ``seed``."""
+        prec = _prec(precision or self.precision)
+        if n <= 0:
+            raise ValueError("n must be positive")
+        if x_T is None or noise is None:
+            g = torch.Generator(device=self.device)
+            g.manual_seed(seed)
+            if x_T is None:
+                x_T = torch.randn((n, LATENT), generator=g, device=self.device, dtype=torch.float32)
+            if noise is None:
+                noise = torch.randn((steps, n, LATENT), generator=g, device=self.device, dtype=torch.float32)
+        x = _as_dev_f32(x_T, self.device, (n, LATENT)).clone()
+        nz = _as_dev_f32(noise, self.device, (steps, n, LATENT))
+        check(self._lib.sdfb_ddpm_sample(self._h, x.data_ptr(), nz.data_ptr(), n, steps, prec,
+                                         _stream_ptr(self.device.index)))
+        return x
+
+    def sample_latents_host(self, x_T: np.ndarray, noise: np.ndarray, steps: int = DDPM_STEPS,
+                            precision: str | None = None) -> np.ndarray:
+        prec = _prec(precision or self.precision)
+        x = np.ascontiguousarray(np.asarray(x_T, dtype=np.float32)).copy()
+        nz = np.ascontiguousarray(np.asarray(noise, dtype=np.float32))
+        n = x.shape[0]
+        if x.shape != (n, LATENT) or nz.shape != (steps, n, LATENT):
+            raise ValueError("expected x_T [n,256] and noise [steps,n,256]")
+        check(self._lib.sdfb_ddpm_sample_host(self._h, x.ctypes.data, nz.ctypes.data, n, steps, prec))
+        return x
+
+
+# ---- functional spellings named in the north star ---------------------------------------------
+def decode_grid(decoder: Decoder, z, res: int, **kw):
+    return decoder.decode_grid(z, res, **kw)
+
+
+def sample_latents(ddpm: LatentDDPM, n: int, **kw):
+    return ddpm.sample_latents(n, **kw)
+
+
+def grid_points(res: int, z0: int = 0, z1: int | None = None, device="cuda:0") -> torch.Tensor:
+    """xyz [(z1-z0)*res*res, 3] of the grid nodes (x fastest), bit-exact rule A1."""
+    lib = _lib.load()
+    dev = torch.device("cuda", _device_index(device))
+    z1 = res if z1 is None else z1
+    out = torch.empty(((z1 - z0) * res * res, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.sdfb_grid_points(res, z0, z1, out.data_ptr(), _stream_ptr(dev.index)))
+    return out
+
+
+def sign_change_mask(sdf: torch.Tensor) -> torch.Tensor:
+    """A4 on a [nz,ny,nx] float32 CUDA tensor -> uint8 [(nz-1),(ny-1),(nx-1)]."""
+    lib = _lib.load()
+    if sdf.ndim != 3 or sdf.dtype != torch.float32 or not sdf.is_cuda:
+        raise ValueError("sdf must be a 3-D float32 CUDA tensor")
+    s = sdf.contiguous()
+    nz, ny, nx = s.shape
+    out = torch.empty((max(nz - 1, 0), max(ny - 1, 0), max(nx - 1, 0)), dtype=torch.uint8, device=s.device)
+    if out.numel():
+        with torch.cuda.device(s.device):
+            check(lib.sdfb_sign_change_mask(s.data_ptr(), nz, ny, nx, out.data_ptr(), _stream_ptr(s.device.index)))
+    return out

@@ -1,0 +1,632 @@
+// C ABI of libsdfb200.so (declared in include/sdfb200.h): contexts, weight packing,
+// argument validation and kernel launches.  No reference interface exists to mirror
+// (/root/reference/README.md:1 is a title); the surface follows SURVEY.md section 8(b).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "../../include/sdfb200.h"
+#include "kernels.h"
+
+using namespace sdfb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU_TRY(expr)                                                                         \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return fail(SDFB_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_device(int device, int* num_sms) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(SDFB_E_DEVICE, "no CUDA device visible: libsdfb200 has no CPU path");
+  if (device < 0 || device >= count) return fail(SDFB_E_INVALID, "device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SDFB_E_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major,
+                prop.minor);
+  *num_sms = prop.multiProcessorCount;
+  return SDFB_OK;
+}
+
+uint16_t to_lowp(float f, bool fp16) {
+  if (fp16) {
+    __half h = __float2half_rn(f);
+    uint16_t u; std::memcpy(&u, &h, 2); return u;
+  }
+  __nv_bfloat16 b = __float2bfloat16_rn(f);
+  uint16_t u; std::memcpy(&u, &b, 2); return u;
+}
+
+// decoder layer l: offsets into the parameter blob
+struct LayerOff { long long w, b; int fin, fout; };
+const int kFin[9] = {259, 512, 512, 512, 512, 512, 512, 512, 512};
+const int kFout[9] = {512, 512, 512, 253, 512, 512, 512, 512, 1};
+
+void decoder_offsets(LayerOff off[9]) {
+  long long o = 0;
+  for (int l = 0; l < 9; ++l) {
+    off[l].fin = kFin[l]; off[l].fout = kFout[l];
+    off[l].w = o; o += static_cast<long long>(kFin[l]) * kFout[l];
+    off[l].b = o; o += kFout[l];
+  }
+}
+
+// The 96-block weight stream of kernels.h, as 128B-swizzled shared-memory images.
+void pack_wstream(const float* P, const LayerOff off[9], bool fp16, std::vector<uint16_t>& out) {
+  out.assign(static_cast<size_t>(kBlocksPerTile) * kBlockBytes / 2, 0);
+  static const int pass_layer[kPasses] = {1, 1, 2, 2, 3, 4, 4, 5, 5, 6, 6, 7, 7};
+  static const int pass_half[kPasses] = {0, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 0, 1};
+  size_t blk = 0;
+  for (int p = 0; p < kPasses; ++p) {
+    const int L = pass_layer[p], h = pass_half[p];
+    const int nk = (L == 4) ? 4 : 8;
+    const int kvalid = (L == 4) ? kSkipOut : 512;   // L4 consumes h3 (253 wide) through the tensor core
+    const float* W = P + off[L].w;
+    const int fin = off[L].fin, fout = off[L].fout;
+    for (int k = 0; k < nk; ++k, ++blk) {
+      uint16_t* dst = out.data() + blk * (kBlockBytes / 2);
+      for (int r = 0; r < kBlockRows; ++r) {
+        const int n = h * 256 + r;
+        for (int u = 0; u < 8; ++u) {
+          uint16_t* d = dst + r * 64 + ((u ^ (r & 7)) * 8);
+          for (int e = 0; e < 8; ++e) {
+            const int kk = k * 64 + u * 8 + e;
+            const float v = (n < fout && kk < kvalid) ? W[static_cast<long long>(n) * fin + kk] : 0.f;
+            d[e] = to_lowp(v, fp16);
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+struct sdfb_decoder {
+  int device = 0, num_sms = 0;
+  LayerOff off[9];
+  float* params = nullptr;       // fp32 blob on device
+  float* w4s = nullptr;          // [512][256]: W4[:, 0:253] | W4[:, 509:512]   (fp32 path)
+  uint8_t* wstream[2] = {nullptr, nullptr};   // [0] bf16, [1] fp16
+  DecConsts* consts = nullptr;
+  float* bias0f = nullptr;       // fp32 path folded biases
+  float* bias4f = nullptr;
+  unsigned int* status = nullptr;
+  // fp32 workspace (lazy)
+  long long ws_rows = 0;
+  float *h0 = nullptr, *h1 = nullptr, *s = nullptr, *x = nullptr;
+  // host staging (lazy, pinned) + device staging for the *_host calls
+  void* pin = nullptr; size_t pin_bytes = 0;
+  void* dstage = nullptr; size_t dstage_bytes = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  unsigned long long timeout_ns = 2000000000ull;
+};
+
+struct sdfb_ddpm {
+  int device = 0, num_sms = 0;
+  float* params = nullptr;
+  long long woff[5], boff[5];
+  float* tb0 = nullptr;          // [1000][1024]: b0 + W0[:, 256:] temb(t)
+  std::vector<float> sra, srm1, c1, c2, sigma;
+  int ws_n = 0;
+  float *h0 = nullptr, *h1 = nullptr, *eps = nullptr;
+  void* dstage = nullptr; size_t dstage_bytes = 0;
+};
+
+namespace {
+
+int ensure_fp32_ws(sdfb_decoder* d, long long rows) {
+  if (d->ws_rows >= rows) return SDFB_OK;
+  cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x);
+  d->h0 = d->h1 = d->s = d->x = nullptr; d->ws_rows = 0;
+  CU_TRY(cudaMalloc(&d->h0, rows * 512 * sizeof(float)));
+  CU_TRY(cudaMalloc(&d->h1, rows * 512 * sizeof(float)));
+  CU_TRY(cudaMalloc(&d->s, rows * 256 * sizeof(float)));
+  CU_TRY(cudaMalloc(&d->x, rows * 3 * sizeof(float)));
+  d->ws_rows = rows;
+  return SDFB_OK;
+}
+
+constexpr long long kFp32Chunk = 32768;
+
+// fp32 SIMT decode of M queries; xyz == nullptr selects grid mode (global query index q0).
+int decode_fp32(sdfb_decoder* d, const float* z, const float* xyz, int res, long long q0, long long M,
+                float* out, cudaStream_t st) {
+  const long long chunk = M < kFp32Chunk ? M : kFp32Chunk;
+  int rc = ensure_fp32_ws(d, chunk);
+  if (rc) return rc;
+  const float* P = d->params;
+  const LayerOff* o = d->off;
+  CU_TRY(launch_fold_bias(P + o[0].w, kDecIn, 0, P + o[0].b, z, kLatent, kHid, d->bias0f, st));
+  CU_TRY(launch_fold_bias(P + o[4].w, kHid, kSkipOut, P + o[4].b, z, kLatent, kHid, d->bias4f, st));
+  for (long long m0 = 0; m0 < M; m0 += chunk) {
+    const long long m = (M - m0) < chunk ? (M - m0) : chunk;
+    const float* X;
+    if (xyz == nullptr) {
+      CU_TRY(launch_grid_xyz(res, q0 + m0, m, d->x, d->s, st));
+      X = d->x;
+    } else {
+      X = xyz + 3 * m0;
+      CU_TRY(launch_scatter_xyz(X, m, d->s, st));
+    }
+    CU_TRY(launch_linear_f32(X, 3, P + o[0].w + kLatent, kDecIn, d->bias0f, d->h0, 512, m, 512, 3, true, st));
+    CU_TRY(launch_linear_f32(d->h0, 512, P + o[1].w, 512, P + o[1].b, d->h1, 512, m, 512, 512, true, st));
+    CU_TRY(launch_linear_f32(d->h1, 512, P + o[2].w, 512, P + o[2].b, d->h0, 512, m, 512, 512, true, st));
+    CU_TRY(launch_linear_f32(d->h0, 512, P + o[3].w, 512, P + o[3].b, d->s, 256, m, kSkipOut, 512, true, st));
+    CU_TRY(launch_linear_f32(d->s, 256, d->w4s, 256, d->bias4f, d->h1, 512, m, 512, 256, true, st));
+    CU_TRY(launch_linear_f32(d->h1, 512, P + o[5].w, 512, P + o[5].b, d->h0, 512, m, 512, 512, true, st));
+    CU_TRY(launch_linear_f32(d->h0, 512, P + o[6].w, 512, P + o[6].b, d->h1, 512, m, 512, 512, true, st));
+    CU_TRY(launch_linear_f32(d->h1, 512, P + o[7].w, 512, P + o[7].b, d->h0, 512, m, 512, 512, true, st));
+    CU_TRY(launch_head_tanh_f32(d->h0, 512, P + o[8].w, P + o[8].b, out + m0, m, 512, st));
+  }
+  return SDFB_OK;
+}
+
+int decode_tc(sdfb_decoder* d, const float* z, const float* xyz, int res, long long q0, long long M, float* out,
+              bool fp16, float* dump, int dump_pass, cudaStream_t st) {
+  const float* P = d->params;
+  const LayerOff* o = d->off;
+  CU_TRY(launch_fold_latent(P + o[0].w, P + o[0].b, P + o[4].w, P + o[4].b, z, d->consts, st));
+  DecodeParams p{};
+  p.wstream = d->wstream[fp16 ? 1 : 0];
+  p.consts = d->consts;
+  p.xyz = xyz;
+  p.out = out;
+  p.M = M;
+  p.q0 = q0;
+  p.res = res;
+  p.status = d->status;
+  p.dump = dump;
+  p.dump_pass = dump_pass;
+  p.timeout_ns = d->timeout_ns;
+  CU_TRY(cudaEventRecord(d->ev0, st));
+  CU_TRY(launch_fused_decoder(p, fp16, d->num_sms, st));
+  CU_TRY(cudaEventRecord(d->ev1, st));
+  d->timed = true;
+  return SDFB_OK;
+}
+
+int decode_any(sdfb_decoder* d, const float* z, const float* xyz, int res, long long q0, long long M, float* out,
+               int precision, cudaStream_t st) {
+  if (M == 0) return SDFB_OK;
+  switch (precision) {
+    case SDFB_PREC_FP32: return decode_fp32(d, z, xyz, res, q0, M, out, st);
+    case SDFB_PREC_BF16: return decode_tc(d, z, xyz, res, q0, M, out, false, nullptr, -1, st);
+    case SDFB_PREC_FP16: return decode_tc(d, z, xyz, res, q0, M, out, true, nullptr, -1, st);
+    default: return fail(SDFB_E_INVALID, "unknown precision %d", precision);
+  }
+}
+
+int kernel_status(sdfb_decoder* d) {
+  unsigned int s = 0;
+  CU_TRY(cudaMemcpy(&s, d->status, sizeof(s), cudaMemcpyDeviceToHost));
+  if (s != 0) {
+    cudaMemset(d->status, 0, sizeof(unsigned int));
+    return fail(SDFB_E_KERNEL, "fused decoder watchdog tripped at wait site 0x%x", s);
+  }
+  return SDFB_OK;
+}
+
+int ensure_stage(void** pin, size_t* pin_bytes, void** dev, size_t* dev_bytes, size_t need_pin, size_t need_dev) {
+  if (pin != nullptr && *pin_bytes < need_pin) {
+    if (*pin) cudaFreeHost(*pin);
+    *pin = nullptr; *pin_bytes = 0;
+    CU_TRY(cudaMallocHost(pin, need_pin));
+    *pin_bytes = need_pin;
+  }
+  if (*dev_bytes < need_dev) {
+    if (*dev) cudaFree(*dev);
+    *dev = nullptr; *dev_bytes = 0;
+    CU_TRY(cudaMalloc(dev, need_dev));
+    *dev_bytes = need_dev;
+  }
+  return SDFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdfb_version(void) { return 100; }
+const char* sdfb_last_error(void) { return g_err; }
+
+int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, sdfb_decoder** out) {
+  if (out == nullptr || params_host == nullptr) return fail(SDFB_E_INVALID, "null argument");
+  *out = nullptr;
+  if (n_floats != static_cast<size_t>(kDecParamFloats))
+    return fail(SDFB_E_INVALID, "decoder blob must hold %lld floats, got %zu", kDecParamFloats, n_floats);
+  int sms = 0;
+  int rc = check_device(device, &sms);
+  if (rc) return rc;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(SDFB_E_CUDA, "cudaSetDevice(%d) failed", device);
+  sdfb_decoder* d = new (std::nothrow) sdfb_decoder();
+  if (!d) return fail(SDFB_E_NOMEM, "out of host memory");
+  d->device = device; d->num_sms = sms;
+  decoder_offsets(d->off);
+  const float* P = params_host;
+  auto bail = [&](int code) { sdfb_decoder_destroy(d); return code; };
+#define CU_TRY_D(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return bail(fail(SDFB_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)));       \
+  } while (0)
+  CU_TRY_D(fused_decoder_init());
+  CU_TRY_D(cudaMalloc(&d->params, n_floats * sizeof(float)));
+  CU_TRY_D(cudaMemcpy(d->params, P, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+  // fp32 path: compact skip-layer matrix
+  {
+    std::vector<float> w4s(512 * 256);
+    const float* W4 = P + d->off[4].w;
+    for (int n = 0; n < 512; ++n) {
+      for (int k = 0; k < kSkipOut; ++k) w4s[n * 256 + k] = W4[n * 512 + k];
+      for (int k = 0; k < 3; ++k) w4s[n * 256 + kSkipOut + k] = W4[n * 512 + kSkipOut + kLatent + k];
+    }
+    CU_TRY_D(cudaMalloc(&d->w4s, w4s.size() * sizeof(float)));
+    CU_TRY_D(cudaMemcpy(d->w4s, w4s.data(), w4s.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // tensor-core path: weight streams and the constant block
+  for (int f = 0; f < 2; ++f) {
+    std::vector<uint16_t> ws;
+    pack_wstream(P, d->off, f == 1, ws);
+    CU_TRY_D(cudaMalloc(&d->wstream[f], ws.size() * 2));
+    CU_TRY_D(cudaMemcpy(d->wstream[f], ws.data(), ws.size() * 2, cudaMemcpyHostToDevice));
+  }
+  {
+    std::vector<DecConsts> hc(1);
+    DecConsts& c = hc[0];
+    std::memset(&c, 0, sizeof(c));
+    const float* W0 = P + d->off[0].w;
+    const float* W4 = P + d->off[4].w;
+    for (int n = 0; n < 512; ++n) {
+      c.l0[n] = make_float4(W0[n * kDecIn + 256], W0[n * kDecIn + 257], W0[n * kDecIn + 258], 0.f);
+      c.l4x[n] = make_float4(W4[n * 512 + 509], W4[n * 512 + 510], W4[n * 512 + 511], 0.f);
+      c.head[n] = P[d->off[8].w + n];
+    }
+    for (int l = 1; l <= 7; ++l)
+      for (int n = 0; n < d->off[l].fout; ++n) c.bias[l - 1][n] = P[d->off[l].b + n];
+    c.head_b[0] = P[d->off[8].b];
+    CU_TRY_D(cudaMalloc(&d->consts, sizeof(DecConsts)));
+    CU_TRY_D(cudaMemcpy(d->consts, &c, sizeof(DecConsts), cudaMemcpyHostToDevice));
+  }
+  CU_TRY_D(cudaMalloc(&d->bias0f, 512 * sizeof(float)));
+  CU_TRY_D(cudaMalloc(&d->bias4f, 512 * sizeof(float)));
+  CU_TRY_D(cudaMalloc(&d->status, sizeof(unsigned int)));
+  CU_TRY_D(cudaMemset(d->status, 0, sizeof(unsigned int)));
+  CU_TRY_D(cudaEventCreate(&d->ev0));
+  CU_TRY_D(cudaEventCreate(&d->ev1));
+#undef CU_TRY_D
+  *out = d;
+  return SDFB_OK;
+}
+
+int sdfb_decoder_destroy(sdfb_decoder* d) {
+  if (!d) return SDFB_OK;
+  DeviceGuard g(d->device);
+  cudaDeviceSynchronize();
+  cudaFree(d->params); cudaFree(d->w4s); cudaFree(d->wstream[0]); cudaFree(d->wstream[1]);
+  cudaFree(d->consts); cudaFree(d->bias0f); cudaFree(d->bias4f); cudaFree(d->status);
+  cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x);
+  if (d->pin) cudaFreeHost(d->pin);
+  cudaFree(d->dstage);
+  if (d->ev0) cudaEventDestroy(d->ev0);
+  if (d->ev1) cudaEventDestroy(d->ev1);
+  delete d;
+  return SDFB_OK;
+}
+
+int sdfb_decode_grid(sdfb_decoder* d, const float* latent_dev, int res, int z0, int z1, float* sdf_dev,
+                     uint8_t* mask_dev, int precision, void* stream) {
+  if (!d || !latent_dev || !sdf_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 2 || res > 2048) return fail(SDFB_E_INVALID, "res %d outside [2, 2048]", res);
+  if (z0 < 0 || z1 > res || z0 > z1) return fail(SDFB_E_INVALID, "bad plane range [%d, %d) for res %d", z0, z1, res);
+  DeviceGuard g(d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long plane = static_cast<long long>(res) * res;
+  int zend = z1;
+  if (mask_dev != nullptr && z1 < res && z1 > z0) zend = z1 + 1;   // halo plane, recomputed locally
+  const long long M = (zend - z0) * plane;
+  int rc = decode_any(d, latent_dev, nullptr, res, z0 * plane, M, sdf_dev, precision, st);
+  if (rc) return rc;
+  if (mask_dev != nullptr && zend - z0 >= 2)
+    CU_TRY(launch_sign_change_mask(sdf_dev, zend - z0, res, res, mask_dev, st));
+  return SDFB_OK;
+}
+
+int sdfb_decode_points(sdfb_decoder* d, const float* latent_dev, const float* xyz_dev, int64_t M, float* sdf_dev,
+                       int precision, void* stream) {
+  if (!d || !latent_dev || (M > 0 && (!xyz_dev || !sdf_dev))) return fail(SDFB_E_INVALID, "null argument");
+  if (M < 0) return fail(SDFB_E_INVALID, "negative point count");
+  DeviceGuard g(d->device);
+  return decode_any(d, latent_dev, xyz_dev, 0, 0, M, sdf_dev, precision, static_cast<cudaStream_t>(stream));
+}
+
+int sdfb_decode_grid_host(sdfb_decoder* d, const float* latent_host, int res, int z0, int z1, float* sdf_host,
+                          uint8_t* mask_host, int precision) {
+  if (!d || !latent_host || !sdf_host) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 2 || res > 2048 || z0 < 0 || z1 > res || z0 > z1) return fail(SDFB_E_INVALID, "bad grid arguments");
+  DeviceGuard g(d->device);
+  const long long plane = static_cast<long long>(res) * res;
+  const bool halo = mask_host != nullptr && z1 < res && z1 > z0;
+  const long long n_sdf = (z1 - z0 + (halo ? 1 : 0)) * plane;
+  const int layers = (halo ? z1 : (z1 < res - 1 ? z1 : res - 1)) - z0;
+  const long long n_mask = mask_host && layers > 0 ? static_cast<long long>(layers) * (res - 1) * (res - 1) : 0;
+  const size_t off_sdf = 1024, off_mask = off_sdf + ((n_sdf * 4 + 255) / 256) * 256;
+  int rc = ensure_stage(&d->pin, &d->pin_bytes, &d->dstage, &d->dstage_bytes, 1024, off_mask + n_mask);
+  if (rc) return rc;
+  uint8_t* base = static_cast<uint8_t*>(d->dstage);
+  std::memcpy(d->pin, latent_host, kLatent * sizeof(float));
+  CU_TRY(cudaMemcpyAsync(base, d->pin, kLatent * sizeof(float), cudaMemcpyHostToDevice, 0));
+  rc = sdfb_decode_grid(d, reinterpret_cast<float*>(base), res, z0, z1, reinterpret_cast<float*>(base + off_sdf),
+                        n_mask ? base + off_mask : nullptr, precision, nullptr);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(sdf_host, base + off_sdf, (z1 - z0) * plane * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  if (n_mask) CU_TRY(cudaMemcpyAsync(mask_host, base + off_mask, n_mask, cudaMemcpyDeviceToHost, 0));
+  CU_TRY(cudaStreamSynchronize(0));
+  return precision == SDFB_PREC_FP32 ? SDFB_OK : kernel_status(d);
+}
+
+int sdfb_decode_points_host(sdfb_decoder* d, const float* latent_host, const float* xyz_host, int64_t M,
+                            float* sdf_host, int precision) {
+  if (!d || !latent_host || M < 0 || (M > 0 && (!xyz_host || !sdf_host))) return fail(SDFB_E_INVALID, "bad argument");
+  if (M == 0) return SDFB_OK;
+  DeviceGuard g(d->device);
+  const size_t off_xyz = 1024, off_sdf = off_xyz + ((M * 12 + 255) / 256) * 256;
+  int rc = ensure_stage(&d->pin, &d->pin_bytes, &d->dstage, &d->dstage_bytes, 1024, off_sdf + M * 4);
+  if (rc) return rc;
+  uint8_t* base = static_cast<uint8_t*>(d->dstage);
+  std::memcpy(d->pin, latent_host, kLatent * sizeof(float));
+  CU_TRY(cudaMemcpyAsync(base, d->pin, kLatent * sizeof(float), cudaMemcpyHostToDevice, 0));
+  CU_TRY(cudaMemcpyAsync(base + off_xyz, xyz_host, M * 12, cudaMemcpyHostToDevice, 0));
+  rc = sdfb_decode_points(d, reinterpret_cast<float*>(base), reinterpret_cast<float*>(base + off_xyz), M,
+                          reinterpret_cast<float*>(base + off_sdf), precision, nullptr);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(sdf_host, base + off_sdf, M * 4, cudaMemcpyDeviceToHost, 0));
+  CU_TRY(cudaStreamSynchronize(0));
+  return precision == SDFB_PREC_FP32 ? SDFB_OK : kernel_status(d);
+}
+
+int sdfb_grid_points(int res, int z0, int z1, float* xyz_dev, void* stream) {
+  if (!xyz_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 2 || res > 2048 || z0 < 0 || z1 > res || z0 > z1) return fail(SDFB_E_INVALID, "bad grid arguments");
+  const long long plane = static_cast<long long>(res) * res;
+  CU_TRY(launch_grid_xyz(res, z0 * plane, (z1 - z0) * plane, xyz_dev, nullptr, static_cast<cudaStream_t>(stream)));
+  return SDFB_OK;
+}
+
+int sdfb_sign_change_mask(const float* sdf_dev, int nz, int ny, int nx, uint8_t* mask_dev, void* stream) {
+  if (!sdf_dev || !mask_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (nz < 1 || ny < 1 || nx < 1) return fail(SDFB_E_INVALID, "bad field shape");
+  CU_TRY(launch_sign_change_mask(sdf_dev, nz, ny, nx, mask_dev, static_cast<cudaStream_t>(stream)));
+  return SDFB_OK;
+}
+
+int sdfb_decode_debug_pass(sdfb_decoder* d, const float* latent_dev, int res, int pass, float* dump_dev,
+                           int precision, void* stream) {
+  if (!d || !latent_dev || !dump_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (pass < 0 || pass >= kPasses) return fail(SDFB_E_INVALID, "pass %d outside [0, 13)", pass);
+  if (precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16)
+    return fail(SDFB_E_INVALID, "debug pass dump exists for the tensor-core path only");
+  if (res < 2 || static_cast<long long>(res) * res * res < kTileM) return fail(SDFB_E_INVALID, "grid too small");
+  DeviceGuard g(d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_stage(nullptr, nullptr, &d->dstage, &d->dstage_bytes, 0, kTileM * sizeof(float));
+  if (rc) return rc;
+  return decode_tc(d, latent_dev, nullptr, res, 0, kTileM, static_cast<float*>(d->dstage),
+                   precision == SDFB_PREC_FP16, dump_dev, pass, st);
+}
+
+int sdfb_decoder_last_kernel_ms(sdfb_decoder* d, float* ms) {
+  if (!d || !ms) return fail(SDFB_E_INVALID, "null argument");
+  if (!d->timed) return fail(SDFB_E_INVALID, "no fused-decoder launch recorded yet");
+  DeviceGuard g(d->device);
+  CU_TRY(cudaEventSynchronize(d->ev1));
+  CU_TRY(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+  return kernel_status(d);
+}
+
+int sdfb_umma_selftest(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int precision, void* stream) {
+  if (!a_dev || !b_dev || !d_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16) return fail(SDFB_E_INVALID, "bf16 or fp16 only");
+  CU_TRY(fused_decoder_init());
+  unsigned int* status = nullptr;
+  CU_TRY(cudaMalloc(&status, sizeof(unsigned int)));
+  CU_TRY(cudaMemset(status, 0, sizeof(unsigned int)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = launch_umma_selftest(a_dev, b_dev, d_dev, status, precision == SDFB_PREC_FP16, st);
+  unsigned int s = 0;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaMemcpy(&s, status, sizeof(s), cudaMemcpyDeviceToHost);
+  cudaFree(status);
+  if (e != cudaSuccess) return fail(SDFB_E_CUDA, "umma selftest: %s", cudaGetErrorString(e));
+  if (s != 0) return fail(SDFB_E_KERNEL, "umma selftest watchdog tripped (0x%x)", s);
+  return SDFB_OK;
+}
+
+// ------------------------------------------------------------------ DDPM ----
+
+int sdfb_ddpm_create(const float* params_host, size_t n_floats, int device, sdfb_ddpm** out) {
+  if (out == nullptr || params_host == nullptr) return fail(SDFB_E_INVALID, "null argument");
+  *out = nullptr;
+  if (n_floats != static_cast<size_t>(kDdpmParamFloats))
+    return fail(SDFB_E_INVALID, "denoiser blob must hold %lld floats, got %zu", kDdpmParamFloats, n_floats);
+  int sms = 0;
+  int rc = check_device(device, &sms);
+  if (rc) return rc;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(SDFB_E_CUDA, "cudaSetDevice(%d) failed", device);
+  sdfb_ddpm* d = new (std::nothrow) sdfb_ddpm();
+  if (!d) return fail(SDFB_E_NOMEM, "out of host memory");
+  d->device = device; d->num_sms = sms;
+  const int fin[5] = {512, 1024, 1024, 1024, 1024}, fout[5] = {1024, 1024, 1024, 1024, 256};
+  long long o = 0;
+  for (int l = 0; l < 5; ++l) { d->woff[l] = o; o += static_cast<long long>(fin[l]) * fout[l]; d->boff[l] = o; o += fout[l]; }
+  auto bail = [&](int code) { sdfb_ddpm_destroy(d); return code; };
+#define CU_TRY_D(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return bail(fail(SDFB_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)));       \
+  } while (0)
+  CU_TRY_D(cudaMalloc(&d->params, n_floats * sizeof(float)));
+  CU_TRY_D(cudaMemcpy(d->params, params_host, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+  // A5: schedule in fp64, cast to fp32 (oracle/ddpm.py ddpm_schedule)
+  {
+    const int T = kDdpmT;
+    d->sra.resize(T); d->srm1.resize(T); d->c1.resize(T); d->c2.resize(T); d->sigma.resize(T);
+    double abar = 1.0, abar_prev = 1.0;
+    for (int t = 0; t < T; ++t) {
+      const double beta = 1e-4 + (0.02 - 1e-4) * static_cast<double>(t) / (T - 1);
+      const double alpha = 1.0 - beta;
+      abar_prev = abar;
+      abar = abar * alpha;
+      d->sra[t] = static_cast<float>(1.0 / std::sqrt(abar));
+      d->srm1[t] = static_cast<float>(std::sqrt(1.0 / abar - 1.0));
+      d->c1[t] = static_cast<float>(beta * std::sqrt(abar_prev) / (1.0 - abar));
+      d->c2[t] = static_cast<float>((1.0 - abar_prev) * std::sqrt(alpha) / (1.0 - abar));
+      d->sigma[t] = t == 0 ? 0.f : static_cast<float>(std::sqrt(beta * (1.0 - abar_prev) / (1.0 - abar)));
+    }
+  }
+  // time-embedding half of layer 0 folded into a per-step bias table
+  {
+    const int T = kDdpmT, half = kDdpmTemb / 2;
+    std::vector<float> temb(static_cast<size_t>(T) * kDdpmTemb);
+    for (int t = 0; t < T; ++t)
+      for (int i = 0; i < half; ++i) {
+        const double f = std::exp(-std::log(10000.0) * i / half);
+        temb[t * kDdpmTemb + i] = static_cast<float>(std::sin(t * f));
+        temb[t * kDdpmTemb + half + i] = static_cast<float>(std::cos(t * f));
+      }
+    float* temb_dev = nullptr;
+    CU_TRY_D(cudaMalloc(&temb_dev, temb.size() * sizeof(float)));
+    CU_TRY_D(cudaMemcpy(temb_dev, temb.data(), temb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY_D(cudaMalloc(&d->tb0, static_cast<size_t>(T) * kDdpmHid * sizeof(float)));
+    cudaError_t e = launch_linear_f32(temb_dev, kDdpmTemb, d->params + d->woff[0] + kDdpmLatent, 512,
+                                      d->params + d->boff[0], d->tb0, kDdpmHid, T, kDdpmHid, kDdpmTemb, false, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(temb_dev);
+    CU_TRY_D(e);
+  }
+#undef CU_TRY_D
+  *out = d;
+  return SDFB_OK;
+}
+
+int sdfb_ddpm_destroy(sdfb_ddpm* d) {
+  if (!d) return SDFB_OK;
+  DeviceGuard g(d->device);
+  cudaDeviceSynchronize();
+  cudaFree(d->params); cudaFree(d->tb0); cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->eps); cudaFree(d->dstage);
+  delete d;
+  return SDFB_OK;
+}
+
+static int ddpm_ws(sdfb_ddpm* d, int n) {
+  if (d->ws_n >= n) return SDFB_OK;
+  cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->eps);
+  d->h0 = d->h1 = d->eps = nullptr; d->ws_n = 0;
+  CU_TRY(cudaMalloc(&d->h0, static_cast<size_t>(n) * kDdpmHid * sizeof(float)));
+  CU_TRY(cudaMalloc(&d->h1, static_cast<size_t>(n) * kDdpmHid * sizeof(float)));
+  CU_TRY(cudaMalloc(&d->eps, static_cast<size_t>(n) * kDdpmLatent * sizeof(float)));
+  d->ws_n = n;
+  return SDFB_OK;
+}
+
+static int denoise_fp32(sdfb_ddpm* d, const float* x, int t, int n, float* eps, cudaStream_t st) {
+  const float* P = d->params;
+  CU_TRY(launch_linear_f32(x, kDdpmLatent, P + d->woff[0], 512, d->tb0 + static_cast<size_t>(t) * kDdpmHid, d->h0,
+                           kDdpmHid, n, kDdpmHid, kDdpmLatent, true, st));
+  CU_TRY(launch_linear_f32(d->h0, kDdpmHid, P + d->woff[1], kDdpmHid, P + d->boff[1], d->h1, kDdpmHid, n, kDdpmHid,
+                           kDdpmHid, true, st));
+  CU_TRY(launch_linear_f32(d->h1, kDdpmHid, P + d->woff[2], kDdpmHid, P + d->boff[2], d->h0, kDdpmHid, n, kDdpmHid,
+                           kDdpmHid, true, st));
+  CU_TRY(launch_linear_f32(d->h0, kDdpmHid, P + d->woff[3], kDdpmHid, P + d->boff[3], d->h1, kDdpmHid, n, kDdpmHid,
+                           kDdpmHid, true, st));
+  CU_TRY(launch_linear_f32(d->h1, kDdpmHid, P + d->woff[4], kDdpmHid, P + d->boff[4], eps, kDdpmLatent, n,
+                           kDdpmLatent, kDdpmHid, false, st));
+  return SDFB_OK;
+}
+
+int sdfb_ddpm_denoise(sdfb_ddpm* d, const float* x_dev, int t, int n, float* eps_dev, int precision, void* stream) {
+  if (!d || !x_dev || !eps_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (n <= 0 || t < 0 || t >= kDdpmT) return fail(SDFB_E_INVALID, "bad n or t");
+  if (precision != SDFB_PREC_FP32) return fail(SDFB_E_INVALID, "denoiser precision %d not built yet (fp32 only)", precision);
+  DeviceGuard g(d->device);
+  int rc = ddpm_ws(d, n);
+  if (rc) return rc;
+  return denoise_fp32(d, x_dev, t, n, eps_dev, static_cast<cudaStream_t>(stream));
+}
+
+int sdfb_ddpm_sample(sdfb_ddpm* d, float* x_dev, const float* noise_dev, int n, int steps, int precision,
+                     void* stream) {
+  if (!d || !x_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (n <= 0 || steps < 1 || steps > kDdpmT) return fail(SDFB_E_INVALID, "bad n or steps");
+  if (steps > 1 && !noise_dev) return fail(SDFB_E_INVALID, "noise stream required");
+  if (precision != SDFB_PREC_FP32) return fail(SDFB_E_INVALID, "denoiser precision %d not built yet (fp32 only)", precision);
+  DeviceGuard g(d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ddpm_ws(d, n);
+  if (rc) return rc;
+  const long long cnt = static_cast<long long>(n) * kDdpmLatent;
+  for (int t = steps - 1; t >= 0; --t) {
+    rc = denoise_fp32(d, x_dev, t, n, d->eps, st);
+    if (rc) return rc;
+    CU_TRY(launch_ddpm_update(x_dev, d->eps, t > 0 ? noise_dev + static_cast<size_t>(t) * cnt : nullptr, cnt,
+                              d->sra[t], d->srm1[t], d->c1[t], d->c2[t], d->sigma[t], st));
+  }
+  return SDFB_OK;
+}
+
+int sdfb_ddpm_sample_host(sdfb_ddpm* d, float* x_host, const float* noise_host, int n, int steps, int precision) {
+  if (!d || !x_host) return fail(SDFB_E_INVALID, "null argument");
+  if (n <= 0 || steps < 1 || steps > kDdpmT) return fail(SDFB_E_INVALID, "bad n or steps");
+  if (steps > 1 && !noise_host) return fail(SDFB_E_INVALID, "noise stream required");
+  DeviceGuard g(d->device);
+  const size_t cnt = static_cast<size_t>(n) * kDdpmLatent;
+  const size_t need = (1 + static_cast<size_t>(steps)) * cnt * sizeof(float);
+  int rc = ensure_stage(nullptr, nullptr, &d->dstage, &d->dstage_bytes, 0, need);
+  if (rc) return rc;
+  float* x = static_cast<float*>(d->dstage);
+  float* nz = x + cnt;
+  CU_TRY(cudaMemcpyAsync(x, x_host, cnt * sizeof(float), cudaMemcpyHostToDevice, 0));
+  if (steps > 1) CU_TRY(cudaMemcpyAsync(nz, noise_host, static_cast<size_t>(steps) * cnt * sizeof(float), cudaMemcpyHostToDevice, 0));
+  rc = sdfb_ddpm_sample(d, x, nz, n, steps, precision, nullptr);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(x_host, x, cnt * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  CU_TRY(cudaStreamSynchronize(0));
+  return SDFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// Internal launcher declarations shared by the translation units of libsdfb200.
+// (The public C ABI is include/sdfb200.h; nothing here is exported.)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sdfb {
+
+// ---- model constants --------------------------------
+constexpr int kLatent = 256;
+constexpr int kHid = 512;
+constexpr int kSkipOut = 253;          // layer-3 width: 512 - 259
+constexpr int kDecIn = 259;
+constexpr int kDecLayers = 9;
+constexpr long long kDecParamFloats = 1835520LL + 3838LL;
+
+constexpr int kDdpmT = 1000;
+constexpr int kDdpmLatent = 256;
+constexpr int kDdpmTemb = 256;
+constexpr int kDdpmHid = 1024;
+constexpr long long kDdpmParamFloats =
+    (512LL * 1024 + 1024) + 3 * (1024LL * 1024 + 1024) + (1024LL * 256 + 256);
+
+// ---- fused tensor-core decoder (fused_decoder.cu) --------------------------
+//
+// One CTA owns a tile of 128 queries and carries it through all layers; the
+// activations never leave the SM.  Per tile the tensor core runs 13 "passes"
+// (a pass = one N=256 half of a layer's output, accumulated over that layer's
+// K in 64-wide chunks):
+//   pass  0, 1 : L1 halves      pass  5, 6 : L4 halves (K = 256: h3 only)
+//   pass  2, 3 : L2 halves      pass  7.. 12 : L5, L6, L7 halves
+//   pass  4    : L3 (N = 253 padded to 256)
+// The weight stream is the concatenation of the 96 (pass, k-chunk) blocks in
+// exactly that order; block = 256 rows x 64 k-elements, 16-bit, stored as the
+// 128B-swizzled shared-memory image (row r at r*128 B, 16-byte unit u at
+// position u ^ (r & 7)), so one linear bulk copy lands an MMA-ready operand.
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;
+constexpr int kBlockRows = 256;
+constexpr int kBlockBytes = kBlockRows * kChunkK * 2;   // 32 KiB
+constexpr int kPasses = 13;
+constexpr int kBlocksPerTile = 96;
+constexpr int kAChunkBytes = kTileM * kChunkK * 2;      // 16 KiB: one 64-wide slice of activations
+constexpr int kAChunks = 8;
+
+// fp32 constant block read by the epilogue warps (one per context, the two
+// folded bias rows are rewritten per latent by fold_latent_kernel)
+struct DecConsts {
+  float4 l0[kHid];        // (W0[n][256..258], b0[n] + W0[n][:256] . z)
+  float bias[7][kHid];    // layers 1..7; row 2 (L3) zero-padded past 253; row 3 (L4) = b4 + W4[n][253:509] . z
+  float4 l4x[kHid];       // (W4[n][509..511], 0)
+  float head[kHid];       // W8[0][:]
+  float head_b[4];        // b8, pad
+};
+
+struct DecodeParams {
+  const uint8_t* wstream;      // kBlocksPerTile blocks of kBlockBytes
+  const DecConsts* consts;
+  const float* xyz;            // points mode: [M][3]; nullptr in grid mode
+  float* out;                  // [M]
+  long long M;                 // number of queries in this launch
+  long long q0;                // grid mode: global index of query 0 (= z0*res*res)
+  int res;
+  unsigned int* status;        // watchdog status word (0 = ok)
+  float* dump;                 // debug: 128x256 pre-activations of pass `dump_pass`, tile 0
+  int dump_pass;
+  unsigned long long timeout_ns;
+};
+
+cudaError_t launch_fused_decoder(const DecodeParams& p, bool fp16, int num_sms, cudaStream_t stream);
+cudaError_t fused_decoder_init();   // opt in to the large dynamic shared memory carve-out
+
+// Unit test of the UMMA plumbing: D[128][256] = A[128][64] * B[256][64]^T, row-major 16-bit inputs.
+cudaError_t launch_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, unsigned int* status,
+                                 bool fp16, cudaStream_t stream);
+
+// Per-latent fold: consts->l0[n].w and consts->bias[3][n] from the fp32 parameters and z.
+cudaError_t launch_fold_latent(const float* W0, const float* b0, const float* W4, const float* b4,
+                               const float* z, DecConsts* consts, cudaStream_t stream);
+
+// ---- fp32 SIMT kernels (fp32_kernels.cu) -----------------------------------
+// C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); row-major, leading dims in elements.
+cudaError_t launch_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
+                              float* C, int ldc, long long M, int N, int K, bool relu,
+                              cudaStream_t stream);
+// out[m] = tanh(dot(H[m,:K], w) + b)
+cudaError_t launch_head_tanh_f32(const float* H, int ldh, const float* w, const float* b, float* out,
+                                 long long M, int K, cudaStream_t stream);
+// xyz of queries [q0, q0+M) of the res^3 grid -> X[M,3] and (optionally) cols 253..255 of S[M,256]
+cudaError_t launch_grid_xyz(int res, long long q0, long long M, float* X, float* S,
+                            cudaStream_t stream);
+// copy xyz[M,3] into cols 253..255 of S[M,256]
+cudaError_t launch_scatter_xyz(const float* xyz, long long M, float* S, cudaStream_t stream);
+// y[j] = b[j] + sum_k W[j*ldw + col0 + k] * z[k], k < K   (one warp per output)
+cudaError_t launch_fold_bias(const float* W, int ldw, int col0, const float* b, const float* z,
+                             int K, int N, float* y, cudaStream_t stream);
+cudaError_t launch_sign_change_mask(const float* sdf, int nz, int ny, int nx, unsigned char* mask,
+                                    cudaStream_t stream);
+// x <- c1*clamp(sra*x - srm1*eps, -1, 1) + c2*x + sigma*noise   (noise may be null)
+cudaError_t launch_ddpm_update(float* x, const float* eps, const float* noise, long long count,
+                               float sra, float srm1, float c1, float c2, float sigma,
+                               cudaStream_t stream);
+
+// A1: node coordinate, one correctly rounded divide of two exact integers.
+__host__ __device__ inline float axis_coord_num(int i, int res) { return static_cast<float>(2 * i - (res - 1)); }
+
+}  // namespace sdfb

@@ -1,0 +1,81 @@
+"""Multi-GPU partitioning: z-slabs of one grid, or independent
+latents.  One process per GPU; the only collective is the final all-gather of the slabs
+(NCCL over NVLink on the box, gloo in the CPU tests).  Index math here is pure Python so
+it is testable without a GPU."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def slab_range(res: int, rank: int, world: int) -> tuple[int, int]:
+    """Planes [z0, z1) owned by ``rank``: ceil(res/world) planes each, the tail ranks may be
+    short or empty.  Equal-sized when world divides res (the all-gather is then in place)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    per = -(-res // world)
+    z0 = min(rank * per, res)
+    return z0, min(z0 + per, res)
+
+
+def batch_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Items [i0, i1) of a batch of n independent latents owned by ``rank`` (balanced +-1)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, extra = divmod(n, world)
+    i0 = rank * base + min(rank, extra)
+    return i0, i0 + base + (1 if rank < extra else 0)
+
+
+def gather_slabs(local: torch.Tensor, res_planes: int, per: int, group=None) -> torch.Tensor:
+    """All-gather equal-sized (padded to ``per`` leading rows) slabs and cut to ``res_planes``."""
+    world = dist.get_world_size(group)
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    full = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full, pad, group=group)
+    return full[:res_planes]
+
+
+def decode_grid_sharded(decoder, latent, res: int, mask: bool = False, precision=None, group=None,
+                        gather: bool = True):
+    """Config 5: every rank decodes its z-slab (plus, for the mask, the halo plane above it,
+    recomputed locally - no halo exchange), then the slabs are all-gathered.
+
+    Returns (sdf, mask_or_None); full [res,res,res] / [(res-1)^3] tensors if ``gather`` else the
+    rank's own slab."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    z0, z1 = slab_range(res, rank, world)
+    per = -(-res // world)
+    even = res % world == 0
+    if even and gather and decoder.device.type == "cuda":
+        # decode straight into this rank's block of the full buffer; NCCL gathers in place
+        # (a rank's halo plane lands in its neighbour's block and is then overwritten by the
+        # neighbour's identical values)
+        full = torch.empty((res, res, res), dtype=torch.float32, device=decoder.device)
+        flat = full.view(-1)[z0 * res * res:]
+        r = decoder.decode_grid(latent, res, z0, z1, mask=mask, precision=precision, out=flat)
+        sdf_local, m_local = (r if mask else (r, None))
+        sdf_full = full
+        dist.all_gather_into_tensor(sdf_full, sdf_full[z0:z1], group=group)
+    else:
+        r = decoder.decode_grid(latent, res, z0, z1, mask=mask, precision=precision)
+        sdf_local, m_local = (r if mask else (r, None))
+        if not gather:
+            return sdf_local, m_local
+        sdf_full = gather_slabs(sdf_local, res, per, group)
+    m_full = None
+    if mask:
+        m_full = gather_slabs(m_local, res - 1, per, group)
+    return sdf_full, m_full
+
+
+def decode_batch_sharded(decoder, latents: torch.Tensor, res: int, precision=None, group=None):
+    """Configs 3/4: latents [B,256] are split across ranks; each rank decodes its share.
+    No communication; returns (i0, sdf [i1-i0, res, res, res])."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    i0, i1 = batch_range(latents.shape[0], rank, world)
+    out = torch.empty((i1 - i0, res, res, res), dtype=torch.float32, device=decoder.device)
+    for j, i in enumerate(range(i0, i1)):
+        decoder.decode_grid(latents[i], res, precision=precision, out=out[j])
+    return i0, out

@@ -70,7 +70,8 @@ def _round_to(t: torch.Tensor, lowp: torch.dtype) -> torch.Tensor:
     return t.to(lowp).to(torch.float32)
 
 
-def decoder_forward_lowp(latent, xyz, params=None, lowp=torch.bfloat16, chunk: int = 1 << 16):
+def decoder_forward_lowp(latent, xyz, params=None, lowp=torch.bfloat16, chunk: int = 1 << 16,
+                         preacts: list | None = None):
     """The arithmetic the tensor-core kernel performs, emulated on the CPU.
 
     * per-shape constants are folded in fp32: bias0' = b0 + W0[:, :256] z and
@@ -81,6 +82,9 @@ def decoder_forward_lowp(latent, xyz, params=None, lowp=torch.bfloat16, chunk: i
       to ``lowp`` after the ReLU; products accumulate in fp32;
     * h7 stays fp32 and the 512 -> 1 head and tanh are evaluated in fp32.
     Only a single shared latent ([256]) is supported, as in the kernel.
+
+    ``preacts`` (diagnostics): if a list is passed, the fp32 pre-activations (before ReLU)
+    of layers 1..7 of the LAST chunk are appended to it, [m, fout] each.
     """
     params = decoder_weights() if params is None else params
     f32 = torch.float32
@@ -101,13 +105,19 @@ def decoder_forward_lowp(latent, xyz, params=None, lowp=torch.bfloat16, chunk: i
         for s in range(0, M, chunk):
             e = min(M, s + chunk)
             x = xyz_t[s:e]
+            pre = []
             h = _round_to(torch.relu(x @ W0x.T + bias0), lowp)
-            h = _round_to(torch.relu(h @ Wq[1].T + B[1]), lowp)
-            h = _round_to(torch.relu(h @ Wq[2].T + B[2]), lowp)
-            h = _round_to(torch.relu(h @ Wq[3].T + B[3]), lowp)
-            h = _round_to(torch.relu(h @ W4h.T + x @ W4x.T + bias4), lowp)
-            h = _round_to(torch.relu(h @ Wq[5].T + B[5]), lowp)
-            h = _round_to(torch.relu(h @ Wq[6].T + B[6]), lowp)
-            h = torch.relu(h @ Wq[7].T + B[7])
+            for li in (1, 2, 3):
+                pre.append(h @ Wq[li].T + B[li])
+                h = _round_to(torch.relu(pre[-1]), lowp)
+            pre.append(h @ W4h.T + x @ W4x.T + bias4)
+            h = _round_to(torch.relu(pre[-1]), lowp)
+            for li in (5, 6):
+                pre.append(h @ Wq[li].T + B[li])
+                h = _round_to(torch.relu(pre[-1]), lowp)
+            pre.append(h @ Wq[7].T + B[7])
+            h = torch.relu(pre[-1])
             out[s:e] = torch.tanh(h @ W[8].T + B[8]).squeeze(1)
+    if preacts is not None:
+        preacts.extend(p.numpy() for p in pre)
     return out.numpy()

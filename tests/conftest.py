@@ -23,3 +23,26 @@ def golden():
     with open(os.path.join(GOLDEN_DIR, "oracle_golden.json")) as f:
         meta = json.load(f)
     return arrays, meta
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    """The product package (hyphenated directory name -> importlib)."""
+    import importlib
+    return importlib.import_module("latent-diffusion-models-for-shape-sdfs_b200")
+
+
+@pytest.fixture(scope="session")
+def cuda_decoder(pkg):
+    import oracle
+    dec = pkg.Decoder(oracle.flatten_params(oracle.decoder_weights()), device="cuda:0", precision="bf16")
+    yield dec
+    dec.close()
+
+
+@pytest.fixture(scope="session")
+def cuda_ddpm(pkg):
+    import oracle
+    m = pkg.LatentDDPM(oracle.flatten_params(oracle.ddpm_weights()), device="cuda:0", precision="fp32")
+    yield m
+    m.close()

@@ -1,0 +1,64 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/sdfb200.h declares, and refuses to run without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sdfb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdfb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.load_library()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"libsdfb200.so does not export {n}"
+    from importlib import import_module
+    sigs = import_module(pkg.__name__ + "._lib").SIGNATURES
+    assert sorted(sigs) == names, "ctypes signature table and header disagree"
+    assert lib.sdfb_version() >= 100
+
+
+def test_header_constants_match_oracle(pkg):
+    import oracle
+    text = open(os.path.join(ROOT, "include", "sdfb200.h")).read()
+    dec = int(re.search(r"SDFB_DECODER_PARAM_FLOATS (\d+)", text).group(1))
+    ddp = int(re.search(r"SDFB_DDPM_PARAM_FLOATS (\d+)", text).group(1))
+    assert dec == oracle.flatten_params(oracle.decoder_weights()).size
+    assert ddp == oracle.flatten_params(oracle.ddpm_weights()).size
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device error path")
+def test_no_cpu_fallback(pkg):
+    import oracle
+    lib = pkg.load_library()
+    flat = oracle.flatten_params(oracle.decoder_weights())
+    h = C.c_void_p()
+    rc = lib.sdfb_decoder_create(flat.ctypes.data, flat.size, 0, C.byref(h))
+    assert rc == -2 and not h.value                      # SDFB_E_DEVICE
+    assert b"no CPU path" in lib.sdfb_last_error() or b"device" in lib.sdfb_last_error()
+    with pytest.raises(Exception):
+        pkg.Decoder(flat, device="cuda:0")
+    with pytest.raises(ValueError):
+        pkg.Decoder(flat, device="cpu")
+
+
+def test_argument_validation_without_device(pkg):
+    lib = pkg.load_library()
+    h = C.c_void_p()
+    bad = np.zeros(10, np.float32)
+    assert lib.sdfb_decoder_create(bad.ctypes.data, bad.size, 0, C.byref(h)) == -1   # wrong blob size
+    assert lib.sdfb_decoder_create(None, 0, 0, C.byref(h)) == -1
+    assert lib.sdfb_ddpm_create(bad.ctypes.data, bad.size, 0, C.byref(h)) == -1
+    assert lib.sdfb_decoder_destroy(None) == 0
+    assert lib.sdfb_ddpm_destroy(None) == 0

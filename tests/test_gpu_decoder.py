@@ -1,0 +1,211 @@
+"""GPU parity tests of the SDF decoder path, through the C ABI (ctypes -> libsdfb200.so).
+
+Tolerances (BASELINE.json north_star):
+  * grid coordinates and masks: bit-exact;
+  * fp32 (FFMA) path vs the fp32 oracle: max-abs 1e-5;
+  * tensor-core path vs the oracle that emulates the same operand rounding: 1e-3 (bf16) /
+    2e-4 (fp16); vs the fp32 oracle: fp16 must meet 2e-3, bf16's distance is reported and
+    bounded at 2e-2 (2e-3 is unattainable with bf16 operands on a non-degenerate field);
+  * >= 99.9% sign agreement where |sdf| > 2e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-5
+TOL_LOWP = {"bf16": 1e-3, "fp16": 2e-4}      # vs the operand-rounding-emulating oracle
+LOWP_T = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def torch_mask(sdf: torch.Tensor) -> torch.Tensor:
+    """oracle.sign_change_mask restated with torch ops (for 512^3 fields on the device)."""
+    inside = sdf < 0
+    nz, ny, nx = sdf.shape
+    any_in = torch.zeros((nz - 1, ny - 1, nx - 1), dtype=torch.bool, device=sdf.device)
+    all_in = torch.ones_like(any_in)
+    for dz in (0, 1):
+        for dy in (0, 1):
+            for dx in (0, 1):
+                c = inside[dz:nz - 1 + dz, dy:ny - 1 + dy, dx:nx - 1 + dx]
+                any_in |= c
+                all_in &= c
+    return (any_in & ~all_in).to(torch.uint8)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_umma_selftest(pkg, prec):
+    """One 128x256x64 tcgen05 product through the kernel's own descriptors / swizzle / TMEM path."""
+    import ctypes as C
+    lib = pkg.load_library()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    dt = LOWP_T[prec]
+    a = torch.randn((128, 64), generator=g, device="cuda").to(dt)
+    b = torch.randn((256, 64), generator=g, device="cuda").to(dt)
+    d = torch.zeros((128, 256), device="cuda")
+    rc = lib.sdfb_umma_selftest(a.data_ptr(), b.data_ptr(), d.data_ptr(), pkg.PRECISIONS[prec], None)
+    assert rc == 0, lib.sdfb_last_error()
+    ref = a.float() @ b.float().T
+    err = (d - ref).abs().max().item()
+    assert err < 1e-3, f"umma selftest max err {err}"
+
+
+@pytest.mark.parametrize("res", [64, 128, 256, 512])
+def test_grid_coordinates_bit_exact(pkg, golden, res):
+    arrays, _ = golden
+    c = arrays[f"coords_{res}"]
+    z0 = res // 2 - 1
+    pts = pkg.grid_points(res, z0, z0 + 2).cpu().numpy().reshape(2, res, res, 3)
+    assert np.array_equal(pts[0, 0, :, 0].view(np.uint32), c.view(np.uint32))          # x along the fast axis
+    assert np.array_equal(pts[0, :, 0, 1].view(np.uint32), c.view(np.uint32))          # y
+    assert np.array_equal(pts[:, 0, 0, 2].view(np.uint32), c[z0:z0 + 2].view(np.uint32))
+    assert np.array_equal(pts.reshape(-1, 3), oracle.grid_points(res, z0, z0 + 2))
+
+
+def test_fp32_path_matches_oracle_64(cuda_decoder, golden):
+    arrays, meta = golden
+    z = oracle.default_latent()
+    sdf = cuda_decoder.decode_grid(z, 64, precision="fp32").cpu().numpy()
+    assert sdf.shape == (64, 64, 64)
+    err = np.abs(sdf.ravel()[arrays["sdf64_idx"]] - arrays["sdf64_fp32"]).max()
+    assert err < TOL_FP32, err
+    assert np.abs(sdf[16:24] - arrays["sdf64_slab_16_24"]).max() < TOL_FP32
+    full = oracle.decode_grid(z, 64)
+    assert np.abs(sdf - full).max() < TOL_FP32
+    assert abs(int((sdf < 0).sum()) - meta["sdf64_inside"]) <= 16
+
+
+def test_fp32_points_second_latent(cuda_decoder, golden):
+    arrays, _ = golden
+    out = cuda_decoder(oracle.default_latent(1), arrays["points_xyz"], precision="fp32").cpu().numpy()
+    assert np.abs(out - arrays["points_fp32"]).max() < TOL_FP32
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_tensor_core_passes_match_oracle_layers(cuda_decoder, prec):
+    """Per-pass pre-activations of the first tile: localises a failing layer."""
+    z = oracle.default_latent()
+    pts = oracle.grid_points(32)[:128]
+    pre = []
+    oracle.decoder_forward_lowp(z, pts, lowp=LOWP_T[prec], preacts=pre)
+    # pass -> (layer index into pre, column offset)
+    table = [(0, 0), (0, 256), (1, 0), (1, 256), (2, 0), (3, 0), (3, 256), (4, 0), (4, 256), (5, 0), (5, 256),
+             (6, 0), (6, 256)]
+    worst = {}
+    for p, (li, c0) in enumerate(table):
+        got = cuda_decoder.debug_pass(z, 32, p, precision=prec).cpu().numpy()
+        want = pre[li][:, c0:c0 + 256]
+        w = want.shape[1]            # L3 has 253 features
+        worst[p] = float(np.abs(got[:, :w] - want).max())
+    print("per-pass max |preact - oracle|:", {k: f"{v:.2e}" for k, v in worst.items()})
+    lim = 2e-2 if prec == "bf16" else 3e-3     # one operand-rounding flip upstream moves a preact by ~1 ulp(16-bit)
+    assert max(worst.values()) < lim, worst
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_tensor_core_path_64(cuda_decoder, golden, prec):
+    arrays, _ = golden
+    z = oracle.default_latent()
+    sdf = cuda_decoder.decode_grid(z, 64, precision=prec).cpu().numpy()
+    got = sdf.ravel()[arrays["sdf64_idx"]]
+    e_emul = np.abs(got - arrays[f"sdf64_{prec}"]).max()
+    e_fp32 = np.abs(got - arrays["sdf64_fp32"]).max()
+    print(f"{prec}: max|kernel - {prec} oracle| = {e_emul:.3e}; max|kernel - fp32 oracle| = {e_fp32:.3e}")
+    assert e_emul < TOL_LOWP[prec], e_emul
+    if prec == "fp16":
+        assert e_fp32 < 2e-3
+    else:
+        assert e_fp32 < 2e-2
+    ref = oracle.decode_grid(z, 64)
+    m = np.abs(ref) > 2e-3
+    agree = ((sdf < 0) == (ref < 0))[m].mean()
+    print(f"{prec}: sign agreement where |sdf|>2e-3: {agree:.6f}; full-grid max|d| vs fp32 = {np.abs(sdf - ref).max():.3e}")
+    assert agree >= 0.999
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_mask_bit_exact_and_slab_halo(cuda_decoder, golden, prec):
+    arrays, meta = golden
+    z = oracle.default_latent()
+    sdf, mask = cuda_decoder.decode_grid(z, 64, mask=True, precision=prec)
+    sdf_np, mask_np = sdf.cpu().numpy(), mask.cpu().numpy()
+    assert mask_np.shape == (63, 63, 63)
+    assert np.array_equal(mask_np, oracle.sign_change_mask(sdf_np))      # bit-exact by definition (H3)
+    golden_mask = np.unpackbits(arrays["mask64_bits"])[:63 ** 3].reshape(63, 63, 63)
+    differing = int((mask_np != golden_mask).sum())
+    print(f"{prec}: cells differing from the oracle's own mask: {differing} of {meta['sdf64_active_cells']} active")
+    assert differing <= (16 if prec == "fp32" else 2000)
+    # a z-slab decoded on its own (+ locally recomputed halo plane) reproduces the full grid bit for bit
+    s2, m2 = cuda_decoder.decode_grid(z, 64, 16, 24, mask=True, precision=prec)
+    assert torch.equal(s2, sdf[16:24]), "a query's value must not depend on its tile position"
+    assert torch.equal(m2, mask[16:24])
+    s3, m3 = cuda_decoder.decode_grid(z, 64, 56, 64, mask=True, precision=prec)     # top slab: no halo
+    assert torch.equal(s3, sdf[56:64]) and torch.equal(m3, mask[56:63])
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_points_and_ragged_sizes(cuda_decoder, golden, prec):
+    arrays, _ = golden
+    z1 = oracle.default_latent(1)
+    out = cuda_decoder(z1, arrays["points_xyz"], precision=prec).cpu().numpy()
+    want = arrays["points_bf16"] if prec == "bf16" else oracle.decoder_forward_lowp(z1, arrays["points_xyz"], lowp=torch.float16)
+    assert np.abs(out - want).max() < TOL_LOWP[prec]
+    # ragged tails: M not a multiple of the 128-query tile, tiny and empty inputs
+    for m in (0, 1, 127, 129, 255):
+        o = cuda_decoder(z1, arrays["points_xyz"][:m], precision=prec).cpu().numpy()
+        assert o.shape == (m,)
+        assert np.array_equal(o, out[:m])
+    # batch of shapes
+    zz = np.stack([z1, oracle.default_latent()])
+    pp = np.stack([arrays["points_xyz"][:100]] * 2)
+    ob = cuda_decoder(zz, pp, precision=prec).cpu().numpy()
+    assert np.array_equal(ob[0], out[:100])
+
+
+def test_host_buffer_entry_points(cuda_decoder):
+    z = oracle.default_latent()
+    sdf_d, mask_d = cuda_decoder.decode_grid(z, 32, 8, 16, mask=True, precision="bf16")
+    sdf_h, mask_h = cuda_decoder.decode_grid_host(z, 32, 8, 16, mask=True, precision="bf16")
+    assert np.array_equal(sdf_h, sdf_d.cpu().numpy()) and np.array_equal(mask_h, mask_d.cpu().numpy())
+    pts = oracle.grid_points(32, 8, 9)
+    out = cuda_decoder.decode_points_host(z, pts, precision="bf16")
+    assert np.array_equal(out.reshape(32, 32), sdf_h[0])      # grid mode and points mode agree bit for bit
+
+
+@pytest.mark.parametrize("res", [256, 512])
+def test_full_size_grids(cuda_decoder, golden, res):
+    """BASELINE configs 2 and 5 at full size: golden samples + size-independent properties."""
+    arrays, _ = golden
+    z = oracle.default_latent()
+    sdf, mask = cuda_decoder.decode_grid(z, res, mask=True, precision="bf16")
+    torch.cuda.synchronize()
+    print(f"{res}^3 fused kernel: {cuda_decoder.last_kernel_ms():.2f} ms")
+    idx = torch.from_numpy(arrays[f"sdf{res}_idx"]).cuda()
+    got = sdf.view(-1)[idx].cpu().numpy()
+    assert np.abs(got - arrays[f"sdf{res}_bf16"]).max() < TOL_LOWP["bf16"]
+    assert np.abs(got - arrays[f"sdf{res}_fp32"]).max() < 2e-2
+    assert torch.equal(mask, torch_mask(sdf))
+    assert torch.isfinite(sdf).all() and sdf.abs().max() <= 1.0
+    # slab-boundary plane pairs decoded as 8 independent slabs agree with the single launch
+    per = res // 8
+    for r in (0, 3, 7):
+        s, m = cuda_decoder.decode_grid(z, res, r * per, (r + 1) * per, mask=True, precision="bf16")
+        assert torch.equal(s, sdf[r * per:(r + 1) * per])
+        assert torch.equal(m, mask[r * per:min((r + 1) * per, res - 1)])
+    # fp32 path on a seeded 16^3 sub-block worth of points
+    rs = np.random.RandomState(res)
+    q = np.sort(rs.choice(res ** 3, 4096, replace=False))
+    c = oracle.axis_coords(res)
+    pts = np.stack([c[q % res], c[(q // res) % res], c[q // (res * res)]], axis=1)
+    f32 = cuda_decoder(z, pts, precision="fp32").cpu().numpy()
+    assert np.abs(f32 - oracle.decoder_forward(z, pts)).max() < TOL_FP32
+    assert np.abs(sdf.view(-1)[torch.from_numpy(q).cuda()].cpu().numpy() - f32).max() < 2e-2
+
+
+def test_torch_mask_helper_matches_oracle():
+    rs = np.random.RandomState(0)
+    f = rs.standard_normal((9, 7, 8)).astype(np.float32)
+    assert np.array_equal(torch_mask(torch.from_numpy(f).cuda()).cpu().numpy(), oracle.sign_change_mask(f))
