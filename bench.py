@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py - SDF decoder queries/s on N B200s (BASELINE.json metric), plus roofline,
+end-to-end (host buffers through the C ABI) and a CPU-oracle baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one pass of the hot path: decode_grid(z, 256) - BASELINE.json configs[1], one latent
+on a 256^3 grid (16,777,216 queries), bf16 operands / fp32 accumulate, fused tcgen05 kernel.
+With N > 1 every rank decodes its own latent's 256^3 grid (the path shards by independent
+latents or z-slabs with no data-path collective; per-GPU work is fixed => weak scaling; the
+per-rank query count equals one z-slab of configs[4]'s 512^3 grid on 8 GPUs).
+
+`--impl reference`: the mounted reference has no source (/root/reference/README.md:1 is a
+title), so the "reference arm" is the frozen CPU oracle (oracle/, a PyTorch fp32 restatement
+of the method) timed on the box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RES = 256
+QUERIES = RES ** 3
+# work per query (SURVEY.md section 8d / DESIGN.md): MACs issued to the tensor pipe with the
+# latent folded into biases and L3 padded to N=256: 6 * 512^2 ; dense count as the oracle computes it
+FLOP_TENSOR_PER_QUERY = 2 * 6 * 512 * 512          # 3,145,728
+FLOP_DENSE_PER_QUERY = 3_671_040
+METRIC = "sdf_decoder_queries_per_s"
+UNIT = "queries/s"
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return {"burst": float(p["bf16_tflops"]), "sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"burst": 1590.0, "sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:                      # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:                   # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:                       # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_oracle_rate(target_s: float = 12.0):
+    """Oracle (fp32 torch CPU) queries/s on a bounded sample: z-slabs of the 256^3 workload."""
+    import torch
+    import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    z = oracle.default_latent()
+    oracle.decode_grid(z, RES, 0, 1)                      # warm-up: one plane (65,536 queries)
+    t0 = time.perf_counter()
+    oracle.decode_grid(z, RES, 0, 2)
+    dt = time.perf_counter() - t0
+    planes = max(2, min(RES, int(target_s / max(dt / 2, 1e-6))))
+    t0 = time.perf_counter()
+    oracle.decode_grid(z, RES, 0, planes)
+    dt = time.perf_counter() - t0
+    q = planes * RES * RES
+    return {"value": q / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"planes [0,{planes}) of the 256^3 grid = {q} queries in {dt:.2f} s, torch {torch.__version__} fp32, "
+                      f"{cores} threads (oracle/decoder.py; no reference source exists to time)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    import torch
+    import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    z = oracle.default_latent()
+    planes = 4                                            # 262,144 queries per step (= configs[0]'s count)
+    for _ in range(min(warm, 2)):
+        oracle.decode_grid(z, RES, 0, planes)
+    steps = min(steps, 12)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        oracle.decode_grid(z, RES, (s * planes) % RES, (s * planes) % RES + planes)
+    dt = time.perf_counter() - t0
+    q = planes * RES * RES
+    value = q * steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(warm, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "decode_grid(z, 256): one latent, 256^3 grid (BASELINE configs[1]); each step a bounded "
+                               f"sample of {planes} z-planes = {q} queries",
+                   "note": "the mounted reference has no source; this arm is the frozen CPU oracle"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps x {q} queries, torch {torch.__version__} fp32, {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    import oracle           # weights/latents only (seeded generators); nothing from it is timed on this arm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = load_package()
+    K, W = max(1, args.steps), max(3, args.warmup)
+    dev = torch.device("cuda", local)
+    dec = pkg.Decoder(oracle.flatten_params(oracle.decoder_weights()), device=dev, precision=args.precision)
+    z_host = oracle.default_latent(rank)                           # each rank: its own latent (weak scaling)
+    z = torch.from_numpy(z_host).to(dev)
+    out = torch.empty((RES, RES, RES), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # 256 MiB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        dec.decode_grid(z, RES, out=out)
+    barrier()
+    kernel_ms, step_ms = [], []
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    with ClockSampler(local) as clk:
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.fill_(float(i))                                  # evict L2 between timed iterations (untimed)
+            ev[i][0].record()
+            dec.decode_grid(z, RES, out=out)                       # fold kernel + fused kernel on the current stream
+            ev[i][1].record()
+            ev[i][1].synchronize()
+            kernel_ms.append(dec.last_kernel_ms())                 # events around the fused kernel itself
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * QUERIES * K / (total_ms * 1e-3)
+
+    # ---- end to end: numpy latent in, numpy sdf out through the host-buffer C-ABI call ----
+    sdf_host = torch.empty((RES, RES, RES), dtype=torch.float32).pin_memory().numpy()
+    for _ in range(2):
+        dec.decode_grid_host(z_host, RES, out=sdf_host)
+    barrier()
+    Ke = max(3, min(K, 10))
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        dec.decode_grid_host(z_host, RES, out=sdf_host)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * QUERIES * Ke / float(e2e_s.item())
+    checksum = float(np.float64(sdf_host[::16, ::16, ::16].sum()))
+
+    if rank == 0:
+        peaks = read_peaks()
+        k_ms = statistics.mean(kernel_ms)
+        achieved = QUERIES * FLOP_TENSOR_PER_QUERY / (k_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "decode_grid(z, 256): one latent per GPU, 256^3 grid = 16,777,216 queries "
+                                   "(BASELINE configs[1]); seeded random-init decoder 8x512, latent 256",
+                       "l2": "256 MiB buffer written between timed iterations (L2 flush, untimed)",
+                       "timing": "CUDA events per step on the launching stream, summed, max over ranks",
+                       "parallelism": f"dp{world} (independent latents, no data-path collective)"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 1024, "d2h_bytes_per_step": QUERIES * 4,
+                    "steps": Ke, "api": "Decoder.decode_grid_host -> sdfb_decode_grid_host (numpy in, pinned numpy out)",
+                    "checksum": checksum},
+            "gpu_launches": 2 * K,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["burst"], "traffic": None,
+                         "peak_kind": "burst bf16 matmul, " + peaks["source"],
+                         "frac_of_sustained": achieved / peaks["sustained"], "peak_sustained": peaks["sustained"],
+                         "kernel": "fused_decoder_kernel", "kernel_ms": k_ms,
+                         "flop_per_query_tensor_pipe": FLOP_TENSOR_PER_QUERY,
+                         "dense_equiv_tflops": QUERIES * FLOP_DENSE_PER_QUERY / (k_ms * 1e-3) / 1e12},
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_oracle_rate()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -144,13 +144,18 @@ class Decoder:
         return (sdf, m) if mask else sdf
 
     def decode_grid_host(self, latent: np.ndarray, res: int, z0: int = 0, z1: int | None = None,
-                         mask: bool = False, precision: str | None = None):
+                         mask: bool = False, precision: str | None = None, out: np.ndarray | None = None):
         """Same result as ``decode_grid`` but through the host-buffer entry point: numpy in,
         numpy out, host<->device copies inside the call (the plugin-style call bench.py times)."""
         prec = _prec(precision or self.precision)
         z1 = res if z1 is None else z1
         lat = np.ascontiguousarray(np.asarray(latent, dtype=np.float32).reshape(LATENT))
-        sdf = np.empty((z1 - z0, res, res), dtype=np.float32)
+        if out is None:
+            sdf = np.empty((z1 - z0, res, res), dtype=np.float32)
+        else:   # caller-owned (ideally pinned) host buffer
+            if out.dtype != np.float32 or not out.flags.c_contiguous or out.size != (z1 - z0) * res * res:
+                raise ValueError("out must be a C-contiguous float32 array of the slab's size")
+            sdf = out.reshape(z1 - z0, res, res)
         halo = mask and z1 < res and z1 > z0
         layers = (z1 if halo else min(z1, res - 1)) - z0
         m = np.empty((max(layers, 0), res - 1, res - 1), dtype=np.uint8) if mask else None
