@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -118,6 +119,8 @@ struct sdfb_decoder {
   float* params = nullptr;       // fp32 blob on device
   float* w4s = nullptr;          // [512][256]: W4[:, 0:253] | W4[:, 509:512]   (fp32 path)
   uint8_t* wstream[2] = {nullptr, nullptr};   // [0] bf16, [1] fp16
+  alignas(64) unsigned char tmap[2][128];     // tensor maps over the two streams (CTA-pair kernel)
+  bool use_pairs = true;                      // SDFB_KERNEL=cg1 selects the single-CTA kernel
   DecConsts* consts = nullptr;
   float* bias0f = nullptr;       // fp32 path folded biases
   float* bias4f = nullptr;
@@ -131,6 +134,8 @@ struct sdfb_decoder {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   unsigned long long timeout_ns = 2000000000ull;
+  unsigned int debug_flags = 0;
+  long long* prof = nullptr;     // wait profile buffer (allocated when SDFB_PROF is set)
 };
 
 struct sdfb_ddpm {
@@ -210,8 +215,13 @@ int decode_tc(sdfb_decoder* d, const float* z, const float* xyz, int res, long l
   p.dump = dump;
   p.dump_pass = dump_pass;
   p.timeout_ns = d->timeout_ns;
+  p.debug_flags = d->debug_flags;
+  p.prof = d->prof;
   CU_TRY(cudaEventRecord(d->ev0, st));
-  CU_TRY(launch_fused_decoder(p, fp16, d->num_sms, st));
+  if (d->use_pairs)
+    CU_TRY(launch_fused_decoder2(p, d->tmap[fp16 ? 1 : 0], fp16, d->num_sms, st));
+  else
+    CU_TRY(launch_fused_decoder(p, fp16, d->num_sms, st));
   CU_TRY(cudaEventRecord(d->ev1, st));
   d->timed = true;
   return SDFB_OK;
@@ -275,7 +285,9 @@ int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, s
   if (!d) return fail(SDFB_E_NOMEM, "out of host memory");
   d->device = device; d->num_sms = sms;
   decoder_offsets(d->off);
+  if (const char* e = std::getenv("SDFB_DEBUG_FLAGS")) d->debug_flags = static_cast<unsigned int>(std::strtoul(e, nullptr, 0));
   const float* P = params_host;
+  const bool want_prof = std::getenv("SDFB_PROF") != nullptr;
   auto bail = [&](int code) { sdfb_decoder_destroy(d); return code; };
 #define CU_TRY_D(expr)                                                                       \
   do {                                                                                       \
@@ -284,6 +296,8 @@ int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, s
       return bail(fail(SDFB_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)));       \
   } while (0)
   CU_TRY_D(fused_decoder_init());
+  CU_TRY_D(fused_decoder2_init());
+  if (const char* e = std::getenv("SDFB_KERNEL")) d->use_pairs = std::strcmp(e, "cg1") != 0;
   CU_TRY_D(cudaMalloc(&d->params, n_floats * sizeof(float)));
   CU_TRY_D(cudaMemcpy(d->params, P, n_floats * sizeof(float), cudaMemcpyHostToDevice));
   // fp32 path: compact skip-layer matrix
@@ -303,6 +317,7 @@ int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, s
     pack_wstream(P, d->off, f == 1, ws);
     CU_TRY_D(cudaMalloc(&d->wstream[f], ws.size() * 2));
     CU_TRY_D(cudaMemcpy(d->wstream[f], ws.data(), ws.size() * 2, cudaMemcpyHostToDevice));
+    CU_TRY_D(make_wstream_tensor_map(d->wstream[f], d->tmap[f]));
   }
   {
     std::vector<DecConsts> hc(1);
@@ -325,6 +340,10 @@ int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, s
   CU_TRY_D(cudaMalloc(&d->bias4f, 512 * sizeof(float)));
   CU_TRY_D(cudaMalloc(&d->status, sizeof(unsigned int)));
   CU_TRY_D(cudaMemset(d->status, 0, sizeof(unsigned int)));
+  if (want_prof) {
+    CU_TRY_D(cudaMalloc(&d->prof, static_cast<size_t>(sms) * 3 * 8 * sizeof(long long)));
+    CU_TRY_D(cudaMemset(d->prof, 0, static_cast<size_t>(sms) * 3 * 8 * sizeof(long long)));
+  }
   CU_TRY_D(cudaEventCreate(&d->ev0));
   CU_TRY_D(cudaEventCreate(&d->ev1));
 #undef CU_TRY_D
@@ -338,7 +357,7 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
   cudaDeviceSynchronize();
   cudaFree(d->params); cudaFree(d->w4s); cudaFree(d->wstream[0]); cudaFree(d->wstream[1]);
   cudaFree(d->consts); cudaFree(d->bias0f); cudaFree(d->bias4f); cudaFree(d->status);
-  cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x);
+  cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x); cudaFree(d->prof);
   if (d->pin) cudaFreeHost(d->pin);
   cudaFree(d->dstage);
   if (d->ev0) cudaEventDestroy(d->ev0);
@@ -454,6 +473,26 @@ int sdfb_decoder_last_kernel_ms(sdfb_decoder* d, float* ms) {
   DeviceGuard g(d->device);
   CU_TRY(cudaEventSynchronize(d->ev1));
   CU_TRY(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+  if (d->prof != nullptr) {   // diagnostics: mean blocked cycles per role and wait class of the last launch
+    std::vector<long long> h(static_cast<size_t>(d->num_sms) * 24);
+    CU_TRY(cudaMemcpy(h.data(), d->prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    static const char* role[3] = {"epilogue", "producer", "mma"};
+    static const char* cls[8] = {"total", "w_full", "w_empty", "acc_full", "acc_empty", "a_ready", "a_free", "tiles"};
+    for (int r = 0; r < 3; ++r) {
+      double m[8] = {0};
+      int n = 0;
+      for (int b = 0; b < d->num_sms; ++b) {
+        const long long* v = h.data() + (static_cast<size_t>(b) * 3 + r) * 8;
+        if (v[0] == 0) continue;
+        ++n;
+        for (int i = 0; i < 8; ++i) m[i] += static_cast<double>(v[i]);
+      }
+      if (n == 0) continue;
+      std::fprintf(stderr, "[sdfb prof] %-8s", role[r]);
+      for (int i = 0; i < 8; ++i) std::fprintf(stderr, " %s=%.0f", cls[i], m[i] / n);
+      std::fprintf(stderr, " (cycles, mean over %d CTAs; %.2f ms)\n", n, *ms);
+    }
+  }
   return kernel_status(d);
 }
 

@@ -93,7 +93,7 @@ __device__ __forceinline__ bool epi_layer0_chunk(const DecConsts* __restrict__ c
     const float f1 = fmaf(z, w1.z, fmaf(y, w1.y, fmaf(x, w1.x, w1.w)));
     packed[j] = pack_relu<FP16>(f0, f1);
   }
-  if (!mbar_wait(bars + 8 * (kBarAFree + c), ((st.wphase >> c) & 1u) ^ 1u, wd, kErrAFree + c)) return false;
+  if (!mbar_wait(bars + 8 * (kBarAFree + c), ((st.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
   st.wphase ^= 1u << c;
   const uint32_t base = a_row_addr + c * kAChunkBytes;
 #pragma unroll
@@ -112,7 +112,7 @@ __device__ __forceinline__ bool epi_hidden_pass(const float* __restrict__ bias, 
                                                 float x, float y, float z, int c0, uint32_t tmem_row,
                                                 int b, uint32_t a_row_addr, uint32_t row7, uint32_t bars,
                                                 EpiState& st, const Watchdog& wd, float* dump_row) {
-  if (!mbar_wait(bars + 8 * (kBarAccFull + b), (st.acc_phase >> b) & 1u, wd, kErrAccFull + b)) return false;
+  if (!mbar_wait(bars + 8 * (kBarAccFull + b), (st.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
   st.acc_phase ^= 1u << b;
   tc_fence_after();
 #pragma unroll 1
@@ -151,7 +151,7 @@ __device__ __forceinline__ bool epi_hidden_pass(const float* __restrict__ bias, 
       mbar_arrive(bars + 8 * (kBarAccEmpty + b));
     }
     const int c = c0 + cc;
-    if (!mbar_wait(bars + 8 * (kBarAFree + c), ((st.wphase >> c) & 1u) ^ 1u, wd, kErrAFree + c)) return false;
+    if (!mbar_wait(bars + 8 * (kBarAFree + c), ((st.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
     st.wphase ^= 1u << c;
     const uint32_t base = a_row_addr + c * kAChunkBytes;
 #pragma unroll
@@ -168,7 +168,7 @@ __device__ __forceinline__ bool epi_hidden_pass(const float* __restrict__ bias, 
 __device__ __forceinline__ bool epi_head_pass(const float* __restrict__ bias, const float* __restrict__ head,
                                               uint32_t tmem_row, int b, uint32_t bars, EpiState& st,
                                               const Watchdog& wd, float& dot, float* dump_row) {
-  if (!mbar_wait(bars + 8 * (kBarAccFull + b), (st.acc_phase >> b) & 1u, wd, kErrAccFull + b)) return false;
+  if (!mbar_wait(bars + 8 * (kBarAccFull + b), (st.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
   st.acc_phase ^= 1u << b;
   tc_fence_after();
 #pragma unroll 1
@@ -257,7 +257,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decoder_kernel(const Decode
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
-  Watchdog wd{misc + 1, p.status, p.timeout_ns};
+  long long waited[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  Watchdog wd{misc + 1, p.status, p.timeout_ns, p.prof != nullptr ? waited : nullptr};
+  const long long t_start = clock64();
 
   if (warp == 4) {
     // ===================== producer: weight stream -> 3-stage ring =====================
@@ -267,10 +269,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decoder_kernel(const Decode
         const uint8_t* src = p.wstream;
 #pragma unroll 1
         for (int blk = 0; blk < kBlocksPerTile; ++blk, src += kBlockBytes) {
-          if (!mbar_wait(bars + 8 * (kBarWEmpty + stage), phase ^ 1u, wd, kErrWEmpty + stage)) goto done;
+          if (!mbar_wait(bars + 8 * (kBarWEmpty + stage), phase ^ 1u, wd, kErrWEmpty, stage)) goto done;
           const uint32_t full = bars + 8 * (kBarWFull + stage);
-          mbar_arrive_expect_tx(full, kBlockBytes);
-          bulk_g2s(smem0 + kSmemW + stage * kBlockBytes, src, kBlockBytes, full);
+          if (p.debug_flags & 1u) {
+            mbar_arrive(full);
+          } else {
+            mbar_arrive_expect_tx(full, kBlockBytes);
+            bulk_g2s(smem0 + kSmemW + stage * kBlockBytes, src, kBlockBytes, full);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -290,15 +296,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decoder_kernel(const Decode
           const bool first = pass_first(ps), last = pass_last(ps);
           const uint32_t b = gpass & 1u;
           const uint32_t d_tmem = tmem_base + b * 256;
-          if (!mbar_wait(bars + 8 * (kBarAccEmpty + b), ((ephase >> b) & 1u) ^ 1u, wd, kErrAccEmpty + b)) goto done;
+          if (!mbar_wait(bars + 8 * (kBarAccEmpty + b), ((ephase >> b) & 1u) ^ 1u, wd, kErrAccEmpty, b)) goto done;
           ephase ^= 1u << b;
 #pragma unroll 1
           for (int k = 0; k < nk; ++k) {
             if (first) {
-              if (!mbar_wait(bars + 8 * (kBarAReady + k), (rphase >> k) & 1u, wd, kErrAReady + k)) goto done;
+              if (!mbar_wait(bars + 8 * (kBarAReady + k), (rphase >> k) & 1u, wd, kErrAReady, k)) goto done;
               rphase ^= 1u << k;
             }
-            if (!mbar_wait(bars + 8 * (kBarWFull + stage), phase, wd, kErrWFull + stage)) goto done;
+            if (!mbar_wait(bars + 8 * (kBarWFull + stage), phase, wd, kErrWFull, stage)) goto done;
             tc_fence_after();
             const uint64_t adesc = umma_desc_sw128(smem0 + kSmemA + k * kAChunkBytes);
             const uint64_t bdesc = umma_desc_sw128(smem0 + kSmemW + stage * kBlockBytes);
@@ -373,9 +379,19 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decoder_kernel(const Decode
     }
   }
 done:
+  if (p.prof != nullptr && (lane == 0) && (warp == 0 || warp >= 4)) {
+    // blocked cycles per wait class (index = site >> 4) and this role's total, per CTA and role
+    const int role = warp == 0 ? 0 : warp - 3;            // 0 epilogue, 1 producer, 2 MMA issuer
+    long long* dst = p.prof + (static_cast<long long>(blockIdx.x) * 3 + role) * 8;
+#pragma unroll
+    for (int i = 1; i < 7; ++i) dst[i] = waited[i];
+    dst[0] = clock64() - t_start;
+    dst[7] = my_tiles;
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }
@@ -420,7 +436,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint16_t* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
-  Watchdog wd{misc + 1, status, 200000000ull};
+  Watchdog wd{misc + 1, status, 200000000ull, nullptr};
   if (threadIdx.x == 0) {
     constexpr uint32_t idesc = umma_idesc(128, 256, FP16 ? 0 : 1);
     const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sb);

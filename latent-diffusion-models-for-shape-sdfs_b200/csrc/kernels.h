@@ -65,10 +65,18 @@ struct DecodeParams {
   float* dump;                 // debug: 128x256 pre-activations of pass `dump_pass`, tile 0
   int dump_pass;
   unsigned long long timeout_ns;
+  long long* prof;             // optional [grid][3 roles][8]: blocked cycles per wait class (diagnostics)
+  unsigned int debug_flags;    // bit0: producer skips the weight copies (timing experiment; results are garbage)
 };
 
 cudaError_t launch_fused_decoder(const DecodeParams& p, bool fp16, int num_sms, cudaStream_t stream);
 cudaError_t fused_decoder_init();   // opt in to the large dynamic shared memory carve-out
+
+// CTA-pair (cta_group::2) version, fused_decoder2.cu: the production kernel.
+cudaError_t fused_decoder2_init();
+cudaError_t make_wstream_tensor_map(const void* wstream, void* tmap_out /* 128 B, 64-byte aligned */);
+cudaError_t launch_fused_decoder2(const DecodeParams& p, const void* tmap, bool fp16, int num_sms,
+                                  cudaStream_t stream);
 
 // Unit test of the UMMA plumbing: D[128][256] = A[128][64] * B[256][64]^T, row-major 16-bit inputs.
 cudaError_t launch_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, unsigned int* status,

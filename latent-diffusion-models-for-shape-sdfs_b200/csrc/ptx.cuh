@@ -73,12 +73,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+// CTA-scope acquire: a cluster-scope acquire makes ptxas emit CCTL.IVALL (an L1 invalidate)
+// after every wait, which turns the epilogue's bias loads into L2 round trips.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
@@ -92,21 +94,27 @@ struct Watchdog {
   volatile uint32_t* abort_flag;   // smem word: non-zero => give up everywhere
   unsigned int* status;            // global word: first failure code wins
   uint64_t timeout_ns;
+  long long* wait_cycles;          // optional per-thread [8] accumulator of blocked cycles per site class
 };
 
-// Bounded wait.  `code` identifies the wait site in the status word.
+// Bounded wait.  `site` (a multiple of 16) + `idx` identify the wait site in the status word;
+// site >> 4 is the class under which blocked cycles are accumulated when profiling.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, const Watchdog& wd,
-                                          uint32_t code) {
+                                          uint32_t site, uint32_t idx = 0) {
   if (mbar_try_wait(bar, parity)) return true;
+  const long long c0 = clock64();
   uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (true) {
-    if (mbar_try_wait(bar, parity)) return true;
+    if (mbar_try_wait(bar, parity)) {
+      if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
+      return true;
+    }
     if ((++spins & 0xFFu) == 0) {
       if (*wd.abort_flag) return false;
       if (global_timer_ns() - t0 > wd.timeout_ns) {
-        *wd.abort_flag = code;
-        atomicCAS(wd.status, 0u, code);
+        *wd.abort_flag = site + idx;
+        atomicCAS(wd.status, 0u, site + idx);
         return false;
       }
     }
