@@ -125,6 +125,11 @@ int sdfb_ddpm_sample_host(sdfb_ddpm* ddpm, float* x_host, const float* noise_hos
 int sdfb_umma_selftest(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int precision,
                        void* stream);
 
+/* Diagnostic: mean SM cycles per back-to-back tcgen05.mma (kind::f16 bf16, N=256, K=16;
+ * M=128 for cta_group 1, M=256 per CTA pair for cta_group 2) over `grid` CTAs. */
+int sdfb_umma_rate(int cta_group, int grid, int iters, int k_per_commit, int n_acc, int flags,
+                   double* cycles_per_mma);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ SIGNATURES = {
     "sdfb_ddpm_denoise": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
     "sdfb_ddpm_sample_host": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "sdfb_umma_selftest": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "sdfb_umma_rate": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -514,6 +514,26 @@ int sdfb_umma_selftest(const uint16_t* a_dev, const uint16_t* b_dev, float* d_de
   return SDFB_OK;
 }
 
+int sdfb_umma_rate(int cta_group, int grid, int iters, int k_per_commit, int n_acc, int flags, double* cycles_per_mma) {
+  if (!cycles_per_mma || (cta_group != 1 && cta_group != 2) || grid < cta_group || iters < 1 || k_per_commit < 1 ||
+      n_acc < 1 || n_acc > 2)
+    return fail(SDFB_E_INVALID, "bad argument");
+  grid -= grid % cta_group;
+  long long* out = nullptr;
+  CU_TRY(cudaMalloc(&out, sizeof(long long) * grid));
+  CU_TRY(cudaMemset(out, 0, sizeof(long long) * grid));
+  cudaError_t e = launch_umma_rate(cta_group, grid, iters, k_per_commit, n_acc, flags, out, 0);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  std::vector<long long> h(grid / cta_group);
+  if (e == cudaSuccess) e = cudaMemcpy(h.data(), out, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+  cudaFree(out);
+  if (e != cudaSuccess) return fail(SDFB_E_CUDA, "umma rate: %s", cudaGetErrorString(e));
+  double s = 0;
+  for (long long v : h) s += static_cast<double>(v);
+  *cycles_per_mma = s / h.size() / (static_cast<double>(iters) * k_per_commit * 4);
+  return SDFB_OK;
+}
+
 // ------------------------------------------------------------------ DDPM ----
 
 int sdfb_ddpm_create(const float* params_host, size_t n_floats, int device, sdfb_ddpm** out) {

@@ -82,6 +82,10 @@ cudaError_t launch_fused_decoder2(const DecodeParams& p, const void* tmap, bool 
 cudaError_t launch_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, unsigned int* status,
                                  bool fp16, cudaStream_t stream);
 
+// Diagnostic: cycles per back-to-back tcgen05.mma (umma_rate.cu).
+cudaError_t launch_umma_rate(int cg, int grid, int iters, int k_per_commit, int n_acc, int flags, long long* out_dev,
+                             cudaStream_t stream);
+
 // Per-latent fold: consts->l0[n].w and consts->bias[3][n] from the fp32 parameters and z.
 cudaError_t launch_fold_latent(const float* W0, const float* b0, const float* W4, const float* b4,
                                const float* z, DecConsts* consts, cudaStream_t stream);

@@ -101,8 +101,11 @@ struct Watchdog {
 // site >> 4 is the class under which blocked cycles are accumulated when profiling.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, const Watchdog& wd,
                                           uint32_t site, uint32_t idx = 0) {
-  if (mbar_try_wait(bar, parity)) return true;
-  const long long c0 = clock64();
+  const long long c0 = wd.wait_cycles != nullptr ? clock64() : 0;
+  if (mbar_try_wait(bar, parity)) {   // try_wait itself may block for a while: count that time too
+    if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
+    return true;
+  }
   uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (true) {
