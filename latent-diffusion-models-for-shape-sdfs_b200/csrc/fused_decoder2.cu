@@ -16,9 +16,13 @@
 //              completion counted on the LEADER's barrier (.cta_group::2)
 //   warp 9     MMA issuer (leader CTA only) + TMEM allocation (both CTAs)
 //
-// Shared memory per CTA: activations 128 KiB (in place, 8 chunks), 4-stage weight ring
-// 64 KiB, all epilogue constants (biases, head, L4's xyz weights) 22 KiB - the epilogue
-// never touches global memory except for the result store.
+// Shared memory per CTA: activations 128 KiB (in place, 8 chunks), 5-slot weight ring 80 KiB,
+// biases and head weights 16 KiB.
+//
+// Commit cadence: a tcgen05.commit after every 4 MMAs costs ~245 cycles per commit point
+// (tools/umma_rate.py: 189 cycles/MMA instead of 128), after every 8 MMAs nothing.  So the
+// issuer commits once per PAIR of weight blocks and releases both ring slots, both activation
+// chunks and (at the end of a pass) the accumulator at that one point.
 #include <cuda.h>
 
 #include "kernels.h"
@@ -28,7 +32,7 @@ namespace sdfb {
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kStages = 5;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 64;
@@ -38,8 +42,7 @@ constexpr uint32_t oA = 0;
 constexpr uint32_t oW = kAChunks * kAChunkBytes;                       // 131072
 constexpr uint32_t oBias = oW + kStages * kHalfBlockBytes;             // 7 x 512 floats
 constexpr uint32_t oHead = oBias + 7 * kHid * 4;                       // 512 floats
-constexpr uint32_t oL4x = oHead + kHid * 4;                            // 3 planes x 512 floats
-constexpr uint32_t oXyz = oL4x + 3 * kHid * 4;                         // 128 x float4: the tile's coordinates
+constexpr uint32_t oXyz = oHead + kHid * 4;                            // 128 x float4: the tile's coordinates
 constexpr uint32_t oDot = oXyz + kTileM * 16;                          // 128 floats: head partial sums
 constexpr uint32_t oBar = oDot + kTileM * 4;
 constexpr int kBarWFull = 0;
@@ -51,7 +54,7 @@ constexpr int kBarAFree = kBarAReady + kAChunks;
 constexpr int kNumBars = kBarAFree + kAChunks;
 constexpr uint32_t oMisc = oBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = oMisc + 16;
-constexpr uint32_t kSmemAlloc = kSmemBytes + 1024;
+constexpr uint32_t kSmemAlloc = kSmemBytes;     // no slack: the dynamic window is declared 1024-byte aligned
 static_assert(kSmemAlloc <= 232448, "exceeds the 227 KiB opt-in shared memory of sm_100");
 static_assert(oBar % 8 == 0, "barriers must be 8-byte aligned");
 
@@ -113,11 +116,14 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity,
     }
   }
 }
-// `count` arrivals on the LEADER CTA's copy of a barrier (local or remote), release at cluster scope
+// `count` arrivals on the LEADER CTA's copy of a barrier (local or remote).  Default semantics
+// (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) does: a cluster-scope release
+// costs a MEMBAR of several hundred cycles per arrival (30% of all epilogue stall samples when it
+// was tried).  The data being published was made visible to the async proxy by each lane's
+// fence.proxy.async and ordered before this arrive by __syncwarp().
 __device__ __forceinline__ void arrive_on_leader(uint32_t local_bar, uint32_t count) {
   const uint32_t remote = map_to_cta(local_bar, 0);
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(count)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(count) : "memory");
 }
 // this CTA's 128 rows of weight block `row0/256`: 2-D tensor-map TMA into local shared memory,
 // transaction bytes counted on the leader's barrier
@@ -165,7 +171,7 @@ struct Epi {
 // Hidden pass: this warp converts chunks {set, set+2} of accumulator half `b` into chunks
 // c0 + {set, set+2} of the activation buffer.
 template <bool FP16, bool XYZ>
-__device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict__ sbias, const float* __restrict__ sl4x,
+__device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict__ sbias, const float4* __restrict__ gl4x,
                                                 Query q, int c0, int b, const Watchdog& wd, float* dump_row) {
   if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
   e.acc_phase ^= 1u << b;
@@ -189,13 +195,11 @@ __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict_
       if constexpr (XYZ) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 wx = *reinterpret_cast<const float4*>(sl4x + col + 4 * j);
-          const float4 wy = *reinterpret_cast<const float4*>(sl4x + kHid + col + 4 * j);
-          const float4 wz = *reinterpret_cast<const float4*>(sl4x + 2 * kHid + col + 4 * j);
-          bb[4 * j] = fmaf(q.z, wz.x, fmaf(q.y, wy.x, fmaf(q.x, wx.x, bb[4 * j])));
-          bb[4 * j + 1] = fmaf(q.z, wz.y, fmaf(q.y, wy.y, fmaf(q.x, wx.y, bb[4 * j + 1])));
-          bb[4 * j + 2] = fmaf(q.z, wz.z, fmaf(q.y, wy.z, fmaf(q.x, wx.z, bb[4 * j + 2])));
-          bb[4 * j + 3] = fmaf(q.z, wz.w, fmaf(q.y, wy.w, fmaf(q.x, wx.w, bb[4 * j + 3])));
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 w = __ldg(&gl4x[col + 4 * j + i4]);
+            bb[4 * j + i4] = fmaf(q.z, w.z, fmaf(q.y, w.y, fmaf(q.x, w.x, bb[4 * j + i4])));
+          }
         }
       }
       tmem_ld_wait();
@@ -288,14 +292,17 @@ __device__ __forceinline__ bool epi_layer0(Epi& e, int warp, const float4 wa, co
 template <bool FP16>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_decoder2_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap tmap) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  uint8_t* gen = smem_raw;
+  if ((smem0 & 1023u) != 0) {   // the swizzled operand layout needs it; never observed, but fail loudly
+    if (threadIdx.x == 0) atomicCAS(p.status, 0u, 0xA11u);
+    return;
+  }
   const uint32_t bars = smem0 + oBar;
   volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(gen + oMisc);   // [0] tmem base, [1] abort
   float* sbias = reinterpret_cast<float*>(gen + oBias);
   float* shead = reinterpret_cast<float*>(gen + oHead);
-  float* sl4x = reinterpret_cast<float*>(gen + oL4x);
   float4* sxyz = reinterpret_cast<float4*>(gen + oXyz);
   float* sdot = reinterpret_cast<float*>(gen + oDot);
   const int warp = threadIdx.x >> 5;
@@ -329,11 +336,7 @@ fused_decoder2_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap 
     const float* gb = &cs->bias[0][0];
     for (int i = threadIdx.x; i < 7 * kHid; i += kThreads) sbias[i] = gb[i];
   }
-  for (int i = threadIdx.x; i < kHid; i += kThreads) {
-    shead[i] = cs->head[i];
-    const float4 w = cs->l4x[i];
-    sl4x[i] = w.x; sl4x[kHid + i] = w.y; sl4x[2 * kHid + i] = w.z;
-  }
+  for (int i = threadIdx.x; i < kHid; i += kThreads) shead[i] = cs->head[i];
   if (warp == 9) {
     tmem_alloc<2>(smem0 + oMisc, 512);
     tmem_relinquish<2>();
@@ -368,9 +371,16 @@ fused_decoder2_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap 
     }
   } else if (warp == 9) {
     // ===================== MMA issuer (leader CTA) =====================
-    if (leader && lane == 0) {
+    // The WHOLE warp runs the loop so that every operand is warp-uniform and only the
+    // tcgen05 instructions sit under elect.sync: issued from a divergent `lane == 0` branch,
+    // ptxas wraps each one in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop and the issuing
+    // thread itself (~440 cycles of instructions per 512-cycle block) becomes the bottleneck.
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc(256, 256, FP16 ? 0 : 1);
-      uint32_t stage = 0, phase = 0, rphase = 0, ephase = 0, gpass = 0;
+      const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+      const uint32_t a_lo0 = ((smem0 + oA) & 0x3FFFFu) >> 4 | (1u << 16);
+      const uint32_t w_lo0 = ((smem0 + oW) & 0x3FFFFu) >> 4 | (1u << 16);
+      uint32_t stage = 0, phase = 0, rphase = 0, ephase = 0, gpass = 0, prev_stage = 0;
       for (long long it = 0; it < my_tiles; ++it) {
 #pragma unroll 1
         for (int ps = 0; ps < kPasses; ++ps, ++gpass) {
@@ -378,27 +388,36 @@ fused_decoder2_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap 
           const bool first = pass_first(ps), last = pass_last(ps);
           const uint32_t b = gpass & 1u;
           const uint32_t d_tmem = tmem_base + b * 256;
-          if (!mbar_wait_cluster(bars + 8 * (kBarAccEmpty + b), ((ephase >> b) & 1u) ^ 1u, wd, kErrAccEmpty, b))
-            goto done;
+          if (!mbar_wait(bars + 8 * (kBarAccEmpty + b), ((ephase >> b) & 1u) ^ 1u, wd, kErrAccEmpty, b)) goto done;
           ephase ^= 1u << b;
 #pragma unroll 1
           for (int k = 0; k < nk; ++k) {
             if (first) {
-              if (!mbar_wait_cluster(bars + 8 * (kBarAReady + k), (rphase >> k) & 1u, wd, kErrAReady, k)) goto done;
+              if (!mbar_wait(bars + 8 * (kBarAReady + k), (rphase >> k) & 1u, wd, kErrAReady, k)) goto done;
               rphase ^= 1u << k;
             }
-            if (!mbar_wait_cluster(bars + 8 * (kBarWFull + stage), phase, wd, kErrWFull, stage)) goto done;
+            if (!mbar_wait(bars + 8 * (kBarWFull + stage), phase, wd, kErrWFull, stage)) goto done;
             tc_fence_after();
-            const uint64_t adesc = umma_desc_sw128(smem0 + oA + k * kAChunkBytes);
-            const uint64_t bdesc = umma_desc_sw128(smem0 + oW + stage * kHalfBlockBytes);
+            const uint64_t adesc = desc_hi | (a_lo0 + k * (kAChunkBytes >> 4));
+            const uint64_t bdesc = desc_hi | (w_lo0 + stage * (kHalfBlockBytes >> 4));
+            if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              umma_ss<2>(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0 ? 1u : 0u);
-            umma_commit<2>(bars + 8 * (kBarWEmpty + stage));
-            if (last) umma_commit<2>(bars + 8 * (kBarAFree + k));
+              for (int j = 0; j < 4; ++j)
+                umma_ss<2>(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0 ? 1u : 0u);
+              if (k & 1) {   // one commit point per pair of blocks (see the header comment)
+                umma_commit<2>(bars + 8 * (kBarWEmpty + prev_stage));
+                umma_commit<2>(bars + 8 * (kBarWEmpty + stage));
+                if (last) {
+                  umma_commit<2>(bars + 8 * (kBarAFree + k - 1));
+                  umma_commit<2>(bars + 8 * (kBarAFree + k));
+                }
+                if (k == nk - 1) umma_commit<2>(bars + 8 * (kBarAccFull + b));
+              }
+            }
+            __syncwarp();
+            prev_stage = stage;
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit<2>(bars + 8 * (kBarAccFull + b));
         }
       }
     }
@@ -441,7 +460,7 @@ fused_decoder2_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap 
           float* dump_row = (dump_tile && ps == p.dump_pass) ? p.dump + row * 256 : nullptr;
           bool ok;
           if (layer == 4)
-            ok = epi_hidden_pass<FP16, true>(e, bias, sl4x + half * 256, q, half * 4, gpass & 1u, wd, dump_row);
+            ok = epi_hidden_pass<FP16, true>(e, bias, cs->l4x + half * 256, q, half * 4, gpass & 1u, wd, dump_row);
           else
             ok = epi_hidden_pass<FP16, false>(e, bias, nullptr, q, half * 4, gpass & 1u, wd, dump_row);
           if (!ok) goto done;
