@@ -91,7 +91,7 @@ void pack_wstream(const float* P, const LayerOff off[9], bool fp16, std::vector<
   for (int p = 0; p < kPasses; ++p) {
     const int L = pass_layer[p], h = pass_half[p];
     const int nk = (L == 4) ? 4 : 8;
-    const int kvalid = (L == 4) ? kSkipOut : 512;   // L4 consumes h3 (253 wide) through the tensor core
+    // L4's K = 256 operand is [h3 (253) | xyz (3)]: its weight columns are W4[:, 0:253] | W4[:, 509:512]
     const float* W = P + off[L].w;
     const int fin = off[L].fin, fout = off[L].fout;
     for (int k = 0; k < nk; ++k, ++blk) {
@@ -102,7 +102,8 @@ void pack_wstream(const float* P, const LayerOff off[9], bool fp16, std::vector<
           uint16_t* d = dst + r * 64 + ((u ^ (r & 7)) * 8);
           for (int e = 0; e < 8; ++e) {
             const int kk = k * 64 + u * 8 + e;
-            const float v = (n < fout && kk < kvalid) ? W[static_cast<long long>(n) * fin + kk] : 0.f;
+            const int src = (L == 4 && kk >= kSkipOut) ? kk + kLatent : kk;
+            const float v = (n < fout) ? W[static_cast<long long>(n) * fin + src] : 0.f;
             d[e] = to_lowp(v, fp16);
           }
         }
@@ -120,7 +121,6 @@ struct sdfb_decoder {
   float* w4s = nullptr;          // [512][256]: W4[:, 0:253] | W4[:, 509:512]   (fp32 path)
   uint8_t* wstream[2] = {nullptr, nullptr};   // [0] bf16, [1] fp16
   alignas(64) unsigned char tmap[2][128];     // tensor maps over the two streams (CTA-pair kernel)
-  bool use_pairs = true;                      // SDFB_KERNEL=cg1 selects the single-CTA kernel
   DecConsts* consts = nullptr;
   float* bias0f = nullptr;       // fp32 path folded biases
   float* bias4f = nullptr;
@@ -218,10 +218,7 @@ int decode_tc(sdfb_decoder* d, const float* z, const float* xyz, int res, long l
   p.debug_flags = d->debug_flags;
   p.prof = d->prof;
   CU_TRY(cudaEventRecord(d->ev0, st));
-  if (d->use_pairs)
-    CU_TRY(launch_fused_decoder2(p, d->tmap[fp16 ? 1 : 0], fp16, d->num_sms, st));
-  else
-    CU_TRY(launch_fused_decoder(p, fp16, d->num_sms, st));
+  CU_TRY(launch_fused_decoder(p, d->tmap[fp16 ? 1 : 0], fp16, d->num_sms, st));
   CU_TRY(cudaEventRecord(d->ev1, st));
   d->timed = true;
   return SDFB_OK;
@@ -296,8 +293,7 @@ int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, s
       return bail(fail(SDFB_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)));       \
   } while (0)
   CU_TRY_D(fused_decoder_init());
-  CU_TRY_D(fused_decoder2_init());
-  if (const char* e = std::getenv("SDFB_KERNEL")) d->use_pairs = std::strcmp(e, "cg1") != 0;
+  CU_TRY_D(tc_common_init());
   CU_TRY_D(cudaMalloc(&d->params, n_floats * sizeof(float)));
   CU_TRY_D(cudaMemcpy(d->params, P, n_floats * sizeof(float), cudaMemcpyHostToDevice));
   // fp32 path: compact skip-layer matrix
@@ -324,10 +320,8 @@ int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, s
     DecConsts& c = hc[0];
     std::memset(&c, 0, sizeof(c));
     const float* W0 = P + d->off[0].w;
-    const float* W4 = P + d->off[4].w;
     for (int n = 0; n < 512; ++n) {
       c.l0[n] = make_float4(W0[n * kDecIn + 256], W0[n * kDecIn + 257], W0[n * kDecIn + 258], 0.f);
-      c.l4x[n] = make_float4(W4[n * 512 + 509], W4[n * 512 + 510], W4[n * 512 + 511], 0.f);
       c.head[n] = P[d->off[8].w + n];
     }
     for (int l = 1; l <= 7; ++l)
@@ -499,7 +493,7 @@ int sdfb_decoder_last_kernel_ms(sdfb_decoder* d, float* ms) {
 int sdfb_umma_selftest(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int precision, void* stream) {
   if (!a_dev || !b_dev || !d_dev) return fail(SDFB_E_INVALID, "null argument");
   if (precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16) return fail(SDFB_E_INVALID, "bf16 or fp16 only");
-  CU_TRY(fused_decoder_init());
+  CU_TRY(tc_common_init());
   unsigned int* status = nullptr;
   CU_TRY(cudaMalloc(&status, sizeof(unsigned int)));
   CU_TRY(cudaMemset(status, 0, sizeof(unsigned int)));

@@ -1,26 +1,37 @@
-// K1: fused persistent SDF decoder for sm_100a (tcgen05 / TMEM / bulk-async copies).
+// K1: fused persistent SDF decoder for sm_100a (tcgen05 / TMEM / TMA, CTA pairs).
 //
-// What it computes (SURVEY.md section 8a, rows A1-A3; oracle: oracle/decoder.py
-// decoder_forward_lowp - there is no upstream source, /root/reference/README.md:1):
-//   h0 = relu(xyz W0x^T + bias0')                     fp32 FFMA in the epilogue warps
-//   h1..h7 chained 512-wide layers                    tcgen05.mma, 16-bit operands, fp32 in TMEM
-//   (L3 emits 253 features, L4 consumes [h3 | xyz] with the latent folded into bias4')
-//   sdf = tanh(h7 . w8 + b8)                          fp32, h7 never rounded
+// What it computes (SURVEY.md section 8a rows A1-A3; oracle: oracle/decoder.py
+// decoder_forward_lowp; no upstream source exists, /root/reference/README.md:1):
+//   h0 = relu(xyz W0x^T + bias0')              fp32 FFMA in the epilogue warps (latent folded)
+//   h1..h7 chained 512-wide layers             tcgen05.mma, 16-bit operands, fp32 accum in TMEM
+//   (L3 emits 253 features; its 3 padding columns carry xyz into L4, latent folded in bias4')
+//   sdf = tanh(h7 . w8 + b8)                   fp32, h7 never rounded
+// One CTA pair carries a tile of 256 queries through all layers; activations never leave the
+// SMs.  Per tile the tensor core runs 13 passes (kernels.h); a layer's output is produced in
+// two N=256 passes that ping-pong between the two halves of TMEM, and the epilogue writes the
+// next layer's A operand IN PLACE over the current one, chunk by chunk, as soon as the last
+// MMA reading a chunk has committed.  The first layer of the NEXT tile is computed while the
+// last layer of the current one is still on the tensor core.
 //
-// Structure: one CTA per SM, persistent over 128-query tiles (static round robin).
-//   warps 0-3  epilogue: TMEM -> registers -> +bias, ReLU, pack -> shared memory (the next
-//              layer's A operand, written IN PLACE over the current one), L0, head, store
-//   warp 4     producer: streams the 96 weight blocks of a tile through a 3-stage ring
-//   warp 5     MMA issuer: one lane issues every tcgen05.mma and the commits
+// Why pairs (cta_group::2): each SM supplies its own 128 rows of A and only HALF of every
+// weight block, which halves the shared-memory operand traffic per MMA and the L2->SM weight
+// stream (a single-CTA version of this kernel measured 54.5 ms for 256^3).
 //
-// The activations of a tile live in eight 16 KiB shared-memory chunks (64 features each,
-// K-major, 128B swizzle).  A layer's output is produced in two N=256 passes that ping-pong
-// between the two 256-column halves of TMEM; the epilogue of one pass runs while the tensor
-// core works on the next.  Chunk c of the next layer's input overwrites chunk c of the
-// current one as soon as the last MMA reading it has committed (a_free[c]); the MMA issuer
-// starts a layer as soon as the chunks it needs have been published (a_ready[c]).  The first
-// layer of the NEXT tile is computed by the epilogue warps while the last layer of the
-// current tile is still on the tensor core, so the pipe never drains between tiles.
+//   cluster = 2 CTAs = 256 queries;  CTA rank r owns rows [128r, 128r+128) of the pair tile
+//   warps 0-7  epilogue  (lane quadrant = warp & 3; the two warp sets split each 64-wide chunk)
+//   warp 8     producer: this CTA's half (16 KiB) of every weight block, tensor-map TMA,
+//              completion counted on the LEADER's barrier (.cta_group::2)
+//   warp 9     MMA issuer (leader CTA only) + TMEM allocation (both CTAs)
+//
+// Shared memory per CTA: activations 128 KiB (in place, 8 chunks), 5-slot weight ring 80 KiB,
+// biases and head weights 16 KiB.
+//
+// Commit cadence: a tcgen05.commit after every 4 MMAs costs ~245 cycles per commit point
+// (tools/umma_rate.py: 189 cycles/MMA instead of 128), after every 8 MMAs nothing.  So the
+// issuer commits once per PAIR of weight blocks and releases both ring slots, both activation
+// chunks and (at the end of a pass) the accumulator at that one point.
+#include <cuda.h>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -28,37 +39,39 @@ namespace sdfb {
 
 namespace {
 
-constexpr int kStages = 3;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kStages = 5;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = kEpiThreads + 64;
+constexpr uint32_t kHalfBlockBytes = kBlockBytes / 2;                  // 16 KiB: 128 weight rows x 64 k
 
-constexpr uint32_t kSmemA = 0;
-constexpr uint32_t kSmemW = kAChunks * kAChunkBytes;                    // 131072
-constexpr uint32_t kSmemBar = kSmemW + kStages * kBlockBytes;           // 229376
-// barrier slots (8 bytes each)
-constexpr int kBarWFull = 0;                   // [kStages]
+constexpr uint32_t oA = 0;
+constexpr uint32_t oW = kAChunks * kAChunkBytes;                       // 131072
+constexpr uint32_t oBias = oW + kStages * kHalfBlockBytes;             // 7 x 512 floats
+constexpr uint32_t oHead = oBias + 7 * kHid * 4;                       // 512 floats
+constexpr uint32_t oXyz = oHead + kHid * 4;                            // 128 x float4: the tile's coordinates
+constexpr uint32_t oDot = oXyz + kTileM * 16;                          // 128 floats: head partial sums
+constexpr uint32_t oBar = oDot + kTileM * 4;
+constexpr int kBarWFull = 0;
 constexpr int kBarWEmpty = kBarWFull + kStages;
-constexpr int kBarAccFull = kBarWEmpty + kStages;   // [2]
-constexpr int kBarAccEmpty = kBarAccFull + 2;       // [2]
-constexpr int kBarAReady = kBarAccEmpty + 2;        // [8]
-constexpr int kBarAFree = kBarAReady + kAChunks;    // [8]
+constexpr int kBarAccFull = kBarWEmpty + kStages;
+constexpr int kBarAccEmpty = kBarAccFull + 2;
+constexpr int kBarAReady = kBarAccEmpty + 2;
+constexpr int kBarAFree = kBarAReady + kAChunks;
 constexpr int kNumBars = kBarAFree + kAChunks;
-constexpr uint32_t kSmemMisc = kSmemBar + kNumBars * 8;                 // tmem ptr, abort flag
-constexpr uint32_t kSmemBytes = kSmemMisc + 16;
-constexpr uint32_t kSmemAlloc = kSmemBytes + 1024;                      // slack for 1024B alignment
+constexpr uint32_t oMisc = oBar + kNumBars * 8;
+constexpr uint32_t kSmemBytes = oMisc + 16;
+constexpr uint32_t kSmemAlloc = kSmemBytes;     // no slack: the dynamic window is declared 1024-byte aligned
 static_assert(kSmemAlloc <= 232448, "exceeds the 227 KiB opt-in shared memory of sm_100");
+static_assert(oBar % 8 == 0, "barriers must be 8-byte aligned");
 
-// watchdog site codes
 enum : uint32_t {
   kErrWFull = 0x10, kErrWEmpty = 0x20, kErrAccFull = 0x30, kErrAccEmpty = 0x40,
   kErrAReady = 0x50, kErrAFree = 0x60,
 };
 
-// static description of the 13 tensor-core passes of a tile
 __device__ __forceinline__ int pass_chunks(int p) { return (p == 5 || p == 6) ? 4 : 8; }
-// does pass p start a layer (must wait for published input chunks)?
 __device__ __forceinline__ bool pass_first(int p) { return (0x0AB5u >> p) & 1u; }  // {0,2,4,5,7,9,11}
-// is pass p the last reader of its layer's input chunks?
 __device__ __forceinline__ bool pass_last(int p) { return (0x155Au >> p) & 1u; }   // {1,3,4,6,8,10,12}
 
 template <bool FP16>
@@ -71,137 +84,69 @@ __device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {
   return d;
 }
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
-struct EpiState {
-  uint32_t wphase;      // bit c: parity of the next a_free[c] wait
-  uint32_t acc_phase;   // bit b: parity of the next acc_full[b] wait
-};
-
-// 64 features of h0 = relu(xyz W0x^T + bias0') for this thread's query -> chunk c (in place).
-template <bool FP16>
-__device__ __forceinline__ bool epi_layer0_chunk(const DecConsts* __restrict__ cs, int c, float x, float y,
-                                                 float z, uint32_t a_row_addr, uint32_t row7,
-                                                 uint32_t bars, EpiState& st, const Watchdog& wd) {
-  uint32_t packed[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int n = c * 64 + 2 * j;
-    const float4 w0 = __ldg(&cs->l0[n]);
-    const float4 w1 = __ldg(&cs->l0[n + 1]);
-    const float f0 = fmaf(z, w0.z, fmaf(y, w0.y, fmaf(x, w0.x, w0.w)));
-    const float f1 = fmaf(z, w1.z, fmaf(y, w1.y, fmaf(x, w1.x, w1.w)));
-    packed[j] = pack_relu<FP16>(f0, f1);
-  }
-  if (!mbar_wait(bars + 8 * (kBarAFree + c), ((st.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
-  st.wphase ^= 1u << c;
-  const uint32_t base = a_row_addr + c * kAChunkBytes;
-#pragma unroll
-  for (int u = 0; u < 8; ++u)
-    st_shared_v4(base + ((u ^ row7) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
-                 packed[4 * u + 3]);
-  fence_proxy_async_smem();
-  mbar_arrive(bars + 8 * (kBarAReady + c));
-  return true;
+// ---- cluster-scope barrier helpers ---------------------------------------------------------
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
-
-// One hidden pass: accumulator half `b` (256 columns) -> +bias (+ xyz term for L4) -> ReLU ->
-// 16-bit -> chunks [c0, c0+4) of the activation buffer.
-template <bool FP16, bool XYZ>
-__device__ __forceinline__ bool epi_hidden_pass(const float* __restrict__ bias, const float4* __restrict__ l4x,
-                                                float x, float y, float z, int c0, uint32_t tmem_row,
-                                                int b, uint32_t a_row_addr, uint32_t row7, uint32_t bars,
-                                                EpiState& st, const Watchdog& wd, float* dump_row) {
-  if (!mbar_wait(bars + 8 * (kBarAccFull + b), (st.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
-  st.acc_phase ^= 1u << b;
-  tc_fence_after();
-#pragma unroll 1
-  for (int cc = 0; cc < 4; ++cc) {
-    uint32_t packed[32];
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      uint32_t v[32];
-      const int col = cc * 64 + g * 32;
-      tmem_ld32(tmem_row + b * 256 + col, v);
-      float bb[32];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = ldg4(bias + col + 4 * j);
-        bb[4 * j] = t.x; bb[4 * j + 1] = t.y; bb[4 * j + 2] = t.z; bb[4 * j + 3] = t.w;
-      }
-      if constexpr (XYZ) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float4 w = __ldg(&l4x[col + j]);
-          bb[j] = fmaf(z, w.z, fmaf(y, w.y, fmaf(x, w.x, bb[j])));
-        }
-      }
-      tmem_ld_wait();
-      if (dump_row != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dump_row[col + j] = __uint_as_float(v[j]) + bb[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        packed[g * 16 + j] = pack_relu<FP16>(__uint_as_float(v[2 * j]) + bb[2 * j],
-                                             __uint_as_float(v[2 * j + 1]) + bb[2 * j + 1]);
-    }
-    if (cc == 3) {  // every column of this half has been read: hand the accumulator back
-      tc_fence_before();
-      mbar_arrive(bars + 8 * (kBarAccEmpty + b));
-    }
-    const int c = c0 + cc;
-    if (!mbar_wait(bars + 8 * (kBarAFree + c), ((st.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
-    st.wphase ^= 1u << c;
-    const uint32_t base = a_row_addr + c * kAChunkBytes;
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      st_shared_v4(base + ((u ^ row7) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
-                   packed[4 * u + 3]);
-    fence_proxy_async_smem();
-    mbar_arrive(bars + 8 * (kBarAReady + c));
+// wait used by the MMA issuer: the arrivals come from both CTAs of the pair
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity, const Watchdog& wd,
+                                                  uint32_t site, uint32_t idx = 0) {
+  const long long c0 = wd.wait_cycles != nullptr ? clock64() : 0;
+  if (mbar_try_wait_cluster(bar, parity)) {   // try_wait itself may block for a while: count that time too
+    if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
+    return true;
   }
-  return true;
+  uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (true) {
+    if (mbar_try_wait_cluster(bar, parity)) {
+      if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
+      return true;
+    }
+    if ((++spins & 0xFFu) == 0) {
+      if (*wd.abort_flag) return false;
+      if (global_timer_ns() - t0 > wd.timeout_ns) {
+        *wd.abort_flag = site + idx;
+        atomicCAS(wd.status, 0u, site + idx);
+        return false;
+      }
+    }
+  }
 }
-
-// One half of the last hidden layer: h7 = relu(acc + b7) stays fp32 and is reduced against w8.
-__device__ __forceinline__ bool epi_head_pass(const float* __restrict__ bias, const float* __restrict__ head,
-                                              uint32_t tmem_row, int b, uint32_t bars, EpiState& st,
-                                              const Watchdog& wd, float& dot, float* dump_row) {
-  if (!mbar_wait(bars + 8 * (kBarAccFull + b), (st.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
-  st.acc_phase ^= 1u << b;
-  tc_fence_after();
-#pragma unroll 1
-  for (int g = 0; g < 8; ++g) {
-    uint32_t v[32];
-    const int col = g * 32;
-    tmem_ld32(tmem_row + b * 256 + col, v);
-    float bb[32], hw[32];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 t = ldg4(bias + col + 4 * j);
-      bb[4 * j] = t.x; bb[4 * j + 1] = t.y; bb[4 * j + 2] = t.z; bb[4 * j + 3] = t.w;
-      const float4 h = ldg4(head + col + 4 * j);
-      hw[4 * j] = h.x; hw[4 * j + 1] = h.y; hw[4 * j + 2] = h.z; hw[4 * j + 3] = h.w;
-    }
-    tmem_ld_wait();
-    if (dump_row != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) dump_row[col + j] = __uint_as_float(v[j]) + bb[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) dot = fmaf(fmaxf(__uint_as_float(v[j]) + bb[j], 0.f), hw[j], dot);
-  }
-  tc_fence_before();
-  mbar_arrive(bars + 8 * (kBarAccEmpty + b));
-  return true;
+// `count` arrivals on the LEADER CTA's copy of a barrier (local or remote).  Default semantics
+// (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) does: a cluster-scope release
+// costs a MEMBAR of several hundred cycles per arrival (30% of all epilogue stall samples when it
+// was tried).  The data being published was made visible to the async proxy by each lane's
+// fence.proxy.async and ordered before this arrive by __syncwarp().
+__device__ __forceinline__ void arrive_on_leader(uint32_t local_bar, uint32_t count) {
+  const uint32_t remote = map_to_cta(local_bar, 0);
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(count) : "memory");
+}
+// this CTA's 128 rows of weight block `row0/256`: 2-D tensor-map TMA into local shared memory,
+// transaction bytes counted on the leader's barrier
+__device__ __forceinline__ void tma_load_half_block(uint32_t dst_smem, const CUtensorMap* tmap, int row0,
+                                                    uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(row0), "r"(leader_bar)
+      : "memory");
 }
 
 struct Query { float x, y, z; };
 
-__device__ __forceinline__ Query load_query(const DecodeParams& p, long long tile, int row) {
+__device__ __forceinline__ Query load_query(const DecodeParams& p, long long m) {
   Query q{0.f, 0.f, 0.f};
-  const long long m = tile * kTileM + row;
   if (m >= p.M) return q;
   if (p.xyz != nullptr) {
     q.x = __ldg(p.xyz + 3 * m); q.y = __ldg(p.xyz + 3 * m + 1); q.z = __ldg(p.xyz + 3 * m + 2);
@@ -219,19 +164,178 @@ __device__ __forceinline__ Query load_query(const DecodeParams& p, long long til
   return q;
 }
 
+struct Epi {
+  uint32_t bars;          // shared address of the barrier array
+  uint32_t tmem_row;      // TMEM address of this warp's lane quadrant, column 0
+  uint32_t a_row_addr;    // shared address of this thread's row in chunk 0
+  uint32_t row7;
+  uint32_t wphase;        // bit c: parity of the next a_free[c] wait (tracked for all chunks)
+  uint32_t acc_phase;     // bit b: parity of the next acc_full[b] wait
+  int set;                // 0/1: which of the two warp sets (splits chunks / head columns)
+  int lane;
+};
+
 template <bool FP16>
-__global__ void __launch_bounds__(kThreads, 1) fused_decoder_kernel(const DecodeParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
-  const uint32_t bars = smem0 + kSmemBar;
-  volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemMisc);   // [0] tmem base, [1] abort
+__device__ __forceinline__ uint32_t pack_plain(float lo, float hi) {   // no ReLU: signed coordinates
+  uint32_t d;
+  if constexpr (FP16)
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// Hidden pass.  The two warp sets work on the SAME chunk at the same time (set s converts
+// columns [32s, 32s+32) of it), chunk after chunk, so chunks become available in the order the
+// next layer's MMAs consume them.  The TMEM load of the next chunk is in flight while the
+// current one is converted.  `L3`: this is layer 3, whose last three (padding) columns carry
+// the query coordinates into layer 4.
+template <bool FP16, bool L3>
+__device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict__ sbias, Query q, int c0, int b,
+                                                const Watchdog& wd, float* dump_row) {
+  if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
+  e.acc_phase ^= 1u << b;
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t tbase = e.tmem_row + b * 256 + e.set * 32;
+  uint32_t v[2][32];
+  tmem_ld32(tbase, v[0]);
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    tmem_ld_wait();
+    if (cc < 3) {
+      tmem_ld32(tbase + (cc + 1) * 64, v[(cc + 1) & 1]);
+    } else {      // every column this warp owns has been read: hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAccEmpty + b), 1);
+    }
+    const uint32_t(&vc)[32] = v[cc & 1];
+    const int col = cc * 64 + e.set * 32;
+    uint32_t packed[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(sbias + col + 4 * j);
+      const float f0 = __uint_as_float(vc[4 * j]) + t.x, f1 = __uint_as_float(vc[4 * j + 1]) + t.y;
+      const float f2 = __uint_as_float(vc[4 * j + 2]) + t.z, f3 = __uint_as_float(vc[4 * j + 3]) + t.w;
+      if (dump_row != nullptr) {
+        dump_row[col + 4 * j] = f0; dump_row[col + 4 * j + 1] = f1;
+        dump_row[col + 4 * j + 2] = f2; dump_row[col + 4 * j + 3] = f3;
+      }
+      packed[2 * j] = pack_relu<FP16>(f0, f1);
+      packed[2 * j + 1] = pack_relu<FP16>(f2, f3);
+      if constexpr (L3) {
+        if (j == 7 && cc == 3 && e.set == 1) {   // features 252 | x, y | z  (x, y, z unrectified)
+          packed[14] = pack_plain<FP16>(fmaxf(f0, 0.f), q.x);
+          packed[15] = pack_plain<FP16>(q.y, q.z);
+        }
+      }
+    }
+    const int c = c0 + cc;
+    if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
+    const uint32_t base = e.a_row_addr + c * kAChunkBytes;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      st_shared_v4(base + (((4 * e.set + u) ^ e.row7) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
+                   packed[4 * u + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c), 1);
+  }
+  e.wphase ^= 0xFu << c0;
+  return true;
+}
+
+// Head pass: this warp reduces columns [128*set, 128*set+128) of half `b` of h7 against w8.
+__device__ __forceinline__ bool epi_head_pass(Epi& e, const float* __restrict__ sbias, const float* __restrict__ shead,
+                                              int b, const Watchdog& wd, float& dot, float* dump_row) {
+  if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
+  e.acc_phase ^= 1u << b;
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t tbase = e.tmem_row + b * 256 + e.set * 128;
+  uint32_t v[2][32];
+  tmem_ld32(tbase, v[0]);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    tmem_ld_wait();
+    if (g < 3) {
+      tmem_ld32(tbase + (g + 1) * 32, v[(g + 1) & 1]);
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAccEmpty + b), 1);
+    }
+    const uint32_t(&vc)[32] = v[g & 1];
+    const int col = e.set * 128 + g * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(sbias + col + 4 * j);
+      const float4 h = *reinterpret_cast<const float4*>(shead + col + 4 * j);
+      const float f0 = __uint_as_float(vc[4 * j]) + t.x, f1 = __uint_as_float(vc[4 * j + 1]) + t.y;
+      const float f2 = __uint_as_float(vc[4 * j + 2]) + t.z, f3 = __uint_as_float(vc[4 * j + 3]) + t.w;
+      if (dump_row != nullptr) {
+        dump_row[col + 4 * j] = f0; dump_row[col + 4 * j + 1] = f1;
+        dump_row[col + 4 * j + 2] = f2; dump_row[col + 4 * j + 3] = f3;
+      }
+      dot = fmaf(fmaxf(f0, 0.f), h.x, dot);
+      dot = fmaf(fmaxf(f1, 0.f), h.y, dot);
+      dot = fmaf(fmaxf(f2, 0.f), h.z, dot);
+      dot = fmaf(fmaxf(f3, 0.f), h.w, dot);
+    }
+  }
+  return true;
+}
+
+// First layer of a tile, column-mapped: warp w owns chunk w; lane l owns features 64w+2l, +1
+// (weights in registers) and walks the 128 rows, whose coordinates sit in shared memory.
+template <bool FP16>
+__device__ __forceinline__ bool epi_layer0(Epi& e, int warp, const float4 wa, const float4 wb,
+                                           const float4* __restrict__ sxyz, uint32_t smem_a, const Watchdog& wd) {
+  const int c = warp;
+  if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
+  const uint32_t chunk = smem_a + c * kAChunkBytes + ((e.lane & 3) << 2);
+  const uint32_t unit = e.lane >> 2;
+#pragma unroll 8
+  for (int r = 0; r < kTileM; ++r) {
+    const float4 q = sxyz[r];
+    const float f0 = fmaf(q.z, wa.z, fmaf(q.y, wa.y, fmaf(q.x, wa.x, wa.w)));
+    const float f1 = fmaf(q.z, wb.z, fmaf(q.y, wb.y, fmaf(q.x, wb.x, wb.w)));
+    const uint32_t v = pack_relu<FP16>(f0, f1);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(chunk + r * 128 + ((unit ^ (r & 7)) << 4)), "r"(v) : "memory");
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c), kEpiWarps);   // stands in for all 8 warps
+  e.wphase ^= 0xFFu;
+  return true;
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(kThreads, 1)
+fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  uint8_t* gen = smem_raw;
+  if ((smem0 & 1023u) != 0) {   // the swizzled operand layout needs it; never observed, but fail loudly
+    if (threadIdx.x == 0) atomicCAS(p.status, 0u, 0xA11u);
+    return;
+  }
+  const uint32_t bars = smem0 + oBar;
+  volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(gen + oMisc);   // [0] tmem base, [1] abort
+  float* sbias = reinterpret_cast<float*>(gen + oBias);
+  float* shead = reinterpret_cast<float*>(gen + oHead);
+  float4* sxyz = reinterpret_cast<float4*>(gen + oXyz);
+  float* sdot = reinterpret_cast<float*>(gen + oDot);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
 
-  const long long num_tiles = (p.M + kTileM - 1) / kTileM;
-  const long long first_tile = blockIdx.x;
-  const long long my_tiles = first_tile < num_tiles ? (num_tiles - first_tile + gridDim.x - 1) / gridDim.x : 0;
+  const long long num_tiles = (p.M + 2 * kTileM - 1) / (2 * kTileM);      // pair tiles of 256 queries
+  const long long npairs = gridDim.x >> 1, pidx = blockIdx.x >> 1;
+  const long long my_tiles = pidx < num_tiles ? (num_tiles - pidx + npairs - 1) / npairs : 0;
+  const DecConsts* __restrict__ cs = p.consts;
 
   if (threadIdx.x == 0) {
     misc[1] = 0;
@@ -241,54 +345,64 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decoder_kernel(const Decode
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bars + 8 * (kBarAccFull + b), 1);
-      mbar_init(bars + 8 * (kBarAccEmpty + b), kEpiThreads);
+      mbar_init(bars + 8 * (kBarAccEmpty + b), 2 * kEpiWarps);      // every epilogue warp of both CTAs
     }
     for (int c = 0; c < kAChunks; ++c) {
-      mbar_init(bars + 8 * (kBarAReady + c), kEpiThreads);
+      mbar_init(bars + 8 * (kBarAReady + c), 2 * kEpiWarps);        // every epilogue warp of both CTAs
       mbar_init(bars + 8 * (kBarAFree + c), 1);
     }
     fence_mbar_init();
   }
-  if (warp == 5) {
-    tmem_alloc<1>(smem0 + kSmemMisc, 512);
-    tmem_relinquish<1>();
+  // epilogue constants -> shared memory (the fold kernel ran earlier on this stream)
+  {
+    const float* gb = &cs->bias[0][0];
+    for (int i = threadIdx.x; i < 7 * kHid; i += kThreads) sbias[i] = gb[i];
+  }
+  for (int i = threadIdx.x; i < kHid; i += kThreads) shead[i] = cs->head[i];
+  if (warp == 9) {
+    tmem_alloc<2>(smem0 + oMisc, 512);
+    tmem_relinquish<2>();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
   long long waited[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   Watchdog wd{misc + 1, p.status, p.timeout_ns, p.prof != nullptr ? waited : nullptr};
   const long long t_start = clock64();
 
-  if (warp == 4) {
-    // ===================== producer: weight stream -> 3-stage ring =====================
+  if (warp == 8) {
+    // ===================== producer: this CTA's half of every weight block =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (long long it = 0; it < my_tiles; ++it) {
-        const uint8_t* src = p.wstream;
 #pragma unroll 1
-        for (int blk = 0; blk < kBlocksPerTile; ++blk, src += kBlockBytes) {
+        for (int blk = 0; blk < kBlocksPerTile; ++blk) {
           if (!mbar_wait(bars + 8 * (kBarWEmpty + stage), phase ^ 1u, wd, kErrWEmpty, stage)) goto done;
           const uint32_t full = bars + 8 * (kBarWFull + stage);
-          if (p.debug_flags & 1u) {
-            mbar_arrive(full);
-          } else {
-            mbar_arrive_expect_tx(full, kBlockBytes);
-            bulk_g2s(smem0 + kSmemW + stage * kBlockBytes, src, kBlockBytes, full);
-          }
+          if (leader) mbar_arrive_expect_tx(full, kBlockBytes);          // both halves land on this barrier
+          if (!(p.debug_flags & 1u))
+            tma_load_half_block(smem0 + oW + stage * kHalfBlockBytes, &tmap, blk * kBlockRows + rank * 128,
+                                map_to_cta(full, 0));
+          else if (leader)
+            asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full), "r"(kBlockBytes) : "memory");
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 5) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(128, 256, FP16 ? 0 : 1);
-      uint32_t stage = 0, phase = 0;
-      uint32_t rphase = 0;      // bit c: parity of the next a_ready[c] wait
-      uint32_t ephase = 0;      // bit b: parity state of acc_empty[b]
-      uint32_t gpass = 0;       // global pass counter -> accumulator half
+  } else if (warp == 9) {
+    // ===================== MMA issuer (leader CTA) =====================
+    // The WHOLE warp runs the loop so that every operand is warp-uniform and only the
+    // tcgen05 instructions sit under elect.sync: issued from a divergent `lane == 0` branch,
+    // ptxas wraps each one in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop and the issuing
+    // thread itself (~440 cycles of instructions per 512-cycle block) becomes the bottleneck.
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc(256, 256, FP16 ? 0 : 1);
+      const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+      const uint32_t a_lo0 = ((smem0 + oA) & 0x3FFFFu) >> 4 | (1u << 16);
+      const uint32_t w_lo0 = ((smem0 + oW) & 0x3FFFFu) >> 4 | (1u << 16);
+      uint32_t stage = 0, phase = 0, rphase = 0, ephase = 0, gpass = 0, prev_stage = 0;
       for (long long it = 0; it < my_tiles; ++it) {
 #pragma unroll 1
         for (int ps = 0; ps < kPasses; ++ps, ++gpass) {
@@ -306,82 +420,103 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decoder_kernel(const Decode
             }
             if (!mbar_wait(bars + 8 * (kBarWFull + stage), phase, wd, kErrWFull, stage)) goto done;
             tc_fence_after();
-            const uint64_t adesc = umma_desc_sw128(smem0 + kSmemA + k * kAChunkBytes);
-            const uint64_t bdesc = umma_desc_sw128(smem0 + kSmemW + stage * kBlockBytes);
+            const uint64_t adesc = desc_hi | (a_lo0 + k * (kAChunkBytes >> 4));
+            const uint64_t bdesc = desc_hi | (w_lo0 + stage * (kHalfBlockBytes >> 4));
+            if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)   // 4 x K=16 inside the 128-byte swizzle atom: +32 B each
-              umma_ss<1>(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0 ? 1u : 0u);
-            umma_commit<1>(bars + 8 * (kBarWEmpty + stage));
-            if (last) umma_commit<1>(bars + 8 * (kBarAFree + k));
+              for (int j = 0; j < 4; ++j)
+                umma_ss<2>(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) != 0 ? 1u : 0u);
+              if (k & 1) {   // one commit point per pair of blocks (see the header comment)
+                umma_commit<2>(bars + 8 * (kBarWEmpty + prev_stage));
+                umma_commit<2>(bars + 8 * (kBarWEmpty + stage));
+                if (last) {
+                  umma_commit<2>(bars + 8 * (kBarAFree + k - 1));
+                  umma_commit<2>(bars + 8 * (kBarAFree + k));
+                }
+                if (k == nk - 1) umma_commit<2>(bars + 8 * (kBarAccFull + b));
+              }
+            }
+            __syncwarp();
+            prev_stage = stage;
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit<1>(bars + 8 * (kBarAccFull + b));
         }
       }
-      // L4 reads only chunks 0..3, so chunks 4..7 see one reader fewer per tile than chunks
-      // 0..3; nothing to fix up: both sides count events per chunk.
     }
   } else {
-    // ===================== epilogue warps (thread <-> query row) =====================
-    const int row = threadIdx.x;                    // 0..127 == TMEM lane
-    const uint32_t row7 = row & 7u;
-    const uint32_t a_row_addr = smem0 + kSmemA + row * 128;
-    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const DecConsts* __restrict__ cs = p.consts;
-    EpiState st{0u, 0u};
+    // ===================== epilogue warps =====================
+    Epi e;
+    e.bars = bars;
+    e.lane = lane;
+    e.set = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;               // row of this CTA's 128 == TMEM lane
+    e.tmem_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    e.a_row_addr = smem0 + oA + row * 128;
+    e.row7 = row & 7u;
+    e.wphase = 0;
+    e.acc_phase = 0;
+    const int n0 = warp * 64 + 2 * lane;                  // layer-0 features of this lane
+    const float4 wa = cs->l0[n0], wb = cs->l0[n0 + 1];
+    const float head_b = cs->head_b[0];
+    const long long tile_stride = npairs * 2 * kTileM;
+    long long row_base = pidx * 2 * kTileM + rank * kTileM;   // first query of this CTA's half tile
     uint32_t gpass = 0;
     if (my_tiles > 0) {
-      Query q = load_query(p, first_tile, row);
-#pragma unroll 1
-      for (int c = 0; c < kAChunks; ++c)
-        if (!epi_layer0_chunk<FP16>(cs, c, q.x, q.y, q.z, a_row_addr, row7, bars, st, wd)) goto done;
-      for (long long it = 0; it < my_tiles; ++it) {
-        const long long tile = first_tile + it * gridDim.x;
-        float* dump_row = nullptr;
+      if (e.set == 0) {
+        const Query q0 = load_query(p, row_base + row);
+        sxyz[row] = make_float4(q0.x, q0.y, q0.z, 0.f);
+      }
+      named_bar_sync(1, kEpiThreads);
+      if (!epi_layer0<FP16>(e, warp, wa, wb, sxyz, smem0 + oA, wd)) goto done;
+      float4 qv = sxyz[row];
+      Query q{qv.x, qv.y, qv.z};
+      for (long long it = 0; it < my_tiles; ++it, row_base += tile_stride) {
+        const bool dump_tile = p.dump != nullptr && row_base == 0;
 #pragma unroll 1
         for (int ps = 0; ps < 11; ++ps, ++gpass) {
-          // pass -> (bias row, column offset, destination chunks)
           int layer, half;
           if (ps < 4) { layer = 1 + (ps >> 1); half = ps & 1; }
           else if (ps == 4) { layer = 3; half = 0; }
           else { layer = 4 + ((ps - 5) >> 1); half = (ps - 5) & 1; }
-          const float* bias = cs->bias[layer - 1] + half * 256;
-          dump_row = (p.dump != nullptr && tile == 0 && ps == p.dump_pass) ? p.dump + row * 256 : nullptr;
+          const float* bias = sbias + (layer - 1) * kHid + half * 256;
+          float* dump_row = (dump_tile && ps == p.dump_pass) ? p.dump + row * 256 : nullptr;
           bool ok;
-          if (layer == 4)
-            ok = epi_hidden_pass<FP16, true>(bias, cs->l4x + half * 256, q.x, q.y, q.z, half * 4, tmem_row,
-                                             gpass & 1u, a_row_addr, row7, bars, st, wd, dump_row);
+          if (layer == 3)
+            ok = epi_hidden_pass<FP16, true>(e, bias, q, half * 4, gpass & 1u, wd, dump_row);
           else
-            ok = epi_hidden_pass<FP16, false>(bias, nullptr, 0.f, 0.f, 0.f, half * 4, tmem_row, gpass & 1u,
-                                              a_row_addr, row7, bars, st, wd, dump_row);
+            ok = epi_hidden_pass<FP16, false>(e, bias, q, half * 4, gpass & 1u, wd, dump_row);
           if (!ok) goto done;
         }
         float dot = 0.f;
-        dump_row = (p.dump != nullptr && tile == 0 && p.dump_pass == 11) ? p.dump + row * 256 : nullptr;
-        if (!epi_head_pass(cs->bias[6], cs->head, tmem_row, gpass & 1u, bars, st, wd, dot, dump_row)) goto done;
+        float* dump_row = (dump_tile && p.dump_pass == 11) ? p.dump + row * 256 : nullptr;
+        if (!epi_head_pass(e, sbias + 6 * kHid, shead, gpass & 1u, wd, dot, dump_row)) goto done;
         ++gpass;
         // first layer of the next tile, written behind the last readers of this tile's h6
-        Query qn{0.f, 0.f, 0.f};
         if (it + 1 < my_tiles) {
-          qn = load_query(p, tile + gridDim.x, row);
-#pragma unroll 1
-          for (int c = 0; c < kAChunks; ++c)
-            if (!epi_layer0_chunk<FP16>(cs, c, qn.x, qn.y, qn.z, a_row_addr, row7, bars, st, wd)) goto done;
+          if (e.set == 0) {
+            const Query qn = load_query(p, row_base + tile_stride + row);
+            sxyz[row] = make_float4(qn.x, qn.y, qn.z, 0.f);
+          }
+          named_bar_sync(1, kEpiThreads);
+          if (!epi_layer0<FP16>(e, warp, wa, wb, sxyz, smem0 + oA, wd)) goto done;
+          qv = sxyz[row];
         }
-        dump_row = (p.dump != nullptr && tile == 0 && p.dump_pass == 12) ? p.dump + row * 256 : nullptr;
-        if (!epi_head_pass(cs->bias[6] + 256, cs->head + 256, tmem_row, gpass & 1u, bars, st, wd, dot, dump_row))
-          goto done;
+        dump_row = (dump_tile && p.dump_pass == 12) ? p.dump + row * 256 : nullptr;
+        if (!epi_head_pass(e, sbias + 6 * kHid + 256, shead + 256, gpass & 1u, wd, dot, dump_row)) goto done;
         ++gpass;
-        const long long m = tile * kTileM + row;
-        if (m < p.M) p.out[m] = tanhf(dot + __ldg(&cs->head_b[0]));
-        q = qn;
+        if (e.set == 1) sdot[row] = dot;
+        named_bar_sync(2, kEpiThreads);
+        if (e.set == 0) {
+          const long long m = row_base + row;
+          if (m < p.M) p.out[m] = tanhf((dot + sdot[row]) + head_b);
+        }
+        q = Query{qv.x, qv.y, qv.z};
       }
     }
   }
 done:
-  if (p.prof != nullptr && (lane == 0) && (warp == 0 || warp >= 4)) {
-    // blocked cycles per wait class (index = site >> 4) and this role's total, per CTA and role
-    const int role = warp == 0 ? 0 : warp - 3;            // 0 epilogue, 1 producer, 2 MMA issuer
+  if (p.prof != nullptr && lane == 0 && (warp == 0 || warp >= 8) && (leader || warp != 9)) {
+    const int role = warp == 0 ? 0 : warp - 7;            // 0 epilogue, 1 producer, 2 MMA issuer
     long long* dst = p.prof + (static_cast<long long>(blockIdx.x) * 3 + role) * 8;
 #pragma unroll
     for (int i = 1; i < 7; ++i) dst[i] = waited[i];
@@ -390,100 +525,17 @@ done:
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  cluster_sync_all();          // the peer's shared memory and barriers stay valid until both are done
+  if (warp == 9) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, 512);
+    tmem_dealloc<2>(tmem_base, 512);
   }
 }
 
-// ---------------------------------------------------------------------------
-// UMMA self-test: one 128x256x64 product through exactly the descriptors, swizzle, TMEM
-// load and commit paths the fused kernel uses.  A and B arrive row-major; the kernel
-// swizzles them into shared memory itself.
-template <bool FP16>
-__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint16_t* __restrict__ a,
-                                                               const uint16_t* __restrict__ b,
-                                                               float* __restrict__ d, unsigned int* status) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (smem0 - smem_u32(smem_raw));
-  const uint32_t sa = smem0, sb = smem0 + kAChunkBytes, bar = smem0 + kAChunkBytes + kBlockBytes;
-  volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(gen + kAChunkBytes + kBlockBytes + 8);
-  const int warp = threadIdx.x >> 5;
-  // stage operands: 16-byte units, swizzled
-  for (int i = threadIdx.x; i < 128 * 8; i += 128) {
-    const int r = i >> 3, u = i & 7;
-    const uint4 v = *reinterpret_cast<const uint4*>(a + r * 64 + u * 8);
-    *reinterpret_cast<uint4*>(gen + r * 128 + ((u ^ (r & 7)) << 4)) = v;
-  }
-  for (int i = threadIdx.x; i < 256 * 8; i += 128) {
-    const int r = i >> 3, u = i & 7;
-    const uint4 v = *reinterpret_cast<const uint4*>(b + r * 64 + u * 8);
-    *reinterpret_cast<uint4*>(gen + kAChunkBytes + r * 128 + ((u ^ (r & 7)) << 4)) = v;
-  }
-  fence_proxy_async_smem();
-  if (threadIdx.x == 0) {
-    misc[1] = 0;
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    tmem_alloc<1>(smem_u32(const_cast<uint32_t*>(misc)), 256);
-    tmem_relinquish<1>();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = misc[0];
-  Watchdog wd{misc + 1, status, 200000000ull, nullptr};
-  if (threadIdx.x == 0) {
-    constexpr uint32_t idesc = umma_idesc(128, 256, FP16 ? 0 : 1);
-    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sb);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) umma_ss<1>(tmem_base, adesc + 2 * j, bdesc + 2 * j, idesc, j != 0 ? 1u : 0u);
-    umma_commit<1>(bar);
-  }
-  if (mbar_wait(bar, 0, wd, 0x70)) {
-    tc_fence_after();
-    const int row = threadIdx.x;
-    for (int g = 0; g < 8; ++g) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + g * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) d[row * 256 + g * 32 + j] = __uint_as_float(v[j]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc<1>(tmem_base, 256);
-  }
-}
-
-// bias0' and bias4': the latent's contribution to layers 0 and 4 (one warp per output feature;
-// lanes stride k, shuffle tree) - fp32, order fixed, independent of everything else.
-__global__ void fold_latent_kernel(const float* __restrict__ W0, const float* __restrict__ b0,
-                                   const float* __restrict__ W4, const float* __restrict__ b4,
-                                   const float* __restrict__ z, DecConsts* __restrict__ consts) {
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // 0..1023
-  const int lane = threadIdx.x & 31;
-  if (j >= 2 * kHid) return;
-  const bool l4 = j >= kHid;
-  const int n = l4 ? j - kHid : j;
-  const float* w = l4 ? W4 + static_cast<long long>(n) * kHid + kSkipOut
-                      : W0 + static_cast<long long>(n) * kDecIn;
-  float s = 0.f;
-  for (int k = lane; k < kLatent; k += 32) s = fmaf(w[k], z[k], s);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) {
-    if (l4) consts->bias[3][n] = b4[n] + s;
-    else consts->l0[n].w = b0[n] + s;
-  }
-}
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 }  // namespace
 
@@ -491,40 +543,49 @@ cudaError_t fused_decoder_init() {
   cudaError_t e = cudaFuncSetAttribute(fused_decoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(kSmemAlloc));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(fused_decoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(kSmemAlloc));
-  if (e != cudaSuccess) return e;
-  constexpr int st_bytes = kAChunkBytes + kBlockBytes + 64 + 1024;
-  e = cudaFuncSetAttribute(umma_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st_bytes);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(umma_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st_bytes);
+  return cudaFuncSetAttribute(fused_decoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              static_cast<int>(kSmemAlloc));
 }
 
-cudaError_t launch_fused_decoder(const DecodeParams& p, bool fp16, int num_sms, cudaStream_t stream) {
+// The weight stream viewed as a [96*256 rows][64] 16-bit matrix; box = 128 rows x 64 = one CTA's
+// half of a block.  The stream already holds swizzled shared-memory images, so no TMA swizzle.
+cudaError_t make_wstream_tensor_map(const void* wstream, void* tmap_out) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess) return e;
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kChunkK), static_cast<cuuint64_t>(kBlocksPerTile) * kBlockRows};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(kChunkK) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), 128u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(static_cast<CUtensorMap*>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
+                                                   const_cast<void*>(wstream), gdim, gstride, box, estr,
+                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t launch_fused_decoder(const DecodeParams& p, const void* tmap, bool fp16, int num_sms,
+                                  cudaStream_t stream) {
   if (p.M <= 0) return cudaSuccess;
-  const long long tiles = (p.M + kTileM - 1) / kTileM;
-  const unsigned grid = static_cast<unsigned>(tiles < num_sms ? tiles : num_sms);
-  if (fp16)
-    fused_decoder_kernel<true><<<grid, kThreads, kSmemAlloc, stream>>>(p);
-  else
-    fused_decoder_kernel<false><<<grid, kThreads, kSmemAlloc, stream>>>(p);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, unsigned int* status,
-                                 bool fp16, cudaStream_t stream) {
-  constexpr int st_bytes = kAChunkBytes + kBlockBytes + 64 + 1024;
-  if (fp16)
-    umma_selftest_kernel<true><<<1, 128, st_bytes, stream>>>(a, b, d, status);
-  else
-    umma_selftest_kernel<false><<<1, 128, st_bytes, stream>>>(a, b, d, status);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_fold_latent(const float* W0, const float* b0, const float* W4, const float* b4,
-                               const float* z, DecConsts* consts, cudaStream_t stream) {
-  fold_latent_kernel<<<(2 * kHid * 32 + 255) / 256, 256, 0, stream>>>(W0, b0, W4, b4, z, consts);
-  return cudaGetLastError();
+  const long long tiles = (p.M + 2 * kTileM - 1) / (2 * kTileM);
+  const long long pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemAlloc;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const CUtensorMap* tm = static_cast<const CUtensorMap*>(tmap);
+  if (fp16) return cudaLaunchKernelEx(&cfg, fused_decoder_kernel<true>, p, *tm);
+  return cudaLaunchKernelEx(&cfg, fused_decoder_kernel<false>, p, *tm);
 }
 
 }  // namespace sdfb

@@ -23,11 +23,11 @@ constexpr long long kDdpmParamFloats =
 
 // ---- fused tensor-core decoder (fused_decoder.cu) --------------------------
 //
-// One CTA owns a tile of 128 queries and carries it through all layers; the
-// activations never leave the SM.  Per tile the tensor core runs 13 "passes"
+// One CTA PAIR owns a tile of 256 queries (128 per CTA) and carries it through all
+// layers; the activations never leave the SMs.  Per tile the tensor core runs 13 "passes"
 // (a pass = one N=256 half of a layer's output, accumulated over that layer's
 // K in 64-wide chunks):
-//   pass  0, 1 : L1 halves      pass  5, 6 : L4 halves (K = 256: h3 only)
+//   pass  0, 1 : L1 halves      pass  5, 6 : L4 halves (K = 256: [h3 | xyz])
 //   pass  2, 3 : L2 halves      pass  7.. 12 : L5, L6, L7 halves
 //   pass  4    : L3 (N = 253 padded to 256)
 // The weight stream is the concatenation of the 96 (pass, k-chunk) blocks in
@@ -48,7 +48,6 @@ constexpr int kAChunks = 8;
 struct DecConsts {
   float4 l0[kHid];        // (W0[n][256..258], b0[n] + W0[n][:256] . z)
   float bias[7][kHid];    // layers 1..7; row 2 (L3) zero-padded past 253; row 3 (L4) = b4 + W4[n][253:509] . z
-  float4 l4x[kHid];       // (W4[n][509..511], 0)
   float head[kHid];       // W8[0][:]
   float head_b[4];        // b8, pad
 };
@@ -69,14 +68,11 @@ struct DecodeParams {
   unsigned int debug_flags;    // bit0: producer skips the weight copies (timing experiment; results are garbage)
 };
 
-cudaError_t launch_fused_decoder(const DecodeParams& p, bool fp16, int num_sms, cudaStream_t stream);
 cudaError_t fused_decoder_init();   // opt in to the large dynamic shared memory carve-out
-
-// CTA-pair (cta_group::2) version, fused_decoder2.cu: the production kernel.
-cudaError_t fused_decoder2_init();
+cudaError_t tc_common_init();
 cudaError_t make_wstream_tensor_map(const void* wstream, void* tmap_out /* 128 B, 64-byte aligned */);
-cudaError_t launch_fused_decoder2(const DecodeParams& p, const void* tmap, bool fp16, int num_sms,
-                                  cudaStream_t stream);
+cudaError_t launch_fused_decoder(const DecodeParams& p, const void* tmap, bool fp16, int num_sms,
+                                 cudaStream_t stream);
 
 // Unit test of the UMMA plumbing: D[128][256] = A[128][64] * B[256][64]^T, row-major 16-bit inputs.
 cudaError_t launch_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, unsigned int* status,

@@ -76,8 +76,11 @@ def decoder_forward_lowp(latent, xyz, params=None, lowp=torch.bfloat16, chunk: i
 
     * per-shape constants are folded in fp32: bias0' = b0 + W0[:, :256] z and
       bias4' = b4 + W4[:, 253:509] z;
-    * the xyz columns of L0 and L4 stay fp32 (the kernel feeds them to the
-      tensor core as exact 3-way bf16 splits of both operands);
+    * the xyz columns of L0 stay fp32 (the kernel evaluates the 3-wide first
+      layer with fp32 FMAs): the geometry enters h0 unrounded;
+    * L4 consumes [h3 | xyz] as ONE ``lowp`` operand: the coordinates ride in the
+      three padding columns of h3's 256-wide slot, rounded to ``lowp`` like every
+      other input of that layer, against W4's xyz columns rounded to ``lowp``;
     * every other weight is rounded to ``lowp``; activations h0..h6 are rounded
       to ``lowp`` after the ReLU; products accumulate in fp32;
     * h7 stays fp32 and the 512 -> 1 head and tanh are evaluated in fp32.
@@ -96,7 +99,7 @@ def decoder_forward_lowp(latent, xyz, params=None, lowp=torch.bfloat16, chunk: i
     bias0 = B[0] + W[0][:, :L] @ z
     bias4 = B[4] + W[4][:, S:S + L] @ z
     W0x = W[0][:, L:L + 3]
-    W4x = W[4][:, S + L:S + L + 3]
+    W4x = _round_to(W[4][:, S + L:S + L + 3], lowp)
     W4h = _round_to(W[4][:, :S], lowp)
     Wq = {i: _round_to(W[i], lowp) for i in (1, 2, 3, 5, 6, 7)}
     M = xyz_t.shape[0]
@@ -110,7 +113,7 @@ def decoder_forward_lowp(latent, xyz, params=None, lowp=torch.bfloat16, chunk: i
             for li in (1, 2, 3):
                 pre.append(h @ Wq[li].T + B[li])
                 h = _round_to(torch.relu(pre[-1]), lowp)
-            pre.append(h @ W4h.T + x @ W4x.T + bias4)
+            pre.append(h @ W4h.T + _round_to(x, lowp) @ W4x.T + bias4)
             h = _round_to(torch.relu(pre[-1]), lowp)
             for li in (5, 6):
                 pre.append(h @ Wq[li].T + B[li])
