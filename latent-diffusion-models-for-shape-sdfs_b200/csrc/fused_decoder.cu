@@ -190,7 +190,7 @@ __device__ __forceinline__ uint32_t pack_plain(float lo, float hi) {   // no ReL
 // next layer's MMAs consume them.  The TMEM load of the next chunk is in flight while the
 // current one is converted.  `L3`: this is layer 3, whose last three (padding) columns carry
 // the query coordinates into layer 4.
-template <bool FP16, bool L3>
+template <bool FP16, bool L3, bool WAIT_FREE>
 __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict__ sbias, Query q, int c0, int b,
                                                 const Watchdog& wd, float* dump_row) {
   if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
@@ -232,7 +232,12 @@ __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict_
       }
     }
     const int c = c0 + cc;
-    if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
+    // Chunks written by a layer's LAST pass were read for the last time by that very pass, whose
+    // completion acc_full already reported: only a first-half pass must wait for the other half's
+    // MMAs to release the chunk.  (The phase bits are advanced by schedule, not by waiting.)
+    if (WAIT_FREE) {
+      if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
+    }
     const uint32_t base = e.a_row_addr + c * kAChunkBytes;
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -287,26 +292,36 @@ __device__ __forceinline__ bool epi_head_pass(Epi& e, const float* __restrict__ 
   return true;
 }
 
-// First layer of a tile, column-mapped: warp w owns chunk w; lane l owns features 64w+2l, +1
-// (weights in registers) and walks the 128 rows, whose coordinates sit in shared memory.
+// First layer of a tile, column-mapped.  Chunks of the activation buffer are released in pairs
+// by the last layer of the previous tile, so all 8 warps work on the pair that was released
+// most recently: in step i warp w takes chunk 2i + (w & 1), rows [32 (w >> 1), +32); lane l owns
+// features 64c + 2l, +1 of that chunk (weights in registers: `wl[i]`), the coordinates of the
+// rows sit in shared memory.
+struct L0Weights { float4 a, b; };
+
 template <bool FP16>
-__device__ __forceinline__ bool epi_layer0(Epi& e, int warp, const float4 wa, const float4 wb,
+__device__ __forceinline__ bool epi_layer0(Epi& e, int warp, const L0Weights (&wl)[4],
                                            const float4* __restrict__ sxyz, uint32_t smem_a, const Watchdog& wd) {
-  const int c = warp;
-  if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
-  const uint32_t chunk = smem_a + c * kAChunkBytes + ((e.lane & 3) << 2);
   const uint32_t unit = e.lane >> 2;
+  const int r0 = (warp >> 1) * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = 2 * i + (warp & 1);
+    if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
+    const uint32_t chunk = smem_a + c * kAChunkBytes + ((e.lane & 3) << 2);
+    const float4 wa = wl[i].a, wb = wl[i].b;
 #pragma unroll 8
-  for (int r = 0; r < kTileM; ++r) {
-    const float4 q = sxyz[r];
-    const float f0 = fmaf(q.z, wa.z, fmaf(q.y, wa.y, fmaf(q.x, wa.x, wa.w)));
-    const float f1 = fmaf(q.z, wb.z, fmaf(q.y, wb.y, fmaf(q.x, wb.x, wb.w)));
-    const uint32_t v = pack_relu<FP16>(f0, f1);
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(chunk + r * 128 + ((unit ^ (r & 7)) << 4)), "r"(v) : "memory");
+    for (int r = r0; r < r0 + 32; ++r) {
+      const float4 q = sxyz[r];
+      const float f0 = fmaf(q.z, wa.z, fmaf(q.y, wa.y, fmaf(q.x, wa.x, wa.w)));
+      const float f1 = fmaf(q.z, wb.z, fmaf(q.y, wb.y, fmaf(q.x, wb.x, wb.w)));
+      const uint32_t v = pack_relu<FP16>(f0, f1);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(chunk + r * 128 + ((unit ^ (r & 7)) << 4)), "r"(v) : "memory");
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c), 2);   // 4 warps x 2 = the 8 expected per CTA
   }
-  fence_proxy_async_smem();
-  __syncwarp();
-  if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c), kEpiWarps);   // stands in for all 8 warps
   e.wphase ^= 0xFFu;
   return true;
 }
@@ -455,8 +470,13 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
     e.row7 = row & 7u;
     e.wphase = 0;
     e.acc_phase = 0;
-    const int n0 = warp * 64 + 2 * lane;                  // layer-0 features of this lane
-    const float4 wa = cs->l0[n0], wb = cs->l0[n0 + 1];
+    L0Weights wl[4];                                      // layer-0 features of this lane, per step
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n0 = (2 * i + (warp & 1)) * 64 + 2 * lane;
+      wl[i].a = cs->l0[n0];
+      wl[i].b = cs->l0[n0 + 1];
+    }
     const float head_b = cs->head_b[0];
     const long long tile_stride = npairs * 2 * kTileM;
     long long row_base = pidx * 2 * kTileM + rank * kTileM;   // first query of this CTA's half tile
@@ -467,7 +487,7 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
         sxyz[row] = make_float4(q0.x, q0.y, q0.z, 0.f);
       }
       named_bar_sync(1, kEpiThreads);
-      if (!epi_layer0<FP16>(e, warp, wa, wb, sxyz, smem0 + oA, wd)) goto done;
+      if (!epi_layer0<FP16>(e, warp, wl, sxyz, smem0 + oA, wd)) goto done;
       float4 qv = sxyz[row];
       Query q{qv.x, qv.y, qv.z};
       for (long long it = 0; it < my_tiles; ++it, row_base += tile_stride) {
@@ -482,9 +502,11 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
           float* dump_row = (dump_tile && ps == p.dump_pass) ? p.dump + row * 256 : nullptr;
           bool ok;
           if (layer == 3)
-            ok = epi_hidden_pass<FP16, true>(e, bias, q, half * 4, gpass & 1u, wd, dump_row);
+            ok = epi_hidden_pass<FP16, true, false>(e, bias, q, 0, gpass & 1u, wd, dump_row);
+          else if (half == 0)
+            ok = epi_hidden_pass<FP16, false, true>(e, bias, q, 0, gpass & 1u, wd, dump_row);
           else
-            ok = epi_hidden_pass<FP16, false>(e, bias, q, half * 4, gpass & 1u, wd, dump_row);
+            ok = epi_hidden_pass<FP16, false, false>(e, bias, q, 4, gpass & 1u, wd, dump_row);
           if (!ok) goto done;
         }
         float dot = 0.f;
@@ -498,7 +520,7 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
             sxyz[row] = make_float4(qn.x, qn.y, qn.z, 0.f);
           }
           named_bar_sync(1, kEpiThreads);
-          if (!epi_layer0<FP16>(e, warp, wa, wb, sxyz, smem0 + oA, wd)) goto done;
+          if (!epi_layer0<FP16>(e, warp, wl, sxyz, smem0 + oA, wd)) goto done;
           qv = sxyz[row];
         }
         dump_row = (dump_tile && p.dump_pass == 12) ? p.dump + row * 256 : nullptr;
