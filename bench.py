@@ -33,6 +33,8 @@ QUERIES = RES ** 3
 # latent folded into biases and L3 padded to N=256: 6 * 512^2 ; dense count as the oracle computes it
 FLOP_TENSOR_PER_QUERY = 2 * 6 * 512 * 512          # 3,145,728
 FLOP_DENSE_PER_QUERY = 3_671_040
+DDPM_LATENTS = 4096
+DDPM_FLOP_PER_LATENT_STEP = 2 * (512 * 1024 + 3 * 1024 * 1024 + 1024 * 256)   # 7,864,320 executed (hi/lo split of x: K = 512)
 METRIC = "sdf_decoder_queries_per_s"
 UNIT = "queries/s"
 
@@ -127,6 +129,24 @@ def cpu_oracle_rate(target_s: float = 12.0):
                       f"{cores} threads (oracle/decoder.py; no reference source exists to time)"}
 
 
+def cpu_ddpm_rate(n: int = 2048, steps: int = 400):
+    """Oracle DDPM sampler (fp32 torch CPU) latents/s on a bounded sample: n latents x `steps` of the 1000 steps."""
+    import numpy as np
+    import torch
+    import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rs = np.random.RandomState(0)
+    x_T = rs.standard_normal((n, 256)).astype(np.float32)
+    noise = rs.standard_normal((steps, n, 256)).astype(np.float32)
+    oracle.sample_latents(n, x_T, noise[:5], steps=5)
+    t0 = time.perf_counter()
+    oracle.sample_latents(n, x_T, noise, steps=steps)
+    dt = time.perf_counter() - t0
+    return {"value": n / (dt * 1000.0 / steps), "unit": "latents/s", "cores": cores, "kind": "port",
+            "sample": f"{n} latents x {steps} of 1000 steps in {dt:.2f} s (scaled to 1000 steps), torch fp32, {cores} threads"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -170,6 +190,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ddpm", action="store_true", help="skip the latent-DDPM leg (second half of the metric)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -240,6 +261,47 @@ def main():
     e2e_value = world * QUERIES * Ke / float(e2e_s.item())
     checksum = float(np.float64(sdf_host[::16, ::16, ::16].sum()))
 
+    # ---- second half of the metric: latent-DDPM latents/s (BASELINE configs[3]: 4096 latents, 1000 steps) ----
+    ddpm_line = None
+    if not args.no_ddpm:
+        n_lat, T = DDPM_LATENTS, 1000
+        sampler = pkg.LatentDDPM(oracle.flatten_params(oracle.ddpm_weights()), device=dev, precision=args.precision)
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        x_T = torch.randn((n_lat, 256), generator=g, device=dev)
+        noise = torch.randn((T, n_lat, 256), generator=g, device=dev)           # 4.2 GB explicit noise stream in HBM
+        dd_ms = []
+        for i in range(1 + 3):                                                   # 1 warm-up + 3 timed full samplings
+            barrier()
+            x0 = sampler.sample_latents(n_lat, x_T=x_T, noise=noise, steps=T)
+            if i:
+                dd_ms.append(sampler.last_kernel_ms())
+        dd = torch.tensor([statistics.mean(dd_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dd, op=dist.ReduceOp.MAX)
+        dd_ms_max = float(dd.item())
+        flop = n_lat * T * DDPM_FLOP_PER_LATENT_STEP
+        ddpm_line = {"metric": "ddpm_latents_per_s", "value": world * n_lat / (dd_ms_max * 1e-3), "unit": "latents/s",
+                     "workload": f"sample_latents({n_lat}) per GPU: MLP denoiser 4x1024, latent 256, {T} steps, explicit noise "
+                                 "stream resident in HBM; ONE persistent cooperative kernel per call",
+                     "ms_per_sampling": dd_ms_max, "us_per_step": dd_ms_max * 1e3 / T,
+                     "kernel": "ddpm_sample_kernel", "achieved_tflops": flop / (dd_ms_max * 1e-3) / 1e12,
+                     "flop_per_latent_step": DDPM_FLOP_PER_LATENT_STEP, "gpu_launches_per_sampling": 2,
+                     "x0_abs_max": float(x0.abs().max().item())}
+        if world == 1:
+            # end to end: host x_T + host noise stream in, host x_0 out (4.2 GB H2D inside the timed call)
+            xh = x_T.cpu().numpy()
+            nh = torch.empty((T, n_lat, 256), dtype=torch.float32).pin_memory()
+            nh.copy_(noise)
+            nh_np = nh.numpy()
+            sampler.sample_latents_host(xh, nh_np, steps=T)
+            t0 = time.perf_counter()
+            sampler.sample_latents_host(xh, nh_np, steps=T)
+            dt = time.perf_counter() - t0
+            ddpm_line["e2e"] = {"value": n_lat / dt, "unit": "latents/s", "h2d_bytes_per_step": int(nh_np.nbytes + xh.nbytes),
+                                "d2h_bytes_per_step": int(xh.nbytes), "api": "LatentDDPM.sample_latents_host -> sdfb_ddpm_sample_host"}
+            del nh, nh_np
+        del noise, sampler
+
     if rank == 0:
         peaks = read_peaks()
         k_ms = statistics.mean(kernel_ms)
@@ -267,8 +329,13 @@ def main():
                          "dense_equiv_tflops": QUERIES * FLOP_DENSE_PER_QUERY / (k_ms * 1e-3) / 1e12},
             "wall_s_timed_region": t_wall,
         }
+        if ddpm_line is not None:
+            ddpm_line["frac_of_burst_peak"] = ddpm_line["achieved_tflops"] / peaks["burst"]
+            line["ddpm"] = ddpm_line
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_oracle_rate()
+            if ddpm_line is not None:
+                line["ddpm"]["cpu_baseline"] = cpu_ddpm_rate()
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

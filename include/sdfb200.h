@@ -106,7 +106,12 @@ int sdfb_decoder_last_kernel_ms(sdfb_decoder* dec, float* ms);
 int sdfb_ddpm_create(const float* params_host, size_t n_floats, int device, sdfb_ddpm** out);
 int sdfb_ddpm_destroy(sdfb_ddpm* ddpm);
 
-/* sample_latents(n): x_dev [n][256] holds x_T on entry and x_0 on return.
+/* precision: SDFB_PREC_FP32 runs the FFMA kernels (one launch per layer and step); BF16 / FP16 run
+ * ALL steps in one persistent cooperative tcgen05 kernel (time embedding folded into a per-step
+ * bias, denoiser MLP and posterior update fused; x stays fp32 and enters layer 0 as an exact
+ * two-way 16-bit split).
+ *
+ * sample_latents(n): x_dev [n][256] holds x_T on entry and x_0 on return.
  * noise_dev [steps][n][256] is the explicit noise stream (noise[t] is consumed
  * at step t, noise[0] is ignored).  Runs t = steps-1 .. 0 of the 1000-step
  * linear-beta schedule with the x0-clipped posterior-mean update. */
@@ -117,6 +122,9 @@ int sdfb_ddpm_denoise(sdfb_ddpm* ddpm, const float* x_dev, int t, int n, float* 
                       int precision, void* stream);
 int sdfb_ddpm_sample_host(sdfb_ddpm* ddpm, float* x_host, const float* noise_host, int n, int steps,
                           int precision);
+/* Elapsed device time (ms) of the last fused (bf16/fp16) sampler launch on this context, CUDA
+ * events on the launching stream; blocks until it has finished and reports a tripped watchdog. */
+int sdfb_ddpm_last_kernel_ms(sdfb_ddpm* ddpm, float* ms);
 
 /* ---- unit-test hook for the UMMA plumbing -------------------------------- */
 /* D[128][256] (fp32) = A[128][64] * B[256][64]^T with A and B given as

@@ -37,6 +37,7 @@ SIGNATURES = {
     "sdfb_ddpm_sample": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "sdfb_ddpm_denoise": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
     "sdfb_ddpm_sample_host": (_i, [_vp, _vp, _vp, _i, _i, _i]),
+    "sdfb_ddpm_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
     "sdfb_umma_selftest": (_i, [_vp, _vp, _vp, _i, _vp]),
     "sdfb_umma_rate": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]),
 }

@@ -191,7 +191,10 @@ class Decoder:
 
 class LatentDDPM:
     """Latent-space DDPM sampler: MLP denoiser 512 -> 1024x4 -> 256 (epsilon prediction,
-    linear beta schedule, 1000 steps, x0-clipped posterior-mean update)."""
+    linear beta schedule, 1000 steps, x0-clipped posterior-mean update).
+
+    ``precision``: "fp32" runs the FFMA kernels (carries the 1e-4 criterion); "bf16" / "fp16" run
+    all steps of a call in one persistent tcgen05 kernel."""
 
     def __init__(self, params, device="cuda:0", precision: str = "fp32"):
         self._lib = _lib.load()
@@ -243,7 +246,15 @@ class LatentDDPM:
         nz = _as_dev_f32(noise, self.device, (steps, n, LATENT))
         check(self._lib.sdfb_ddpm_sample(self._h, x.data_ptr(), nz.data_ptr(), n, steps, prec,
                                          _stream_ptr(self.device.index)))
+        if prec != _lib.PREC_FP32:
+            self.last_kernel_ms()       # waits for the persistent kernel and raises if its watchdog tripped
         return x
+
+    def last_kernel_ms(self) -> float:
+        """Device time of the last fused (bf16/fp16) sampler launch; raises SdfbError on a tripped watchdog."""
+        ms = C.c_float()
+        check(self._lib.sdfb_ddpm_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def sample_latents_host(self, x_T: np.ndarray, noise: np.ndarray, steps: int = DDPM_STEPS,
                             precision: str | None = None) -> np.ndarray:

@@ -112,6 +112,25 @@ void pack_wstream(const float* P, const LayerOff off[9], bool fp16, std::vector<
   }
 }
 
+// Denoiser weights as pre-swizzled 128-byte rows (kernels.h, "fused DDPM sampler"):
+// row (layer, k-chunk, feature n) holds W[n][64 kc .. 64 kc + 64), 16-byte unit u at u ^ (n & 7).
+void pack_ddpm_weights(const float* P, const long long woff[5], bool fp16, std::vector<uint16_t>& out) {
+  out.assign(static_cast<size_t>(kDdpmWRows) * 64, 0);
+  size_t row = 0;
+  for (int l = 0; l < 5; ++l) {
+    const int fin = l == 0 ? 512 : 1024, fout = l == 4 ? 256 : 1024;
+    const int nk = l == 0 ? 4 : 16;             // layer 0: only the latent half of W0 (the time half is folded into tb0)
+    const float* W = P + woff[l];
+    for (int kc = 0; kc < nk; ++kc)
+      for (int n = 0; n < fout; ++n, ++row) {
+        uint16_t* dst = out.data() + row * 64;
+        for (int u = 0; u < 8; ++u)
+          for (int e = 0; e < 8; ++e)
+            dst[((u ^ (n & 7)) * 8) + e] = to_lowp(W[static_cast<long long>(n) * fin + kc * 64 + u * 8 + e], fp16);
+      }
+  }
+}
+
 }  // namespace
 
 struct sdfb_decoder {
@@ -147,6 +166,16 @@ struct sdfb_ddpm {
   int ws_n = 0;
   float *h0 = nullptr, *h1 = nullptr, *eps = nullptr;
   void* dstage = nullptr; size_t dstage_bytes = 0;
+  // tensor-core path (ddpm_step.cu)
+  uint8_t* wpack[2] = {nullptr, nullptr};     // [0] bf16, [1] fp16: kDdpmWRows rows of 128 B
+  float* bias_dev = nullptr;                  // [3][1024] + [256]
+  float* coef_dev = nullptr;                  // [1000][8]
+  uint8_t* act = nullptr; int act_tiles = 0;  // activation images, kDdpmActTileBytes per 128-latent tile
+  unsigned int* counter = nullptr;            // grid barrier
+  unsigned int* status = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  unsigned long long timeout_ns = 4000000000ull;
 };
 
 namespace {
@@ -592,6 +621,33 @@ int sdfb_ddpm_create(const float* params_host, size_t n_floats, int device, sdfb
     cudaFree(temb_dev);
     CU_TRY_D(e);
   }
+  // tensor-core path: packed weights, bias rows, per-step coefficients, barrier and status words
+  CU_TRY_D(ddpm_step_init());
+  for (int f = 0; f < 2; ++f) {
+    std::vector<uint16_t> wp;
+    pack_ddpm_weights(params_host, d->woff, f == 1, wp);
+    CU_TRY_D(cudaMalloc(&d->wpack[f], wp.size() * 2));
+    CU_TRY_D(cudaMemcpy(d->wpack[f], wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  }
+  {
+    std::vector<float> hb(3 * kDdpmHid + kDdpmLatent);
+    for (int l = 1; l <= 3; ++l) std::memcpy(hb.data() + (l - 1) * kDdpmHid, params_host + d->boff[l], kDdpmHid * sizeof(float));
+    std::memcpy(hb.data() + 3 * kDdpmHid, params_host + d->boff[4], kDdpmLatent * sizeof(float));
+    CU_TRY_D(cudaMalloc(&d->bias_dev, hb.size() * sizeof(float)));
+    CU_TRY_D(cudaMemcpy(d->bias_dev, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> hc(static_cast<size_t>(kDdpmT) * 8, 0.f);
+    for (int t = 0; t < kDdpmT; ++t) {
+      hc[t * 8 + 0] = d->sra[t]; hc[t * 8 + 1] = d->srm1[t]; hc[t * 8 + 2] = d->c1[t]; hc[t * 8 + 3] = d->c2[t];
+      hc[t * 8 + 4] = d->sigma[t];
+    }
+    CU_TRY_D(cudaMalloc(&d->coef_dev, hc.size() * sizeof(float)));
+    CU_TRY_D(cudaMemcpy(d->coef_dev, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  CU_TRY_D(cudaMalloc(&d->counter, sizeof(unsigned int)));
+  CU_TRY_D(cudaMalloc(&d->status, sizeof(unsigned int)));
+  CU_TRY_D(cudaMemset(d->status, 0, sizeof(unsigned int)));
+  CU_TRY_D(cudaEventCreate(&d->ev0));
+  CU_TRY_D(cudaEventCreate(&d->ev1));
 #undef CU_TRY_D
   *out = d;
   return SDFB_OK;
@@ -602,6 +658,10 @@ int sdfb_ddpm_destroy(sdfb_ddpm* d) {
   DeviceGuard g(d->device);
   cudaDeviceSynchronize();
   cudaFree(d->params); cudaFree(d->tb0); cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->eps); cudaFree(d->dstage);
+  cudaFree(d->wpack[0]); cudaFree(d->wpack[1]); cudaFree(d->bias_dev); cudaFree(d->coef_dev); cudaFree(d->act);
+  cudaFree(d->counter); cudaFree(d->status);
+  if (d->ev0) cudaEventDestroy(d->ev0);
+  if (d->ev1) cudaEventDestroy(d->ev1);
   delete d;
   return SDFB_OK;
 }
@@ -632,11 +692,75 @@ static int denoise_fp32(sdfb_ddpm* d, const float* x, int t, int n, float* eps, 
   return SDFB_OK;
 }
 
+// Tensor-core path: `steps` fused denoise+update steps t = t_first, t_first-1, ... in ONE cooperative
+// launch (eps_out != nullptr: a single denoiser evaluation, no update).
+static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps, int t_first, float* eps_out,
+                   bool fp16, cudaStream_t st) {
+  const int m_pairs = (n + 255) / 256, m_tiles = 2 * m_pairs;
+  if (d->act_tiles < m_tiles) {
+    cudaFree(d->act); d->act = nullptr; d->act_tiles = 0;
+    CU_TRY(cudaMalloc(&d->act, static_cast<size_t>(m_tiles) * kDdpmActTileBytes));
+    CU_TRY(cudaMemset(d->act, 0, static_cast<size_t>(m_tiles) * kDdpmActTileBytes));
+    d->act_tiles = m_tiles;
+  }
+  // tile width: the widest that still gives about one pair tile per CTA pair
+  const int max_pairs = d->num_sms / 2;
+  int bn_h = 64;
+  for (int bn : {256, 128}) {
+    if (m_pairs * (kDdpmHid / bn) * 4 >= max_pairs * 3) { bn_h = bn; break; }
+  }
+  if (const char* e = std::getenv("SDFB_DDPM_BN")) {
+    const int v = std::atoi(e);
+    if (v == 64 || v == 128 || v == 256) bn_h = v;
+  }
+  DdpmParams p{};
+  p.tb0 = d->tb0; p.bias = d->bias_dev; p.coef = d->coef_dev;
+  p.x = x; p.noise = noise; p.eps_out = eps_out; p.act = d->act;
+  p.n = n; p.pair_m_tiles = m_pairs; p.steps = steps; p.t_first = t_first;
+  p.bn_h = bn_h; p.bn_o = bn_h / 4;
+  p.nstages = bn_h == 256 ? 6 : kDdpmMaxStages;
+  p.counter = d->counter; p.status = d->status; p.timeout_ns = d->timeout_ns;
+  alignas(64) unsigned char tm_act[128], tm_wh[128], tm_wo[128];
+  CU_TRY(make_rows_tensor_map(d->act, static_cast<unsigned long long>(d->act_tiles) * (kDdpmActTileBytes / 128), 128, tm_act));
+  CU_TRY(make_rows_tensor_map(d->wpack[fp16 ? 1 : 0], kDdpmWRows, p.bn_h / 2, tm_wh));
+  CU_TRY(make_rows_tensor_map(d->wpack[fp16 ? 1 : 0], kDdpmWRows, p.bn_o / 2, tm_wo));
+  CU_TRY(launch_ddpm_split(x, n, m_tiles, d->act, fp16, st));
+  CU_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), st));
+  CU_TRY(cudaEventRecord(d->ev0, st));
+  CU_TRY(launch_ddpm_sample(p, tm_act, tm_wh, tm_wo, fp16, d->num_sms, st));
+  CU_TRY(cudaEventRecord(d->ev1, st));
+  d->timed = true;
+  return SDFB_OK;
+}
+
+static int ddpm_status(sdfb_ddpm* d) {
+  unsigned int s = 0;
+  CU_TRY(cudaMemcpy(&s, d->status, sizeof(s), cudaMemcpyDeviceToHost));
+  if (s != 0) {
+    cudaMemset(d->status, 0, sizeof(unsigned int));
+    return fail(SDFB_E_KERNEL, "fused DDPM kernel watchdog tripped at wait site 0x%x", s);
+  }
+  return SDFB_OK;
+}
+
+int sdfb_ddpm_last_kernel_ms(sdfb_ddpm* d, float* ms) {
+  if (!d || !ms) return fail(SDFB_E_INVALID, "null argument");
+  if (!d->timed) return fail(SDFB_E_INVALID, "no fused DDPM launch recorded yet");
+  DeviceGuard g(d->device);
+  CU_TRY(cudaEventSynchronize(d->ev1));
+  CU_TRY(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+  return ddpm_status(d);
+}
+
 int sdfb_ddpm_denoise(sdfb_ddpm* d, const float* x_dev, int t, int n, float* eps_dev, int precision, void* stream) {
   if (!d || !x_dev || !eps_dev) return fail(SDFB_E_INVALID, "null argument");
   if (n <= 0 || t < 0 || t >= kDdpmT) return fail(SDFB_E_INVALID, "bad n or t");
-  if (precision != SDFB_PREC_FP32) return fail(SDFB_E_INVALID, "denoiser precision %d not built yet (fp32 only)", precision);
+  if (precision != SDFB_PREC_FP32 && precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16)
+    return fail(SDFB_E_INVALID, "unknown precision %d", precision);
   DeviceGuard g(d->device);
+  if (precision != SDFB_PREC_FP32)
+    return ddpm_tc(d, const_cast<float*>(x_dev), nullptr, n, 1, t, eps_dev, precision == SDFB_PREC_FP16,
+                   static_cast<cudaStream_t>(stream));
   int rc = ddpm_ws(d, n);
   if (rc) return rc;
   return denoise_fp32(d, x_dev, t, n, eps_dev, static_cast<cudaStream_t>(stream));
@@ -647,9 +771,12 @@ int sdfb_ddpm_sample(sdfb_ddpm* d, float* x_dev, const float* noise_dev, int n, 
   if (!d || !x_dev) return fail(SDFB_E_INVALID, "null argument");
   if (n <= 0 || steps < 1 || steps > kDdpmT) return fail(SDFB_E_INVALID, "bad n or steps");
   if (steps > 1 && !noise_dev) return fail(SDFB_E_INVALID, "noise stream required");
-  if (precision != SDFB_PREC_FP32) return fail(SDFB_E_INVALID, "denoiser precision %d not built yet (fp32 only)", precision);
+  if (precision != SDFB_PREC_FP32 && precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16)
+    return fail(SDFB_E_INVALID, "unknown precision %d", precision);
   DeviceGuard g(d->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision != SDFB_PREC_FP32)
+    return ddpm_tc(d, x_dev, noise_dev, n, steps, steps - 1, nullptr, precision == SDFB_PREC_FP16, st);
   int rc = ddpm_ws(d, n);
   if (rc) return rc;
   const long long cnt = static_cast<long long>(n) * kDdpmLatent;
@@ -679,7 +806,7 @@ int sdfb_ddpm_sample_host(sdfb_ddpm* d, float* x_host, const float* noise_host, 
   if (rc) return rc;
   CU_TRY(cudaMemcpyAsync(x_host, x, cnt * sizeof(float), cudaMemcpyDeviceToHost, 0));
   CU_TRY(cudaStreamSynchronize(0));
-  return SDFB_OK;
+  return precision == SDFB_PREC_FP32 ? SDFB_OK : ddpm_status(d);
 }
 
 }  // extern "C"

@@ -1,0 +1,518 @@
+// K2: fused latent-DDPM sampler for sm_100a (tcgen05 / TMEM / TMA, CTA pairs, one persistent
+// cooperative launch for all steps of a sample_latents call).
+//
+// What it computes (oracle: oracle/ddpm.py denoiser_forward_lowp,
+// ddpm_step, sample_latents; no upstream source exists, /root/reference/README.md:1):
+//   per step t:  h0 = relu([x_hi | x_lo] [W0x | W0x]^T + tb0[t])      K = 512, time embedding folded
+//                h1..h3 = relu(h W^T + b)                             K = 1024
+//                eps = h3 W4^T + b4                                   fp32, never rounded
+//                x0 = clamp(sra x - srm1 eps, -1, 1);  x <- c1 x0 + c2 x + sigma noise[t]
+// 16-bit operands, fp32 accumulation in TMEM; the state x stays fp32 and enters layer 0 as an
+// exact two-way 16-bit split.
+//
+// Mapping.  Every layer is cut into pair tiles of 256 latents x BN output features
+// (cta_group::2: each CTA holds 128 rows of A and half of the weight rows) that are spread over
+// all CTA pairs; K is streamed in 64-wide chunks through a shared-memory ring.  The epilogue
+// warps store a tile's activations as pre-swizzled operand images in an L2-resident buffer, so
+// the next layer's loads are plain TMA boxes that land MMA-ready.  Layers are separated by a
+// grid-wide barrier (one release-add per CTA, acquire spin in the producer); weights do not
+// depend on it and are prefetched across it.  The last layer's epilogue is the DDPM update.
+//
+//   warps 0-7  epilogue   (TMEM lane quadrant = warp & 3; the two warp sets split the columns)
+//   warp 8     producer   (TMA; completion counted on the LEADER's barrier)
+//   warp 9     MMA issuer (leader CTA only) + TMEM allocation (both CTAs)
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace sdfb {
+
+namespace {
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = kEpiThreads + 64;
+constexpr int kTileRows = (8 + 16 + 16) * 128;        // image rows per 128-latent tile in the activation allocation
+constexpr int kLayers = 5;
+
+constexpr int kBarFull = 0;
+constexpr int kBarEmpty = kBarFull + kDdpmMaxStages;
+constexpr int kBarAccFull = kBarEmpty + kDdpmMaxStages;
+constexpr int kBarAccEmpty = kBarAccFull + 2;
+constexpr int kNumBars = kBarAccEmpty + 2;
+
+enum : uint32_t { kErrFull = 0x110, kErrEmpty = 0x120, kErrAccFull = 0x130, kErrAccEmpty = 0x140, kErrGrid = 0x150 };
+
+struct Geo {
+  int nk;          // 64-wide k-chunks
+  int a_chunk0;    // first chunk (of the 40 per tile) of the layer's A operand
+  int o_chunk0;    // first chunk of the buffer the layer's epilogue writes
+  int w_row0;      // first weight row of the layer
+  int n_total;     // output features
+  int bn;          // tile width
+};
+
+__device__ __forceinline__ Geo layer_geo(const DdpmParams& p, int l) {
+  Geo g;
+  g.nk = l == 0 ? 8 : 16;
+  g.a_chunk0 = l == 0 ? 0 : ((l & 1) ? 8 : 24);       // L1, L3 read buffer 0; L2, L4 read buffer 1
+  g.o_chunk0 = l == 4 ? 0 : ((l & 1) ? 24 : 8);       // L0, L2 write buffer 0; L1, L3 write buffer 1; L4 writes [x_hi | x_lo]
+  g.w_row0 = l == 0 ? 0 : (l < 4 ? kDdpmW0Rows + (l - 1) * kDdpmWHidRows : kDdpmW0Rows + 3 * kDdpmWHidRows);
+  g.n_total = l == 4 ? kDdpmLatent : kDdpmHid;
+  g.bn = l == 4 ? p.bn_o : p.bn_h;
+  return g;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy global writes <-> async-proxy (TMA) global reads
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// Wait until `target` CTAs have arrived on the grid barrier counter (bounded).
+__device__ __forceinline__ bool grid_wait(const DdpmParams& p, uint32_t target, const Watchdog& wd) {
+  if (ld_acquire_gpu(p.counter) >= target) return true;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (true) {
+    if (ld_acquire_gpu(p.counter) >= target) return true;
+    if ((++spins & 0x3Fu) == 0) {
+      if (*wd.abort_flag) return false;
+      if (*reinterpret_cast<volatile unsigned int*>(p.status) != 0) { *wd.abort_flag = kErrGrid; return false; }
+      if (global_timer_ns() - t0 > wd.timeout_ns) {
+        *wd.abort_flag = kErrGrid;
+        atomicCAS(wd.status, 0u, static_cast<unsigned int>(kErrGrid));
+        return false;
+      }
+    }
+  }
+}
+
+template <bool FP16>
+__device__ __forceinline__ float lowp_hi_to_float(uint32_t packed_lo16) {
+  if constexpr (FP16) {
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(packed_lo16 & 0xFFFFu)));
+  } else {
+    return __uint_as_float(packed_lo16 << 16);
+  }
+}
+// (hi, lo) 16-bit split of two consecutive fp32 values: x = hi + lo + O(2^-16 |x|)
+template <bool FP16>
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_plain<FP16>(a, b);
+  const float ra = a - lowp_hi_to_float<FP16>(hi & 0xFFFFu);
+  const float rb = b - lowp_hi_to_float<FP16>(hi >> 16);
+  lo = pack_plain<FP16>(ra, rb);
+}
+
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// byte address of 16-byte unit `unit` of row `row` of chunk `chunk` (0..39) of 128-latent tile `m`
+__device__ __forceinline__ uint8_t* image_ptr(uint8_t* act, int m, int chunk, int row, int unit) {
+  return act + ((static_cast<long long>(m) * kTileRows + chunk * 128 + row) << 7) + ((unit ^ (row & 7)) << 4);
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(kThreads, 1)
+ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_act,
+                   const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wo) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  if ((smem0 & 1023u) != 0) {
+    if (threadIdx.x == 0) atomicCAS(p.status, 0u, 0xA12u);
+    return;
+  }
+  const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(p.bn_h) * 64u;   // A chunk + this CTA's half of a weight chunk
+  const uint32_t o_bar = static_cast<uint32_t>(p.nstages) * stage_bytes;
+  const uint32_t bars = smem0 + o_bar;
+  volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(smem_raw + o_bar + kNumBars * 8);   // [0] tmem base, [1] abort
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int ntn = kDdpmHid / p.bn_h;                       // n-tiles per layer (= 256 / bn_o for the last layer)
+  const int T = p.pair_m_tiles * ntn;                      // pair tiles per layer
+  const int npairs = gridDim.x >> 1, pidx = blockIdx.x >> 1;
+
+  if (threadIdx.x == 0) {
+    misc[1] = 0;
+    for (int s = 0; s < kDdpmMaxStages; ++s) {
+      mbar_init(bars + 8 * (kBarFull + s), 1);
+      mbar_init(bars + 8 * (kBarEmpty + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bars + 8 * (kBarAccFull + b), 1);
+      mbar_init(bars + 8 * (kBarAccEmpty + b), 2 * kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc<2>(smem0 + o_bar + kNumBars * 8, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = misc[0];
+  Watchdog wd{misc + 1, p.status, p.timeout_ns, nullptr};
+
+  if (warp == 8) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t nst = static_cast<uint32_t>(p.nstages);
+      for (int s = 0; s < p.steps; ++s) {
+        for (int l = 0; l < kLayers; ++l) {
+          const Geo g = layer_geo(p, l);
+          const CUtensorMap* tmw = l == 4 ? &tm_wo : &tm_wh;
+          const uint32_t tx = 2u * 16384u + static_cast<uint32_t>(g.bn) * 128u;
+          bool need_sync = !(s == 0 && l == 0);            // the operand of the very first layer was written by an earlier kernel
+          for (int tile = pidx; tile < T; tile += npairs) {
+            const int pm = tile / ntn, j = tile - pm * ntn;
+            const int a_row = ((2 * pm + static_cast<int>(rank)) * 40 + g.a_chunk0) * 128;
+            const int w_row = g.w_row0 + j * g.bn + static_cast<int>(rank) * (g.bn >> 1);
+            int kc = 0;
+            if (need_sync) {
+              // weights first (they do not depend on the previous layer), then the grid barrier, then A
+              const int pre = g.nk < static_cast<int>(nst) ? g.nk : static_cast<int>(nst);
+              uint32_t st = stage, ph = phase;
+              for (int i = 0; i < pre; ++i) {
+                if (!mbar_wait(bars + 8 * (kBarEmpty + st), ph ^ 1u, wd, kErrEmpty, st)) goto done;
+                const uint32_t full = bars + 8 * (kBarFull + st);
+                if (leader) mbar_arrive_expect_tx(full, tx);
+                const int wk = l == 0 ? (i & 3) : i;
+                tma_load_half_block(smem0 + st * stage_bytes + 16384u, tmw, w_row + wk * g.n_total, map_to_cta(full, 0));
+                if (++st == nst) { st = 0; ph ^= 1u; }
+              }
+              if (!grid_wait(p, static_cast<uint32_t>(s * kLayers + l) * gridDim.x, wd)) goto done;
+              fence_proxy_async_global();
+              st = stage;
+              for (int i = 0; i < pre; ++i) {
+                tma_load_half_block(smem0 + st * stage_bytes, &tm_act, a_row + i * 128, map_to_cta(bars + 8 * (kBarFull + st), 0));
+                if (++st == nst) st = 0;
+              }
+              stage = st;
+              phase = ph;
+              kc = pre;
+              need_sync = false;
+            }
+            for (; kc < g.nk; ++kc) {
+              if (!mbar_wait(bars + 8 * (kBarEmpty + stage), phase ^ 1u, wd, kErrEmpty, stage)) goto done;
+              const uint32_t full = bars + 8 * (kBarFull + stage);
+              if (leader) mbar_arrive_expect_tx(full, tx);
+              const int wk = l == 0 ? (kc & 3) : kc;
+              const uint32_t full_l = map_to_cta(full, 0);
+              tma_load_half_block(smem0 + stage * stage_bytes + 16384u, tmw, w_row + wk * g.n_total, full_l);
+              tma_load_half_block(smem0 + stage * stage_bytes, &tm_act, a_row + kc * 128, full_l);
+              if (++stage == nst) { stage = 0; phase ^= 1u; }
+            }
+          }
+          if (need_sync) {   // this pair had no tile in the layer (cannot happen: grid <= 2 T), keep the barrier count anyway
+            if (!grid_wait(p, static_cast<uint32_t>(s * kLayers + l) * gridDim.x, wd)) goto done;
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer (leader CTA; whole warp runs the loop, see fused_decoder.cu) =====================
+    if (leader) {
+      const uint32_t idesc_h = umma_idesc(256, p.bn_h, FP16 ? 0 : 1);
+      const uint32_t idesc_o = umma_idesc(256, p.bn_o, FP16 ? 0 : 1);
+      const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+      const uint32_t nst = static_cast<uint32_t>(p.nstages);
+      uint32_t stage = 0, phase = 0, ephase = 0, gt = 0, prev_stage = 0;
+      for (int s = 0; s < p.steps; ++s) {
+        for (int l = 0; l < kLayers; ++l) {
+          const int nk = l == 0 ? 8 : 16;
+          const uint32_t idesc = l == 4 ? idesc_o : idesc_h;
+          for (int tile = pidx; tile < T; tile += npairs, ++gt) {
+            const uint32_t b = gt & 1u;
+            const uint32_t d_tmem = tmem_base + b * 256;
+            if (!mbar_wait(bars + 8 * (kBarAccEmpty + b), ((ephase >> b) & 1u) ^ 1u, wd, kErrAccEmpty, b)) goto done;
+            ephase ^= 1u << b;
+#pragma unroll 1
+            for (int k = 0; k < nk; ++k) {
+              if (!mbar_wait(bars + 8 * (kBarFull + stage), phase, wd, kErrFull, stage)) goto done;
+              tc_fence_after();
+              const uint32_t a_lo = (((smem0 + stage * stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+              const uint64_t adesc = desc_hi | a_lo;
+              const uint64_t bdesc = desc_hi | (a_lo + (16384u >> 4));
+              if (elect_one()) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) umma_ss<2>(d_tmem, adesc + 2 * jj, bdesc + 2 * jj, idesc, (k | jj) != 0 ? 1u : 0u);
+                if (k & 1) {   // one commit point per pair of chunks
+                  umma_commit<2>(bars + 8 * (kBarEmpty + prev_stage));
+                  umma_commit<2>(bars + 8 * (kBarEmpty + stage));
+                  if (k == nk - 1) umma_commit<2>(bars + 8 * (kBarAccFull + b));
+                }
+              }
+              __syncwarp();
+              prev_stage = stage;
+              if (++stage == nst) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3, set = warp >> 2;
+    const int row = q * 32 + lane;                       // row of this CTA's 128 = TMEM lane
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t acc_phase = 0, gt = 0;
+    for (int s = 0; s < p.steps; ++s) {
+      const int t = p.t_first - s;
+      const float4 cf = *reinterpret_cast<const float4*>(p.coef + t * 8);        // sra, srm1, c1, c2
+      const float sigma = p.coef[t * 8 + 4];
+      for (int l = 0; l < kLayers; ++l) {
+        const Geo g = layer_geo(p, l);
+        const float* bias = l == 0 ? p.tb0 + static_cast<long long>(t) * kDdpmHid
+                                   : (l < 4 ? p.bias + (l - 1) * kDdpmHid : p.bias + 3 * kDdpmHid);
+        const int nu = g.bn >> 4;                          // 16-column units in the tile
+        for (int tile = pidx; tile < T; tile += npairs, ++gt) {
+          const int pm = tile / ntn, j = tile - pm * ntn;
+          const int m_tile = 2 * pm + static_cast<int>(rank);
+          const uint32_t b = gt & 1u;
+          const uint32_t tbase = tmem_row + b * 256;
+          const long long m = static_cast<long long>(m_tile) * 128 + row;        // latent index
+          const bool valid = m < p.n;
+          // first unit of this warp set: units u with ((u >> 1) & 1) == set
+          const int u_first = 2 * set;
+          float xv[2][16], nz[2][16];
+          if (l == 4) {
+            // state and noise of this thread's (at most two) units: loaded before the accumulator is waited for
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int u = u_first + i;
+              const int col = j * g.bn + u * 16;
+#pragma unroll
+              for (int e = 0; e < 16; ++e) { xv[i][e] = 0.f; nz[i][e] = 0.f; }
+              if (u < nu && valid) {
+                const float4* xs4 = reinterpret_cast<const float4*>(p.x + m * kDdpmLatent + col);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float4 v = xs4[e];
+                  xv[i][4 * e] = v.x; xv[i][4 * e + 1] = v.y; xv[i][4 * e + 2] = v.z; xv[i][4 * e + 3] = v.w;
+                }
+                if (t > 0 && p.noise != nullptr && p.eps_out == nullptr) {
+                  const float4* n4 = reinterpret_cast<const float4*>(
+                      p.noise + (static_cast<long long>(t) * p.n + m) * kDdpmLatent + col);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float4 v = __ldcs(n4 + e);
+                    nz[i][4 * e] = v.x; nz[i][4 * e + 1] = v.y; nz[i][4 * e + 2] = v.z; nz[i][4 * e + 3] = v.w;
+                  }
+                }
+              }
+            }
+          }
+          if (!mbar_wait(bars + 8 * (kBarAccFull + b), (acc_phase >> b) & 1u, wd, kErrAccFull, b)) goto done;
+          acc_phase ^= 1u << b;
+          __syncwarp();
+          tc_fence_after();
+          if (l < 4) {
+            // hidden layer: + bias, ReLU, round to 16 bits, store as operand image of the next layer
+            for (int u0 = u_first; u0 < nu; u0 += 4) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const int u = u0 + i;
+                uint32_t v[16];
+                tmem_ld16(tbase + u * 16, v);
+                const int col = j * g.bn + u * 16;
+                const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+                float4 bb[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) bb[e] = __ldg(b4 + e);
+                tmem_ld_wait();
+                uint32_t pk[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  pk[2 * e] = pack_relu<FP16>(__uint_as_float(v[4 * e]) + bb[e].x, __uint_as_float(v[4 * e + 1]) + bb[e].y);
+                  pk[2 * e + 1] = pack_relu<FP16>(__uint_as_float(v[4 * e + 2]) + bb[e].z, __uint_as_float(v[4 * e + 3]) + bb[e].w);
+                }
+                const int chunk = g.o_chunk0 + (col >> 6), unit = (col & 63) >> 3;
+                st_global_v4(image_ptr(p.act, m_tile, chunk, row, unit), pk[0], pk[1], pk[2], pk[3]);
+                st_global_v4(image_ptr(p.act, m_tile, chunk, row, unit + 1), pk[4], pk[5], pk[6], pk[7]);
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1);
+          } else {
+            // last layer: eps -> x0-clipped posterior-mean update (op for op as oracle/ddpm.py ddpm_step)
+            uint32_t v[2][16];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              if (u_first + i < nu) tmem_ld16(tbase + (u_first + i) * 16, v[i]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int u = u_first + i;
+              if (u >= nu) continue;
+              const int col = j * g.bn + u * 16;
+              float o[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float eps = __uint_as_float(v[i][e]) + __ldg(bias + col + e);
+                if (p.eps_out != nullptr) {
+                  o[e] = eps;
+                } else {
+                  float x0 = __fsub_rn(__fmul_rn(cf.x, xv[i][e]), __fmul_rn(cf.y, eps));
+                  x0 = fminf(fmaxf(x0, -1.f), 1.f);
+                  float r = __fadd_rn(__fmul_rn(cf.z, x0), __fmul_rn(cf.w, xv[i][e]));
+                  if (t > 0) r = __fadd_rn(r, __fmul_rn(sigma, nz[i][e]));
+                  o[e] = valid ? r : 0.f;
+                }
+              }
+              if (p.eps_out != nullptr) {
+                if (valid) {
+                  float4* dst = reinterpret_cast<float4*>(p.eps_out + m * kDdpmLatent + col);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+                }
+              } else {
+                if (valid) {
+                  float4* dst = reinterpret_cast<float4*>(p.x + m * kDdpmLatent + col);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+                }
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split2<FP16>(o[2 * e], o[2 * e + 1], hi[e], lo[e]);
+                const int chunk = col >> 6, unit = (col & 63) >> 3;
+                st_global_v4(image_ptr(p.act, m_tile, chunk, row, unit), hi[0], hi[1], hi[2], hi[3]);
+                st_global_v4(image_ptr(p.act, m_tile, chunk, row, unit + 1), hi[4], hi[5], hi[6], hi[7]);
+                st_global_v4(image_ptr(p.act, m_tile, 4 + chunk, row, unit), lo[0], lo[1], lo[2], lo[3]);
+                st_global_v4(image_ptr(p.act, m_tile, 4 + chunk, row, unit + 1), lo[4], lo[5], lo[6], lo[7]);
+              }
+            }
+          }
+        }
+        // end of the layer: publish this CTA's stores and arrive on the grid barrier
+        fence_proxy_async_global();
+        __threadfence();
+        named_bar_sync(1, kEpiThreads);
+        if (threadIdx.x == 0) red_release_gpu_add(p.counter, 1u);
+      }
+    }
+  }
+done:
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 9) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<2>(tmem_base, 512);
+  }
+}
+
+// x fp32 -> [x_hi | x_lo] operand images (chunks 0..7 of every tile); rows >= n are zero.
+template <bool FP16>
+__global__ void ddpm_split_kernel(const float* __restrict__ x, int n, int m_tiles, uint8_t* __restrict__ act) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // (row, 8-column unit)
+  const long long total = static_cast<long long>(m_tiles) * 128 * 32;
+  if (i >= total) return;
+  const long long m = i >> 5;
+  const int u8 = static_cast<int>(i & 31);
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (m < n) {
+    const float4* src = reinterpret_cast<const float4*>(x + m * kDdpmLatent + u8 * 8);
+    const float4 a = src[0], b = src[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split2<FP16>(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+  const int m_tile = static_cast<int>(m >> 7), row = static_cast<int>(m & 127);
+  const int chunk = u8 >> 3, unit = u8 & 7;
+  st_global_v4(image_ptr(act, m_tile, chunk, row, unit), hi[0], hi[1], hi[2], hi[3]);
+  st_global_v4(image_ptr(act, m_tile, 4 + chunk, row, unit), lo[0], lo[1], lo[2], lo[3]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+uint32_t smem_bytes_for(int bn_h, int nstages) {
+  return static_cast<uint32_t>(nstages) * (16384u + static_cast<uint32_t>(bn_h) * 64u) + kNumBars * 8 + 16;
+}
+
+}  // namespace
+
+cudaError_t ddpm_step_init() {
+  const int max_smem = 6 * 32768 + kNumBars * 8 + 16;     // bn_h = 256, 6 stages (the largest configuration)
+  cudaError_t e = cudaFuncSetAttribute(ddpm_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(ddpm_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+cudaError_t make_rows_tensor_map(const void* base, unsigned long long rows, unsigned box_rows, void* tmap_out) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess) return e;
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+  const cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {64u, box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(static_cast<CUtensorMap*>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
+                                                   const_cast<void*>(base), gdim, gstride, box, estr,
+                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t launch_ddpm_split(const float* x, int n, int m_tiles, uint8_t* act, bool fp16, cudaStream_t stream) {
+  const long long total = static_cast<long long>(m_tiles) * 128 * 32;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (fp16) ddpm_split_kernel<true><<<blocks, 256, 0, stream>>>(x, n, m_tiles, act);
+  else ddpm_split_kernel<false><<<blocks, 256, 0, stream>>>(x, n, m_tiles, act);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ddpm_sample(const DdpmParams& p, const void* tm_act, const void* tm_wh, const void* tm_wo,
+                               bool fp16, int num_sms, cudaStream_t stream) {
+  const int ntn = kDdpmHid / p.bn_h;
+  const int T = p.pair_m_tiles * ntn;
+  const int max_pairs = num_sms / 2;
+  const int pairs = T < max_pairs ? T : max_pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes_for(p.bn_h, p.nstages);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;           // every CTA must be resident: they wait on one another
+  attr[1].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  const CUtensorMap* a = static_cast<const CUtensorMap*>(tm_act);
+  const CUtensorMap* wh = static_cast<const CUtensorMap*>(tm_wh);
+  const CUtensorMap* wo = static_cast<const CUtensorMap*>(tm_wo);
+  if (fp16) return cudaLaunchKernelEx(&cfg, ddpm_sample_kernel<true>, p, *a, *wh, *wo);
+  return cudaLaunchKernelEx(&cfg, ddpm_sample_kernel<false>, p, *a, *wh, *wo);
+}
+
+}  // namespace sdfb

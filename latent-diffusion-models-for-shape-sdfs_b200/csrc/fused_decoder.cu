@@ -74,75 +74,6 @@ __device__ __forceinline__ int pass_chunks(int p) { return (p == 5 || p == 6) ? 
 __device__ __forceinline__ bool pass_first(int p) { return (0x0AB5u >> p) & 1u; }  // {0,2,4,5,7,9,11}
 __device__ __forceinline__ bool pass_last(int p) { return (0x155Au >> p) & 1u; }   // {1,3,4,6,8,10,12}
 
-template <bool FP16>
-__device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {
-  uint32_t d;
-  if constexpr (FP16)
-    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  else
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-
-// ---- cluster-scope barrier helpers ---------------------------------------------------------
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// wait used by the MMA issuer: the arrivals come from both CTAs of the pair
-__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity, const Watchdog& wd,
-                                                  uint32_t site, uint32_t idx = 0) {
-  const long long c0 = wd.wait_cycles != nullptr ? clock64() : 0;
-  if (mbar_try_wait_cluster(bar, parity)) {   // try_wait itself may block for a while: count that time too
-    if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
-    return true;
-  }
-  uint64_t t0 = global_timer_ns();
-  uint32_t spins = 0;
-  while (true) {
-    if (mbar_try_wait_cluster(bar, parity)) {
-      if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
-      return true;
-    }
-    if ((++spins & 0xFFu) == 0) {
-      if (*wd.abort_flag) return false;
-      if (global_timer_ns() - t0 > wd.timeout_ns) {
-        *wd.abort_flag = site + idx;
-        atomicCAS(wd.status, 0u, site + idx);
-        return false;
-      }
-    }
-  }
-}
-// `count` arrivals on the LEADER CTA's copy of a barrier (local or remote).  Default semantics
-// (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) does: a cluster-scope release
-// costs a MEMBAR of several hundred cycles per arrival (30% of all epilogue stall samples when it
-// was tried).  The data being published was made visible to the async proxy by each lane's
-// fence.proxy.async and ordered before this arrive by __syncwarp().
-__device__ __forceinline__ void arrive_on_leader(uint32_t local_bar, uint32_t count) {
-  const uint32_t remote = map_to_cta(local_bar, 0);
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(count) : "memory");
-}
-// this CTA's 128 rows of weight block `row0/256`: 2-D tensor-map TMA into local shared memory,
-// transaction bytes counted on the leader's barrier
-__device__ __forceinline__ void tma_load_half_block(uint32_t dst_smem, const CUtensorMap* tmap, int row0,
-                                                    uint32_t leader_bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(row0), "r"(leader_bar)
-      : "memory");
-}
-
 struct Query { float x, y, z; };
 
 __device__ __forceinline__ Query load_query(const DecodeParams& p, long long m) {
@@ -174,16 +105,6 @@ struct Epi {
   int set;                // 0/1: which of the two warp sets (splits chunks / head columns)
   int lane;
 };
-
-template <bool FP16>
-__device__ __forceinline__ uint32_t pack_plain(float lo, float hi) {   // no ReLU: signed coordinates
-  uint32_t d;
-  if constexpr (FP16)
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  else
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
 
 // Hidden pass.  The two warp sets work on the SAME chunk at the same time (set s converts
 // columns [32s, 32s+32) of it), chunk after chunk, so chunks become available in the order the

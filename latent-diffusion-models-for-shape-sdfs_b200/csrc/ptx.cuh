@@ -254,6 +254,100 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// TMEM -> registers: 32 lanes x 16 consecutive 32-bit columns.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// ---- 16-bit packing ------------------------------------------------------------------------
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {
+  uint32_t d;
+  if constexpr (FP16)
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// ---- cluster-scope barrier helpers ---------------------------------------------------------
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// wait used by the MMA issuer: the arrivals come from both CTAs of the pair
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity, const Watchdog& wd,
+                                                  uint32_t site, uint32_t idx = 0) {
+  const long long c0 = wd.wait_cycles != nullptr ? clock64() : 0;
+  if (mbar_try_wait_cluster(bar, parity)) {   // try_wait itself may block for a while: count that time too
+    if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
+    return true;
+  }
+  uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (true) {
+    if (mbar_try_wait_cluster(bar, parity)) {
+      if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
+      return true;
+    }
+    if ((++spins & 0xFFu) == 0) {
+      if (*wd.abort_flag) return false;
+      if (global_timer_ns() - t0 > wd.timeout_ns) {
+        *wd.abort_flag = site + idx;
+        atomicCAS(wd.status, 0u, site + idx);
+        return false;
+      }
+    }
+  }
+}
+// `count` arrivals on the LEADER CTA's copy of a barrier (local or remote).  Default semantics
+// (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) does: a cluster-scope release
+// costs a MEMBAR of several hundred cycles per arrival (30% of all epilogue stall samples when it
+// was tried).  The data being published was made visible to the async proxy by each lane's
+// fence.proxy.async and ordered before this arrive by __syncwarp().
+__device__ __forceinline__ void arrive_on_leader(uint32_t local_bar, uint32_t count) {
+  const uint32_t remote = map_to_cta(local_bar, 0);
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(count) : "memory");
+}
+// Rows [row0, row0 + box rows) of a [rows][64] 16-bit tensor map -> local shared memory; the
+// transaction bytes are counted on the LEADER CTA's barrier (.cta_group::2).  (The fused decoder
+// loads its half of a weight block with this.)
+__device__ __forceinline__ void tma_load_half_block(uint32_t dst_smem, const void* tmap, int row0,
+                                                    uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(row0), "r"(leader_bar)
+      : "memory");
+}
+
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack_plain(float lo, float hi) {   // no ReLU: signed coordinates
+  uint32_t d;
+  if constexpr (FP16)
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
                                              uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)

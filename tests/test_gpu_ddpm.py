@@ -41,3 +41,87 @@ def test_sample_latents_short_runs_and_device_noise(cuda_ddpm):
     assert torch.equal(a, b) and a.shape == (3, 256)
     with pytest.raises(ValueError):
         cuda_ddpm.sample_latents(0)
+
+
+# ---- fused tensor-core sampler (K2) ---------------------------------------------------------------
+# Gate: the oracle that emulates the same operand rounding (oracle/ddpm.py denoiser_forward_lowp);
+# kernel and oracle differ only in fp32 summation order, invisible (~1e-6) except where it flips
+# a 16-bit rounding of a hidden activation (one flip moves eps by ~1 ulp(16-bit) x |w|).
+LOWP_T = {"bf16": torch.bfloat16, "fp16": torch.float16}
+TOL_EPS_MAX = {"bf16": 2e-2, "fp16": 3e-3}
+TOL_EPS_P90 = {"bf16": 1e-3, "fp16": 1.5e-4}      # 90th percentile: a few flips upstream
+TOL_EPS_P50 = {"bf16": 5e-6, "fp16": 1e-4}        # median: summation order only (fp16: flips are ~8x more frequent, ~8x smaller)
+
+
+def _stats(d):
+    d = np.abs(d).ravel()
+    q = np.quantile(d, [0.5, 0.9, 0.99])
+    return f"p50 {q[0]:.2e} p90 {q[1]:.2e} p99 {q[2]:.2e} max {d.max():.2e}", q, d.max()
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("n,bn", [(37, 0), (300, 256), (300, 128), (1280, 64)])
+def test_denoiser_single_step_tensor_core(cuda_ddpm, monkeypatch, prec, n, bn):
+    """One denoiser evaluation; ragged n, every tile width, and more pair tiles than CTA pairs."""
+    if bn:
+        monkeypatch.setenv("SDFB_DDPM_BN", str(bn))
+    rs = np.random.RandomState(n)
+    x = rs.standard_normal((n, 256)).astype(np.float32)
+    for t in (0, 999) if n > 300 else (0, 1, 500, 999):
+        eps = cuda_ddpm.denoise(x, t, precision=prec).cpu().numpy()
+        cuda_ddpm.last_kernel_ms()
+        ref = oracle.denoiser_forward_lowp(x, t, lowp=LOWP_T[prec]).numpy()
+        msg, q, mx = _stats(eps - ref)
+        print(f"{prec} n={n} bn={bn} t={t}: |eps - {prec} oracle| {msg}")
+        assert mx < TOL_EPS_MAX[prec] and q[1] < TOL_EPS_P90[prec] and q[0] < TOL_EPS_P50[prec]
+        e32 = np.abs(eps - oracle.denoiser_forward(x, t).numpy()).max()
+        assert e32 < (5e-2 if prec == "bf16" else 8e-3), e32
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_sample_latents_tensor_core_golden(cuda_ddpm, golden, prec):
+    """1000 steps, n = 8, identical noise stream: vs the bf16-emulating golden run and vs fp32."""
+    arrays, _ = golden
+    x_T, noise = ddpm_golden_inputs()
+    x = cuda_ddpm.sample_latents(8, x_T=x_T, noise=noise, precision=prec).cpu().numpy()
+    ms = cuda_ddpm.last_kernel_ms()
+    ref = arrays["ddpm_bf16"] if prec == "bf16" else oracle.sample_latents(8, x_T, noise, lowp=torch.float16)
+    msg, q, mx = _stats(x - ref)
+    e32 = np.abs(x - arrays["ddpm_fp32"]).max()
+    print(f"{prec} ddpm 1000 steps n=8 ({ms:.2f} ms): |kernel - {prec} oracle| {msg}; max|kernel - fp32 oracle| = {e32:.3e}")
+    assert np.isfinite(x).all() and np.abs(x).max() <= 1.0 + 1e-6
+    assert mx < (3e-2 if prec == "bf16" else 4e-3)
+    assert e32 < (3e-2 if prec == "bf16" else 4e-3)
+    xh = cuda_ddpm.sample_latents_host(x_T, noise, precision=prec)
+    assert np.array_equal(xh, x)            # deterministic, and the host entry point is the same path
+
+
+@pytest.mark.parametrize("n,bn,steps", [(300, 256, 12), (1280, 64, 6), (515, 0, 12)])
+def test_sample_latents_tensor_core_short_runs(cuda_ddpm, monkeypatch, n, bn, steps):
+    if bn:
+        monkeypatch.setenv("SDFB_DDPM_BN", str(bn))
+    x_T, noise = ddpm_golden_inputs(n=n, steps=steps)
+    x = cuda_ddpm.sample_latents(n, x_T=x_T, noise=noise, steps=steps, precision="bf16").cpu().numpy()
+    ref = oracle.sample_latents(n, x_T, noise, steps=steps, lowp=torch.bfloat16)
+    msg, q, mx = _stats(x - ref)
+    print(f"bf16 n={n} bn={bn} steps={steps}: |kernel - bf16 oracle| {msg}")
+    assert mx < 3e-2 and q[1] < 2e-3
+    x2 = cuda_ddpm.sample_latents(n, x_T=x_T, noise=noise, steps=steps, precision="bf16").cpu().numpy()
+    assert np.array_equal(x, x2)
+
+
+def test_sample_latents_full_batch_properties(cuda_ddpm):
+    """BASELINE configs[3] batch size (4096 latents), 1000 steps, device-generated noise:
+    finite, clipped range, rows independent of batch composition (a latent's trajectory does not
+    depend on which tile it sits in)."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    steps = 1000
+    x_T = torch.randn((4096, 256), generator=g, device="cuda")
+    noise = torch.randn((steps, 4096, 256), generator=g, device="cuda")
+    x = cuda_ddpm.sample_latents(4096, x_T=x_T, noise=noise, steps=steps, precision="bf16")
+    ms = cuda_ddpm.last_kernel_ms()
+    print(f"bf16 ddpm 4096 latents x {steps} steps: {ms:.1f} ms = {4096 / ms * 1e3:.0f} latents/s")
+    assert torch.isfinite(x).all() and x.abs().max() <= 1.0 + 1e-6
+    sub = slice(1000, 1300)
+    xs = cuda_ddpm.sample_latents(300, x_T=x_T[sub], noise=noise[:, sub].contiguous(), steps=steps, precision="bf16")
+    assert torch.equal(xs, x[sub])
