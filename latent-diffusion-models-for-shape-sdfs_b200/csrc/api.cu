@@ -171,11 +171,13 @@ struct sdfb_ddpm {
   float* bias_dev = nullptr;                  // [3][1024] + [256]
   float* coef_dev = nullptr;                  // [1000][8]
   uint8_t* act = nullptr; int act_tiles = 0;  // activation images, kDdpmActTileBytes per 128-latent tile
-  unsigned int* counter = nullptr;            // grid barrier
+  unsigned int* counter = nullptr;            // [act_tiles / 2] barrier counters (one per 256-latent group)
   unsigned int* status = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   unsigned long long timeout_ns = 4000000000ull;
+  long long* prof = nullptr;                  // wait profile buffer (allocated when SDFB_PROF is set)
+  int last_grid = 0;
 };
 
 namespace {
@@ -643,9 +645,12 @@ int sdfb_ddpm_create(const float* params_host, size_t n_floats, int device, sdfb
     CU_TRY_D(cudaMalloc(&d->coef_dev, hc.size() * sizeof(float)));
     CU_TRY_D(cudaMemcpy(d->coef_dev, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
-  CU_TRY_D(cudaMalloc(&d->counter, sizeof(unsigned int)));
   CU_TRY_D(cudaMalloc(&d->status, sizeof(unsigned int)));
   CU_TRY_D(cudaMemset(d->status, 0, sizeof(unsigned int)));
+  if (std::getenv("SDFB_PROF") != nullptr) {
+    CU_TRY_D(cudaMalloc(&d->prof, (static_cast<size_t>(148) * 24 + 96) * sizeof(long long)));
+    CU_TRY_D(cudaMemset(d->prof, 0, (static_cast<size_t>(148) * 24 + 96) * sizeof(long long)));
+  }
   CU_TRY_D(cudaEventCreate(&d->ev0));
   CU_TRY_D(cudaEventCreate(&d->ev1));
 #undef CU_TRY_D
@@ -659,7 +664,7 @@ int sdfb_ddpm_destroy(sdfb_ddpm* d) {
   cudaDeviceSynchronize();
   cudaFree(d->params); cudaFree(d->tb0); cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->eps); cudaFree(d->dstage);
   cudaFree(d->wpack[0]); cudaFree(d->wpack[1]); cudaFree(d->bias_dev); cudaFree(d->coef_dev); cudaFree(d->act);
-  cudaFree(d->counter); cudaFree(d->status);
+  cudaFree(d->counter); cudaFree(d->status); cudaFree(d->prof);
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
   delete d;
@@ -698,7 +703,8 @@ static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps,
                    bool fp16, cudaStream_t st) {
   const int m_pairs = (n + 255) / 256, m_tiles = 2 * m_pairs;
   if (d->act_tiles < m_tiles) {
-    cudaFree(d->act); d->act = nullptr; d->act_tiles = 0;
+    cudaFree(d->act); cudaFree(d->counter); d->act = nullptr; d->counter = nullptr; d->act_tiles = 0;
+    CU_TRY(cudaMalloc(&d->counter, static_cast<size_t>(m_pairs) * sizeof(unsigned int)));
     CU_TRY(cudaMalloc(&d->act, static_cast<size_t>(m_tiles) * kDdpmActTileBytes));
     CU_TRY(cudaMemset(d->act, 0, static_cast<size_t>(m_tiles) * kDdpmActTileBytes));
     d->act_tiles = m_tiles;
@@ -718,14 +724,16 @@ static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps,
   p.x = x; p.noise = noise; p.eps_out = eps_out; p.act = d->act;
   p.n = n; p.pair_m_tiles = m_pairs; p.steps = steps; p.t_first = t_first;
   p.bn_h = bn_h; p.bn_o = bn_h / 4;
-  p.nstages = bn_h == 256 ? 6 : kDdpmMaxStages;
-  p.counter = d->counter; p.status = d->status; p.timeout_ns = d->timeout_ns;
+  p.nstages = bn_h == 256 ? 5 : kDdpmMaxStages;   // 5 x 32 KiB + 64 KiB staging | 8 x 24 + 32 | 8 x 20 + 16
+  p.counter = d->counter; p.status = d->status; p.timeout_ns = d->timeout_ns; p.prof = d->prof;
   alignas(64) unsigned char tm_act[128], tm_wh[128], tm_wo[128];
   CU_TRY(make_rows_tensor_map(d->act, static_cast<unsigned long long>(d->act_tiles) * (kDdpmActTileBytes / 128), 128, tm_act));
   CU_TRY(make_rows_tensor_map(d->wpack[fp16 ? 1 : 0], kDdpmWRows, p.bn_h / 2, tm_wh));
   CU_TRY(make_rows_tensor_map(d->wpack[fp16 ? 1 : 0], kDdpmWRows, p.bn_o / 2, tm_wo));
   CU_TRY(launch_ddpm_split(x, n, m_tiles, d->act, fp16, st));
-  CU_TRY(cudaMemsetAsync(d->counter, 0, sizeof(unsigned int), st));
+  CU_TRY(cudaMemsetAsync(d->counter, 0, static_cast<size_t>(m_pairs) * sizeof(unsigned int), st));
+  if (d->prof) CU_TRY(cudaMemsetAsync(d->prof, 0, (static_cast<size_t>(148) * 24 + 96) * sizeof(long long), st));
+  d->last_grid = 2 * (m_pairs * (kDdpmHid / bn_h) < max_pairs ? m_pairs * (kDdpmHid / bn_h) : max_pairs);
   CU_TRY(cudaEventRecord(d->ev0, st));
   CU_TRY(launch_ddpm_sample(p, tm_act, tm_wh, tm_wo, fp16, d->num_sms, st));
   CU_TRY(cudaEventRecord(d->ev1, st));
@@ -749,6 +757,38 @@ int sdfb_ddpm_last_kernel_ms(sdfb_ddpm* d, float* ms) {
   DeviceGuard g(d->device);
   CU_TRY(cudaEventSynchronize(d->ev1));
   CU_TRY(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+  if (d->prof != nullptr) {   // diagnostics: mean blocked cycles per role and wait class of the last launch
+    std::vector<long long> h(static_cast<size_t>(d->num_sms) * 24);
+    CU_TRY(cudaMemcpy(h.data(), d->prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    static const char* role[3] = {"epilogue", "producer", "mma"};
+    static const char* cls[8] = {"total", "full", "empty", "acc_full", "acc_empty", "group_barrier", "full_first", "-"};
+    for (int r = 0; r < 3; ++r) {
+      double m[8] = {0};
+      int n = 0;
+      for (int b = 0; b < d->num_sms; ++b) {
+        const long long* v = h.data() + (static_cast<size_t>(b) * 3 + r) * 8;
+        if (v[0] == 0) continue;
+        ++n;
+        for (int i = 0; i < 8; ++i) m[i] += static_cast<double>(v[i]);
+      }
+      if (n == 0) continue;
+      std::fprintf(stderr, "[sdfb ddpm prof] %-8s", role[r]);
+      for (int i = 0; i < 7; ++i) std::fprintf(stderr, " %s=%.0f", cls[i], m[i] / n);
+      std::fprintf(stderr, " (cycles, mean over %d CTAs; %.2f ms)\n", n, *ms);
+    }
+    // event trace of CTA 0, step 5 (ddpm_step.cu SDFB_TRACE): cycles relative to layer 0's first MMA
+    std::vector<long long> tr(96);
+    CU_TRY(cudaMemcpy(tr.data(), d->prof + 148 * 24, 96 * sizeof(long long), cudaMemcpyDeviceToHost));
+    static const char* ev[13] = {"mma_start", "mma_issued", "epi_acc_full", "epi_chunk0_ready", "epi_stores_issued",
+                                 "epi_stores_done", "epi_arrived", "prod_at_barrier", "prod_barrier_done", "prod_A_issued",
+                                 "L4_tmem_read", "L4_unit0_computed", "L4_unit0_stored"};
+    if (tr[0] != 0)
+      for (int l = 0; l < 6; ++l) {   // row 5 = layer 0 of the following step
+        std::fprintf(stderr, "[sdfb ddpm trace] L%d", l);
+        for (int e = 0; e < 13; ++e) std::fprintf(stderr, " %s=%lld", ev[e], tr[l * 16 + e] ? tr[l * 16 + e] - tr[0] : -1);
+        std::fprintf(stderr, "\n");
+      }
+  }
   return ddpm_status(d);
 }
 

@@ -44,7 +44,17 @@ constexpr int kBarAccFull = kBarEmpty + kDdpmMaxStages;
 constexpr int kBarAccEmpty = kBarAccFull + 2;
 constexpr int kNumBars = kBarAccEmpty + 2;
 
-enum : uint32_t { kErrFull = 0x110, kErrEmpty = 0x120, kErrAccFull = 0x130, kErrAccEmpty = 0x140, kErrGrid = 0x150 };
+// wait sites (status codes); (site >> 4) & 7 is the class under which blocked cycles are profiled
+enum : uint32_t { kErrFull = 0x110, kErrEmpty = 0x120, kErrAccFull = 0x130, kErrAccEmpty = 0x140, kErrGrid = 0x150,
+                  kErrFullFirst = 0x160 };
+
+// Diagnostics: with profiling on, CTA 0 stamps clock64() at key events of every layer of step 5
+// into the tail of the profile buffer ([148 * 24 + layer * 16 + event]).
+#define SDFB_TRACE(ev)                                                                              \
+  do {                                                                                              \
+    if (p.prof != nullptr && blockIdx.x == 0 && (s == 5 || (s == 6 && l == 0)))                     \
+      p.prof[148 * 24 + (s == 6 ? 5 : l) * 16 + (ev)] = clock64();                                  \
+  } while (0)
 
 struct Geo {
   int nk;          // 64-wide k-chunks
@@ -77,13 +87,17 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, uint32_t v)
 // generic-proxy global writes <-> async-proxy (TMA) global reads
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-// Wait until `target` CTAs have arrived on the grid barrier counter (bounded).
-__device__ __forceinline__ bool grid_wait(const DdpmParams& p, uint32_t target, const Watchdog& wd) {
-  if (ld_acquire_gpu(p.counter) >= target) return true;
+// Wait until `target` CTAs have arrived on a barrier counter (bounded).
+__device__ __forceinline__ bool grid_wait(const DdpmParams& p, const unsigned int* counter, uint32_t target, const Watchdog& wd) {
+  if (ld_acquire_gpu(counter) >= target) return true;
+  const long long c0 = wd.wait_cycles != nullptr ? clock64() : 0;
   const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (true) {
-    if (ld_acquire_gpu(p.counter) >= target) return true;
+    if (ld_acquire_gpu(counter) >= target) {
+      if (wd.wait_cycles != nullptr) wd.wait_cycles[(kErrGrid >> 4) & 7u] += clock64() - c0;
+      return true;
+    }
     if ((++spins & 0x3Fu) == 0) {
       if (*wd.abort_flag) return false;
       if (*reinterpret_cast<volatile unsigned int*>(p.status) != 0) { *wd.abort_flag = kErrGrid; return false; }
@@ -113,6 +127,17 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = pack_plain<FP16>(ra, rb);
 }
 
+// 128 rows x 64 columns (one operand image) shared -> global through the tensor map, bulk-group completion
+__device__ __forceinline__ void tma_store_rows(const void* tmap, int row0, uint32_t src_smem) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(0), "r"(row0), "r"(src_smem)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -133,9 +158,11 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
     return;
   }
   const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(p.bn_h) * 64u;   // A chunk + this CTA's half of a weight chunk
-  const uint32_t o_bar = static_cast<uint32_t>(p.nstages) * stage_bytes;
+  const uint32_t o_stage = static_cast<uint32_t>(p.nstages) * stage_bytes;     // epilogue staging: bn_h / 64 operand images of 16 KiB
+  const uint32_t o_bar = o_stage + static_cast<uint32_t>(p.bn_h) * 256u;
   const uint32_t bars = smem0 + o_bar;
   volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(smem_raw + o_bar + kNumBars * 8);   // [0] tmem base, [1] abort
+  float* sbias = reinterpret_cast<float*>(smem_raw + o_bar + kNumBars * 8 + 16);                    // 2 x 256 floats: the tile's bias slice
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -165,7 +192,12 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
-  Watchdog wd{misc + 1, p.status, p.timeout_ns, nullptr};
+  long long waited[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  Watchdog wd{misc + 1, p.status, p.timeout_ns, p.prof != nullptr ? waited : nullptr};
+  const long long t_start = clock64();
+  // A layer's tile (pm, j) consumes what the 2 ntn CTAs that own pair-row pm wrote in the previous layer:
+  // one barrier counter per pm, 2 ntn CTAs x 2 warp sets arrive per layer.
+  const uint32_t group_ctas = 4u * static_cast<uint32_t>(ntn);   // x 2 warp sets per CTA
 
   if (warp == 8) {
     // ===================== producer =====================
@@ -177,7 +209,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
           const Geo g = layer_geo(p, l);
           const CUtensorMap* tmw = l == 4 ? &tm_wo : &tm_wh;
           const uint32_t tx = 2u * 16384u + static_cast<uint32_t>(g.bn) * 128u;
-          bool need_sync = !(s == 0 && l == 0);            // the operand of the very first layer was written by an earlier kernel
+          const bool need_sync = !(s == 0 && l == 0);      // the operand of the very first layer was written by an earlier kernel
           for (int tile = pidx; tile < T; tile += npairs) {
             const int pm = tile / ntn, j = tile - pm * ntn;
             const int a_row = ((2 * pm + static_cast<int>(rank)) * 40 + g.a_chunk0) * 128;
@@ -195,17 +227,19 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
                 tma_load_half_block(smem0 + st * stage_bytes + 16384u, tmw, w_row + wk * g.n_total, map_to_cta(full, 0));
                 if (++st == nst) { st = 0; ph ^= 1u; }
               }
-              if (!grid_wait(p, static_cast<uint32_t>(s * kLayers + l) * gridDim.x, wd)) goto done;
+              SDFB_TRACE(7);
+              if (!grid_wait(p, p.counter + pm, static_cast<uint32_t>(s * kLayers + l) * group_ctas, wd)) goto done;
+              SDFB_TRACE(8);
               fence_proxy_async_global();
               st = stage;
               for (int i = 0; i < pre; ++i) {
                 tma_load_half_block(smem0 + st * stage_bytes, &tm_act, a_row + i * 128, map_to_cta(bars + 8 * (kBarFull + st), 0));
                 if (++st == nst) st = 0;
               }
+              SDFB_TRACE(9);
               stage = st;
               phase = ph;
               kc = pre;
-              need_sync = false;
             }
             for (; kc < g.nk; ++kc) {
               if (!mbar_wait(bars + 8 * (kBarEmpty + stage), phase ^ 1u, wd, kErrEmpty, stage)) goto done;
@@ -217,9 +251,6 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               tma_load_half_block(smem0 + stage * stage_bytes, &tm_act, a_row + kc * 128, full_l);
               if (++stage == nst) { stage = 0; phase ^= 1u; }
             }
-          }
-          if (need_sync) {   // this pair had no tile in the layer (cannot happen: grid <= 2 T), keep the barrier count anyway
-            if (!grid_wait(p, static_cast<uint32_t>(s * kLayers + l) * gridDim.x, wd)) goto done;
           }
         }
       }
@@ -243,8 +274,9 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             ephase ^= 1u << b;
 #pragma unroll 1
             for (int k = 0; k < nk; ++k) {
-              if (!mbar_wait(bars + 8 * (kBarFull + stage), phase, wd, kErrFull, stage)) goto done;
+              if (!mbar_wait(bars + 8 * (kBarFull + stage), phase, wd, k == 0 ? kErrFullFirst : kErrFull, stage)) goto done;
               tc_fence_after();
+              if (k == 0 && lane == 0) SDFB_TRACE(0);
               const uint32_t a_lo = (((smem0 + stage * stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
               const uint64_t adesc = desc_hi | a_lo;
               const uint64_t bdesc = desc_hi | (a_lo + (16384u >> 4));
@@ -258,6 +290,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
                 }
               }
               __syncwarp();
+              if (k == nk - 1 && lane == 0) SDFB_TRACE(1);
               prev_stage = stage;
               if (++stage == nst) { stage = 0; phase ^= 1u; }
             }
@@ -287,6 +320,12 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
           const uint32_t tbase = tmem_row + b * 256;
           const long long m = static_cast<long long>(m_tile) * 128 + row;        // latent index
           const bool valid = m < p.n;
+          // The tile's bias slice -> shared memory, off the critical path (the producer's gpu-scope
+          // acquires invalidate L1, so reading it from global after the accumulator wait costs an L2
+          // round trip per load).  Double-buffered by tile parity; the barrier orders it for all warps.
+          float* sb = sbias + (gt & 1u) * 256;
+          if (static_cast<int>(threadIdx.x) < g.bn) sb[threadIdx.x] = bias[j * g.bn + threadIdx.x];
+          named_bar_sync(1, kEpiThreads);
           // first unit of this warp set: units u with ((u >> 1) & 1) == set
           const int u_first = 2 * set;
           float xv[2][16], nz[2][16];
@@ -321,34 +360,61 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
           acc_phase ^= 1u << b;
           __syncwarp();
           tc_fence_after();
+          if (threadIdx.x == 0) SDFB_TRACE(2);
           if (l < 4) {
-            // hidden layer: + bias, ReLU, round to 16 bits, store as operand image of the next layer
-            for (int u0 = u_first; u0 < nu; u0 += 4) {
+            // hidden layer: + bias, ReLU, round to 16 bits -> swizzled operand image in the staging
+            // buffer -> one TMA store per 64-feature chunk (set s owns chunks c = s, s + 2, ...)
+            const int nch = g.bn >> 6;
+            const bool set_leader = (q == 0 && lane == 0);
+            if (set_leader) bulk_wait_group_read0();        // the previous tile's stores have finished reading the staging buffer
+            named_bar_sync(2 + set, kEpiThreads / 2);
+            for (int c = set; c < nch; c += 2) {
+              uint32_t v[2][32];
+              tmem_ld32(tbase + c * 64, v[0]);
+              tmem_ld32(tbase + c * 64 + 32, v[1]);
+              const int col = j * g.bn + c * 64;
+              const uint32_t srow = smem0 + o_stage + c * 16384u + row * 128u;
+              tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const int u = u0 + i;
-                uint32_t v[16];
-                tmem_ld16(tbase + u * 16, v);
-                const int col = j * g.bn + u * 16;
-                const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-                float4 bb[4];
+              for (int h = 0; h < 2; ++h) {
+                const float4* b4 = reinterpret_cast<const float4*>(sb + c * 64 + 32 * h);
+                uint32_t pk[16];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) bb[e] = __ldg(b4 + e);
-                tmem_ld_wait();
-                uint32_t pk[8];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  pk[2 * e] = pack_relu<FP16>(__uint_as_float(v[4 * e]) + bb[e].x, __uint_as_float(v[4 * e + 1]) + bb[e].y);
-                  pk[2 * e + 1] = pack_relu<FP16>(__uint_as_float(v[4 * e + 2]) + bb[e].z, __uint_as_float(v[4 * e + 3]) + bb[e].w);
+                for (int e = 0; e < 8; ++e) {
+                  const float4 bb = b4[e];
+                  pk[2 * e] = pack_relu<FP16>(__uint_as_float(v[h][4 * e]) + bb.x, __uint_as_float(v[h][4 * e + 1]) + bb.y);
+                  pk[2 * e + 1] = pack_relu<FP16>(__uint_as_float(v[h][4 * e + 2]) + bb.z, __uint_as_float(v[h][4 * e + 3]) + bb.w);
                 }
-                const int chunk = g.o_chunk0 + (col >> 6), unit = (col & 63) >> 3;
-                st_global_v4(image_ptr(p.act, m_tile, chunk, row, unit), pk[0], pk[1], pk[2], pk[3]);
-                st_global_v4(image_ptr(p.act, m_tile, chunk, row, unit + 1), pk[4], pk[5], pk[6], pk[7]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  st_shared_v4(srow + (((4 * h + u) ^ (row & 7)) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+              }
+              if (c + 2 >= nch) {      // every column this warp owns has been read: hand the accumulator back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1);
+              }
+              fence_proxy_async_smem();
+              named_bar_sync(2 + set, kEpiThreads / 2);
+              if (set_leader) {
+                if (c == 0 && threadIdx.x == 0) SDFB_TRACE(3);
+                tma_store_rows(&tm_act, (m_tile * 40 + g.o_chunk0 + (col >> 6)) * 128, smem0 + o_stage + c * 16384u);
+                bulk_commit_group();
               }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1);
+            if (threadIdx.x == 0) SDFB_TRACE(4);
+            if (set >= nch) {          // a set without a chunk (bn = 64) still owes its accumulator arrival
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1);
+            }
+            if (set_leader) {          // stores complete -> arrive on the barrier of this latent group
+              bulk_wait_group0();
+              if (threadIdx.x == 0) SDFB_TRACE(5);
+              fence_proxy_async_global();
+              red_release_gpu_add(p.counter + pm, 1u);
+              if (threadIdx.x == 0) SDFB_TRACE(6);
+            }
           } else {
             // last layer: eps -> x0-clipped posterior-mean update (op for op as oracle/ddpm.py ddpm_step)
             uint32_t v[2][16];
@@ -359,6 +425,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             tc_fence_before();
             __syncwarp();
             if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1);
+            if (threadIdx.x == 0) SDFB_TRACE(10);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const int u = u_first + i;
@@ -367,7 +434,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               float o[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                const float eps = __uint_as_float(v[i][e]) + __ldg(bias + col + e);
+                const float eps = __uint_as_float(v[i][e]) + sb[u * 16 + e];
                 if (p.eps_out != nullptr) {
                   o[e] = eps;
                 } else {
@@ -378,6 +445,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
                   o[e] = valid ? r : 0.f;
                 }
               }
+              if (threadIdx.x == 0 && i == 0 && o[3] != 12345.f) SDFB_TRACE(11);
               if (p.eps_out != nullptr) {
                 if (valid) {
                   float4* dst = reinterpret_cast<float4*>(p.eps_out + m * kDdpmLatent + col);
@@ -399,18 +467,35 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
                 st_global_v4(image_ptr(p.act, m_tile, 4 + chunk, row, unit), lo[0], lo[1], lo[2], lo[3]);
                 st_global_v4(image_ptr(p.act, m_tile, 4 + chunk, row, unit + 1), lo[4], lo[5], lo[6], lo[7]);
               }
+              if (threadIdx.x == 0 && i == 0) SDFB_TRACE(12);
             }
           }
+          if (l == 4) {
+            // generic stores: the barrier orders every thread's stores before the set leader, whose single
+            // gpu-scope fence + release then publishes them (a fence per thread serialises: 8 warps x ~1.2k cycles)
+            if (threadIdx.x == 0) SDFB_TRACE(4);
+            named_bar_sync(2 + set, kEpiThreads / 2);
+            if (threadIdx.x == 0) SDFB_TRACE(5);
+            if (q == 0 && lane == 0) {
+              __threadfence();
+              fence_proxy_async_global();
+              red_release_gpu_add(p.counter + pm, 1u);
+            }
+            if (threadIdx.x == 0) SDFB_TRACE(6);
+          }
         }
-        // end of the layer: publish this CTA's stores and arrive on the grid barrier
-        fence_proxy_async_global();
-        __threadfence();
-        named_bar_sync(1, kEpiThreads);
-        if (threadIdx.x == 0) red_release_gpu_add(p.counter, 1u);
       }
     }
   }
 done:
+  if (p.prof != nullptr && lane == 0 && (warp == 0 || warp >= 8) && (leader || warp != 9)) {
+    const int role = warp == 0 ? 0 : warp - 7;            // 0 epilogue, 1 producer, 2 MMA issuer
+    long long* dst = p.prof + (static_cast<long long>(blockIdx.x) * 3 + role) * 8;
+#pragma unroll
+    for (int i = 1; i < 7; ++i) dst[i] = waited[i];
+    dst[0] = clock64() - t_start;
+    dst[7] = 0;
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -449,13 +534,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 uint32_t smem_bytes_for(int bn_h, int nstages) {
-  return static_cast<uint32_t>(nstages) * (16384u + static_cast<uint32_t>(bn_h) * 64u) + kNumBars * 8 + 16;
+  return static_cast<uint32_t>(nstages) * (16384u + static_cast<uint32_t>(bn_h) * 64u) + static_cast<uint32_t>(bn_h) * 256u +
+         kNumBars * 8 + 16 + 2048;
 }
 
 }  // namespace
 
 cudaError_t ddpm_step_init() {
-  const int max_smem = 6 * 32768 + kNumBars * 8 + 16;     // bn_h = 256, 6 stages (the largest configuration)
+  const int max_smem = 5 * 32768 + 65536 + kNumBars * 8 + 16 + 2048;     // bn_h = 256: 5 stages + 64 KiB staging (the largest configuration)
   cudaError_t e = cudaFuncSetAttribute(ddpm_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(ddpm_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);

@@ -118,9 +118,10 @@ struct DdpmParams {
   int t_first;
   int bn_h, bn_o;          // output-tile widths of the hidden layers and of the last layer (bn_o = bn_h / 4)
   int nstages;
-  unsigned int* counter;   // grid barrier (zeroed before the launch)
+  unsigned int* counter;   // [pair_m_tiles] barrier counters, one per group of pair tiles that share 256 latents (zeroed before the launch)
   unsigned int* status;
   unsigned long long timeout_ns;
+  long long* prof;         // optional [grid][3 roles][8]: blocked cycles per wait class (diagnostics)
 };
 
 cudaError_t ddpm_step_init();

@@ -103,14 +103,14 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, const W
                                           uint32_t site, uint32_t idx = 0) {
   const long long c0 = wd.wait_cycles != nullptr ? clock64() : 0;
   if (mbar_try_wait(bar, parity)) {   // try_wait itself may block for a while: count that time too
-    if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
+    if (wd.wait_cycles != nullptr) wd.wait_cycles[(site >> 4) & 7u] += clock64() - c0;
     return true;
   }
   uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (true) {
     if (mbar_try_wait(bar, parity)) {
-      if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
+      if (wd.wait_cycles != nullptr) wd.wait_cycles[(site >> 4) & 7u] += clock64() - c0;
       return true;
     }
     if ((++spins & 0xFFu) == 0) {
@@ -296,14 +296,14 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity,
                                                   uint32_t site, uint32_t idx = 0) {
   const long long c0 = wd.wait_cycles != nullptr ? clock64() : 0;
   if (mbar_try_wait_cluster(bar, parity)) {   // try_wait itself may block for a while: count that time too
-    if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
+    if (wd.wait_cycles != nullptr) wd.wait_cycles[(site >> 4) & 7u] += clock64() - c0;
     return true;
   }
   uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (true) {
     if (mbar_try_wait_cluster(bar, parity)) {
-      if (wd.wait_cycles != nullptr) wd.wait_cycles[site >> 4] += clock64() - c0;
+      if (wd.wait_cycles != nullptr) wd.wait_cycles[(site >> 4) & 7u] += clock64() - c0;
       return true;
     }
     if ((++spins & 0xFFu) == 0) {
