@@ -170,14 +170,13 @@ struct sdfb_ddpm {
   uint8_t* wpack[2] = {nullptr, nullptr};     // [0] bf16, [1] fp16: kDdpmWRows rows of 128 B
   float* bias_dev = nullptr;                  // [3][1024] + [256]
   float* coef_dev = nullptr;                  // [1000][8]
-  uint8_t* act = nullptr; int act_tiles = 0;  // activation images, kDdpmActTileBytes per 128-latent tile
-  unsigned int* counter = nullptr;            // [act_tiles / 2] barrier counters (one per 256-latent group)
+  uint16_t* act = nullptr; int act_rows = 0;  // row-major activations [act_rows][kDdpmActCols], 16-bit
+  unsigned int* counter = nullptr;            // [act_rows / 256] barrier counters (one per 256-latent group)
   unsigned int* status = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   unsigned long long timeout_ns = 4000000000ull;
   long long* prof = nullptr;                  // wait profile buffer (allocated when SDFB_PROF is set)
-  int last_grid = 0;
 };
 
 namespace {
@@ -701,41 +700,57 @@ static int denoise_fp32(sdfb_ddpm* d, const float* x, int t, int n, float* eps, 
 // launch (eps_out != nullptr: a single denoiser evaluation, no update).
 static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps, int t_first, float* eps_out,
                    bool fp16, cudaStream_t st) {
-  const int m_pairs = (n + 255) / 256, m_tiles = 2 * m_pairs;
-  if (d->act_tiles < m_tiles) {
-    cudaFree(d->act); cudaFree(d->counter); d->act = nullptr; d->counter = nullptr; d->act_tiles = 0;
+  const int m_pairs = (n + 255) / 256, n_pad = 256 * m_pairs;
+  if (d->act_rows < n_pad) {
+    cudaFree(d->act); cudaFree(d->counter); d->act = nullptr; d->counter = nullptr; d->act_rows = 0;
     CU_TRY(cudaMalloc(&d->counter, static_cast<size_t>(m_pairs) * sizeof(unsigned int)));
-    CU_TRY(cudaMalloc(&d->act, static_cast<size_t>(m_tiles) * kDdpmActTileBytes));
-    CU_TRY(cudaMemset(d->act, 0, static_cast<size_t>(m_tiles) * kDdpmActTileBytes));
-    d->act_tiles = m_tiles;
+    CU_TRY(cudaMalloc(&d->act, static_cast<size_t>(n_pad) * kDdpmActCols * 2));
+    CU_TRY(cudaMemset(d->act, 0, static_cast<size_t>(n_pad) * kDdpmActCols * 2));
+    d->act_rows = n_pad;
   }
-  // tile width: the widest that still gives about one pair tile per CTA pair
+  // tile width of the hidden layers: 256 if that still gives about one pair tile per CTA pair
   const int max_pairs = d->num_sms / 2;
-  int bn_h = 64;
-  for (int bn : {256, 128}) {
-    if (m_pairs * (kDdpmHid / bn) * 4 >= max_pairs * 3) { bn_h = bn; break; }
-  }
+  int bn_h = (m_pairs * (kDdpmHid / 256) * 4 >= max_pairs * 3) ? 256 : 128;
   if (const char* e = std::getenv("SDFB_DDPM_BN")) {
     const int v = std::atoi(e);
-    if (v == 64 || v == 128 || v == 256) bn_h = v;
+    if (v == 128 || v == 256) bn_h = v;
   }
   DdpmParams p{};
   p.tb0 = d->tb0; p.bias = d->bias_dev; p.coef = d->coef_dev;
-  p.x = x; p.noise = noise; p.eps_out = eps_out; p.act = d->act;
+  p.eps_mode = eps_out != nullptr ? 1 : 0;
   p.n = n; p.pair_m_tiles = m_pairs; p.steps = steps; p.t_first = t_first;
-  p.bn_h = bn_h; p.bn_o = bn_h / 4;
-  p.nstages = bn_h == 256 ? 5 : kDdpmMaxStages;   // 5 x 32 KiB + 64 KiB staging | 8 x 24 + 32 | 8 x 20 + 16
+  p.bn_h = bn_h;
+  p.nstages = bn_h == 256 ? 4 : 5;   // 4 x 32 KiB or 5 x 24 KiB of operand ring + 96 KiB of epilogue staging
   p.counter = d->counter; p.status = d->status; p.timeout_ns = d->timeout_ns; p.prof = d->prof;
-  alignas(64) unsigned char tm_act[128], tm_wh[128], tm_wo[128];
-  CU_TRY(make_rows_tensor_map(d->act, static_cast<unsigned long long>(d->act_tiles) * (kDdpmActTileBytes / 128), 128, tm_act));
-  CU_TRY(make_rows_tensor_map(d->wpack[fp16 ? 1 : 0], kDdpmWRows, p.bn_h / 2, tm_wh));
-  CU_TRY(make_rows_tensor_map(d->wpack[fp16 ? 1 : 0], kDdpmWRows, p.bn_o / 2, tm_wo));
-  CU_TRY(launch_ddpm_split(x, n, m_tiles, d->act, fp16, st));
+  DdpmMaps maps;
+  {
+    const unsigned long long a_dims[2] = {kDdpmActCols, static_cast<unsigned long long>(d->act_rows)};
+    const unsigned long long a_str[1] = {kDdpmActCols * 2ull};
+    const unsigned a_box[2] = {64, 128};
+    CU_TRY(make_tensor_map(maps.act, d->act, 2, 2, a_dims, a_str, a_box, true));
+    const unsigned long long w_dims[2] = {64, kDdpmWRows};
+    const unsigned long long w_str[1] = {128};
+    const unsigned wh_box[2] = {64, static_cast<unsigned>(bn_h / 2)}, wo_box[2] = {64, kDdpmOutTile / 2};
+    CU_TRY(make_tensor_map(maps.wh, d->wpack[fp16 ? 1 : 0], 2, 2, w_dims, w_str, wh_box, false));
+    CU_TRY(make_tensor_map(maps.wo, d->wpack[fp16 ? 1 : 0], 2, 2, w_dims, w_str, wo_box, false));
+    const unsigned long long x_dims[2] = {kDdpmLatent, static_cast<unsigned long long>(n)};
+    const unsigned long long x_str[1] = {kDdpmLatent * 4ull};
+    const unsigned x_box[2] = {32, 128};
+    CU_TRY(make_tensor_map(maps.x, eps_out != nullptr ? eps_out : x, 4, 2, x_dims, x_str, x_box, true));
+    if (noise != nullptr && eps_out == nullptr) {
+      const unsigned long long n_dims[3] = {kDdpmLatent, static_cast<unsigned long long>(n), static_cast<unsigned long long>(t_first + 1)};
+      const unsigned long long n_str[2] = {kDdpmLatent * 4ull, static_cast<unsigned long long>(n) * kDdpmLatent * 4ull};
+      const unsigned n_box[3] = {32, 128, 1};
+      CU_TRY(make_tensor_map(maps.nz, noise, 4, 3, n_dims, n_str, n_box, true));
+    } else {
+      std::memcpy(maps.nz, maps.x, 128);   // never dereferenced (t_first == 0 or eps_mode)
+    }
+  }
+  CU_TRY(launch_ddpm_split(x, n, n_pad, d->act, fp16, st));
   CU_TRY(cudaMemsetAsync(d->counter, 0, static_cast<size_t>(m_pairs) * sizeof(unsigned int), st));
   if (d->prof) CU_TRY(cudaMemsetAsync(d->prof, 0, (static_cast<size_t>(148) * 24 + 96) * sizeof(long long), st));
-  d->last_grid = 2 * (m_pairs * (kDdpmHid / bn_h) < max_pairs ? m_pairs * (kDdpmHid / bn_h) : max_pairs);
   CU_TRY(cudaEventRecord(d->ev0, st));
-  CU_TRY(launch_ddpm_sample(p, tm_act, tm_wh, tm_wo, fp16, d->num_sms, st));
+  CU_TRY(launch_ddpm_sample(p, maps, fp16, d->num_sms, st));
   CU_TRY(cudaEventRecord(d->ev1, st));
   d->timed = true;
   return SDFB_OK;

@@ -12,11 +12,16 @@
 //
 // Mapping.  Every layer is cut into pair tiles of 256 latents x BN output features
 // (cta_group::2: each CTA holds 128 rows of A and half of the weight rows) that are spread over
-// all CTA pairs; K is streamed in 64-wide chunks through a shared-memory ring.  The epilogue
-// warps store a tile's activations as pre-swizzled operand images in an L2-resident buffer, so
-// the next layer's loads are plain TMA boxes that land MMA-ready.  Layers are separated by a
-// grid-wide barrier (one release-add per CTA, acquire spin in the producer); weights do not
-// depend on it and are prefetched across it.  The last layer's epilogue is the DDPM update.
+// all CTA pairs; K is streamed in 64-wide chunks through a shared-memory ring.  ALL global
+// traffic of the kernel goes through the TMA unit: the epilogue warps build a tile's output in
+// a swizzled shared-memory staging buffer and store it with one bulk tensor copy per 64-feature
+// chunk into an L2-resident row-major activation buffer, from which the next layer's operand
+// boxes are loaded (scattered per-thread stores cost 32 LSU wavefronts per instruction and a
+// write-drain fence; the profile of the first version was dominated by them).  A tile waits
+// only for the CTAs that share its 256 latents (one barrier counter per latent group: release-add
+// by the storing thread after its bulk stores completed, acquire spin in the producer); weights
+// do not depend on it and are prefetched across it.  The last layer's epilogue is the DDPM
+// update: x and noise[t] arrive as TMA boxes, x_new, x_hi and x_lo leave as TMA boxes.
 //
 //   warps 0-7  epilogue   (TMEM lane quadrant = warp & 3; the two warp sets split the columns)
 //   warp 8     producer   (TMA; completion counted on the LEADER's barrier)
@@ -35,21 +40,24 @@ namespace {
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 64;
-constexpr int kTileRows = (8 + 16 + 16) * 128;        // image rows per 128-latent tile in the activation allocation
 constexpr int kLayers = 5;
+constexpr uint32_t kStagingBytes = 96 * 1024;   // hidden: bn_h / 64 chunk images | last layer: x (32K), noise (32K), x_hi, x_lo (16K each)
+constexpr uint32_t kChunk = 16384;
 
 constexpr int kBarFull = 0;
 constexpr int kBarEmpty = kBarFull + kDdpmMaxStages;
 constexpr int kBarAccFull = kBarEmpty + kDdpmMaxStages;
 constexpr int kBarAccEmpty = kBarAccFull + 2;
-constexpr int kNumBars = kBarAccEmpty + 2;
+constexpr int kBarXn = kBarAccEmpty + 2;
+constexpr int kNumBars = kBarXn + 1;
+constexpr uint32_t kBarBytes = (kNumBars * 8 + 15) & ~15u;   // keeps what follows 16-byte aligned
 
 // wait sites (status codes); (site >> 4) & 7 is the class under which blocked cycles are profiled
 enum : uint32_t { kErrFull = 0x110, kErrEmpty = 0x120, kErrAccFull = 0x130, kErrAccEmpty = 0x140, kErrGrid = 0x150,
-                  kErrFullFirst = 0x160 };
+                  kErrFullFirst = 0x160, kErrXn = 0x170 };
 
-// Diagnostics: with profiling on, CTA 0 stamps clock64() at key events of every layer of step 5
-// into the tail of the profile buffer ([148 * 24 + layer * 16 + event]).
+// Diagnostics: with profiling on, CTA 0 stamps clock64() at key events of every layer of step 5 (and
+// of layer 0 of step 6, row 5) into the tail of the profile buffer ([148 * 24 + row * 16 + event]).
 #define SDFB_TRACE(ev)                                                                              \
   do {                                                                                              \
     if (p.prof != nullptr && blockIdx.x == 0 && (s == 5 || (s == 6 && l == 0)))                     \
@@ -58,21 +66,23 @@ enum : uint32_t { kErrFull = 0x110, kErrEmpty = 0x120, kErrAccFull = 0x130, kErr
 
 struct Geo {
   int nk;          // 64-wide k-chunks
-  int a_chunk0;    // first chunk (of the 40 per tile) of the layer's A operand
-  int o_chunk0;    // first chunk of the buffer the layer's epilogue writes
+  int a_col0;      // first column of the layer's A operand in the activation buffer
+  int o_col0;      // first column of the buffer the layer's epilogue writes
   int w_row0;      // first weight row of the layer
   int n_total;     // output features
   int bn;          // tile width
+  int ntn;         // n-tiles
 };
 
 __device__ __forceinline__ Geo layer_geo(const DdpmParams& p, int l) {
   Geo g;
   g.nk = l == 0 ? 8 : 16;
-  g.a_chunk0 = l == 0 ? 0 : ((l & 1) ? 8 : 24);       // L1, L3 read buffer 0; L2, L4 read buffer 1
-  g.o_chunk0 = l == 4 ? 0 : ((l & 1) ? 24 : 8);       // L0, L2 write buffer 0; L1, L3 write buffer 1; L4 writes [x_hi | x_lo]
+  g.a_col0 = l == 0 ? 0 : ((l & 1) ? 512 : 1536);      // L1, L3 read buffer 0; L2, L4 read buffer 1
+  g.o_col0 = l == 4 ? 0 : ((l & 1) ? 1536 : 512);      // L0, L2 write buffer 0; L1, L3 write buffer 1; L4 writes [x_hi | x_lo]
   g.w_row0 = l == 0 ? 0 : (l < 4 ? kDdpmW0Rows + (l - 1) * kDdpmWHidRows : kDdpmW0Rows + 3 * kDdpmWHidRows);
   g.n_total = l == 4 ? kDdpmLatent : kDdpmHid;
-  g.bn = l == 4 ? p.bn_o : p.bn_h;
+  g.bn = l == 4 ? kDdpmOutTile : p.bn_h;
+  g.ntn = g.n_total / g.bn;
   return g;
 }
 
@@ -84,10 +94,10 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
 __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// generic-proxy global writes <-> async-proxy (TMA) global reads
+// generic-proxy <-> async-proxy (TMA) ordering on global memory
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-// Wait until `target` CTAs have arrived on a barrier counter (bounded).
+// Wait until `target` arrivals have been counted on a barrier counter (bounded).
 __device__ __forceinline__ bool grid_wait(const DdpmParams& p, const unsigned int* counter, uint32_t target, const Watchdog& wd) {
   if (ld_acquire_gpu(counter) >= target) return true;
   const long long c0 = wd.wait_cycles != nullptr ? clock64() : 0;
@@ -111,65 +121,90 @@ __device__ __forceinline__ bool grid_wait(const DdpmParams& p, const unsigned in
 }
 
 template <bool FP16>
-__device__ __forceinline__ float lowp_hi_to_float(uint32_t packed_lo16) {
+__device__ __forceinline__ float lowp_to_float(uint32_t bits16) {
   if constexpr (FP16) {
-    return __half2float(__ushort_as_half(static_cast<unsigned short>(packed_lo16 & 0xFFFFu)));
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(bits16 & 0xFFFFu)));
   } else {
-    return __uint_as_float(packed_lo16 << 16);
+    return __uint_as_float(bits16 << 16);
   }
 }
 // (hi, lo) 16-bit split of two consecutive fp32 values: x = hi + lo + O(2^-16 |x|)
 template <bool FP16>
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   hi = pack_plain<FP16>(a, b);
-  const float ra = a - lowp_hi_to_float<FP16>(hi & 0xFFFFu);
-  const float rb = b - lowp_hi_to_float<FP16>(hi >> 16);
+  const float ra = a - lowp_to_float<FP16>(hi & 0xFFFFu);
+  const float rb = b - lowp_to_float<FP16>(hi >> 16);
   lo = pack_plain<FP16>(ra, rb);
 }
 
-// 128 rows x 64 columns (one operand image) shared -> global through the tensor map, bulk-group completion
-__device__ __forceinline__ void tma_store_rows(const void* tmap, int row0, uint32_t src_smem) {
+// ---- TMA helpers (tensor maps passed as __grid_constant__ kernel parameters) ----
+// box at (c0, c1) -> local shared memory, bytes counted on the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+// box -> local shared memory, bytes counted on a local barrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, uint32_t src_smem) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
                    reinterpret_cast<uint64_t>(tmap)),
-               "r"(0), "r"(row0), "r"(src_smem)
+               "r"(c0), "r"(c1), "r"(src_smem)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
-
-// byte address of 16-byte unit `unit` of row `row` of chunk `chunk` (0..39) of 128-latent tile `m`
-__device__ __forceinline__ uint8_t* image_ptr(uint8_t* act, int m, int chunk, int row, int unit) {
-  return act + ((static_cast<long long>(m) * kTileRows + chunk * 128 + row) << 7) + ((unit ^ (row & 7)) << 4);
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 template <bool FP16>
 __global__ void __launch_bounds__(kThreads, 1)
-ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_act,
-                   const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wo) {
+ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wh,
+                   const __grid_constant__ CUtensorMap tm_wo, const __grid_constant__ CUtensorMap tm_x,
+                   const __grid_constant__ CUtensorMap tm_nz) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem0 = smem_u32(smem_raw);
   if ((smem0 & 1023u) != 0) {
     if (threadIdx.x == 0) atomicCAS(p.status, 0u, 0xA12u);
     return;
   }
-  const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(p.bn_h) * 64u;   // A chunk + this CTA's half of a weight chunk
-  const uint32_t o_stage = static_cast<uint32_t>(p.nstages) * stage_bytes;     // epilogue staging: bn_h / 64 operand images of 16 KiB
-  const uint32_t o_bar = o_stage + static_cast<uint32_t>(p.bn_h) * 256u;
+  const uint32_t stage_bytes = kChunk + static_cast<uint32_t>(p.bn_h) * 64u;   // A chunk + this CTA's half of a weight chunk
+  const uint32_t o_stage = static_cast<uint32_t>(p.nstages) * stage_bytes;     // epilogue staging
+  const uint32_t o_bar = o_stage + kStagingBytes;
+  const uint32_t stg = smem0 + o_stage;
   const uint32_t bars = smem0 + o_bar;
-  volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(smem_raw + o_bar + kNumBars * 8);   // [0] tmem base, [1] abort
-  float* sbias = reinterpret_cast<float*>(smem_raw + o_bar + kNumBars * 8 + 16);                    // 2 x 256 floats: the tile's bias slice
+  volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(smem_raw + o_bar + kBarBytes);   // [0] tmem base, [1] abort
+  float* sbias = reinterpret_cast<float*>(smem_raw + o_bar + kBarBytes + 16);                    // 2 x 256 floats: the tile's bias slice
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int ntn = kDdpmHid / p.bn_h;                       // n-tiles per layer (= 256 / bn_o for the last layer)
-  const int T = p.pair_m_tiles * ntn;                      // pair tiles per layer
   const int npairs = gridDim.x >> 1, pidx = blockIdx.x >> 1;
+  // Barrier arithmetic: a pair tile contributes 4 arrivals (2 CTAs x 2 warp sets) to the counter of its
+  // latent group pm.  A hidden layer has kDdpmHid / bn_h tiles per group, the last layer 4.
+  const uint32_t arr_h = 4u * static_cast<uint32_t>(kDdpmHid / p.bn_h);
+  const uint32_t arr_step = 4u * arr_h + 16u;
 
   if (threadIdx.x == 0) {
     misc[1] = 0;
@@ -181,10 +216,11 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
       mbar_init(bars + 8 * (kBarAccFull + b), 1);
       mbar_init(bars + 8 * (kBarAccEmpty + b), 2 * kEpiWarps);
     }
+    mbar_init(bars + 8 * kBarXn, 1);
     fence_mbar_init();
   }
   if (warp == 9) {
-    tmem_alloc<2>(smem0 + o_bar + kNumBars * 8, 512);
+    tmem_alloc<2>(smem0 + o_bar + kBarBytes, 512);
     tmem_relinquish<2>();
   }
   tc_fence_before();
@@ -195,9 +231,6 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
   long long waited[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   Watchdog wd{misc + 1, p.status, p.timeout_ns, p.prof != nullptr ? waited : nullptr};
   const long long t_start = clock64();
-  // A layer's tile (pm, j) consumes what the 2 ntn CTAs that own pair-row pm wrote in the previous layer:
-  // one barrier counter per pm, 2 ntn CTAs x 2 warp sets arrive per layer.
-  const uint32_t group_ctas = 4u * static_cast<uint32_t>(ntn);   // x 2 warp sets per CTA
 
   if (warp == 8) {
     // ===================== producer =====================
@@ -208,15 +241,17 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
         for (int l = 0; l < kLayers; ++l) {
           const Geo g = layer_geo(p, l);
           const CUtensorMap* tmw = l == 4 ? &tm_wo : &tm_wh;
-          const uint32_t tx = 2u * 16384u + static_cast<uint32_t>(g.bn) * 128u;
+          const uint32_t tx = 2u * kChunk + static_cast<uint32_t>(g.bn) * 128u;
           const bool need_sync = !(s == 0 && l == 0);      // the operand of the very first layer was written by an earlier kernel
+          const uint32_t target = static_cast<uint32_t>(s) * arr_step + static_cast<uint32_t>(l) * arr_h;
+          const int T = p.pair_m_tiles * g.ntn;
           for (int tile = pidx; tile < T; tile += npairs) {
-            const int pm = tile / ntn, j = tile - pm * ntn;
-            const int a_row = ((2 * pm + static_cast<int>(rank)) * 40 + g.a_chunk0) * 128;
+            const int pm = tile / g.ntn, j = tile - pm * g.ntn;
+            const int a_row = (2 * pm + static_cast<int>(rank)) * 128;
             const int w_row = g.w_row0 + j * g.bn + static_cast<int>(rank) * (g.bn >> 1);
             int kc = 0;
             if (need_sync) {
-              // weights first (they do not depend on the previous layer), then the grid barrier, then A
+              // weights first (they do not depend on the previous layer), then the group barrier, then A
               const int pre = g.nk < static_cast<int>(nst) ? g.nk : static_cast<int>(nst);
               uint32_t st = stage, ph = phase;
               for (int i = 0; i < pre; ++i) {
@@ -224,16 +259,16 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
                 const uint32_t full = bars + 8 * (kBarFull + st);
                 if (leader) mbar_arrive_expect_tx(full, tx);
                 const int wk = l == 0 ? (i & 3) : i;
-                tma_load_half_block(smem0 + st * stage_bytes + 16384u, tmw, w_row + wk * g.n_total, map_to_cta(full, 0));
+                tma_load_2d_pair(smem0 + st * stage_bytes + kChunk, tmw, 0, w_row + wk * g.n_total, map_to_cta(full, 0));
                 if (++st == nst) { st = 0; ph ^= 1u; }
               }
               SDFB_TRACE(7);
-              if (!grid_wait(p, p.counter + pm, static_cast<uint32_t>(s * kLayers + l) * group_ctas, wd)) goto done;
+              if (!grid_wait(p, p.counter + pm, target, wd)) goto done;
               SDFB_TRACE(8);
               fence_proxy_async_global();
               st = stage;
               for (int i = 0; i < pre; ++i) {
-                tma_load_half_block(smem0 + st * stage_bytes, &tm_act, a_row + i * 128, map_to_cta(bars + 8 * (kBarFull + st), 0));
+                tma_load_2d_pair(smem0 + st * stage_bytes, &tm_act, g.a_col0 + i * 64, a_row, map_to_cta(bars + 8 * (kBarFull + st), 0));
                 if (++st == nst) st = 0;
               }
               SDFB_TRACE(9);
@@ -247,8 +282,8 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               if (leader) mbar_arrive_expect_tx(full, tx);
               const int wk = l == 0 ? (kc & 3) : kc;
               const uint32_t full_l = map_to_cta(full, 0);
-              tma_load_half_block(smem0 + stage * stage_bytes + 16384u, tmw, w_row + wk * g.n_total, full_l);
-              tma_load_half_block(smem0 + stage * stage_bytes, &tm_act, a_row + kc * 128, full_l);
+              tma_load_2d_pair(smem0 + stage * stage_bytes + kChunk, tmw, 0, w_row + wk * g.n_total, full_l);
+              tma_load_2d_pair(smem0 + stage * stage_bytes, &tm_act, g.a_col0 + kc * 64, a_row, full_l);
               if (++stage == nst) { stage = 0; phase ^= 1u; }
             }
           }
@@ -259,7 +294,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
     // ===================== MMA issuer (leader CTA; whole warp runs the loop, see fused_decoder.cu) =====================
     if (leader) {
       const uint32_t idesc_h = umma_idesc(256, p.bn_h, FP16 ? 0 : 1);
-      const uint32_t idesc_o = umma_idesc(256, p.bn_o, FP16 ? 0 : 1);
+      const uint32_t idesc_o = umma_idesc(256, kDdpmOutTile, FP16 ? 0 : 1);
       const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
       const uint32_t nst = static_cast<uint32_t>(p.nstages);
       uint32_t stage = 0, phase = 0, ephase = 0, gt = 0, prev_stage = 0;
@@ -267,6 +302,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
         for (int l = 0; l < kLayers; ++l) {
           const int nk = l == 0 ? 8 : 16;
           const uint32_t idesc = l == 4 ? idesc_o : idesc_h;
+          const int T = p.pair_m_tiles * (l == 4 ? kDdpmLatent / kDdpmOutTile : kDdpmHid / p.bn_h);
           for (int tile = pidx; tile < T; tile += npairs, ++gt) {
             const uint32_t b = gt & 1u;
             const uint32_t d_tmem = tmem_base + b * 256;
@@ -279,7 +315,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               if (k == 0 && lane == 0) SDFB_TRACE(0);
               const uint32_t a_lo = (((smem0 + stage * stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
               const uint64_t adesc = desc_hi | a_lo;
-              const uint64_t bdesc = desc_hi | (a_lo + (16384u >> 4));
+              const uint64_t bdesc = desc_hi | (a_lo + (kChunk >> 4));
               if (elect_one()) {
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) umma_ss<2>(d_tmem, adesc + 2 * jj, bdesc + 2 * jj, idesc, (k | jj) != 0 ? 1u : 0u);
@@ -302,8 +338,10 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
     // ===================== epilogue warps =====================
     const int q = warp & 3, set = warp >> 2;
     const int row = q * 32 + lane;                       // row of this CTA's 128 = TMEM lane
+    const uint32_t row7 = static_cast<uint32_t>(row & 7);
     const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint32_t acc_phase = 0, gt = 0;
+    const bool set_leader = (q == 0 && lane == 0);
+    uint32_t acc_phase = 0, gt = 0, xn_phase = 0;
     for (int s = 0; s < p.steps; ++s) {
       const int t = p.t_first - s;
       const float4 cf = *reinterpret_cast<const float4*>(p.coef + t * 8);        // sra, srm1, c1, c2
@@ -312,48 +350,29 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
         const Geo g = layer_geo(p, l);
         const float* bias = l == 0 ? p.tb0 + static_cast<long long>(t) * kDdpmHid
                                    : (l < 4 ? p.bias + (l - 1) * kDdpmHid : p.bias + 3 * kDdpmHid);
-        const int nu = g.bn >> 4;                          // 16-column units in the tile
+        const int T = p.pair_m_tiles * g.ntn;
         for (int tile = pidx; tile < T; tile += npairs, ++gt) {
-          const int pm = tile / ntn, j = tile - pm * ntn;
-          const int m_tile = 2 * pm + static_cast<int>(rank);
+          const int pm = tile / g.ntn, j = tile - pm * g.ntn;
+          const int g_row = (2 * pm + static_cast<int>(rank)) * 128;             // first latent of this CTA's half tile
           const uint32_t b = gt & 1u;
           const uint32_t tbase = tmem_row + b * 256;
-          const long long m = static_cast<long long>(m_tile) * 128 + row;        // latent index
-          const bool valid = m < p.n;
           // The tile's bias slice -> shared memory, off the critical path (the producer's gpu-scope
           // acquires invalidate L1, so reading it from global after the accumulator wait costs an L2
-          // round trip per load).  Double-buffered by tile parity; the barrier orders it for all warps.
+          // round trip per load).  Double-buffered by tile parity.  The barrier also orders the
+          // staging buffer: every bulk store of the previous tile has completed (its issuing thread
+          // waited for that before it got here).
           float* sb = sbias + (gt & 1u) * 256;
           if (static_cast<int>(threadIdx.x) < g.bn) sb[threadIdx.x] = bias[j * g.bn + threadIdx.x];
           named_bar_sync(1, kEpiThreads);
-          // first unit of this warp set: units u with ((u >> 1) & 1) == set
-          const int u_first = 2 * set;
-          float xv[2][16], nz[2][16];
-          if (l == 4) {
-            // state and noise of this thread's (at most two) units: loaded before the accumulator is waited for
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int u = u_first + i;
-              const int col = j * g.bn + u * 16;
-#pragma unroll
-              for (int e = 0; e < 16; ++e) { xv[i][e] = 0.f; nz[i][e] = 0.f; }
-              if (u < nu && valid) {
-                const float4* xs4 = reinterpret_cast<const float4*>(p.x + m * kDdpmLatent + col);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float4 v = xs4[e];
-                  xv[i][4 * e] = v.x; xv[i][4 * e + 1] = v.y; xv[i][4 * e + 2] = v.z; xv[i][4 * e + 3] = v.w;
-                }
-                if (t > 0 && p.noise != nullptr && p.eps_out == nullptr) {
-                  const float4* n4 = reinterpret_cast<const float4*>(
-                      p.noise + (static_cast<long long>(t) * p.n + m) * kDdpmLatent + col);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float4 v = __ldcs(n4 + e);
-                    nz[i][4 * e] = v.x; nz[i][4 * e + 1] = v.y; nz[i][4 * e + 2] = v.z; nz[i][4 * e + 3] = v.w;
-                  }
-                }
-              }
+          if (l == 4 && threadIdx.x == 0 && !p.eps_mode) {
+            // x and noise[t] of this half tile: two 32-column fp32 boxes each
+            const uint32_t xn = bars + 8 * kBarXn;
+            mbar_arrive_expect_tx(xn, (t > 0 ? 4u : 2u) * kChunk);
+            tma_load_2d(stg, &tm_x, j * 64, g_row, xn);
+            tma_load_2d(stg + kChunk, &tm_x, j * 64 + 32, g_row, xn);
+            if (t > 0) {
+              tma_load_3d(stg + 2 * kChunk, &tm_nz, j * 64, g_row, t, xn);
+              tma_load_3d(stg + 3 * kChunk, &tm_nz, j * 64 + 32, g_row, t, xn);
             }
           }
           if (!mbar_wait(bars + 8 * (kBarAccFull + b), (acc_phase >> b) & 1u, wd, kErrAccFull, b)) goto done;
@@ -365,15 +384,11 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             // hidden layer: + bias, ReLU, round to 16 bits -> swizzled operand image in the staging
             // buffer -> one TMA store per 64-feature chunk (set s owns chunks c = s, s + 2, ...)
             const int nch = g.bn >> 6;
-            const bool set_leader = (q == 0 && lane == 0);
-            if (set_leader) bulk_wait_group_read0();        // the previous tile's stores have finished reading the staging buffer
-            named_bar_sync(2 + set, kEpiThreads / 2);
             for (int c = set; c < nch; c += 2) {
               uint32_t v[2][32];
               tmem_ld32(tbase + c * 64, v[0]);
               tmem_ld32(tbase + c * 64 + 32, v[1]);
-              const int col = j * g.bn + c * 64;
-              const uint32_t srow = smem0 + o_stage + c * 16384u + row * 128u;
+              const uint32_t srow = stg + c * kChunk + row * 128u;
               tmem_ld_wait();
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
@@ -387,7 +402,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                  st_shared_v4(srow + (((4 * h + u) ^ (row & 7)) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                  st_shared_v4(srow + (((4 * h + u) ^ row7) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
               }
               if (c + 2 >= nch) {      // every column this warp owns has been read: hand the accumulator back
                 tc_fence_before();
@@ -397,17 +412,12 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               fence_proxy_async_smem();
               named_bar_sync(2 + set, kEpiThreads / 2);
               if (set_leader) {
-                if (c == 0 && threadIdx.x == 0) SDFB_TRACE(3);
-                tma_store_rows(&tm_act, (m_tile * 40 + g.o_chunk0 + (col >> 6)) * 128, smem0 + o_stage + c * 16384u);
+                if (c == 0) SDFB_TRACE(3);
+                tma_store_2d(&tm_act, g.o_col0 + j * g.bn + c * 64, g_row, stg + c * kChunk);
                 bulk_commit_group();
               }
             }
             if (threadIdx.x == 0) SDFB_TRACE(4);
-            if (set >= nch) {          // a set without a chunk (bn = 64) still owes its accumulator arrival
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1);
-            }
             if (set_leader) {          // stores complete -> arrive on the barrier of this latent group
               bulk_wait_group0();
               if (threadIdx.x == 0) SDFB_TRACE(5);
@@ -416,72 +426,76 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               if (threadIdx.x == 0) SDFB_TRACE(6);
             }
           } else {
-            // last layer: eps -> x0-clipped posterior-mean update (op for op as oracle/ddpm.py ddpm_step)
-            uint32_t v[2][16];
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-              if (u_first + i < nu) tmem_ld16(tbase + (u_first + i) * 16, v[i]);
+            // last layer (64 features per tile; set s owns columns [32 s, 32 s + 32)):
+            // eps -> x0-clipped posterior-mean update, op for op as oracle/ddpm.py ddpm_step
+            uint32_t v[32];
+            tmem_ld32(tbase + set * 32, v);
+            if (!p.eps_mode) {
+              if (!mbar_wait(bars + 8 * kBarXn, xn_phase, wd, kErrXn)) goto done;
+              xn_phase ^= 1u;
+            }
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1);
             if (threadIdx.x == 0) SDFB_TRACE(10);
+            const uint32_t xrow = stg + set * kChunk + row * 128u;             // this thread's 32 floats of x (swizzled 16-byte units)
+            const uint32_t nrow = xrow + 2 * kChunk;
+            const uint32_t hrow = stg + 4 * kChunk + row * 128u, lrow = hrow + kChunk;
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int u = u_first + i;
-              if (u >= nu) continue;
-              const int col = j * g.bn + u * 16;
-              float o[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const float eps = __uint_as_float(v[i][e]) + sb[u * 16 + e];
-                if (p.eps_out != nullptr) {
-                  o[e] = eps;
-                } else {
-                  float x0 = __fsub_rn(__fmul_rn(cf.x, xv[i][e]), __fmul_rn(cf.y, eps));
-                  x0 = fminf(fmaxf(x0, -1.f), 1.f);
-                  float r = __fadd_rn(__fmul_rn(cf.z, x0), __fmul_rn(cf.w, xv[i][e]));
-                  if (t > 0) r = __fadd_rn(r, __fmul_rn(sigma, nz[i][e]));
-                  o[e] = valid ? r : 0.f;
-                }
-              }
-              if (threadIdx.x == 0 && i == 0 && o[3] != 12345.f) SDFB_TRACE(11);
-              if (p.eps_out != nullptr) {
-                if (valid) {
-                  float4* dst = reinterpret_cast<float4*>(p.eps_out + m * kDdpmLatent + col);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
-                }
+            for (int u = 0; u < 8; ++u) {
+              const uint32_t off = (static_cast<uint32_t>(u) ^ row7) << 4;
+              const float4 bb = *reinterpret_cast<const float4*>(sb + set * 32 + 4 * u);
+              const float e0 = __uint_as_float(v[4 * u]) + bb.x, e1 = __uint_as_float(v[4 * u + 1]) + bb.y;
+              const float e2 = __uint_as_float(v[4 * u + 2]) + bb.z, e3 = __uint_as_float(v[4 * u + 3]) + bb.w;
+              float4 o;
+              if (p.eps_mode) {
+                o = make_float4(e0, e1, e2, e3);
               } else {
-                if (valid) {
-                  float4* dst = reinterpret_cast<float4*>(p.x + m * kDdpmLatent + col);
+                const float4 xv = ld_shared_f4(xrow + off);
+                float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t > 0) nz = ld_shared_f4(nrow + off);
+                const float ev[4] = {e0, e1, e2, e3};
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                const float ns[4] = {nz.x, nz.y, nz.z, nz.w};
+                float r[4];
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+                for (int e = 0; e < 4; ++e) {
+                  float x0 = __fsub_rn(__fmul_rn(cf.x, xs[e]), __fmul_rn(cf.y, ev[e]));
+                  x0 = fminf(fmaxf(x0, -1.f), 1.f);
+                  r[e] = __fadd_rn(__fmul_rn(cf.z, x0), __fmul_rn(cf.w, xs[e]));
+                  if (t > 0) r[e] = __fadd_rn(r[e], __fmul_rn(sigma, ns[e]));
                 }
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split2<FP16>(o[2 * e], o[2 * e + 1], hi[e], lo[e]);
-                const int chunk = col >> 6, unit = (col & 63) >> 3;
-                st_global_v4(image_ptr(p.act, m_tile, chunk, row, unit), hi[0], hi[1], hi[2], hi[3]);
-                st_global_v4(image_ptr(p.act, m_tile, chunk, row, unit + 1), hi[4], hi[5], hi[6], hi[7]);
-                st_global_v4(image_ptr(p.act, m_tile, 4 + chunk, row, unit), lo[0], lo[1], lo[2], lo[3]);
-                st_global_v4(image_ptr(p.act, m_tile, 4 + chunk, row, unit + 1), lo[4], lo[5], lo[6], lo[7]);
+                o = make_float4(r[0], r[1], r[2], r[3]);
+                split2<FP16>(r[0], r[1], hi[2 * (u & 1)], lo[2 * (u & 1)]);
+                split2<FP16>(r[2], r[3], hi[2 * (u & 1) + 1], lo[2 * (u & 1) + 1]);
+                if (u & 1) {   // 8 values = one 16-byte unit of the x_hi / x_lo operand images
+                  const uint32_t hoff = ((static_cast<uint32_t>(4 * set + (u >> 1))) ^ row7) << 4;
+                  st_shared_v4(hrow + hoff, hi[0], hi[1], hi[2], hi[3]);
+                  st_shared_v4(lrow + hoff, lo[0], lo[1], lo[2], lo[3]);
+                }
               }
-              if (threadIdx.x == 0 && i == 0) SDFB_TRACE(12);
+              st_shared_f4(xrow + off, o);                                      // in place (eps_mode: the eps tile)
             }
-          }
-          if (l == 4) {
-            // generic stores: the barrier orders every thread's stores before the set leader, whose single
-            // gpu-scope fence + release then publishes them (a fence per thread serialises: 8 warps x ~1.2k cycles)
-            if (threadIdx.x == 0) SDFB_TRACE(4);
-            named_bar_sync(2 + set, kEpiThreads / 2);
-            if (threadIdx.x == 0) SDFB_TRACE(5);
-            if (q == 0 && lane == 0) {
-              __threadfence();
+            if (threadIdx.x == 0) SDFB_TRACE(11);
+            fence_proxy_async_smem();
+            named_bar_sync(1, kEpiThreads);
+            if (threadIdx.x == 0) {
+              tma_store_2d(&tm_x, j * 64, g_row, stg);                          // rows >= n are clipped by the TMA unit
+              tma_store_2d(&tm_x, j * 64 + 32, g_row, stg + kChunk);
+              if (!p.eps_mode) {
+                tma_store_2d(&tm_act, j * 64, g_row, stg + 4 * kChunk);
+                tma_store_2d(&tm_act, 256 + j * 64, g_row, stg + 5 * kChunk);
+              }
+              bulk_commit_group();
+              SDFB_TRACE(4);
+              bulk_wait_group0();
+              SDFB_TRACE(5);
               fence_proxy_async_global();
-              red_release_gpu_add(p.counter + pm, 1u);
+              red_release_gpu_add(p.counter + pm, 2u);                          // both warp sets' worth
+              SDFB_TRACE(6);
             }
-            if (threadIdx.x == 0) SDFB_TRACE(6);
           }
         }
       }
@@ -492,9 +506,8 @@ done:
     const int role = warp == 0 ? 0 : warp - 7;            // 0 epilogue, 1 producer, 2 MMA issuer
     long long* dst = p.prof + (static_cast<long long>(blockIdx.x) * 3 + role) * 8;
 #pragma unroll
-    for (int i = 1; i < 7; ++i) dst[i] = waited[i];
+    for (int i = 1; i < 8; ++i) dst[i] = waited[i];
     dst[0] = clock64() - t_start;
-    dst[7] = 0;
   }
   tc_fence_before();
   __syncthreads();
@@ -506,11 +519,11 @@ done:
   }
 }
 
-// x fp32 -> [x_hi | x_lo] operand images (chunks 0..7 of every tile); rows >= n are zero.
+// x fp32 -> [x_hi | x_lo] columns (0..511) of the row-major activation buffer; rows >= n are zero.
 template <bool FP16>
-__global__ void ddpm_split_kernel(const float* __restrict__ x, int n, int m_tiles, uint8_t* __restrict__ act) {
+__global__ void ddpm_split_kernel(const float* __restrict__ x, int n, int n_pad, uint16_t* __restrict__ act) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // (row, 8-column unit)
-  const long long total = static_cast<long long>(m_tiles) * 128 * 32;
+  const long long total = static_cast<long long>(n_pad) * 32;
   if (i >= total) return;
   const long long m = i >> 5;
   const int u8 = static_cast<int>(i & 31);
@@ -523,10 +536,9 @@ __global__ void ddpm_split_kernel(const float* __restrict__ x, int n, int m_tile
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) split2<FP16>(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-  const int m_tile = static_cast<int>(m >> 7), row = static_cast<int>(m & 127);
-  const int chunk = u8 >> 3, unit = u8 & 7;
-  st_global_v4(image_ptr(act, m_tile, chunk, row, unit), hi[0], hi[1], hi[2], hi[3]);
-  st_global_v4(image_ptr(act, m_tile, 4 + chunk, row, unit), lo[0], lo[1], lo[2], lo[3]);
+  uint16_t* rowp = act + m * kDdpmActCols + u8 * 8;
+  *reinterpret_cast<uint4*>(rowp) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(rowp + 256) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -534,50 +546,47 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 uint32_t smem_bytes_for(int bn_h, int nstages) {
-  return static_cast<uint32_t>(nstages) * (16384u + static_cast<uint32_t>(bn_h) * 64u) + static_cast<uint32_t>(bn_h) * 256u +
-         kNumBars * 8 + 16 + 2048;
+  return static_cast<uint32_t>(nstages) * (kChunk + static_cast<uint32_t>(bn_h) * 64u) + kStagingBytes + kBarBytes + 16 + 2048;
 }
 
 }  // namespace
 
 cudaError_t ddpm_step_init() {
-  const int max_smem = 5 * 32768 + 65536 + kNumBars * 8 + 16 + 2048;     // bn_h = 256: 5 stages + 64 KiB staging (the largest configuration)
+  const int max_smem = static_cast<int>(smem_bytes_for(256, 4));   // = smem_bytes_for(128, 5) + 8 KiB: the largest configuration
   cudaError_t e = cudaFuncSetAttribute(ddpm_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(ddpm_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  if (e != cudaSuccess) return e;
-  return cudaSuccess;
+  return cudaFuncSetAttribute(ddpm_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
 }
 
-cudaError_t make_rows_tensor_map(const void* base, unsigned long long rows, unsigned box_rows, void* tmap_out) {
+cudaError_t make_tensor_map(void* tmap_out, const void* base, int elem_bytes, int rank, const unsigned long long* dims,
+                            const unsigned long long* strides_bytes, const unsigned* box, bool swizzle128) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess) return e;
   if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
-  const cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstride[1] = {128};
-  const cuuint32_t box[2] = {64u, box_rows};
-  const cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(static_cast<CUtensorMap*>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
-                                                   const_cast<void*>(base), gdim, gstride, box, estr,
-                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  cuuint64_t gdim[3], gstride[2];
+  cuuint32_t bx[3], estr[3] = {1u, 1u, 1u};
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides_bytes[i];
+  CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(
+      static_cast<CUtensorMap*>(tmap_out), elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16,
+      static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstride, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-cudaError_t launch_ddpm_split(const float* x, int n, int m_tiles, uint8_t* act, bool fp16, cudaStream_t stream) {
-  const long long total = static_cast<long long>(m_tiles) * 128 * 32;
+cudaError_t launch_ddpm_split(const float* x, int n, int n_pad, uint16_t* act, bool fp16, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n_pad) * 32;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  if (fp16) ddpm_split_kernel<true><<<blocks, 256, 0, stream>>>(x, n, m_tiles, act);
-  else ddpm_split_kernel<false><<<blocks, 256, 0, stream>>>(x, n, m_tiles, act);
+  if (fp16) ddpm_split_kernel<true><<<blocks, 256, 0, stream>>>(x, n, n_pad, act);
+  else ddpm_split_kernel<false><<<blocks, 256, 0, stream>>>(x, n, n_pad, act);
   return cudaGetLastError();
 }
 
-cudaError_t launch_ddpm_sample(const DdpmParams& p, const void* tm_act, const void* tm_wh, const void* tm_wo,
-                               bool fp16, int num_sms, cudaStream_t stream) {
-  const int ntn = kDdpmHid / p.bn_h;
-  const int T = p.pair_m_tiles * ntn;
+cudaError_t launch_ddpm_sample(const DdpmParams& p, const DdpmMaps& maps, bool fp16, int num_sms, cudaStream_t stream) {
+  const int T = p.pair_m_tiles * (kDdpmHid / p.bn_h);       // pair tiles of a hidden layer (>= those of the last layer)
   const int max_pairs = num_sms / 2;
   const int pairs = T < max_pairs ? T : max_pairs;
   cudaLaunchConfig_t cfg{};
@@ -594,11 +603,13 @@ cudaError_t launch_ddpm_sample(const DdpmParams& p, const void* tm_act, const vo
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  const CUtensorMap* a = static_cast<const CUtensorMap*>(tm_act);
-  const CUtensorMap* wh = static_cast<const CUtensorMap*>(tm_wh);
-  const CUtensorMap* wo = static_cast<const CUtensorMap*>(tm_wo);
-  if (fp16) return cudaLaunchKernelEx(&cfg, ddpm_sample_kernel<true>, p, *a, *wh, *wo);
-  return cudaLaunchKernelEx(&cfg, ddpm_sample_kernel<false>, p, *a, *wh, *wo);
+  const CUtensorMap* a = reinterpret_cast<const CUtensorMap*>(maps.act);
+  const CUtensorMap* wh = reinterpret_cast<const CUtensorMap*>(maps.wh);
+  const CUtensorMap* wo = reinterpret_cast<const CUtensorMap*>(maps.wo);
+  const CUtensorMap* x = reinterpret_cast<const CUtensorMap*>(maps.x);
+  const CUtensorMap* nz = reinterpret_cast<const CUtensorMap*>(maps.nz);
+  if (fp16) return cudaLaunchKernelEx(&cfg, ddpm_sample_kernel<true>, p, *a, *wh, *wo, *x, *nz);
+  return cudaLaunchKernelEx(&cfg, ddpm_sample_kernel<false>, p, *a, *wh, *wo, *x, *nz);
 }
 
 }  // namespace sdfb

@@ -90,49 +90,54 @@ cudaError_t launch_fold_latent(const float* W0, const float* b0, const float* W4
 //
 // One persistent cooperative kernel runs `steps` denoiser evaluations + posterior updates.
 // Every layer is cut into pair tiles (256 latents x BN output features, cta_group::2) spread
-// over all CTA pairs; layers are separated by a grid-wide barrier.  Operands live in two
-// device allocations addressed as [rows][64] 16-bit matrices whose 128-byte rows are stored
-// pre-swizzled (16-byte unit u of row r at position u ^ (r & 7)), so a TMA box of R rows
-// lands an MMA-ready K-major operand:
-//   weights     : layer 0: 4 k-chunks x 1024 rows (the latent half of W0; the [x_hi | x_lo]
-//                 operand reuses chunk k & 3), layers 1-3: 16 x 1024 rows each, layer 4: 16 x 256
-//   activations : per 128-row tile m: [x_hi | x_lo] 8 chunks x 128 rows, then two ping-pong
-//                 hidden buffers of 16 chunks x 128 rows
+// over all CTA pairs; a tile waits only for the CTAs that share its 256 latents.
+//   weights     : [rows][64] 16-bit, 128-byte rows stored PRE-SWIZZLED (16-byte unit u of row r
+//                 at u ^ (r & 7)) so an un-swizzled TMA box lands an MMA-ready K-major operand:
+//                 layer 0: 4 k-chunks x 1024 rows (the latent half of W0; the [x_hi | x_lo] operand
+//                 reuses chunk k & 3), layers 1-3: 16 x 1024 rows each, layer 4: 16 x 256 rows
+//   activations : row-major [n_pad][kDdpmActCols] 16-bit: [x_hi | x_lo] (512), hidden buffer 0
+//                 (1024), hidden buffer 1 (1024); moved with 128B-swizzling TMA boxes of 64 x 128
 constexpr int kDdpmW0Rows = 4 * 1024;
 constexpr int kDdpmWHidRows = 16 * 1024;
 constexpr int kDdpmW4Rows = 16 * 256;
 constexpr int kDdpmWRows = kDdpmW0Rows + 3 * kDdpmWHidRows + kDdpmW4Rows;   // 57,344 rows of 128 B = 7 MiB
-constexpr int kDdpmMaxStages = 8;
+constexpr int kDdpmMaxStages = 6;
+constexpr int kDdpmActCols = 512 + 1024 + 1024;
+constexpr int kDdpmOutTile = 64;          // output-layer tile width (fixed)
 
 struct DdpmParams {
   const float* tb0;        // [1000][1024]: b0 + W0[:, 256:] temb(t)
   const float* bias;       // [3][1024] (layers 1-3) then [256] (layer 4)
   const float* coef;       // [1000][8]: sra, srm1, c1, c2, sigma
-  float* x;                // [n][256] fp32 state: x_T in, x_0 out
-  const float* noise;      // [..][n][256]; row t is consumed at step t (may be null when steps == 1)
-  float* eps_out;          // denoise mode: eps_hat [n][256] is written instead of the update
-  uint8_t* act;            // activation allocation (see above)
+  int eps_mode;            // 1: a single denoiser evaluation, eps_hat is stored through tm_x (no update)
   int n;
   int pair_m_tiles;        // ceil(n / 256)
   int steps;               // steps to run: t = t_first, t_first - 1, ...
   int t_first;
-  int bn_h, bn_o;          // output-tile widths of the hidden layers and of the last layer (bn_o = bn_h / 4)
+  int bn_h;                // output-tile width of the hidden layers (256 or 128)
   int nstages;
   unsigned int* counter;   // [pair_m_tiles] barrier counters, one per group of pair tiles that share 256 latents (zeroed before the launch)
   unsigned int* status;
   unsigned long long timeout_ns;
-  long long* prof;         // optional [grid][3 roles][8]: blocked cycles per wait class (diagnostics)
+  long long* prof;         // optional diagnostics: [148][3 roles][8] blocked cycles per wait class + an event trace
+};
+
+// the five tensor maps of a launch (128 B each, 64-byte aligned)
+struct DdpmMaps {
+  alignas(64) unsigned char act[128];   // activations, 16-bit, box 64 x 128, SWIZZLE_128B
+  alignas(64) unsigned char wh[128];    // weights, box 64 x bn_h / 2, no swizzle
+  alignas(64) unsigned char wo[128];    // weights, box 64 x 32
+  alignas(64) unsigned char x[128];     // fp32 state [n][256] (eps_mode: the eps output), box 32 x 128, SWIZZLE_128B
+  alignas(64) unsigned char nz[128];    // fp32 noise [steps][n][256], box 32 x 128 x 1, SWIZZLE_128B
 };
 
 cudaError_t ddpm_step_init();
-// tensor maps over the weight allocation (box = 64 x box_rows) and the activation allocation (box = 64 x 128)
-cudaError_t make_rows_tensor_map(const void* base, unsigned long long rows, unsigned box_rows, void* tmap_out);
-// x [n][256] fp32 -> [x_hi | x_lo] operand images of every 128-row tile (rows >= n zero)
-cudaError_t launch_ddpm_split(const float* x, int n, int m_tiles, uint8_t* act, bool fp16, cudaStream_t stream);
-cudaError_t launch_ddpm_sample(const DdpmParams& p, const void* tm_act, const void* tm_wh, const void* tm_wo,
-                               bool fp16, int num_sms, cudaStream_t stream);
-// bytes of activation allocation per 128-row tile
-constexpr long long kDdpmActTileBytes = (8 + 16 + 16) * 128LL * 128;
+// generic tiled tensor map: `rank` dims (innermost first), strides in bytes for dims 1.., elem_bytes 2 or 4
+cudaError_t make_tensor_map(void* tmap_out, const void* base, int elem_bytes, int rank, const unsigned long long* dims,
+                            const unsigned long long* strides_bytes, const unsigned* box, bool swizzle128);
+// x [n][256] fp32 -> [x_hi | x_lo] columns of the activation buffer (rows >= n zero)
+cudaError_t launch_ddpm_split(const float* x, int n, int n_pad, uint16_t* act, bool fp16, cudaStream_t stream);
+cudaError_t launch_ddpm_sample(const DdpmParams& p, const DdpmMaps& maps, bool fp16, int num_sms, cudaStream_t stream);
 
 // ---- fp32 SIMT kernels (fp32_kernels.cu) -----------------------------------
 // C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); row-major, leading dims in elements.

@@ -60,7 +60,7 @@ def _stats(d):
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
-@pytest.mark.parametrize("n,bn", [(37, 0), (300, 256), (300, 128), (1280, 64)])
+@pytest.mark.parametrize("n,bn", [(37, 0), (300, 256), (300, 128), (2400, 128)])
 def test_denoiser_single_step_tensor_core(cuda_ddpm, monkeypatch, prec, n, bn):
     """One denoiser evaluation; ragged n, every tile width, and more pair tiles than CTA pairs."""
     if bn:
@@ -96,7 +96,7 @@ def test_sample_latents_tensor_core_golden(cuda_ddpm, golden, prec):
     assert np.array_equal(xh, x)            # deterministic, and the host entry point is the same path
 
 
-@pytest.mark.parametrize("n,bn,steps", [(300, 256, 12), (1280, 64, 6), (515, 0, 12)])
+@pytest.mark.parametrize("n,bn,steps", [(300, 256, 12), (2400, 128, 6), (515, 0, 12)])
 def test_sample_latents_tensor_core_short_runs(cuda_ddpm, monkeypatch, n, bn, steps):
     if bn:
         monkeypatch.setenv("SDFB_DDPM_BN", str(bn))
