@@ -721,6 +721,10 @@ static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps,
   p.n = n; p.pair_m_tiles = m_pairs; p.steps = steps; p.t_first = t_first;
   p.bn_h = bn_h;
   p.nstages = bn_h == 256 ? 4 : 5;   // 4 x 32 KiB or 5 x 24 KiB of operand ring + 96 KiB of epilogue staging
+  if (const char* e = std::getenv("SDFB_DDPM_STAGES")) {   // diagnostics: a shallower ring (leaves shared memory to a profiler)
+    const int v = std::atoi(e);
+    if (v >= 2 && v < p.nstages) p.nstages = v;
+  }
   p.counter = d->counter; p.status = d->status; p.timeout_ns = d->timeout_ns; p.prof = d->prof;
   DdpmMaps maps;
   {

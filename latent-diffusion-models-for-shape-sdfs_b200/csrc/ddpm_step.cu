@@ -26,6 +26,8 @@
 //   warps 0-7  epilogue   (TMEM lane quadrant = warp & 3; the two warp sets split the columns)
 //   warp 8     producer   (TMA; completion counted on the LEADER's barrier)
 //   warp 9     MMA issuer (leader CTA only) + TMEM allocation (both CTAs)
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -588,7 +590,8 @@ cudaError_t launch_ddpm_split(const float* x, int n, int n_pad, uint16_t* act, b
 cudaError_t launch_ddpm_sample(const DdpmParams& p, const DdpmMaps& maps, bool fp16, int num_sms, cudaStream_t stream) {
   const int T = p.pair_m_tiles * (kDdpmHid / p.bn_h);       // pair tiles of a hidden layer (>= those of the last layer)
   const int max_pairs = num_sms / 2;
-  const int pairs = T < max_pairs ? T : max_pairs;
+  const int rounds = (T + max_pairs - 1) / max_pairs;       // tiles per pair and layer
+  const int pairs = (T + rounds - 1) / rounds;              // balanced: no pair gets more than `rounds`, few get less
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
   cfg.blockDim = dim3(kThreads);
@@ -602,7 +605,9 @@ cudaError_t launch_ddpm_sample(const DdpmParams& p, const DdpmMaps& maps, bool f
   attr[1].id = cudaLaunchAttributeCooperative;           // every CTA must be resident: they wait on one another
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 2;
+  // SDFB_DDPM_NO_COOP=1 (profiling only): drop the co-residency guarantee - ncu cannot launch a cooperative
+  // cluster kernel; on an otherwise idle GPU the grid (<= 1 CTA per SM) is resident anyway.
+  cfg.numAttrs = std::getenv("SDFB_DDPM_NO_COOP") != nullptr ? 1 : 2;
   const CUtensorMap* a = reinterpret_cast<const CUtensorMap*>(maps.act);
   const CUtensorMap* wh = reinterpret_cast<const CUtensorMap*>(maps.wh);
   const CUtensorMap* wo = reinterpret_cast<const CUtensorMap*>(maps.wo);
