@@ -726,6 +726,7 @@ static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps,
     if (v >= 2 && v < p.nstages) p.nstages = v;
   }
   p.counter = d->counter; p.status = d->status; p.timeout_ns = d->timeout_ns; p.prof = d->prof;
+  if (const char* e = std::getenv("SDFB_DDPM_FLAGS")) p.flags = static_cast<unsigned int>(std::strtoul(e, nullptr, 0));
   DdpmMaps maps;
   {
     const unsigned long long a_dims[2] = {kDdpmActCols, static_cast<unsigned long long>(d->act_rows)};

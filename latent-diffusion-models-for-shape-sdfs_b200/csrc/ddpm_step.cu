@@ -51,12 +51,13 @@ constexpr int kBarEmpty = kBarFull + kDdpmMaxStages;
 constexpr int kBarAccFull = kBarEmpty + kDdpmMaxStages;
 constexpr int kBarAccEmpty = kBarAccFull + 2;
 constexpr int kBarXn = kBarAccEmpty + 2;
-constexpr int kNumBars = kBarXn + 1;
+constexpr int kBarOwn = kBarXn + 1;          // staging slot s holds a finished operand chunk (6 slots)
+constexpr int kNumBars = kBarOwn + 6;
 constexpr uint32_t kBarBytes = (kNumBars * 8 + 15) & ~15u;   // keeps what follows 16-byte aligned
 
 // wait sites (status codes); (site >> 4) & 7 is the class under which blocked cycles are profiled
 enum : uint32_t { kErrFull = 0x110, kErrEmpty = 0x120, kErrAccFull = 0x130, kErrAccEmpty = 0x140, kErrGrid = 0x150,
-                  kErrFullFirst = 0x160, kErrXn = 0x170 };
+                  kErrFullFirst = 0x160, kErrXn = 0x170, kErrOwn = 0x180 };
 
 // Diagnostics: with profiling on, CTA 0 stamps clock64() at key events of every layer of step 5 (and
 // of layer 0 of step 6, row 5) into the tail of the profile buffer ([148 * 24 + row * 16 + event]).
@@ -88,10 +89,40 @@ __device__ __forceinline__ Geo layer_geo(const DdpmParams& p, int l) {
   return g;
 }
 
+// Own chunks.  With one tile per pair and layer, the k-chunks a pair produced in the previous layer are
+// still in its staging buffer in operand layout: the next layer starts on them at once (weights come
+// through the ring, A straight from staging) while the peers' chunks travel through L2.
+//   layers 1-3: the bn_h / 64 chunks [j bn_h / 64, ...) in staging slots 0..   (L4 reuses those slots for x / noise: no own chunks)
+//   layer 0   : x_hi chunk j and x_lo chunk 4 + j in slots 4, 5 (needs the same tile index in L4 and L0: bn_h = 256)
+struct Own { int n, kc0, kstride, slot0; };
+__device__ __forceinline__ Own own_chunks(const DdpmParams& p, int s, int l, int j, bool single_round) {
+  Own o{0, 0, 1, 0};
+  if (!single_round) return o;
+  if (l == 0) {
+    if (s > 0 && p.bn_h == 256) { o.n = 2; o.kc0 = j; o.kstride = 4; o.slot0 = 4; }
+  } else if (l < 4) {
+    o.n = p.bn_h >> 6; o.kc0 = j * o.n; o.slot0 = 0;
+  }
+  return o;
+}
+// i-th k-chunk of a tile: own chunks first, then the rest in increasing order
+__device__ __forceinline__ int kc_of(const Own& o, int i) {
+  if (i < o.n) return o.kc0 + i * o.kstride;
+  int idx = i - o.n;
+  if (o.n == 0) return idx;
+  if (o.kstride == 1) return idx < o.kc0 ? idx : idx + o.n;
+  if (idx >= o.kc0) ++idx;
+  if (idx >= o.kc0 + o.kstride) ++idx;
+  return idx;
+}
+
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void red_relaxed_gpu_add(unsigned int* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -219,6 +250,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
       mbar_init(bars + 8 * (kBarAccEmpty + b), 2 * kEpiWarps);
     }
     mbar_init(bars + 8 * kBarXn, 1);
+    for (int c = 0; c < 6; ++c) mbar_init(bars + 8 * (kBarOwn + c), c < 4 ? kEpiWarps : 2 * kEpiWarps);   // one warp set | both, x 2 CTAs
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -247,42 +279,55 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
           const bool need_sync = !(s == 0 && l == 0);      // the operand of the very first layer was written by an earlier kernel
           const uint32_t target = static_cast<uint32_t>(s) * arr_step + static_cast<uint32_t>(l) * arr_h;
           const int T = p.pair_m_tiles * g.ntn;
+          const bool single_round = p.pair_m_tiles * (kDdpmHid / p.bn_h) <= npairs;
           for (int tile = pidx; tile < T; tile += npairs) {
             const int pm = tile / g.ntn, j = tile - pm * g.ntn;
             const int a_row = (2 * pm + static_cast<int>(rank)) * 128;
             const int w_row = g.w_row0 + j * g.bn + static_cast<int>(rank) * (g.bn >> 1);
-            int kc = 0;
+            const Own o = own_chunks(p, s, l, j, single_round);
+            int i = 0;
+            // own chunks: only their weights travel
+            for (; i < o.n; ++i) {
+              if (!mbar_wait(bars + 8 * (kBarEmpty + stage), phase ^ 1u, wd, kErrEmpty, stage)) goto done;
+              const uint32_t full = bars + 8 * (kBarFull + stage);
+              if (leader) mbar_arrive_expect_tx(full, static_cast<uint32_t>(g.bn) * 128u);
+              const int kc = kc_of(o, i), wk = l == 0 ? (kc & 3) : kc;
+              tma_load_2d_pair(smem0 + stage * stage_bytes + kChunk, tmw, 0, w_row + wk * g.n_total, map_to_cta(full, 0));
+              if (++stage == nst) { stage = 0; phase ^= 1u; }
+            }
             if (need_sync) {
               // weights first (they do not depend on the previous layer), then the group barrier, then A
-              const int pre = g.nk < static_cast<int>(nst) ? g.nk : static_cast<int>(nst);
+              const int rest = g.nk - o.n;
+              const int pre = rest < static_cast<int>(nst) ? rest : static_cast<int>(nst);
               uint32_t st = stage, ph = phase;
-              for (int i = 0; i < pre; ++i) {
+              for (int k = 0; k < pre; ++k) {
                 if (!mbar_wait(bars + 8 * (kBarEmpty + st), ph ^ 1u, wd, kErrEmpty, st)) goto done;
                 const uint32_t full = bars + 8 * (kBarFull + st);
                 if (leader) mbar_arrive_expect_tx(full, tx);
-                const int wk = l == 0 ? (i & 3) : i;
+                const int kc = kc_of(o, i + k), wk = l == 0 ? (kc & 3) : kc;
                 tma_load_2d_pair(smem0 + st * stage_bytes + kChunk, tmw, 0, w_row + wk * g.n_total, map_to_cta(full, 0));
                 if (++st == nst) { st = 0; ph ^= 1u; }
               }
               SDFB_TRACE(7);
               if (!grid_wait(p, p.counter + pm, target, wd)) goto done;
               SDFB_TRACE(8);
-              fence_proxy_async_global();
+              if (!(p.flags & 1u)) fence_proxy_async_global();
               st = stage;
-              for (int i = 0; i < pre; ++i) {
-                tma_load_2d_pair(smem0 + st * stage_bytes, &tm_act, g.a_col0 + i * 64, a_row, map_to_cta(bars + 8 * (kBarFull + st), 0));
+              for (int k = 0; k < pre; ++k) {
+                tma_load_2d_pair(smem0 + st * stage_bytes, &tm_act, g.a_col0 + kc_of(o, i + k) * 64, a_row,
+                                 map_to_cta(bars + 8 * (kBarFull + st), 0));
                 if (++st == nst) st = 0;
               }
               SDFB_TRACE(9);
               stage = st;
               phase = ph;
-              kc = pre;
+              i += pre;
             }
-            for (; kc < g.nk; ++kc) {
+            for (; i < g.nk; ++i) {
               if (!mbar_wait(bars + 8 * (kBarEmpty + stage), phase ^ 1u, wd, kErrEmpty, stage)) goto done;
               const uint32_t full = bars + 8 * (kBarFull + stage);
               if (leader) mbar_arrive_expect_tx(full, tx);
-              const int wk = l == 0 ? (kc & 3) : kc;
+              const int kc = kc_of(o, i), wk = l == 0 ? (kc & 3) : kc;
               const uint32_t full_l = map_to_cta(full, 0);
               tma_load_2d_pair(smem0 + stage * stage_bytes + kChunk, tmw, 0, w_row + wk * g.n_total, full_l);
               tma_load_2d_pair(smem0 + stage * stage_bytes, &tm_act, g.a_col0 + kc * 64, a_row, full_l);
@@ -299,25 +344,41 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
       const uint32_t idesc_o = umma_idesc(256, kDdpmOutTile, FP16 ? 0 : 1);
       const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
       const uint32_t nst = static_cast<uint32_t>(p.nstages);
-      uint32_t stage = 0, phase = 0, ephase = 0, gt = 0, prev_stage = 0;
+      uint32_t stage = 0, phase = 0, ephase = 0, gt = 0, prev_stage = 0, own_phase = 0, own_pending = 0;
+      const bool single_round = p.pair_m_tiles * (kDdpmHid / p.bn_h) <= npairs;
+      const uint32_t stg_lo = ((smem0 + o_stage) & 0x3FFFFu) >> 4;
       for (int s = 0; s < p.steps; ++s) {
         for (int l = 0; l < kLayers; ++l) {
           const int nk = l == 0 ? 8 : 16;
           const uint32_t idesc = l == 4 ? idesc_o : idesc_h;
-          const int T = p.pair_m_tiles * (l == 4 ? kDdpmLatent / kDdpmOutTile : kDdpmHid / p.bn_h);
+          const int ntn = l == 4 ? kDdpmLatent / kDdpmOutTile : kDdpmHid / p.bn_h;
+          const int T = p.pair_m_tiles * ntn;
+          // staging slots this pair's epilogue fills in this layer (one barrier phase each per tile)
+          const uint32_t my_slots = l == 4 ? (p.eps_mode ? 0u : 0x30u) : ((1u << (p.bn_h >> 6)) - 1u);
+          bool had_tile = false;
           for (int tile = pidx; tile < T; tile += npairs, ++gt) {
+            had_tile = true;
             const uint32_t b = gt & 1u;
             const uint32_t d_tmem = tmem_base + b * 256;
+            const Own o = own_chunks(p, s, l, tile % ntn, single_round);
             if (!mbar_wait(bars + 8 * (kBarAccEmpty + b), ((ephase >> b) & 1u) ^ 1u, wd, kErrAccEmpty, b)) goto done;
             ephase ^= 1u << b;
 #pragma unroll 1
             for (int k = 0; k < nk; ++k) {
+              uint32_t a_lo;
+              if (k < o.n) {   // own chunk: A from the staging buffer, as soon as both CTAs' epilogues have finished it
+                const uint32_t slot = static_cast<uint32_t>(o.slot0 + k);
+                if (!mbar_wait(bars + 8 * (kBarOwn + slot), (own_phase >> slot) & 1u, wd, kErrOwn, slot)) goto done;
+                a_lo = (stg_lo + slot * (kChunk >> 4)) | (1u << 16);
+              } else {
+                a_lo = (((smem0 + stage * stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+              }
               if (!mbar_wait(bars + 8 * (kBarFull + stage), phase, wd, k == 0 ? kErrFullFirst : kErrFull, stage)) goto done;
               tc_fence_after();
               if (k == 0 && lane == 0) SDFB_TRACE(0);
-              const uint32_t a_lo = (((smem0 + stage * stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+              const uint32_t b_lo = ((((smem0 + stage * stage_bytes) & 0x3FFFFu) >> 4) + (kChunk >> 4)) | (1u << 16);
               const uint64_t adesc = desc_hi | a_lo;
-              const uint64_t bdesc = desc_hi | (a_lo + (kChunk >> 4));
+              const uint64_t bdesc = desc_hi | b_lo;
               if (elect_one()) {
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) umma_ss<2>(d_tmem, adesc + 2 * jj, bdesc + 2 * jj, idesc, (k | jj) != 0 ? 1u : 0u);
@@ -333,6 +394,10 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               if (++stage == nst) { stage = 0; phase ^= 1u; }
             }
           }
+          // (single-round launches: at most one tile per pair and layer.)  The phases the previous layer's
+          // epilogue completed are behind us now, whether or not they were waited for.
+          own_phase ^= own_pending;
+          own_pending = had_tile ? my_slots : 0u;
         }
       }
     }
@@ -412,6 +477,8 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
                 if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1);
               }
               fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) arrive_on_leader(bars + 8 * (kBarOwn + c), 1);     // the pair's next layer may start on this chunk
               named_bar_sync(2 + set, kEpiThreads / 2);
               if (set_leader) {
                 if (c == 0) SDFB_TRACE(3);
@@ -423,8 +490,12 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             if (set_leader) {          // stores complete -> arrive on the barrier of this latent group
               bulk_wait_group0();
               if (threadIdx.x == 0) SDFB_TRACE(5);
-              fence_proxy_async_global();
-              red_release_gpu_add(p.counter + pm, 1u);
+              if (p.flags & 2u) {
+                red_relaxed_gpu_add(p.counter + pm, 1u);
+              } else {
+                fence_proxy_async_global();
+                red_release_gpu_add(p.counter + pm, 1u);
+              }
               if (threadIdx.x == 0) SDFB_TRACE(6);
             }
           } else {
@@ -482,6 +553,11 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             }
             if (threadIdx.x == 0) SDFB_TRACE(11);
             fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !p.eps_mode) {   // x_hi / x_lo chunks of this tile: own chunks of the next step's layer 0
+              arrive_on_leader(bars + 8 * (kBarOwn + 4), 1);
+              arrive_on_leader(bars + 8 * (kBarOwn + 5), 1);
+            }
             named_bar_sync(1, kEpiThreads);
             if (threadIdx.x == 0) {
               tma_store_2d(&tm_x, j * 64, g_row, stg);                          // rows >= n are clipped by the TMA unit
@@ -494,8 +570,12 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               SDFB_TRACE(4);
               bulk_wait_group0();
               SDFB_TRACE(5);
-              fence_proxy_async_global();
-              red_release_gpu_add(p.counter + pm, 2u);                          // both warp sets' worth
+              if (p.flags & 2u) {
+                red_relaxed_gpu_add(p.counter + pm, 2u);
+              } else {
+                fence_proxy_async_global();
+                red_release_gpu_add(p.counter + pm, 2u);                        // both warp sets' worth
+              }
               SDFB_TRACE(6);
             }
           }

@@ -116,6 +116,7 @@ struct DdpmParams {
   int t_first;
   int bn_h;                // output-tile width of the hidden layers (256 or 128)
   int nstages;
+  unsigned int flags;      // experiments: bit0 no consumer-side proxy fence, bit1 relaxed (not release) barrier arrival
   unsigned int* counter;   // [pair_m_tiles] barrier counters, one per group of pair tiles that share 256 latents (zeroed before the launch)
   unsigned int* status;
   unsigned long long timeout_ns;

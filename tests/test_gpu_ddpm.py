@@ -110,10 +110,12 @@ def test_sample_latents_tensor_core_short_runs(cuda_ddpm, monkeypatch, n, bn, st
     assert np.array_equal(x, x2)
 
 
-def test_sample_latents_full_batch_properties(cuda_ddpm):
+def test_sample_latents_full_batch_properties(cuda_ddpm, monkeypatch):
     """BASELINE configs[3] batch size (4096 latents), 1000 steps, device-generated noise:
     finite, clipped range, rows independent of batch composition (a latent's trajectory does not
-    depend on which tile it sits in)."""
+    depend on which tile it sits in; the tile width is pinned because it fixes the fp32 summation
+    order over K)."""
+    monkeypatch.setenv("SDFB_DDPM_BN", "256")
     g = torch.Generator(device="cuda").manual_seed(4)
     steps = 1000
     x_T = torch.randn((4096, 256), generator=g, device="cuda")
