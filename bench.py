@@ -287,19 +287,31 @@ def main():
                      "kernel": "ddpm_sample_kernel", "achieved_tflops": flop / (dd_ms_max * 1e-3) / 1e12,
                      "flop_per_latent_step": DDPM_FLOP_PER_LATENT_STEP, "gpu_launches_per_sampling": 2,
                      "x0_abs_max": float(x0.abs().max().item())}
-        if world == 1:
-            # end to end: host x_T + host noise stream in, host x_0 out (4.2 GB H2D inside the timed call)
-            xh = x_T.cpu().numpy()
-            nh = torch.empty((T, n_lat, 256), dtype=torch.float32).pin_memory()
-            nh.copy_(noise)
-            nh_np = nh.numpy()
-            sampler.sample_latents_host(xh, nh_np, steps=T)
-            t0 = time.perf_counter()
-            sampler.sample_latents_host(xh, nh_np, steps=T)
-            dt = time.perf_counter() - t0
-            ddpm_line["e2e"] = {"value": n_lat / dt, "unit": "latents/s", "h2d_bytes_per_step": int(nh_np.nbytes + xh.nbytes),
-                                "d2h_bytes_per_step": int(xh.nbytes), "api": "LatentDDPM.sample_latents_host -> sdfb_ddpm_sample_host"}
-            del nh, nh_np
+        # sample_latents(n) as the north star spells it - no stream argument: noise generated in the kernel
+        # (Philox4x32-10), device-timed, then end to end through the host-buffer call (x_0 [n,256] comes back)
+        sd_ms = []
+        for i in range(1 + 3):
+            barrier()
+            xs0 = sampler.sample_latents(n_lat, steps=T, seed=7 + rank)
+            if i:
+                sd_ms.append(sampler.last_kernel_ms())
+        sd = torch.tensor([statistics.mean(sd_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(sd, op=dist.ReduceOp.MAX)
+        ddpm_line["seeded"] = {"value": world * n_lat / (float(sd.item()) * 1e-3), "unit": "latents/s", "ms_per_sampling": float(sd.item()),
+                               "noise": "generated in the update epilogue (Philox4x32-10 + Box-Muller), no noise stream in memory",
+                               "x0_abs_max": float(xs0.abs().max().item())}
+        sampler.sample_latents_seeded_host(n_lat, 7 + rank, steps=T)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            xh = sampler.sample_latents_seeded_host(n_lat, 7 + rank, steps=T)
+        e2 = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+        ddpm_line["e2e"] = {"value": world * n_lat / float(e2.item()), "unit": "latents/s", "h2d_bytes_per_step": 0,
+                            "d2h_bytes_per_step": int(xh.nbytes),
+                            "api": "LatentDDPM.sample_latents_seeded_host -> sdfb_ddpm_sample_philox_host (x_T and noise generated on the device, x_0 returned to the host)"}
         del noise, sampler
 
     if rank == 0:

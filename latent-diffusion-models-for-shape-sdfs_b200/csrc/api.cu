@@ -152,6 +152,9 @@ struct sdfb_decoder {
   void* dstage = nullptr; size_t dstage_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  // *_host calls: compute and copy-out streams, one event per z-chunk (the D2H copy of a chunk overlaps the next chunk's kernel)
+  cudaStream_t st_compute = nullptr, st_copy = nullptr;
+  cudaEvent_t chunk_ev[17] = {};
   unsigned long long timeout_ns = 2000000000ull;
   unsigned int debug_flags = 0;
   long long* prof = nullptr;     // wait profile buffer (allocated when SDFB_PROF is set)
@@ -166,6 +169,7 @@ struct sdfb_ddpm {
   int ws_n = 0;
   float *h0 = nullptr, *h1 = nullptr, *eps = nullptr;
   void* dstage = nullptr; size_t dstage_bytes = 0;
+  void* nstage = nullptr; size_t nstage_bytes = 0;   // materialised Philox stream (fp32 path of the seeded sampler)
   // tensor-core path (ddpm_step.cu)
   uint8_t* wpack[2] = {nullptr, nullptr};     // [0] bf16, [1] fp16: kDdpmWRows rows of 128 B
   float* bias_dev = nullptr;                  // [3][1024] + [256]
@@ -370,6 +374,9 @@ int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, s
   }
   CU_TRY_D(cudaEventCreate(&d->ev0));
   CU_TRY_D(cudaEventCreate(&d->ev1));
+  CU_TRY_D(cudaStreamCreateWithFlags(&d->st_compute, cudaStreamNonBlocking));
+  CU_TRY_D(cudaStreamCreateWithFlags(&d->st_copy, cudaStreamNonBlocking));
+  for (cudaEvent_t& e : d->chunk_ev) CU_TRY_D(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 #undef CU_TRY_D
   *out = d;
   return SDFB_OK;
@@ -386,6 +393,9 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
   cudaFree(d->dstage);
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
+  for (cudaEvent_t e : d->chunk_ev) if (e) cudaEventDestroy(e);
+  if (d->st_compute) cudaStreamDestroy(d->st_compute);
+  if (d->st_copy) cudaStreamDestroy(d->st_copy);
   delete d;
   return SDFB_OK;
 }
@@ -430,14 +440,34 @@ int sdfb_decode_grid_host(sdfb_decoder* d, const float* latent_host, int res, in
   int rc = ensure_stage(&d->pin, &d->pin_bytes, &d->dstage, &d->dstage_bytes, 1024, off_mask + n_mask);
   if (rc) return rc;
   uint8_t* base = static_cast<uint8_t*>(d->dstage);
+  float* lat_dev = reinterpret_cast<float*>(base);
+  float* sdf_dev = reinterpret_cast<float*>(base + off_sdf);
   std::memcpy(d->pin, latent_host, kLatent * sizeof(float));
-  CU_TRY(cudaMemcpyAsync(base, d->pin, kLatent * sizeof(float), cudaMemcpyHostToDevice, 0));
-  rc = sdfb_decode_grid(d, reinterpret_cast<float*>(base), res, z0, z1, reinterpret_cast<float*>(base + off_sdf),
-                        n_mask ? base + off_mask : nullptr, precision, nullptr);
-  if (rc) return rc;
-  CU_TRY(cudaMemcpyAsync(sdf_host, base + off_sdf, (z1 - z0) * plane * sizeof(float), cudaMemcpyDeviceToHost, 0));
-  if (n_mask) CU_TRY(cudaMemcpyAsync(mask_host, base + off_mask, n_mask, cudaMemcpyDeviceToHost, 0));
-  CU_TRY(cudaStreamSynchronize(0));
+  CU_TRY(cudaMemcpyAsync(lat_dev, d->pin, kLatent * sizeof(float), cudaMemcpyHostToDevice, d->st_compute));
+  // z-chunks: the copy-out of chunk c runs on the copy stream while chunk c + 1 is being decoded
+  const int planes = z1 - z0 + (halo ? 1 : 0);
+  long long per = (2097152 + plane - 1) / plane;                   // >= 2^21 queries per chunk keeps the persistent kernel's tail < 1 %
+  if (per * 16 < planes) per = (planes + 15) / 16;
+  int nchunk = 0;
+  for (long long za = 0; za < planes; za += per, ++nchunk) {
+    const long long zb = za + per < planes ? za + per : planes;
+    rc = decode_any(d, lat_dev, nullptr, res, (z0 + za) * plane, (zb - za) * plane, sdf_dev + za * plane, precision, d->st_compute);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(d->chunk_ev[nchunk], d->st_compute));
+    CU_TRY(cudaStreamWaitEvent(d->st_copy, d->chunk_ev[nchunk], 0));
+    const long long zc = zb < (z1 - z0) ? zb : (z1 - z0);           // the halo plane stays on the device
+    if (zc > za)
+      CU_TRY(cudaMemcpyAsync(sdf_host + za * plane, sdf_dev + za * plane, (zc - za) * plane * sizeof(float),
+                             cudaMemcpyDeviceToHost, d->st_copy));
+  }
+  if (n_mask) {
+    CU_TRY(launch_sign_change_mask(sdf_dev, planes, res, res, base + off_mask, d->st_compute));
+    CU_TRY(cudaEventRecord(d->chunk_ev[16], d->st_compute));
+    CU_TRY(cudaStreamWaitEvent(d->st_copy, d->chunk_ev[16], 0));
+    CU_TRY(cudaMemcpyAsync(mask_host, base + off_mask, n_mask, cudaMemcpyDeviceToHost, d->st_copy));
+  }
+  CU_TRY(cudaStreamSynchronize(d->st_compute));
+  CU_TRY(cudaStreamSynchronize(d->st_copy));
   return precision == SDFB_PREC_FP32 ? SDFB_OK : kernel_status(d);
 }
 
@@ -663,7 +693,7 @@ int sdfb_ddpm_destroy(sdfb_ddpm* d) {
   cudaDeviceSynchronize();
   cudaFree(d->params); cudaFree(d->tb0); cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->eps); cudaFree(d->dstage);
   cudaFree(d->wpack[0]); cudaFree(d->wpack[1]); cudaFree(d->bias_dev); cudaFree(d->coef_dev); cudaFree(d->act);
-  cudaFree(d->counter); cudaFree(d->status); cudaFree(d->prof);
+  cudaFree(d->counter); cudaFree(d->status); cudaFree(d->prof); cudaFree(d->nstage);
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
   delete d;
@@ -699,7 +729,7 @@ static int denoise_fp32(sdfb_ddpm* d, const float* x, int t, int n, float* eps, 
 // Tensor-core path: `steps` fused denoise+update steps t = t_first, t_first-1, ... in ONE cooperative
 // launch (eps_out != nullptr: a single denoiser evaluation, no update).
 static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps, int t_first, float* eps_out,
-                   bool fp16, cudaStream_t st) {
+                   bool fp16, cudaStream_t st, bool philox = false, unsigned long long seed = 0) {
   const int m_pairs = (n + 255) / 256, n_pad = 256 * m_pairs;
   if (d->act_rows < n_pad) {
     cudaFree(d->act); cudaFree(d->counter); d->act = nullptr; d->counter = nullptr; d->act_rows = 0;
@@ -718,6 +748,7 @@ static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps,
   DdpmParams p{};
   p.tb0 = d->tb0; p.bias = d->bias_dev; p.coef = d->coef_dev;
   p.eps_mode = eps_out != nullptr ? 1 : 0;
+  p.philox = philox ? 1 : 0; p.seed = seed;
   p.n = n; p.pair_m_tiles = m_pairs; p.steps = steps; p.t_first = t_first;
   p.bn_h = bn_h;
   p.nstages = bn_h == 256 ? 4 : 5;   // 4 x 32 KiB or 5 x 24 KiB of operand ring + 96 KiB of epilogue staging
@@ -847,6 +878,48 @@ int sdfb_ddpm_sample(sdfb_ddpm* d, float* x_dev, const float* noise_dev, int n, 
                               d->sra[t], d->srm1[t], d->c1[t], d->c2[t], d->sigma[t], st));
   }
   return SDFB_OK;
+}
+
+int sdfb_philox_normal(uint64_t seed, int n, int t0, int t1, float* out_dev, void* stream) {
+  if (!out_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (n <= 0 || t0 < 0 || t1 < t0) return fail(SDFB_E_INVALID, "bad n or step range");
+  CU_TRY(launch_philox_normal(seed, n, t0, t1, out_dev, static_cast<cudaStream_t>(stream)));
+  return SDFB_OK;
+}
+
+int sdfb_ddpm_sample_philox(sdfb_ddpm* d, float* x_dev, uint64_t seed, int n, int steps, int gen_xT, int precision,
+                            void* stream) {
+  if (!d || !x_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (n <= 0 || steps < 1 || steps > kDdpmT) return fail(SDFB_E_INVALID, "bad n or steps");
+  if (precision != SDFB_PREC_FP32 && precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16)
+    return fail(SDFB_E_INVALID, "unknown precision %d", precision);
+  DeviceGuard g(d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gen_xT) CU_TRY(launch_philox_normal(seed, n, steps, steps + 1, x_dev, st));      // x_T = row t = steps of the stream
+  if (precision != SDFB_PREC_FP32)
+    return ddpm_tc(d, x_dev, nullptr, n, steps, steps - 1, nullptr, precision == SDFB_PREC_FP16, st, true, seed);
+  // fp32 path: materialise the same stream (bit for bit the in-kernel one) and run the FFMA sampler on it
+  const size_t cnt = static_cast<size_t>(n) * kDdpmLatent;
+  int rc = ensure_stage(nullptr, nullptr, &d->nstage, &d->nstage_bytes, 0, static_cast<size_t>(steps) * cnt * sizeof(float));
+  if (rc) return rc;
+  CU_TRY(launch_philox_normal(seed, n, 0, steps, static_cast<float*>(d->nstage), st));
+  return sdfb_ddpm_sample(d, x_dev, static_cast<float*>(d->nstage), n, steps, precision, stream);
+}
+
+int sdfb_ddpm_sample_philox_host(sdfb_ddpm* d, float* x_host, uint64_t seed, int n, int steps, int gen_xT, int precision) {
+  if (!d || !x_host) return fail(SDFB_E_INVALID, "null argument");
+  if (n <= 0 || steps < 1 || steps > kDdpmT) return fail(SDFB_E_INVALID, "bad n or steps");
+  DeviceGuard g(d->device);
+  const size_t cnt = static_cast<size_t>(n) * kDdpmLatent;
+  int rc = ensure_stage(nullptr, nullptr, &d->dstage, &d->dstage_bytes, 0, cnt * sizeof(float));
+  if (rc) return rc;
+  float* x = static_cast<float*>(d->dstage);
+  if (!gen_xT) CU_TRY(cudaMemcpyAsync(x, x_host, cnt * sizeof(float), cudaMemcpyHostToDevice, 0));
+  rc = sdfb_ddpm_sample_philox(d, x, seed, n, steps, gen_xT, precision, nullptr);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(x_host, x, cnt * sizeof(float), cudaMemcpyDeviceToHost, 0));
+  CU_TRY(cudaStreamSynchronize(0));
+  return precision == SDFB_PREC_FP32 ? SDFB_OK : ddpm_status(d);
 }
 
 int sdfb_ddpm_sample_host(sdfb_ddpm* d, float* x_host, const float* noise_host, int n, int steps, int precision) {

@@ -33,6 +33,7 @@
 #include <cuda_fp16.h>
 
 #include "kernels.h"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace sdfb {
@@ -434,13 +435,25 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
           if (l == 4 && threadIdx.x == 0 && !p.eps_mode) {
             // x and noise[t] of this half tile: two 32-column fp32 boxes each
             const uint32_t xn = bars + 8 * kBarXn;
-            mbar_arrive_expect_tx(xn, (t > 0 ? 4u : 2u) * kChunk);
+            const bool nz_box = t > 0 && !p.philox;
+            mbar_arrive_expect_tx(xn, (nz_box ? 4u : 2u) * kChunk);
             tma_load_2d(stg, &tm_x, j * 64, g_row, xn);
             tma_load_2d(stg + kChunk, &tm_x, j * 64 + 32, g_row, xn);
-            if (t > 0) {
+            if (nz_box) {
               tma_load_3d(stg + 2 * kChunk, &tm_nz, j * 64, g_row, t, xn);
               tma_load_3d(stg + 3 * kChunk, &tm_nz, j * 64 + 32, g_row, t, xn);
             }
+          }
+          if (l == 4 && p.philox && !p.eps_mode && t > 0) {
+            // in-kernel noise: this thread's 32 normals -> its row of the noise box (the layout the TMA box would
+            // have had), generated while the tensor core is still busy with this tile
+            const uint32_t nrow_w = stg + (2 + set) * kChunk + row * 128u;
+            const uint2 key = make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32));
+#pragma unroll 2
+            for (int u = 0; u < 8; ++u)
+              st_shared_f4(nrow_w + ((static_cast<uint32_t>(u) ^ row7) << 4),
+                           philox_normal4(static_cast<uint32_t>(j * 16 + set * 8 + u), static_cast<uint32_t>(g_row + row),
+                                          static_cast<uint32_t>(t), key));
           }
           if (!mbar_wait(bars + 8 * (kBarAccFull + b), (acc_phase >> b) & 1u, wd, kErrAccFull, b)) goto done;
           acc_phase ^= 1u << b;
@@ -623,6 +636,18 @@ __global__ void ddpm_split_kernel(const float* __restrict__ x, int n, int n_pad,
   *reinterpret_cast<uint4*>(rowp + 256) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// noise rows [t0, t1) of n latents -> out [(t1 - t0)][n][256] (what the sampler generates in-kernel)
+__global__ void philox_normal_kernel(unsigned long long seed, int n, int t0, int t1, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // (t, row, column group)
+  const long long total = static_cast<long long>(t1 - t0) * n * 64;
+  if (i >= total) return;
+  const uint32_t g = static_cast<uint32_t>(i & 63);
+  const long long rt = i >> 6;
+  const uint32_t row = static_cast<uint32_t>(rt % n), t = static_cast<uint32_t>(t0 + rt / n);
+  const float4 z = philox_normal4(g, row, t, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  reinterpret_cast<float4*>(out)[i] = z;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -657,6 +682,13 @@ cudaError_t make_tensor_map(void* tmap_out, const void* base, int elem_bytes, in
       swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t launch_philox_normal(unsigned long long seed, int n, int t0, int t1, float* out, cudaStream_t stream) {
+  const long long total = static_cast<long long>(t1 - t0) * n * 64;
+  if (total <= 0) return cudaSuccess;
+  philox_normal_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(seed, n, t0, t1, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_ddpm_split(const float* x, int n, int n_pad, uint16_t* act, bool fp16, cudaStream_t stream) {

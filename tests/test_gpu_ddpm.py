@@ -127,3 +127,38 @@ def test_sample_latents_full_batch_properties(cuda_ddpm, monkeypatch):
     sub = slice(1000, 1300)
     xs = cuda_ddpm.sample_latents(300, x_T=x_T[sub], noise=noise[:, sub].contiguous(), steps=steps, precision="bf16")
     assert torch.equal(xs, x[sub])
+
+
+# ---- seeded sampling with in-kernel Philox noise -----------------------------------------------------
+def test_philox_stream_matches_oracle(pkg):
+    """The device stream vs oracle/philox.py: same integers, normals within a few ulp of logf/sincospif."""
+    dev = pkg.philox_normal(12345678901234, 37, 5, 9).cpu().numpy()
+    ref = oracle.philox_normal_rows(12345678901234, 37, 5, 9)
+    assert dev.shape == ref.shape == (4, 37, 256)
+    err = np.abs(dev - ref).max()
+    print(f"philox normals: max |device - oracle| = {err:.2e}")
+    assert err < 5e-6
+    assert abs(float(dev.mean())) < 0.02 and abs(float(dev.std()) - 1.0) < 0.02
+
+
+def test_seeded_sampler_equals_explicit_stream(cuda_ddpm, pkg, monkeypatch):
+    """In-kernel noise == the same stream passed explicitly, bit for bit (bf16 fused kernel); and the
+    fp32 seeded path against the oracle driven by the oracle's own Philox."""
+    monkeypatch.setenv("SDFB_DDPM_BN", "256")
+    n, steps, seed = 300, 20, 2024
+    noise = pkg.philox_normal(seed, n, 0, steps)
+    x_T = pkg.philox_normal(seed, n, steps, steps + 1)[0]
+    a = cuda_ddpm.sample_latents(n, steps=steps, seed=seed, precision="bf16")                 # x_T and noise generated
+    b = cuda_ddpm.sample_latents(n, x_T=x_T, steps=steps, seed=seed, precision="bf16")        # noise generated
+    c = cuda_ddpm.sample_latents(n, x_T=x_T, noise=noise, steps=steps, precision="bf16")      # explicit stream
+    assert torch.equal(a, b) and torch.equal(a, c)
+    h = cuda_ddpm.sample_latents_seeded_host(n, seed, steps=steps, precision="bf16")
+    assert np.array_equal(h, a.cpu().numpy())
+    # fp32 + oracle
+    n2, steps2 = 8, 50
+    x32 = cuda_ddpm.sample_latents(n2, steps=steps2, seed=seed, precision="fp32").cpu().numpy()
+    ox_T, onoise = oracle.philox_sampler_inputs(seed, n2, steps2)
+    ref = oracle.sample_latents(n2, ox_T, onoise, steps=steps2)
+    err = np.abs(x32 - ref).max()
+    print(f"seeded fp32 sampler vs oracle with oracle Philox: {err:.2e}")
+    assert err < 1e-4

@@ -190,6 +190,20 @@ def test_host_buffer_entry_points(cuda_decoder):
     assert np.array_equal(out.reshape(32, 32), sdf_h[0])      # grid mode and points mode agree bit for bit
 
 
+def test_host_entry_point_chunked_copy_out(cuda_decoder):
+    """The host-buffer call decodes in z-chunks and overlaps each chunk's copy-out with the next chunk's
+    kernel: same bits as one device-side launch, including the mask over chunk boundaries and the halo."""
+    z = oracle.default_latent(2)
+    for (res, z0, z1) in ((160, 10, 150), (256, 0, 256)):
+        sdf_d, mask_d = cuda_decoder.decode_grid(z, res, z0, z1, mask=True, precision="bf16")
+        sdf_h, mask_h = cuda_decoder.decode_grid_host(z, res, z0, z1, mask=True, precision="bf16")
+        assert np.array_equal(sdf_h, sdf_d.cpu().numpy())
+        assert np.array_equal(mask_h, mask_d.cpu().numpy())
+    pinned = torch.empty((256, 256, 256), dtype=torch.float32).pin_memory().numpy()
+    out = cuda_decoder.decode_grid_host(z, 256, out=pinned)
+    assert np.array_equal(out, sdf_d.cpu().numpy())
+
+
 @pytest.mark.parametrize("res", [256, 512])
 def test_full_size_grids(cuda_decoder, golden, res):
     """BASELINE configs 2 and 5 at full size: golden samples + size-independent properties."""
