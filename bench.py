@@ -35,6 +35,7 @@ FLOP_TENSOR_PER_QUERY = 2 * 6 * 512 * 512          # 3,145,728
 FLOP_DENSE_PER_QUERY = 3_671_040
 DDPM_LATENTS = 4096
 DDPM_FLOP_PER_LATENT_STEP = 2 * (512 * 1024 + 3 * 1024 * 1024 + 1024 * 256)   # 7,864,320 executed (hi/lo split of x: K = 512)
+NCU_DRAM_BYTES_PER_LAUNCH = 3445504 + 13815552      # profiles/r1_fused_decoder_ncu_full.csv
 METRIC = "sdf_decoder_queries_per_s"
 UNIT = "queries/s"
 
@@ -190,6 +191,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 512^3 z-slab-sharded case that runs when N > 1")
     ap.add_argument("--no-ddpm", action="store_true", help="skip the latent-DDPM leg (second half of the metric)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -199,7 +201,6 @@ def main():
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_package
-    import oracle           # weights/latents only (seeded generators); nothing from it is timed on this arm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -212,8 +213,8 @@ def main():
     pkg = load_package()
     K, W = max(1, args.steps), max(3, args.warmup)
     dev = torch.device("cuda", local)
-    dec = pkg.Decoder(oracle.flatten_params(oracle.decoder_weights()), device=dev, precision=args.precision)
-    z_host = oracle.default_latent(rank)                           # each rank: its own latent (weak scaling)
+    dec = pkg.Decoder(pkg.synthetic.decoder_params(), device=dev, precision=args.precision)
+    z_host = pkg.synthetic.latent(rank)                            # each rank: its own latent (weak scaling)
     z = torch.from_numpy(z_host).to(dev)
     out = torch.empty((RES, RES, RES), dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # 256 MiB > 126 MB L2
@@ -261,11 +262,39 @@ def main():
     e2e_value = world * QUERIES * Ke / float(e2e_s.item())
     checksum = float(np.float64(sdf_host[::16, ::16, ::16].sum()))
 
+    # ---- BASELINE configs[4] (the north star's target case) when there is more than one GPU: ONE latent, 512^3 grid,
+    # z-slab per rank, fused-path decode + sign-change mask (halo plane recomputed locally) + in-place NCCL all-gather
+    cfg5 = None
+    if world > 1 and not args.no_config5:
+        res5 = 512
+        z5 = torch.from_numpy(pkg.synthetic.latent(0)).to(dev)
+        del out, flush
+        for _ in range(2):
+            s5, m5 = pkg.decode_grid_sharded(dec, z5, res5, mask=True)
+        t5 = []
+        for _ in range(5):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            s5, m5 = pkg.decode_grid_sharded(dec, z5, res5, mask=True)
+            b.record()
+            b.synchronize()
+            t5.append(a.elapsed_time(b))
+        t5 = torch.tensor([statistics.median(t5)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        ms5 = float(t5.item())
+        per_gpu_tflops = (res5 ** 3 / world) * FLOP_TENSOR_PER_QUERY / (ms5 * 1e-3) / 1e12
+        cfg5 = {"workload": f"decode_grid_sharded(z, 512, mask=True) on {world} GPUs: z-slabs, mask with locally recomputed halo plane, "
+                            "in-place NCCL all-gather of the sdf slabs and gather of the mask slabs; median of 5, max over ranks",
+                "ms": ms5, "queries_per_s": res5 ** 3 / (ms5 * 1e-3), "tflops_per_gpu_incl_mask_and_gather": per_gpu_tflops,
+                "active_cells": int(m5.sum().item()), "sdf_checksum": float(s5[::32, ::32, ::32].double().sum().item())}
+        del s5, m5
+
     # ---- second half of the metric: latent-DDPM latents/s (BASELINE configs[3]: 4096 latents, 1000 steps) ----
     ddpm_line = None
     if not args.no_ddpm:
         n_lat, T = DDPM_LATENTS, 1000
-        sampler = pkg.LatentDDPM(oracle.flatten_params(oracle.ddpm_weights()), device=dev, precision=args.precision)
+        sampler = pkg.LatentDDPM(pkg.synthetic.ddpm_params(), device=dev, precision=args.precision)
         g = torch.Generator(device=dev).manual_seed(100 + rank)
         x_T = torch.randn((n_lat, 256), generator=g, device=dev)
         noise = torch.randn((T, n_lat, 256), generator=g, device=dev)           # 4.2 GB explicit noise stream in HBM
@@ -333,7 +362,10 @@ def main():
                     "checksum": checksum},
             "gpu_launches": 2 * K,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["burst"], "traffic": None,
+                         "frac": achieved / peaks["burst"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture "
+                                           "profiles/r1_fused_decoder_ncu_full.csv (not re-measured in this run); algorithmic "
+                                           "bytes = 67,108,864 output bytes, part of which is still in L2 when the launch ends",
                          "peak_kind": "burst bf16 matmul, " + peaks["source"],
                          "frac_of_sustained": achieved / peaks["sustained"], "peak_sustained": peaks["sustained"],
                          "kernel": "fused_decoder_kernel", "kernel_ms": k_ms,
@@ -341,6 +373,9 @@ def main():
                          "dense_equiv_tflops": QUERIES * FLOP_DENSE_PER_QUERY / (k_ms * 1e-3) / 1e12},
             "wall_s_timed_region": t_wall,
         }
+        if cfg5 is not None:
+            cfg5["frac_of_burst_peak_per_gpu"] = cfg5["tflops_per_gpu_incl_mask_and_gather"] / peaks["burst"]
+            line["config5_512cubed_sharded"] = cfg5
         if ddpm_line is not None:
             ddpm_line["frac_of_burst_peak"] = ddpm_line["achieved_tflops"] / peaks["burst"]
             line["ddpm"] = ddpm_line

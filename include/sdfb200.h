@@ -74,6 +74,10 @@ int sdfb_decoder_destroy(sdfb_decoder* dec);
 int sdfb_decode_grid(sdfb_decoder* dec, const float* latent_dev, int res, int z0, int z1,
                      float* sdf_dev, uint8_t* mask_dev, int precision, void* stream);
 
+/* A batch of shapes (BASELINE configs 3 and 4): latents_dev [batch][256] -> sdf_dev [batch][res^3]. */
+int sdfb_decode_grid_batch(sdfb_decoder* dec, const float* latents_dev, int batch, int res, float* sdf_dev,
+                           int precision, void* stream);
+
 /* Decoder(latent, xyz) -> sdf for M arbitrary points, xyz_dev [M][3]. */
 int sdfb_decode_points(sdfb_decoder* dec, const float* latent_dev, const float* xyz_dev, int64_t M,
                        float* sdf_dev, int precision, void* stream);

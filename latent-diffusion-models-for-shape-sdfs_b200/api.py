@@ -143,6 +143,21 @@ class Decoder:
         sdf = buf.view(-1)[: (z1 - z0) * res * res].view(z1 - z0, res, res)
         return (sdf, m) if mask else sdf
 
+    def decode_grid_batch(self, latents, res: int, precision: str | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+        """sdf [B, res, res, res] for latents [B,256] (independent shapes, one C call)."""
+        prec = _prec(precision or self.precision)
+        lat = _as_dev_f32(latents, self.device)
+        if lat.ndim != 2 or lat.shape[1] != LATENT:
+            raise ValueError("latents must be [B,256]")
+        B = lat.shape[0]
+        if out is None:
+            out = torch.empty((B, res, res, res), dtype=torch.float32, device=self.device)
+        elif out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous() or out.numel() != B * res ** 3:
+            raise ValueError("out must be a contiguous float32 CUDA tensor of B * res^3 elements")
+        check(self._lib.sdfb_decode_grid_batch(self._h, lat.data_ptr() if B else None, B, res, out.data_ptr() if B else None, prec,
+                                               _stream_ptr(self.device.index)))
+        return out.view(B, res, res, res)
+
     def decode_grid_host(self, latent: np.ndarray, res: int, z0: int = 0, z1: int | None = None,
                          mask: bool = False, precision: str | None = None, out: np.ndarray | None = None):
         """Same result as ``decode_grid`` but through the host-buffer entry point: numpy in,

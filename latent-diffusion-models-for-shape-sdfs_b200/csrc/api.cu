@@ -418,6 +418,20 @@ int sdfb_decode_grid(sdfb_decoder* d, const float* latent_dev, int res, int z0, 
   return SDFB_OK;
 }
 
+int sdfb_decode_grid_batch(sdfb_decoder* d, const float* latents_dev, int batch, int res, float* sdf_dev, int precision,
+                           void* stream) {
+  if (!d || (batch > 0 && (!latents_dev || !sdf_dev))) return fail(SDFB_E_INVALID, "null argument");
+  if (batch < 0 || res < 2 || res > 2048) return fail(SDFB_E_INVALID, "bad batch or res");
+  DeviceGuard g(d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long M = static_cast<long long>(res) * res * res;
+  for (int b = 0; b < batch; ++b) {   // shapes are independent: one fold + one persistent launch each, back to back on the stream
+    int rc = decode_any(d, latents_dev + static_cast<long long>(b) * kLatent, nullptr, res, 0, M, sdf_dev + b * M, precision, st);
+    if (rc) return rc;
+  }
+  return SDFB_OK;
+}
+
 int sdfb_decode_points(sdfb_decoder* d, const float* latent_dev, const float* xyz_dev, int64_t M, float* sdf_dev,
                        int precision, void* stream) {
   if (!d || !latent_dev || (M > 0 && (!xyz_dev || !sdf_dev))) return fail(SDFB_E_INVALID, "null argument");

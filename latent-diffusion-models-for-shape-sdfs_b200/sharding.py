@@ -75,6 +75,8 @@ def decode_batch_sharded(decoder, latents: torch.Tensor, res: int, precision=Non
     No communication; returns (i0, sdf [i1-i0, res, res, res])."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     i0, i1 = batch_range(latents.shape[0], rank, world)
+    if hasattr(decoder, "decode_grid_batch"):
+        return i0, decoder.decode_grid_batch(latents[i0:i1], res, precision=precision)
     out = torch.empty((i1 - i0, res, res, res), dtype=torch.float32, device=decoder.device)
     for j, i in enumerate(range(i0, i1)):
         decoder.decode_grid(latents[i], res, precision=precision, out=out[j])

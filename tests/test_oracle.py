@@ -145,3 +145,12 @@ def test_philox_known_answers_and_normals():
     assert np.array_equal(oracle.philox_normal_rows(7, 64, 3, 5), z[3:5])
     x_T, noise = oracle.philox_sampler_inputs(7, 64, 8)
     assert np.array_equal(noise, z) and x_T.shape == (64, 256) and not np.array_equal(x_T, z[0])
+
+
+def test_synthetic_parameters_equal_the_oracle_weights(pkg):
+    """bench.py's random-init parameters (product-side generator) are byte-identical to the frozen
+    oracle weights, so the benchmark never has to import the oracle for its inputs."""
+    assert np.array_equal(pkg.synthetic.decoder_params(), oracle.flatten_params(oracle.decoder_weights()))
+    assert np.array_equal(pkg.synthetic.ddpm_params(), oracle.flatten_params(oracle.ddpm_weights()))
+    for i in (0, 1, 5):
+        assert np.array_equal(pkg.synthetic.latent(i), oracle.default_latent(i))
