@@ -197,6 +197,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -383,7 +388,8 @@ def main():
             line["cpu_baseline"] = cpu_oracle_rate()
             if ddpm_line is not None:
                 line["ddpm"]["cpu_baseline"] = cpu_ddpm_rate()
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
