@@ -67,12 +67,21 @@ int sdfb_decoder_destroy(sdfb_decoder* dec);
 /* decode_grid(z, res) restricted to planes [z0, z1): writes
  * sdf_dev[(z1-z0)*res*res] (C order z,y,x).  Node (iz,iy,ix) sits at
  * c_i = float(2i-(res-1))/float(res-1) on each axis (bit-exact rule A1).
- * If mask_dev != NULL the sign-change mask (A4) of the cell layers
+ * If mask_dev != NULL the sign-change mask (A4; built from sign bit-planes that the decoder
+ * kernel emits together with the values) of the cell layers
  * [z0, min(z1,res-1)) is written as uint8 [(layers)*(res-1)*(res-1)]; when
  * z1 < res this needs the halo plane z1, which is then decoded too and stored
  * after the slab, so sdf_dev must hold (z1-z0+1)*res*res floats in that case. */
 int sdfb_decode_grid(sdfb_decoder* dec, const float* latent_dev, int res, int z0, int z1,
                      float* sdf_dev, uint8_t* mask_dev, int precision, void* stream);
+
+/* Packed variant: besides the sdf, the SIGN BIT-PLANES of the decoded planes (bit (q & 31) of word
+ * q >> 5 = sdf[q] < 0, q = query index within the call, halo plane included; ceil(M / 32) words) and,
+ * if mask_bits_dev != NULL, the sign-change mask PACKED one bit per cell (cell c -> bit c & 31 of
+ * word c >> 5; ceil(cells / 32) words; same halo rule and sdf_dev size as sdfb_decode_grid).  The
+ * tensor-core kernel writes the sign words itself, next to the values. */
+int sdfb_decode_grid_bits(sdfb_decoder* dec, const float* latent_dev, int res, int z0, int z1, float* sdf_dev,
+                          uint32_t* sign_bits_dev, uint32_t* mask_bits_dev, int precision, void* stream);
 
 /* A batch of shapes (BASELINE configs 3 and 4): latents_dev [batch][256] -> sdf_dev [batch][res^3]. */
 int sdfb_decode_grid_batch(sdfb_decoder* dec, const float* latents_dev, int batch, int res, float* sdf_dev,

@@ -25,6 +25,7 @@ SIGNATURES = {
     "sdfb_decoder_create": (_i, [_vp, _sz, _i, C.POINTER(_vp)]),
     "sdfb_decoder_destroy": (_i, [_vp]),
     "sdfb_decode_grid": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "sdfb_decode_grid_bits": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "sdfb_decode_grid_batch": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
     "sdfb_decode_points": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _vp]),
     "sdfb_decode_grid_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i]),

@@ -143,6 +143,29 @@ class Decoder:
         sdf = buf.view(-1)[: (z1 - z0) * res * res].view(z1 - z0, res, res)
         return (sdf, m) if mask else sdf
 
+    def decode_grid_bits(self, latent, res: int, z0: int = 0, z1: int | None = None, mask: bool = True,
+                         precision: str | None = None):
+        """(sdf [z1-z0,res,res], sign_words int32 [ceil(M/32)], mask_words int32 [ceil(cells/32)] or None):
+        the packed outputs - sign bit-planes written by the decoder kernel itself (bit q & 31 of word
+        q >> 5, halo plane included) and the sign-change mask at one bit per cell."""
+        prec = _prec(precision or self.precision)
+        z1 = res if z1 is None else z1
+        if not (0 <= z0 <= z1 <= res) or res < 2:
+            raise ValueError(f"bad plane range [{z0}, {z1}) for res {res}")
+        lat = _as_dev_f32(latent, self.device, (LATENT,))
+        halo = 1 if (mask and z1 < res and z1 > z0) else 0
+        planes = z1 - z0 + halo
+        buf = torch.empty((planes, res, res), dtype=torch.float32, device=self.device)
+        signs = torch.zeros(((planes * res * res + 31) // 32,), dtype=torch.int32, device=self.device)
+        layers = (z1 if halo else min(z1, res - 1)) - z0
+        cells = max(layers, 0) * (res - 1) * (res - 1)
+        mw = torch.zeros(((cells + 31) // 32,), dtype=torch.int32, device=self.device) if mask else None
+        check(self._lib.sdfb_decode_grid_bits(self._h, lat.data_ptr(), res, z0, z1, buf.data_ptr(),
+                                              signs.data_ptr() if signs.numel() else None,
+                                              mw.data_ptr() if (mw is not None and mw.numel()) else None, prec,
+                                              _stream_ptr(self.device.index)))
+        return buf[: z1 - z0], signs, mw
+
     def decode_grid_batch(self, latents, res: int, precision: str | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
         """sdf [B, res, res, res] for latents [B,256] (independent shapes, one C call)."""
         prec = _prec(precision or self.precision)

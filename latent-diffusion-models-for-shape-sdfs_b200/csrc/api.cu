@@ -144,6 +144,7 @@ struct sdfb_decoder {
   float* bias0f = nullptr;       // fp32 path folded biases
   float* bias4f = nullptr;
   unsigned int* status = nullptr;
+  unsigned int* signs = nullptr; long long sign_words = 0;   // sign bit-planes of the last masked decode (lazy)
   // fp32 workspace (lazy)
   long long ws_rows = 0;
   float *h0 = nullptr, *h1 = nullptr, *s = nullptr, *x = nullptr;
@@ -233,7 +234,7 @@ int decode_fp32(sdfb_decoder* d, const float* z, const float* xyz, int res, long
 }
 
 int decode_tc(sdfb_decoder* d, const float* z, const float* xyz, int res, long long q0, long long M, float* out,
-              bool fp16, float* dump, int dump_pass, cudaStream_t st) {
+              bool fp16, float* dump, int dump_pass, cudaStream_t st, unsigned int* signs = nullptr) {
   const float* P = d->params;
   const LayerOff* o = d->off;
   CU_TRY(launch_fold_latent(P + o[0].w, P + o[0].b, P + o[4].w, P + o[4].b, z, d->consts, st));
@@ -242,6 +243,7 @@ int decode_tc(sdfb_decoder* d, const float* z, const float* xyz, int res, long l
   p.consts = d->consts;
   p.xyz = xyz;
   p.out = out;
+  p.signs = signs;
   p.M = M;
   p.q0 = q0;
   p.res = res;
@@ -258,15 +260,30 @@ int decode_tc(sdfb_decoder* d, const float* z, const float* xyz, int res, long l
   return SDFB_OK;
 }
 
+// `signs` (optional): the sign bit of every output, 32 queries per word - written by the fused kernel
+// itself on the tensor-core path, by a small kernel behind the FFMA chain on the fp32 path.
 int decode_any(sdfb_decoder* d, const float* z, const float* xyz, int res, long long q0, long long M, float* out,
-               int precision, cudaStream_t st) {
+               int precision, cudaStream_t st, unsigned int* signs = nullptr) {
   if (M == 0) return SDFB_OK;
   switch (precision) {
-    case SDFB_PREC_FP32: return decode_fp32(d, z, xyz, res, q0, M, out, st);
-    case SDFB_PREC_BF16: return decode_tc(d, z, xyz, res, q0, M, out, false, nullptr, -1, st);
-    case SDFB_PREC_FP16: return decode_tc(d, z, xyz, res, q0, M, out, true, nullptr, -1, st);
+    case SDFB_PREC_FP32: {
+      int rc = decode_fp32(d, z, xyz, res, q0, M, out, st);
+      if (rc) return rc;
+      if (signs != nullptr) CU_TRY(launch_sign_bits(out, M, signs, st));
+      return SDFB_OK;
+    }
+    case SDFB_PREC_BF16: return decode_tc(d, z, xyz, res, q0, M, out, false, nullptr, -1, st, signs);
+    case SDFB_PREC_FP16: return decode_tc(d, z, xyz, res, q0, M, out, true, nullptr, -1, st, signs);
     default: return fail(SDFB_E_INVALID, "unknown precision %d", precision);
   }
+}
+
+int ensure_signs(sdfb_decoder* d, long long words) {
+  if (d->sign_words >= words) return SDFB_OK;
+  cudaFree(d->signs); d->signs = nullptr; d->sign_words = 0;
+  CU_TRY(cudaMalloc(&d->signs, static_cast<size_t>(words) * sizeof(unsigned int)));
+  d->sign_words = words;
+  return SDFB_OK;
 }
 
 int kernel_status(sdfb_decoder* d) {
@@ -388,7 +405,7 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
   cudaDeviceSynchronize();
   cudaFree(d->params); cudaFree(d->w4s); cudaFree(d->wstream[0]); cudaFree(d->wstream[1]);
   cudaFree(d->consts); cudaFree(d->bias0f); cudaFree(d->bias4f); cudaFree(d->status);
-  cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x); cudaFree(d->prof);
+  cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x); cudaFree(d->prof); cudaFree(d->signs);
   if (d->pin) cudaFreeHost(d->pin);
   cudaFree(d->dstage);
   if (d->ev0) cudaEventDestroy(d->ev0);
@@ -411,10 +428,32 @@ int sdfb_decode_grid(sdfb_decoder* d, const float* latent_dev, int res, int z0, 
   int zend = z1;
   if (mask_dev != nullptr && z1 < res && z1 > z0) zend = z1 + 1;   // halo plane, recomputed locally
   const long long M = (zend - z0) * plane;
-  int rc = decode_any(d, latent_dev, nullptr, res, z0 * plane, M, sdf_dev, precision, st);
+  if (mask_dev == nullptr || zend - z0 < 2) return decode_any(d, latent_dev, nullptr, res, z0 * plane, M, sdf_dev, precision, st);
+  // the decoder emits the sign bit of every value it stores; the cell mask is a combine of those bit-planes
+  // (1/32 of the field's bytes) instead of a second pass over the fp32 field
+  int rc = ensure_signs(d, (M + 31) >> 5);
   if (rc) return rc;
-  if (mask_dev != nullptr && zend - z0 >= 2)
-    CU_TRY(launch_sign_change_mask(sdf_dev, zend - z0, res, res, mask_dev, st));
+  rc = decode_any(d, latent_dev, nullptr, res, z0 * plane, M, sdf_dev, precision, st, d->signs);
+  if (rc) return rc;
+  CU_TRY(launch_mask_from_bits(d->signs, zend - z0, res, res, mask_dev, nullptr, st));
+  return SDFB_OK;
+}
+
+int sdfb_decode_grid_bits(sdfb_decoder* d, const float* latent_dev, int res, int z0, int z1, float* sdf_dev,
+                          uint32_t* sign_bits_dev, uint32_t* mask_bits_dev, int precision, void* stream) {
+  if (!d || !latent_dev || !sdf_dev || !sign_bits_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 2 || res > 2048) return fail(SDFB_E_INVALID, "res %d outside [2, 2048]", res);
+  if (z0 < 0 || z1 > res || z0 > z1) return fail(SDFB_E_INVALID, "bad plane range [%d, %d) for res %d", z0, z1, res);
+  DeviceGuard g(d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long plane = static_cast<long long>(res) * res;
+  int zend = z1;
+  if (mask_bits_dev != nullptr && z1 < res && z1 > z0) zend = z1 + 1;
+  const long long M = (zend - z0) * plane;
+  int rc = decode_any(d, latent_dev, nullptr, res, z0 * plane, M, sdf_dev, precision, st, sign_bits_dev);
+  if (rc) return rc;
+  if (mask_bits_dev != nullptr && zend - z0 >= 2)
+    CU_TRY(launch_mask_from_bits(sign_bits_dev, zend - z0, res, res, nullptr, mask_bits_dev, st));
   return SDFB_OK;
 }
 

@@ -138,6 +138,52 @@ __global__ void sign_change_mask_kernel(const float* __restrict__ sdf, int nz, i
   }
 }
 
+__global__ void sign_bits_kernel(const float* __restrict__ sdf, long long M, unsigned int* __restrict__ bits) {
+  const long long words = (M + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < words;
+       w += (static_cast<long long>(gridDim.x) * blockDim.x) >> 5) {
+    const long long m = (w << 5) + lane;
+    const unsigned int b = __ballot_sync(0xffffffffu, m < M && sdf[m] < 0.f);
+    if (lane == 0) bits[w] = b;
+  }
+}
+
+// A4 from sign bits.  A warp owns 32 consecutive cells; every lane reads the 8 corner bits of its cell.
+// IdxT = unsigned int when every index fits 32 bits (grids up to 1290^3): 64-bit div/mod per cell
+// was most of this kernel's time.
+template <typename IdxT>
+__global__ void mask_from_bits_kernel(const unsigned int* __restrict__ bits, int nz, int ny, int nx,
+                                      unsigned char* __restrict__ mask_u8, unsigned int* __restrict__ mask_bits) {
+  const IdxT cx = nx - 1, cy = ny - 1, cz = nz - 1;
+  const IdxT total = cx * cy * cz;
+  const IdxT groups = (total + 31) >> 5;
+  const IdxT lane = threadIdx.x & 31;
+  const IdxT sy = nx, sz = static_cast<IdxT>(nx) * ny;
+  const IdxT stride = (static_cast<IdxT>(gridDim.x) * blockDim.x) >> 5;
+  for (IdxT gidx = (static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; gidx < groups; gidx += stride) {
+    const IdxT c = (gidx << 5) + lane;
+    bool active = false;
+    if (c < total) {
+      const IdxT t = c / cx;
+      const IdxT x = c - t * cx;
+      const IdxT z = t / cy;
+      const IdxT y = t - z * cy;
+      const IdxT q = (z * ny + y) * nx + x;
+      unsigned int n_in = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const IdxT qq = q + (k & 1) + ((k >> 1) & 1) * sy + (k >> 2) * sz;
+        n_in += (bits[qq >> 5] >> (qq & 31)) & 1u;
+      }
+      active = n_in != 0 && n_in != 8;
+      if (mask_u8 != nullptr) mask_u8[c] = active ? 1 : 0;
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, active);
+    if (mask_bits != nullptr && lane == 0) mask_bits[gidx] = w;
+  }
+}
+
 // A7, op-for-op as the oracle evaluates it (separately rounded multiplies and adds).
 __global__ void ddpm_update_kernel(float* __restrict__ x, const float* __restrict__ eps,
                                    const float* __restrict__ noise, long long count, float sra,
@@ -199,6 +245,28 @@ cudaError_t launch_sign_change_mask(const float* sdf, int nz, int ny, int nx, un
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   sign_change_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(sdf, nz, ny, nx, mask);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sign_bits(const float* sdf, long long M, unsigned int* bits, cudaStream_t stream) {
+  if (M <= 0) return cudaSuccess;
+  long long blocks = (((M + 31) >> 5) * 32 + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  sign_bits_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(sdf, M, bits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mask_from_bits(const unsigned int* bits, int nz, int ny, int nx, unsigned char* mask_u8,
+                                  unsigned int* mask_bits, cudaStream_t stream) {
+  const long long total = static_cast<long long>(nx - 1) * (ny - 1) * (nz - 1);
+  if (total <= 0) return cudaSuccess;
+  long long blocks = (((total + 31) >> 5) * 32 + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  const long long nodes = static_cast<long long>(nx) * ny * nz;
+  if (nodes + 64 < (1LL << 31))
+    mask_from_bits_kernel<unsigned int><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(bits, nz, ny, nx, mask_u8, mask_bits);
+  else
+    mask_from_bits_kernel<unsigned long long><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(bits, nz, ny, nx, mask_u8, mask_bits);
   return cudaGetLastError();
 }
 

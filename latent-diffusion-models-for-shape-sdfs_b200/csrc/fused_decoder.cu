@@ -451,7 +451,12 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
         named_bar_sync(2, kEpiThreads);
         if (e.set == 0) {
           const long long m = row_base + row;
-          if (m < p.M) p.out[m] = tanhf((dot + sdot[row]) + head_b);
+          const float v = tanhf((dot + sdot[row]) + head_b);
+          if (m < p.M) p.out[m] = v;
+          if (p.signs != nullptr) {   // inside(v) := v < 0 of the value just stored, 32 queries per word (bit = query & 31)
+            const unsigned int bits = __ballot_sync(0xffffffffu, m < p.M && v < 0.f);
+            if (lane == 0 && m < p.M) p.signs[m >> 5] = bits;
+          }
         }
         q = Query{qv.x, qv.y, qv.z};
       }

@@ -57,6 +57,7 @@ struct DecodeParams {
   const DecConsts* consts;
   const float* xyz;            // points mode: [M][3]; nullptr in grid mode
   float* out;                  // [M]
+  unsigned int* signs;         // optional [ceil(M / 32)]: bit (m & 31) of word m >> 5 = (out[m] < 0)
   long long M;                 // number of queries in this launch
   long long q0;                // grid mode: global index of query 0 (= z0*res*res)
   int res;
@@ -162,6 +163,11 @@ cudaError_t launch_fold_bias(const float* W, int ldw, int col0, const float* b, 
                              int K, int N, float* y, cudaStream_t stream);
 cudaError_t launch_sign_change_mask(const float* sdf, int nz, int ny, int nx, unsigned char* mask,
                                     cudaStream_t stream);
+// bits[m >> 5] bit (m & 31) = (sdf[m] < 0), m < M   (the fused decoder writes the same words itself)
+cudaError_t launch_sign_bits(const float* sdf, long long M, unsigned int* bits, cudaStream_t stream);
+// A4 from the sign bits of an [nz][ny][nx] field: uint8 per cell and / or packed (cell c -> bit c & 31 of word c >> 5)
+cudaError_t launch_mask_from_bits(const unsigned int* bits, int nz, int ny, int nx, unsigned char* mask_u8,
+                                  unsigned int* mask_bits, cudaStream_t stream);
 // x <- c1*clamp(sra*x - srm1*eps, -1, 1) + c2*x + sigma*noise   (noise may be null)
 cudaError_t launch_ddpm_update(float* x, const float* eps, const float* noise, long long count,
                                float sra, float srm1, float c1, float c2, float sigma,

@@ -190,6 +190,26 @@ def test_host_buffer_entry_points(cuda_decoder):
     assert np.array_equal(out.reshape(32, 32), sdf_h[0])      # grid mode and points mode agree bit for bit
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_packed_sign_planes_and_mask_bits(cuda_decoder, prec):
+    """The sign bit-planes the decoder writes next to its values, and the mask at one bit per cell, are exactly
+    the packed forms of (sdf < 0) and of the oracle mask of the same field; odd sizes exercise unaligned rows."""
+    z = oracle.default_latent()
+    for (res, z0, z1) in ((64, 0, 64), (37, 5, 30), (23, 0, 23)):
+        sdf, signs, mw = cuda_decoder.decode_grid_bits(z, res, z0, z1, precision=prec)
+        ref_sdf, ref_mask = cuda_decoder.decode_grid(z, res, z0, z1, mask=True, precision=prec)
+        assert torch.equal(sdf, ref_sdf)
+        halo = 1 if z1 < res else 0
+        full = cuda_decoder.decode_grid(z, res, z0, z1 + halo, precision=prec).cpu().numpy()
+        want = np.packbits((full < 0).ravel(), bitorder="little")
+        got = signs.cpu().numpy().view(np.uint8)[: want.size]
+        assert np.array_equal(got, want)
+        m = ref_mask.cpu().numpy()
+        assert np.array_equal(m, oracle.sign_change_mask(full))
+        wantm = np.packbits(m.ravel(), bitorder="little")
+        assert np.array_equal(mw.cpu().numpy().view(np.uint8)[: wantm.size], wantm)
+
+
 def test_host_entry_point_chunked_copy_out(cuda_decoder):
     """The host-buffer call decodes in z-chunks and overlaps each chunk's copy-out with the next chunk's
     kernel: same bits as one device-side launch, including the mask over chunk boundaries and the halo."""
