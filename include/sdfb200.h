@@ -104,6 +104,21 @@ int sdfb_grid_points(int res, int z0, int z1, float* xyz_dev, void* stream);
 int sdfb_sign_change_mask(const float* sdf_dev, int nz, int ny, int nx, uint8_t* mask_dev,
                           void* stream);
 
+/* ---- isosurface extraction: marching cubes over the sign-change cells ------
+ * Field sdf_dev [nz][ny][nx] (C order), e.g. a decoded slab with ny = nx = res whose first plane is
+ * plane z0 of the res^3 grid.  Output: a triangle soup [n][3 vertices][x, y, z] in cell order,
+ * normals pointing from inside (sdf < 0) to outside; vertices interpolated from an edge's lower corner to
+ * its upper corner, so cells sharing an edge emit identical bits (watertight, and bit-exact against
+ * oracle/marching.py).  Two calls: count (classifies cells from the sign bit-planes - pass the words
+ * sdfb_decode_grid_bits produced, or NULL to have them computed - scans, synchronises the stream and
+ * returns the number of triangles), then generate into a caller-allocated buffer.  The workspace
+ * (sdfb_mc_workspace_bytes) carries the classification from count to generate. */
+int sdfb_mc_workspace_bytes(int nz, int ny, int nx, size_t* bytes);
+int sdfb_mc_count(const float* sdf_dev, const uint32_t* sign_bits_dev, int nz, int ny, int nx, void* workspace_dev,
+                  size_t workspace_bytes, int64_t* n_triangles_host, void* stream);
+int sdfb_mc_generate(const float* sdf_dev, int nz, int ny, int nx, int res, int z0, const void* workspace_dev,
+                     float* triangles_dev, void* stream);
+
 /* Debug/diagnostic: pre-activation (accumulator + bias, before ReLU) of
  * tensor-core pass `pass` (0..12) for the first 128 queries of a grid decode,
  * 128 x 256 floats.  Used by the parity tests to localise a failing layer. */

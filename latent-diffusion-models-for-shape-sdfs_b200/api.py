@@ -166,6 +166,12 @@ class Decoder:
                                               _stream_ptr(self.device.index)))
         return buf[: z1 - z0], signs, mw
 
+    def extract_surface(self, latent, res: int, precision: str | None = None) -> torch.Tensor:
+        """decode_grid + marching cubes: triangles [n,3,3] of the zero level set on the res^3 grid
+        (the decoder's own sign bit-planes classify the cells)."""
+        sdf, signs, _ = self.decode_grid_bits(latent, res, mask=False, precision=precision)
+        return extract_surface(sdf, res, 0, sign_words=signs)
+
     def decode_grid_batch(self, latents, res: int, precision: str | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
         """sdf [B, res, res, res] for latents [B,256] (independent shapes, one C call)."""
         prec = _prec(precision or self.precision)
@@ -339,6 +345,32 @@ def philox_normal(seed: int, n: int, t0: int, t1: int, device="cuda:0") -> torch
         with torch.cuda.device(dev):
             check(lib.sdfb_philox_normal(int(seed), n, t0, t1, out.data_ptr(), _stream_ptr(dev.index)))
     return out
+
+
+def extract_surface(sdf: torch.Tensor, res: int | None = None, z0: int = 0, sign_words: torch.Tensor | None = None) -> torch.Tensor:
+    """Marching cubes on a [nz,ny,nx] float32 CUDA field -> triangles [n,3,3] (x,y,z), cell order, normals
+    from inside (sdf < 0) to outside.  ``res``/``z0`` place a slab in the res^3 grid of rule A1 (default:
+    the field is the whole grid); ``sign_words`` are the bit-planes from ``Decoder.decode_grid_bits``."""
+    lib = _lib.load()
+    if sdf.ndim != 3 or sdf.dtype != torch.float32 or not sdf.is_cuda:
+        raise ValueError("sdf must be a 3-D float32 CUDA tensor")
+    s = sdf.contiguous()
+    nz, ny, nx = s.shape
+    res = nx if res is None else res
+    if min(nz, ny, nx) < 2:
+        return torch.empty((0, 3, 3), dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        nbytes = C.c_size_t()
+        check(lib.sdfb_mc_workspace_bytes(nz, ny, nx, C.byref(nbytes)))
+        ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=s.device)
+        n = C.c_int64()
+        st = _stream_ptr(s.device.index)
+        check(lib.sdfb_mc_count(s.data_ptr(), sign_words.data_ptr() if sign_words is not None else None, nz, ny, nx,
+                                ws.data_ptr(), nbytes.value, C.byref(n), st))
+        tris = torch.empty((n.value, 3, 3), dtype=torch.float32, device=s.device)
+        if n.value:
+            check(lib.sdfb_mc_generate(s.data_ptr(), nz, ny, nx, res, z0, ws.data_ptr(), tris.data_ptr(), st))
+    return tris
 
 
 def grid_points(res: int, z0: int = 0, z1: int | None = None, device="cuda:0") -> torch.Tensor:

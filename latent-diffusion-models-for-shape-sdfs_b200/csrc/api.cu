@@ -559,6 +559,65 @@ int sdfb_sign_change_mask(const float* sdf_dev, int nz, int ny, int nx, uint8_t*
   return SDFB_OK;
 }
 
+// ------------------------------------------------------------ marching cubes ----
+namespace {
+struct McLayout { size_t off_bits, off_groups, off_temp, total; long long groups, nodes; size_t temp_bytes; };
+McLayout mc_layout(int nz, int ny, int nx) {
+  McLayout L{};
+  L.nodes = static_cast<long long>(nz) * ny * nx;
+  const long long cells = static_cast<long long>(nz - 1) * (ny - 1) * (nx - 1);
+  L.groups = (cells + 31) >> 5;
+  L.temp_bytes = mc_scan_temp_bytes(L.groups);
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  L.off_bits = 0;
+  L.off_groups = up(static_cast<size_t>((L.nodes + 31) >> 5) * 4);
+  L.off_temp = L.off_groups + up(static_cast<size_t>(L.groups + 1) * 4);
+  L.total = L.off_temp + up(L.temp_bytes);
+  return L;
+}
+}  // namespace
+
+int sdfb_mc_workspace_bytes(int nz, int ny, int nx, size_t* bytes) {
+  if (!bytes) return fail(SDFB_E_INVALID, "null argument");
+  if (nz < 2 || ny < 2 || nx < 2) return fail(SDFB_E_INVALID, "the field must have at least 2 nodes per axis");
+  *bytes = mc_layout(nz, ny, nx).total;
+  return SDFB_OK;
+}
+
+int sdfb_mc_count(const float* sdf_dev, const uint32_t* sign_bits_dev, int nz, int ny, int nx, void* workspace_dev,
+                  size_t workspace_bytes, int64_t* n_triangles_host, void* stream) {
+  if (!sdf_dev || !workspace_dev || !n_triangles_host) return fail(SDFB_E_INVALID, "null argument");
+  if (nz < 2 || ny < 2 || nx < 2) return fail(SDFB_E_INVALID, "the field must have at least 2 nodes per axis");
+  const McLayout L = mc_layout(nz, ny, nx);
+  if (workspace_bytes < L.total) return fail(SDFB_E_INVALID, "workspace holds %zu bytes, %zu needed", workspace_bytes, L.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  unsigned int* bits = reinterpret_cast<unsigned int*>(ws + L.off_bits);
+  unsigned int* groups = reinterpret_cast<unsigned int*>(ws + L.off_groups);
+  if (sign_bits_dev != nullptr)
+    CU_TRY(cudaMemcpyAsync(bits, sign_bits_dev, static_cast<size_t>((L.nodes + 31) >> 5) * 4, cudaMemcpyDeviceToDevice, st));
+  else
+    CU_TRY(launch_sign_bits(sdf_dev, L.nodes, bits, st));
+  CU_TRY(launch_mc_count_scan(bits, nz, ny, nx, groups, ws + L.off_temp, L.temp_bytes, st));
+  unsigned int total = 0;
+  CU_TRY(cudaMemcpyAsync(&total, groups + L.groups, sizeof(total), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  *n_triangles_host = total;
+  return SDFB_OK;
+}
+
+int sdfb_mc_generate(const float* sdf_dev, int nz, int ny, int nx, int res, int z0, const void* workspace_dev,
+                     float* triangles_dev, void* stream) {
+  if (!sdf_dev || !workspace_dev || !triangles_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (nz < 2 || ny < 2 || nx < 2 || res < 2 || z0 < 0) return fail(SDFB_E_INVALID, "bad field shape");
+  const McLayout L = mc_layout(nz, ny, nx);
+  const uint8_t* ws = static_cast<const uint8_t*>(workspace_dev);
+  CU_TRY(launch_mc_generate(sdf_dev, reinterpret_cast<const unsigned int*>(ws + L.off_bits),
+                            reinterpret_cast<const unsigned int*>(ws + L.off_groups), nz, ny, nx, res, z0, triangles_dev,
+                            static_cast<cudaStream_t>(stream)));
+  return SDFB_OK;
+}
+
 int sdfb_decode_debug_pass(sdfb_decoder* d, const float* latent_dev, int res, int pass, float* dump_dev,
                            int precision, void* stream) {
   if (!d || !latent_dev || !dump_dev) return fail(SDFB_E_INVALID, "null argument");

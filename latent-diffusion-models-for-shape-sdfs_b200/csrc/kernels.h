@@ -173,6 +173,13 @@ cudaError_t launch_ddpm_update(float* x, const float* eps, const float* noise, l
                                float sra, float srm1, float c1, float c2, float sigma,
                                cudaStream_t stream);
 
+// ---- marching cubes (marching.cu) --------------------------------------------
+size_t mc_scan_temp_bytes(long long groups);
+cudaError_t launch_mc_count_scan(const unsigned int* bits, int nz, int ny, int nx, unsigned int* group_tris, void* temp,
+                                 size_t temp_bytes, cudaStream_t stream);
+cudaError_t launch_mc_generate(const float* sdf, const unsigned int* bits, const unsigned int* group_first, int nz, int ny,
+                               int nx, int res, int z0, float* tris, cudaStream_t stream);
+
 // A1: node coordinate, one correctly rounded divide of two exact integers.
 __host__ __device__ inline float axis_coord_num(int i, int res) { return static_cast<float>(2 * i - (res - 1)); }
 

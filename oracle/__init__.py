@@ -21,3 +21,4 @@ from .decoder import decoder_forward, decode_grid, decoder_forward_lowp
 from .ddpm import (ddpm_schedule, time_embedding, denoiser_forward,
                    ddpm_step, sample_latents, denoiser_forward_lowp)
 from .philox import philox4x32_10, philox_normal_rows, philox_sampler_inputs
+from .marching import marching_cubes, mesh_is_closed

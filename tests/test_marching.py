@@ -1,0 +1,91 @@
+"""Marching cubes: generated case tables, the numpy oracle, and - on the GPU -
+the CUDA extraction compared bit for bit with the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import mc_tables
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _sphere(res, r=0.6, c=(0.05, -0.1, 0.02)):
+    a = oracle.axis_coords(res)
+    zz, yy, xx = np.meshgrid(a, a, a, indexing="ij")
+    return (np.sqrt((xx - c[0]) ** 2 + (yy - c[1]) ** 2 + (zz - c[2]) ** 2) - r).astype(np.float32)
+
+
+def test_tables_are_consistent_and_header_is_current():
+    assert mc_tables.MC_MAX_TRI == 5
+    assert mc_tables.MC_NTRI[0] == 0 and mc_tables.MC_NTRI[255] == 0
+    for case in range(256):
+        n = mc_tables.MC_NTRI[case]
+        used = mc_tables.MC_TRI[case, : 3 * n]
+        assert (used >= 0).all() and (mc_tables.MC_TRI[case, 3 * n:] == -1).all()
+        inside = [(case >> i) & 1 for i in range(8)]
+        crossed = {e for e, (a, b) in enumerate(mc_tables.EDGES) if inside[a] != inside[b]}
+        assert set(int(e) for e in used) == crossed          # every crossed edge carries a vertex, no other edge does
+    with open(mc_tables.HEADER_PATH) as f:
+        assert f.read() == mc_tables.header_text(), "run `python -m oracle.mc_tables` to regenerate csrc/mc_tables.h"
+
+
+def test_oracle_sphere_area_orientation_and_watertightness():
+    res, r = 48, 0.6
+    tris = oracle.marching_cubes(_sphere(res, r))
+    area = np.linalg.norm(np.cross(tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0]), axis=1).sum() / 2
+    assert abs(area / (4 * np.pi * r * r) - 1) < 5e-3
+    n = np.cross(tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0])
+    cen = tris.mean(axis=1) - np.array([0.05, -0.1, 0.02], np.float32)
+    assert ((n * cen).sum(1) > 0).all()                       # normals point outward (towards sdf > 0)
+    assert oracle.mesh_is_closed(tris)
+    # every ambiguous configuration: a random field inside a positive shell still gives a closed, consistently oriented mesh
+    rs = np.random.RandomState(0)
+    g = np.ones((14, 15, 16), np.float32)
+    g[1:-1, 1:-1, 1:-1] = rs.standard_normal((12, 13, 14))
+    assert oracle.mesh_is_closed(oracle.marching_cubes(g, res=16))
+    assert oracle.marching_cubes(np.ones((4, 4, 4), np.float32)).shape == (0, 3, 3)
+
+
+@pytest.mark.gpu
+def test_cuda_marching_cubes_bit_exact(pkg, cuda_decoder):
+    rs = np.random.RandomState(3)
+    fields = [(_sphere(40), 40, 0), (rs.standard_normal((9, 13, 13)).astype(np.float32), 13, 2),
+              (rs.standard_normal((33, 35, 35)).astype(np.float32), 35, 0), (np.ones((5, 6, 6), np.float32), 6, 0)]
+    for f, res, z0 in fields:
+        got = pkg.extract_surface(torch.from_numpy(f).cuda(), res=res, z0=z0).cpu().numpy()
+        want = oracle.marching_cubes(f, res=res, z0=z0)
+        assert got.shape == want.shape
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # decoded shape: the decoder's own sign bit-planes drive the classification
+    z = oracle.default_latent()
+    tris = cuda_decoder.extract_surface(z, 64).cpu().numpy()
+    sdf = cuda_decoder.decode_grid(z, 64).cpu().numpy()
+    want = oracle.marching_cubes(sdf)
+    assert np.array_equal(tris.view(np.uint32), want.view(np.uint32))
+    assert tris.shape[0] > 10000
+    # a z-slab placed in the grid: same triangles as the corresponding cells of the full extraction
+    slab, signs, _ = cuda_decoder.decode_grid_bits(z, 64, 16, 25, mask=False)
+    part = pkg.extract_surface(slab, res=64, z0=16, sign_words=signs).cpu().numpy()
+    assert np.array_equal(part.view(np.uint32), oracle.marching_cubes(sdf[16:25], res=64, z0=16).view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_cuda_marching_cubes_full_size(pkg, cuda_decoder):
+    """256^3 (BASELINE configs[1]'s grid): finite, inside the cube, and a 20-plane slab of it bit-exact with the oracle."""
+    z = oracle.default_latent()
+    sdf, signs, _ = cuda_decoder.decode_grid_bits(z, 256, mask=False)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    tris = pkg.extract_surface(sdf, 256, 0, sign_words=signs)
+    b.record()
+    b.synchronize()
+    print(f"256^3 marching cubes: {tris.shape[0]} triangles in {a.elapsed_time(b):.2f} ms")
+    assert tris.shape[0] > 200000 and torch.isfinite(tris).all() and tris.abs().max() <= 1.0
+    slab = sdf[100:120].contiguous()
+    part = pkg.extract_surface(slab, 256, 100).cpu().numpy()
+    want = oracle.marching_cubes(slab.cpu().numpy(), res=256, z0=100)
+    assert np.array_equal(part.view(np.uint32), want.view(np.uint32))
