@@ -201,7 +201,6 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, u
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   float4 v;
