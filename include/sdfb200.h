@@ -91,6 +91,13 @@ int sdfb_decode_grid_batch(sdfb_decoder* dec, const float* latents_dev, int batc
 int sdfb_decode_points(sdfb_decoder* dec, const float* latent_dev, const float* xyz_dev, int64_t M,
                        float* sdf_dev, int precision, void* stream);
 
+/* Vector-Jacobian product w.r.t. the latent (what auto-decoder latent fitting
+ * needs): grad_latent_dev[256] = sum_m dLdy_dev[m] * d sdf(latent, xyz_m) / d latent, fp32 FFMA path
+ * (forward with stored activations + backward, deterministic reduction).  sdf_dev (optional, [M])
+ * receives the forward values. */
+int sdfb_decoder_vjp_latent(sdfb_decoder* dec, const float* latent_dev, const float* xyz_dev, int64_t M,
+                            const float* dLdy_dev, float* grad_latent_dev, float* sdf_dev, void* stream);
+
 /* Host-buffer forms (what a plugin caller with CPU arrays uses): stage through
  * pinned memory owned by the context, run, copy back, synchronise. */
 int sdfb_decode_grid_host(sdfb_decoder* dec, const float* latent_host, int res, int z0, int z1,

@@ -166,6 +166,50 @@ class Decoder:
                                               _stream_ptr(self.device.index)))
         return buf[: z1 - z0], signs, mw
 
+    # ---- gradient w.r.t. the latent (auto-decoder fitting) ----------------------------------------
+    def latent_vjp(self, latent, xyz, dLdy):
+        """(grad [256], sdf [M]): grad = sum_m dLdy[m] * d sdf(latent, xyz_m) / d latent, fp32 path."""
+        lat = _as_dev_f32(latent, self.device, (LATENT,))
+        pts = _as_dev_f32(xyz, self.device)
+        up = _as_dev_f32(dLdy, self.device)
+        if pts.ndim != 2 or pts.shape[1] != 3 or up.shape != (pts.shape[0],):
+            raise ValueError("expected xyz [M,3] and dLdy [M]")
+        M = pts.shape[0]
+        grad = torch.empty(LATENT, dtype=torch.float32, device=self.device)
+        sdf = torch.empty(M, dtype=torch.float32, device=self.device)
+        check(self._lib.sdfb_decoder_vjp_latent(self._h, lat.data_ptr(), pts.data_ptr() if M else None, M,
+                                                up.data_ptr() if M else None, grad.data_ptr(),
+                                                sdf.data_ptr() if M else None, _stream_ptr(self.device.index)))
+        return grad, sdf
+
+    def fit_latent(self, xyz, sdf_target, steps: int = 300, lr: float = 5e-3, clamp: float = 0.1, reg: float = 1e-4,
+                   init=None):
+        """Auto-decoder inference (DeepSDF's reconstruction step): Adam on the latent so that the decoded
+        field matches ``sdf_target`` at ``xyz``; loss = mean |clamp(y) - clamp(s)| + reg |z|^2.
+        Returns (latent [256], last loss)."""
+        pts = _as_dev_f32(xyz, self.device)
+        tgt = torch.clamp(_as_dev_f32(sdf_target, self.device), -clamp, clamp)
+        z = torch.zeros(LATENT, device=self.device) if init is None else _as_dev_f32(init, self.device, (LATENT,)).clone()
+        m = torch.zeros_like(z)
+        v = torch.zeros_like(z)
+        M = pts.shape[0]
+        ones = torch.ones(M, device=self.device)
+        loss = float("nan")
+        for it in range(1, steps + 1):
+            if it == 1:
+                y = self(z, pts, precision="fp32")
+            inside = (y > -clamp) & (y < clamp)
+            dLdy = torch.sign(torch.clamp(y, -clamp, clamp) - tgt) * inside / M
+            g, y_chk = self.latent_vjp(z, pts, dLdy)
+            loss = float((torch.clamp(y_chk, -clamp, clamp) - tgt).abs().mean() + reg * (z * z).sum())
+            g = g + 2 * reg * z
+            m = 0.9 * m + 0.1 * g
+            v = 0.999 * v + 0.001 * g * g
+            z = z - lr * (m / (1 - 0.9 ** it)) / ((v / (1 - 0.999 ** it)).sqrt() + 1e-8)
+            y = self(z, pts, precision="fp32")
+        del ones
+        return z, loss
+
     def extract_surface(self, latent, res: int, precision: str | None = None) -> torch.Tensor:
         """decode_grid + marching cubes: triangles [n,3,3] of the zero level set on the res^3 grid
         (the decoder's own sign bit-planes classify the cells)."""

@@ -145,6 +145,9 @@ struct sdfb_decoder {
   float* bias4f = nullptr;
   unsigned int* status = nullptr;
   unsigned int* signs = nullptr; long long sign_words = 0;   // sign bit-planes of the last masked decode (lazy)
+  // backward workspace (lazy): stored activations of one chunk, two delta buffers, column-sum partials
+  float* bw_act[8] = {}; float *bw_d0 = nullptr, *bw_d1 = nullptr, *bw_y = nullptr, *bw_partial = nullptr;
+  long long bw_rows = 0, bw_blocks = 0;
   // fp32 workspace (lazy)
   long long ws_rows = 0;
   float *h0 = nullptr, *h1 = nullptr, *s = nullptr, *x = nullptr;
@@ -406,6 +409,8 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
   cudaFree(d->params); cudaFree(d->w4s); cudaFree(d->wstream[0]); cudaFree(d->wstream[1]);
   cudaFree(d->consts); cudaFree(d->bias0f); cudaFree(d->bias4f); cudaFree(d->status);
   cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x); cudaFree(d->prof); cudaFree(d->signs);
+  for (float* a : d->bw_act) cudaFree(a);
+  cudaFree(d->bw_d0); cudaFree(d->bw_d1); cudaFree(d->bw_y); cudaFree(d->bw_partial);
   if (d->pin) cudaFreeHost(d->pin);
   cudaFree(d->dstage);
   if (d->ev0) cudaEventDestroy(d->ev0);
@@ -477,6 +482,71 @@ int sdfb_decode_points(sdfb_decoder* d, const float* latent_dev, const float* xy
   if (M < 0) return fail(SDFB_E_INVALID, "negative point count");
   DeviceGuard g(d->device);
   return decode_any(d, latent_dev, xyz_dev, 0, 0, M, sdf_dev, precision, static_cast<cudaStream_t>(stream));
+}
+
+// g = sum_m dLdy[m] d sdf_m / d latent on the fp32 path: forward with stored activations, backward with the
+// FFMA kernels, deterministic column sums; chunks of 8192 points.
+int sdfb_decoder_vjp_latent(sdfb_decoder* d, const float* latent_dev, const float* xyz_dev, int64_t M, const float* dLdy_dev,
+                            float* grad_latent_dev, float* sdf_dev, void* stream) {
+  if (!d || !latent_dev || !grad_latent_dev || (M > 0 && (!xyz_dev || !dLdy_dev))) return fail(SDFB_E_INVALID, "null argument");
+  if (M < 0) return fail(SDFB_E_INVALID, "negative point count");
+  DeviceGuard g(d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M == 0) { CU_TRY(cudaMemsetAsync(grad_latent_dev, 0, kLatent * sizeof(float), st)); return SDFB_OK; }
+  constexpr long long kChunkRows = 8192;
+  const long long rows = M < kChunkRows ? M : kChunkRows;
+  if (d->bw_rows < rows) {
+    for (float*& a : d->bw_act) { cudaFree(a); a = nullptr; }
+    cudaFree(d->bw_d0); cudaFree(d->bw_d1); cudaFree(d->bw_y); d->bw_d0 = d->bw_d1 = d->bw_y = nullptr; d->bw_rows = 0;
+    for (int i = 0; i < 8; ++i) CU_TRY(cudaMalloc(&d->bw_act[i], rows * (i == 3 ? 256 : 512) * sizeof(float)));
+    CU_TRY(cudaMalloc(&d->bw_d0, rows * 512 * sizeof(float)));
+    CU_TRY(cudaMalloc(&d->bw_d1, rows * 512 * sizeof(float)));
+    CU_TRY(cudaMalloc(&d->bw_y, rows * sizeof(float)));
+    d->bw_rows = rows;
+  }
+  const long long nblk = (M + 255) / 256 + (M + rows - 1) / rows;
+  if (d->bw_blocks < nblk) {
+    cudaFree(d->bw_partial); d->bw_partial = nullptr; d->bw_blocks = 0;
+    CU_TRY(cudaMalloc(&d->bw_partial, nblk * 1024 * sizeof(float)));
+    d->bw_blocks = nblk;
+  }
+  const float* P = d->params;
+  const LayerOff* o = d->off;
+  float** a = d->bw_act;
+  CU_TRY(launch_fold_bias(P + o[0].w, kDecIn, 0, P + o[0].b, latent_dev, kLatent, kHid, d->bias0f, st));
+  CU_TRY(launch_fold_bias(P + o[4].w, kHid, kSkipOut, P + o[4].b, latent_dev, kLatent, kHid, d->bias4f, st));
+  long long blk = 0;
+  for (long long m0 = 0; m0 < M; m0 += rows) {
+    const long long m = (M - m0) < rows ? (M - m0) : rows;
+    const float* X = xyz_dev + 3 * m0;
+    float* y = sdf_dev != nullptr ? sdf_dev + m0 : d->bw_y;
+    // forward, every activation kept
+    CU_TRY(launch_scatter_xyz(X, m, a[3], st));
+    CU_TRY(launch_linear_f32(X, 3, P + o[0].w + kLatent, kDecIn, d->bias0f, a[0], 512, m, 512, 3, true, st));
+    CU_TRY(launch_linear_f32(a[0], 512, P + o[1].w, 512, P + o[1].b, a[1], 512, m, 512, 512, true, st));
+    CU_TRY(launch_linear_f32(a[1], 512, P + o[2].w, 512, P + o[2].b, a[2], 512, m, 512, 512, true, st));
+    CU_TRY(launch_linear_f32(a[2], 512, P + o[3].w, 512, P + o[3].b, a[3], 256, m, kSkipOut, 512, true, st));
+    CU_TRY(launch_linear_f32(a[3], 256, d->w4s, 256, d->bias4f, a[4], 512, m, 512, 256, true, st));
+    CU_TRY(launch_linear_f32(a[4], 512, P + o[5].w, 512, P + o[5].b, a[5], 512, m, 512, 512, true, st));
+    CU_TRY(launch_linear_f32(a[5], 512, P + o[6].w, 512, P + o[6].b, a[6], 512, m, 512, 512, true, st));
+    CU_TRY(launch_linear_f32(a[6], 512, P + o[7].w, 512, P + o[7].b, a[7], 512, m, 512, 512, true, st));
+    CU_TRY(launch_head_tanh_f32(a[7], 512, P + o[8].w, P + o[8].b, y, m, 512, st));
+    // backward
+    float *da = d->bw_d0, *db = d->bw_d1;
+    CU_TRY(launch_head_bwd_f32(dLdy_dev + m0, y, P + o[8].w, a[7], db, m, st));                               // delta7
+    CU_TRY(launch_linear_bwd_f32(db, 512, P + o[7].w, 512, a[6], 512, da, 512, m, 512, 512, st));              // delta6
+    CU_TRY(launch_linear_bwd_f32(da, 512, P + o[6].w, 512, a[5], 512, db, 512, m, 512, 512, st));              // delta5
+    CU_TRY(launch_linear_bwd_f32(db, 512, P + o[5].w, 512, a[4], 512, da, 512, m, 512, 512, st));              // delta4
+    CU_TRY(launch_colsum_f32(da, m, d->bw_partial + blk * 1024, 1, st));
+    CU_TRY(launch_linear_bwd_f32(da, 512, P + o[4].w, 512, a[3], 256, db, 512, m, 512, kSkipOut, st));         // delta3 (253 wide)
+    CU_TRY(launch_linear_bwd_f32(db, 512, P + o[3].w, 512, a[2], 512, da, 512, m, kSkipOut, 512, st));         // delta2
+    CU_TRY(launch_linear_bwd_f32(da, 512, P + o[2].w, 512, a[1], 512, db, 512, m, 512, 512, st));              // delta1
+    CU_TRY(launch_linear_bwd_f32(db, 512, P + o[1].w, 512, a[0], 512, da, 512, m, 512, 512, st));              // delta0
+    CU_TRY(launch_colsum_f32(da, m, d->bw_partial + blk * 1024, 0, st));
+    blk += (m + 255) / 256;
+  }
+  CU_TRY(launch_vjp_finish(d->bw_partial, static_cast<int>(blk), P + o[0].w, P + o[4].w, grad_latent_dev, st));
+  return SDFB_OK;
 }
 
 int sdfb_decode_grid_host(sdfb_decoder* d, const float* latent_host, int res, int z0, int z1, float* sdf_host,

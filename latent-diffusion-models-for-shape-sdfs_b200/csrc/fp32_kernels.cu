@@ -66,6 +66,107 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
   }
 }
 
+// Backward of a linear layer w.r.t. its input, fused with the ReLU mask of the layer below:
+// C[M,K] = (A[M,N] * W[N,K]) .* (H[M,K] > 0)     (W row-major [N][K], i.e. NOT transposed; H = stored activations)
+__global__ void __launch_bounds__(256) linear_bwd_f32_kernel(const float* __restrict__ A, int lda,
+                                                             const float* __restrict__ W, int ldw,
+                                                             const float* __restrict__ H, int ldh,
+                                                             float* __restrict__ C, int ldc, long long M, int N, int K) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long m0 = static_cast<long long>(blockIdx.x) * BM;
+  const int k0 = blockIdx.y * BN;
+  float acc[4][4] = {};
+  for (int n0 = 0; n0 < N; n0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + 256 * i;
+      {
+        const int r = e >> 4, nn = e & 15;             // A tile: 64 rows x 16 reduction indices
+        const long long m = m0 + r;
+        As[nn][r] = (m < M && n0 + nn < N) ? A[m * lda + n0 + nn] : 0.f;
+      }
+      {
+        const int nn = e >> 6, c = e & 63;             // W tile: 16 reduction indices x 64 output columns (coalesced)
+        Ws[nn][c] = (n0 + nn < N && k0 + c < K) ? W[static_cast<long long>(n0 + nn) * ldw + k0 + c] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int nn = 0; nn < BK; ++nn) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[nn][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Ws[nn][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k >= K) continue;
+      C[m * ldc + k] = H[m * ldh + k] > 0.f ? acc[i][j] : 0.f;
+    }
+  }
+}
+
+// delta7[m,k] = dLdy[m] (1 - y[m]^2) w8[k] [h7[m,k] > 0]
+__global__ void head_bwd_f32_kernel(const float* __restrict__ dLdy, const float* __restrict__ y,
+                                    const float* __restrict__ w8, const float* __restrict__ H7, float* __restrict__ D,
+                                    long long M) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M * 512) return;
+  const long long m = i >> 9;
+  const int k = static_cast<int>(i & 511);
+  const float yy = y[m];
+  const float g = dLdy[m] * (1.f - yy * yy);
+  D[i] = H7[i] > 0.f ? g * w8[k] : 0.f;
+}
+
+// partial[b][half * 512 + col] = sum over the block's 256 rows of D[m][col]   (fixed order: deterministic)
+__global__ void colsum_f32_kernel(const float* __restrict__ D, long long M, float* __restrict__ partial, int half) {
+  const long long r0 = static_cast<long long>(blockIdx.x) * 256;
+  const long long r1 = r0 + 256 < M ? r0 + 256 : M;
+  float s0 = 0.f, s1 = 0.f;
+  for (long long m = r0; m < r1; ++m) {
+    s0 += D[m * 512 + threadIdx.x];
+    s1 += D[m * 512 + 256 + threadIdx.x];
+  }
+  float* dst = partial + static_cast<long long>(blockIdx.x) * 1024 + half * 512;
+  dst[threadIdx.x] = s0;
+  dst[256 + threadIdx.x] = s1;
+}
+
+// grad[k] = sum_n s0[n] W0[n][k] + sum_n s4[n] W4[n][253 + k], s0 / s4 = column sums over all partial blocks
+__global__ void vjp_finish_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ W0,
+                                  const float* __restrict__ W4, float* __restrict__ grad) {
+  __shared__ float s[1024];
+  for (int c = threadIdx.x; c < 1024; c += blockDim.x) {
+    float a = 0.f;
+    for (int b = 0; b < nblk; ++b) a += partial[static_cast<long long>(b) * 1024 + c];
+    s[c] = a;
+  }
+  __syncthreads();
+  const int k = threadIdx.x;
+  if (k < 256) {
+    float g = 0.f;
+    for (int n = 0; n < 512; ++n) g = fmaf(s[n], W0[n * 259 + k], g);
+    for (int n = 0; n < 512; ++n) g = fmaf(s[512 + n], W4[n * 512 + 253 + k], g);
+    grad[k] = g;
+  }
+}
+
 // one warp per query row: out = tanh(dot + b)
 __global__ void head_tanh_f32_kernel(const float* __restrict__ H, int ldh, const float* __restrict__ w,
                                      const float* __restrict__ b, float* __restrict__ out, long long M,
@@ -208,6 +309,33 @@ cudaError_t launch_linear_f32(const float* A, int lda, const float* W, int ldw, 
   if (M <= 0) return cudaSuccess;
   dim3 grid(blocks_for(M, BM), blocks_for(N, BN));
   linear_f32_kernel<<<grid, 256, 0, stream>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, relu ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_linear_bwd_f32(const float* A, int lda, const float* W, int ldw, const float* H, int ldh, float* C,
+                                  int ldc, long long M, int N, int K, cudaStream_t stream) {
+  if (M <= 0) return cudaSuccess;
+  dim3 grid(blocks_for(M, BM), blocks_for(K, BN));
+  linear_bwd_f32_kernel<<<grid, 256, 0, stream>>>(A, lda, W, ldw, H, ldh, C, ldc, M, N, K);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_head_bwd_f32(const float* dLdy, const float* y, const float* w8, const float* H7, float* D, long long M,
+                                cudaStream_t stream) {
+  if (M <= 0) return cudaSuccess;
+  head_bwd_f32_kernel<<<blocks_for(M * 512, 256), 256, 0, stream>>>(dLdy, y, w8, H7, D, M);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_colsum_f32(const float* D, long long M, float* partial, int half, cudaStream_t stream) {
+  if (M <= 0) return cudaSuccess;
+  colsum_f32_kernel<<<blocks_for(M, 256), 256, 0, stream>>>(D, M, partial, half);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vjp_finish(const float* partial, int nblk, const float* W0, const float* W4, float* grad,
+                              cudaStream_t stream) {
+  vjp_finish_kernel<<<1, 256, 0, stream>>>(partial, nblk, W0, W4, grad);
   return cudaGetLastError();
 }
 

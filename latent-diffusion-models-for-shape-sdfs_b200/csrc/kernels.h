@@ -153,6 +153,15 @@ cudaError_t launch_linear_f32(const float* A, int lda, const float* W, int ldw, 
 // out[m] = tanh(dot(H[m,:K], w) + b)
 cudaError_t launch_head_tanh_f32(const float* H, int ldh, const float* w, const float* b, float* out,
                                  long long M, int K, cudaStream_t stream);
+// backward pieces of the fp32 path (vector-Jacobian product w.r.t. the latent)
+// C[M,K] = (A[M,N] * W[N,K]) .* (H[M,K] > 0)
+cudaError_t launch_linear_bwd_f32(const float* A, int lda, const float* W, int ldw, const float* H, int ldh, float* C,
+                                  int ldc, long long M, int N, int K, cudaStream_t stream);
+cudaError_t launch_head_bwd_f32(const float* dLdy, const float* y, const float* w8, const float* H7, float* D, long long M,
+                                cudaStream_t stream);
+cudaError_t launch_colsum_f32(const float* D, long long M, float* partial, int half, cudaStream_t stream);
+cudaError_t launch_vjp_finish(const float* partial, int nblk, const float* W0, const float* W4, float* grad,
+                              cudaStream_t stream);
 // xyz of queries [q0, q0+M) of the res^3 grid -> X[M,3] and (optionally) cols 253..255 of S[M,256]
 cudaError_t launch_grid_xyz(int res, long long q0, long long M, float* X, float* S,
                             cudaStream_t stream);

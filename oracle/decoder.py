@@ -124,3 +124,26 @@ def decoder_forward_lowp(latent, xyz, params=None, lowp=torch.bfloat16, chunk: i
     if preacts is not None:
         preacts.extend(p.numpy() for p in pre)
     return out.numpy()
+
+
+def decoder_vjp_latent(latent, xyz, dLdy, params=None, dtype=torch.float64):
+    """grad[256] = sum_m dLdy[m] * d sdf(latent, xyz_m) / d latent, by torch autograd on the plain dense
+    forward (the oracle of the CUDA backward path).  Returns (grad, sdf) numpy."""
+    params = decoder_weights() if params is None else params
+    W = [_as_t(w, dtype) for w, _ in params]
+    B = [_as_t(b, dtype) for _, b in params]
+    x = _as_t(xyz, dtype).reshape(-1, 3)
+    up = _as_t(dLdy, dtype).reshape(-1)
+    z = _as_t(latent, dtype).reshape(DEC_LATENT).clone().requires_grad_(True)
+    inp = torch.cat([z.expand(x.shape[0], DEC_LATENT), x], dim=1)
+    h = torch.relu(inp @ W[0].T + B[0])
+    h = torch.relu(h @ W[1].T + B[1])
+    h = torch.relu(h @ W[2].T + B[2])
+    h = torch.relu(h @ W[3].T + B[3])
+    h = torch.relu(torch.cat([h, inp], dim=1) @ W[4].T + B[4])
+    h = torch.relu(h @ W[5].T + B[5])
+    h = torch.relu(h @ W[6].T + B[6])
+    h = torch.relu(h @ W[7].T + B[7])
+    y = torch.tanh(h @ W[8].T + B[8]).squeeze(1)
+    (y * up).sum().backward()
+    return z.grad.detach().numpy(), y.detach().numpy()
