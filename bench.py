@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the 512^3 z-slab-sharded case that runs when N > 1")
+    ap.add_argument("--no-config4", action="store_true", help="skip the sample-then-decode leg (configs[3])")
     ap.add_argument("--no-ddpm", action="store_true", help="skip the latent-DDPM leg (second half of the metric)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -348,6 +349,36 @@ def main():
                             "api": "LatentDDPM.sample_latents_seeded_host -> sdfb_ddpm_sample_philox_host (x_T and noise generated on the device, x_0 returned to the host)"}
         del noise, sampler
 
+    # ---- BASELINE configs[3], one GPU's share when it is spread over 8: 512 of the 4096 latents are sampled (1000 steps,
+    # noise generated in the kernel) and each is decoded on a 128^3 grid (64 shapes per call into a reused buffer; 34 GB of
+    # sdf in total for the full config, so the fields are consumed / discarded as they are produced)
+    cfg4 = None
+    if not args.no_config4:
+        n4, res4 = 512, 128
+        smp = pkg.LatentDDPM(pkg.synthetic.ddpm_params(), device=dev, precision=args.precision)
+        buf4 = torch.empty((64, res4, res4, res4), dtype=torch.float32, device=dev)
+        lat4 = smp.sample_latents(n4, seed=1000 + rank)
+        dec.decode_grid_batch(lat4[:64], res4, out=buf4)
+        barrier()
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        lat4 = smp.sample_latents(n4, seed=1000 + rank)
+        b.record()
+        for i0 in range(0, n4, 64):
+            dec.decode_grid_batch(lat4[i0:i0 + 64], res4, out=buf4)
+        c.record()
+        c.synchronize()
+        t4 = torch.tensor([a.elapsed_time(b), b.elapsed_time(c)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        q4 = n4 * res4 ** 3
+        cfg4 = {"workload": f"per GPU: sample_latents({n4}) (1000 steps, in-kernel noise) then decode_grid_batch of the {n4} samples at "
+                            f"{res4}^3 (64 per call); {world} GPUs cover {world * n4} latents (BASELINE configs[3] = 4096 latents on 8 GPUs)",
+                "ddpm_ms": float(t4[0].item()), "decode_ms": float(t4[1].item()), "total_ms": float(t4.sum().item()),
+                "decode_queries_per_s": world * q4 / (float(t4[1].item()) * 1e-3),
+                "decode_tflops_per_gpu": q4 * FLOP_TENSOR_PER_QUERY / (float(t4[1].item()) * 1e-3) / 1e12}
+        del buf4, smp, lat4
+
     if rank == 0:
         peaks = read_peaks()
         k_ms = statistics.mean(kernel_ms)
@@ -381,6 +412,8 @@ def main():
         if cfg5 is not None:
             cfg5["frac_of_burst_peak_per_gpu"] = cfg5["tflops_per_gpu_incl_mask_and_gather"] / peaks["burst"]
             line["config5_512cubed_sharded"] = cfg5
+        if cfg4 is not None:
+            line["config4_sample_then_decode"] = cfg4
         if ddpm_line is not None:
             ddpm_line["frac_of_burst_peak"] = ddpm_line["achieved_tflops"] / peaks["burst"]
             line["ddpm"] = ddpm_line
