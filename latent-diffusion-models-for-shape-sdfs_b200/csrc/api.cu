@@ -632,10 +632,9 @@ int sdfb_sign_change_mask(const float* sdf_dev, int nz, int ny, int nx, uint8_t*
 // ------------------------------------------------------------ marching cubes ----
 namespace {
 struct McLayout { size_t off_bits, off_groups, off_temp, total; long long groups, nodes; size_t temp_bytes; };
-McLayout mc_layout(int nz, int ny, int nx) {
+McLayout mc_layout(long long nodes, long long cells) {
   McLayout L{};
-  L.nodes = static_cast<long long>(nz) * ny * nx;
-  const long long cells = static_cast<long long>(nz - 1) * (ny - 1) * (nx - 1);
+  L.nodes = nodes;
   L.groups = (cells + 31) >> 5;
   L.temp_bytes = mc_scan_temp_bytes(L.groups);
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -645,22 +644,11 @@ McLayout mc_layout(int nz, int ny, int nx) {
   L.total = L.off_temp + up(L.temp_bytes);
   return L;
 }
-}  // namespace
 
-int sdfb_mc_workspace_bytes(int nz, int ny, int nx, size_t* bytes) {
-  if (!bytes) return fail(SDFB_E_INVALID, "null argument");
-  if (nz < 2 || ny < 2 || nx < 2) return fail(SDFB_E_INVALID, "the field must have at least 2 nodes per axis");
-  *bytes = mc_layout(nz, ny, nx).total;
-  return SDFB_OK;
-}
-
-int sdfb_mc_count(const float* sdf_dev, const uint32_t* sign_bits_dev, int nz, int ny, int nx, void* workspace_dev,
-                  size_t workspace_bytes, int64_t* n_triangles_host, void* stream) {
-  if (!sdf_dev || !workspace_dev || !n_triangles_host) return fail(SDFB_E_INVALID, "null argument");
-  if (nz < 2 || ny < 2 || nx < 2) return fail(SDFB_E_INVALID, "the field must have at least 2 nodes per axis");
-  const McLayout L = mc_layout(nz, ny, nx);
+int mc_count_impl(const float* sdf_dev, const uint32_t* sign_bits_dev, const McGeom& g, void* workspace_dev,
+                  size_t workspace_bytes, int64_t* n_triangles_host, cudaStream_t st) {
+  const McLayout L = mc_layout(g.total_nodes, g.total_cells);
   if (workspace_bytes < L.total) return fail(SDFB_E_INVALID, "workspace holds %zu bytes, %zu needed", workspace_bytes, L.total);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
   unsigned int* bits = reinterpret_cast<unsigned int*>(ws + L.off_bits);
   unsigned int* groups = reinterpret_cast<unsigned int*>(ws + L.off_groups);
@@ -668,7 +656,7 @@ int sdfb_mc_count(const float* sdf_dev, const uint32_t* sign_bits_dev, int nz, i
     CU_TRY(cudaMemcpyAsync(bits, sign_bits_dev, static_cast<size_t>((L.nodes + 31) >> 5) * 4, cudaMemcpyDeviceToDevice, st));
   else
     CU_TRY(launch_sign_bits(sdf_dev, L.nodes, bits, st));
-  CU_TRY(launch_mc_count_scan(bits, nz, ny, nx, groups, ws + L.off_temp, L.temp_bytes, st));
+  CU_TRY(launch_mc_count_scan(bits, g, groups, ws + L.off_temp, L.temp_bytes, st));
   unsigned int total = 0;
   CU_TRY(cudaMemcpyAsync(&total, groups + L.groups, sizeof(total), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
@@ -676,16 +664,112 @@ int sdfb_mc_count(const float* sdf_dev, const uint32_t* sign_bits_dev, int nz, i
   return SDFB_OK;
 }
 
+int mc_generate_impl(const float* sdf_dev, const McGeom& g, const void* workspace_dev, float* triangles_dev, cudaStream_t st) {
+  const McLayout L = mc_layout(g.total_nodes, g.total_cells);
+  const uint8_t* ws = static_cast<const uint8_t*>(workspace_dev);
+  CU_TRY(launch_mc_generate(sdf_dev, reinterpret_cast<const unsigned int*>(ws + L.off_bits),
+                            reinterpret_cast<const unsigned int*>(ws + L.off_groups), g, triangles_dev, st));
+  return SDFB_OK;
+}
+}  // namespace
+
+int sdfb_mc_workspace_bytes(int nz, int ny, int nx, size_t* bytes) {
+  if (!bytes) return fail(SDFB_E_INVALID, "null argument");
+  if (nz < 2 || ny < 2 || nx < 2) return fail(SDFB_E_INVALID, "the field must have at least 2 nodes per axis");
+  const McGeom g = mc_dense_geom(nz, ny, nx, nx, 0);
+  *bytes = mc_layout(g.total_nodes, g.total_cells).total;
+  return SDFB_OK;
+}
+
+int sdfb_mc_count(const float* sdf_dev, const uint32_t* sign_bits_dev, int nz, int ny, int nx, void* workspace_dev,
+                  size_t workspace_bytes, int64_t* n_triangles_host, void* stream) {
+  if (!sdf_dev || !workspace_dev || !n_triangles_host) return fail(SDFB_E_INVALID, "null argument");
+  if (nz < 2 || ny < 2 || nx < 2) return fail(SDFB_E_INVALID, "the field must have at least 2 nodes per axis");
+  return mc_count_impl(sdf_dev, sign_bits_dev, mc_dense_geom(nz, ny, nx, nx, 0), workspace_dev, workspace_bytes, n_triangles_host,
+                       static_cast<cudaStream_t>(stream));
+}
+
 int sdfb_mc_generate(const float* sdf_dev, int nz, int ny, int nx, int res, int z0, const void* workspace_dev,
                      float* triangles_dev, void* stream) {
   if (!sdf_dev || !workspace_dev || !triangles_dev) return fail(SDFB_E_INVALID, "null argument");
   if (nz < 2 || ny < 2 || nx < 2 || res < 2 || z0 < 0) return fail(SDFB_E_INVALID, "bad field shape");
-  const McLayout L = mc_layout(nz, ny, nx);
-  const uint8_t* ws = static_cast<const uint8_t*>(workspace_dev);
-  CU_TRY(launch_mc_generate(sdf_dev, reinterpret_cast<const unsigned int*>(ws + L.off_bits),
-                            reinterpret_cast<const unsigned int*>(ws + L.off_groups), nz, ny, nx, res, z0, triangles_dev,
-                            static_cast<cudaStream_t>(stream)));
+  return mc_generate_impl(sdf_dev, mc_dense_geom(nz, ny, nx, res, z0), workspace_dev, triangles_dev, static_cast<cudaStream_t>(stream));
+}
+
+// ---- sparse extraction: coarse block corners -> block selection -> nodes of the selected blocks -> marching cubes ----
+int sdfb_sparse_corner_points(int res, int block, float* xyz_dev, void* stream) {
+  if (!xyz_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 2 || block < 1 || block > 64) return fail(SDFB_E_INVALID, "bad res or block size");
+  const int nb = (res - 1 + block - 1) / block;
+  CU_TRY(launch_block_corner_points(res, block, nb, xyz_dev, static_cast<cudaStream_t>(stream)));
   return SDFB_OK;
+}
+
+int sdfb_sparse_select_workspace_bytes(int res, int block, size_t* bytes) {
+  if (!bytes) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 2 || block < 1 || block > 64) return fail(SDFB_E_INVALID, "bad res or block size");
+  const long long nb = (res - 1 + block - 1) / block, total = nb * nb * nb;
+  *bytes = static_cast<size_t>((total + 255) / 256 * 256) + static_cast<size_t>(total) * 4 + 256 + block_select_temp_bytes(total) + 256;
+  return SDFB_OK;
+}
+
+int sdfb_sparse_select_blocks(const float* corner_sdf_dev, int res, int block, float tau, int32_t* block_ids_dev,
+                              void* workspace_dev, size_t workspace_bytes, int64_t* n_blocks_host, void* stream) {
+  if (!corner_sdf_dev || !block_ids_dev || !workspace_dev || !n_blocks_host) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 2 || block < 1 || block > 64 || !(tau >= 0.f)) return fail(SDFB_E_INVALID, "bad res, block size or tau");
+  size_t need = 0;
+  sdfb_sparse_select_workspace_bytes(res, block, &need);
+  if (workspace_bytes < need) return fail(SDFB_E_INVALID, "workspace holds %zu bytes, %zu needed", workspace_bytes, need);
+  const long long nb = (res - 1 + block - 1) / block, total = nb * nb * nb;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  unsigned char* flags = ws;
+  int* ids_all = reinterpret_cast<int*>(ws + (total + 255) / 256 * 256);
+  int* count_dev = ids_all + total;
+  void* temp = reinterpret_cast<uint8_t*>(count_dev) + 256;
+  CU_TRY(launch_block_select(corner_sdf_dev, static_cast<int>(nb), tau, flags, ids_all, block_ids_dev, count_dev, temp,
+                             block_select_temp_bytes(total), st));
+  int count = 0;
+  CU_TRY(cudaMemcpyAsync(&count, count_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  *n_blocks_host = count;
+  return SDFB_OK;
+}
+
+int sdfb_sparse_block_points(int res, int block, const int32_t* block_ids_dev, int64_t n_blocks, float* xyz_dev, void* stream) {
+  if (n_blocks > 0 && (!block_ids_dev || !xyz_dev)) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 2 || block < 1 || block > 64 || n_blocks < 0) return fail(SDFB_E_INVALID, "bad arguments");
+  const int nb = (res - 1 + block - 1) / block;
+  CU_TRY(launch_block_points(res, block, nb, block_ids_dev, n_blocks, xyz_dev, static_cast<cudaStream_t>(stream)));
+  return SDFB_OK;
+}
+
+int sdfb_mc_blocks_workspace_bytes(int block, int64_t n_blocks, size_t* bytes) {
+  if (!bytes || block < 1 || block > 64 || n_blocks < 0) return fail(SDFB_E_INVALID, "bad arguments");
+  const McGeom g = mc_block_geom(2, block, 1, nullptr, n_blocks);
+  *bytes = mc_layout(g.total_nodes, g.total_cells).total;
+  return SDFB_OK;
+}
+
+int sdfb_mc_blocks_count(const float* fields_dev, const int32_t* block_ids_dev, int64_t n_blocks, int res, int block,
+                         void* workspace_dev, size_t workspace_bytes, int64_t* n_triangles_host, void* stream) {
+  if (!n_triangles_host) return fail(SDFB_E_INVALID, "null argument");
+  if (n_blocks == 0) { *n_triangles_host = 0; return SDFB_OK; }
+  if (!fields_dev || !block_ids_dev || !workspace_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 2 || block < 1 || block > 64 || n_blocks < 0) return fail(SDFB_E_INVALID, "bad arguments");
+  const int nb = (res - 1 + block - 1) / block;
+  return mc_count_impl(fields_dev, nullptr, mc_block_geom(res, block, nb, block_ids_dev, n_blocks), workspace_dev, workspace_bytes,
+                       n_triangles_host, static_cast<cudaStream_t>(stream));
+}
+
+int sdfb_mc_blocks_generate(const float* fields_dev, const int32_t* block_ids_dev, int64_t n_blocks, int res, int block,
+                            const void* workspace_dev, float* triangles_dev, void* stream) {
+  if (n_blocks == 0) return SDFB_OK;
+  if (!fields_dev || !block_ids_dev || !workspace_dev || !triangles_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 2 || block < 1 || block > 64 || n_blocks < 0) return fail(SDFB_E_INVALID, "bad arguments");
+  const int nb = (res - 1 + block - 1) / block;
+  return mc_generate_impl(fields_dev, mc_block_geom(res, block, nb, block_ids_dev, n_blocks), workspace_dev, triangles_dev,
+                          static_cast<cudaStream_t>(stream));
 }
 
 int sdfb_decode_debug_pass(sdfb_decoder* d, const float* latent_dev, int res, int pass, float* dump_dev,
