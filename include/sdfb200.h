@@ -179,17 +179,20 @@ int sdfb_ddpm_denoise(sdfb_ddpm* ddpm, const float* x_dev, int t, int n, float* 
 int sdfb_ddpm_sample_host(sdfb_ddpm* ddpm, float* x_host, const float* noise_host, int n, int steps,
                           int precision);
 /* Seeded sampling with IN-KERNEL noise (no [steps][n][256] stream in memory or over PCIe):
- * noise[t] = Philox4x32-10 normals, counter (column / 4, latent, t, 0x53444642), key = seed
- * (csrc/philox.cuh; oracle/philox.py reproduces the stream on the CPU).  gen_xT != 0: x_T is
+ * noise[t] = Philox4x32-10 normals, counter (column / 4, first_latent + latent, t, 0x53444642),
+ * key = seed (csrc/philox.cuh; oracle/philox.py reproduces the stream on the CPU).  first_latent is
+ * the global index of this call's latent 0: ranks that each sample a share of one batch draw exactly the
+ * numbers a single call over the whole batch would.  gen_xT != 0: x_T is
  * generated too (row t = steps of the same stream) and x_dev is output only; otherwise x_dev holds
  * x_T on entry.  bf16/fp16: generated inside the fused kernel's update epilogue; fp32: the same
  * stream is materialised on the device first, then the FFMA sampler runs on it. */
-int sdfb_ddpm_sample_philox(sdfb_ddpm* ddpm, float* x_dev, uint64_t seed, int n, int steps, int gen_xT,
-                            int precision, void* stream);
-int sdfb_ddpm_sample_philox_host(sdfb_ddpm* ddpm, float* x_host, uint64_t seed, int n, int steps, int gen_xT,
-                                 int precision);
-/* The stream itself: normals of steps [t0, t1) for n latents -> out_dev [(t1-t0)][n][256]. */
-int sdfb_philox_normal(uint64_t seed, int n, int t0, int t1, float* out_dev, void* stream);
+int sdfb_ddpm_sample_philox(sdfb_ddpm* ddpm, float* x_dev, uint64_t seed, int64_t first_latent, int n, int steps,
+                            int gen_xT, int precision, void* stream);
+int sdfb_ddpm_sample_philox_host(sdfb_ddpm* ddpm, float* x_host, uint64_t seed, int64_t first_latent, int n, int steps,
+                                 int gen_xT, int precision);
+/* The stream itself: normals of steps [t0, t1) for latents [first_latent, first_latent + n)
+ * -> out_dev [(t1-t0)][n][256]. */
+int sdfb_philox_normal(uint64_t seed, int64_t first_latent, int n, int t0, int t1, float* out_dev, void* stream);
 /* Elapsed device time (ms) of the last fused (bf16/fp16) sampler launch on this context, CUDA
  * events on the launching stream; blocks until it has finished and reports a tripped watchdog. */
 int sdfb_ddpm_last_kernel_ms(sdfb_ddpm* ddpm, float* ms);

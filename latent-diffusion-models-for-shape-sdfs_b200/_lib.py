@@ -51,9 +51,9 @@ SIGNATURES = {
     "sdfb_ddpm_denoise": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
     "sdfb_ddpm_sample_host": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "sdfb_ddpm_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
-    "sdfb_ddpm_sample_philox": (_i, [_vp, _vp, C.c_uint64, _i, _i, _i, _i, _vp]),
-    "sdfb_ddpm_sample_philox_host": (_i, [_vp, _vp, C.c_uint64, _i, _i, _i, _i]),
-    "sdfb_philox_normal": (_i, [C.c_uint64, _i, _i, _i, _vp, _vp]),
+    "sdfb_ddpm_sample_philox": (_i, [_vp, _vp, C.c_uint64, _i64, _i, _i, _i, _i, _vp]),
+    "sdfb_ddpm_sample_philox_host": (_i, [_vp, _vp, C.c_uint64, _i64, _i, _i, _i, _i]),
+    "sdfb_philox_normal": (_i, [C.c_uint64, _i64, _i, _i, _i, _vp, _vp]),
     "sdfb_umma_selftest": (_i, [_vp, _vp, _vp, _i, _vp]),
     "sdfb_umma_rate": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]),
 }

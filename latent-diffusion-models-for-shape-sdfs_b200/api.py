@@ -366,10 +366,12 @@ class LatentDDPM:
         return eps
 
     def sample_latents(self, n: int, x_T=None, noise=None, steps: int = DDPM_STEPS, seed: int = 0,
-                       precision: str | None = None) -> torch.Tensor:
+                       precision: str | None = None, first_latent: int = 0) -> torch.Tensor:
         """x_0 [n,256].  ``noise`` [steps,n,256] (with ``x_T`` [n,256]) is the explicit noise stream of
         the parity tests.  Without ``noise`` the stream is generated in the kernel from ``seed``
-        (Philox4x32-10, reproducible on the CPU with oracle/philox.py); ``x_T`` is then optional too."""
+        (Philox4x32-10, reproducible on the CPU with oracle/philox.py); ``x_T`` is then optional too.
+        ``first_latent`` is the global index of this call's latent 0 in the generator's counters, so shares of
+        one batch sampled by different ranks draw the numbers a single call over the whole batch would."""
         prec = _prec(precision or self.precision)
         if n <= 0:
             raise ValueError("n must be positive")
@@ -378,7 +380,7 @@ class LatentDDPM:
                 x = torch.empty((n, LATENT), dtype=torch.float32, device=self.device)
             else:
                 x = _as_dev_f32(x_T, self.device, (n, LATENT)).clone()
-            check(self._lib.sdfb_ddpm_sample_philox(self._h, x.data_ptr(), int(seed), n, steps, 1 if x_T is None else 0, prec,
+            check(self._lib.sdfb_ddpm_sample_philox(self._h, x.data_ptr(), int(seed), int(first_latent), n, steps, 1 if x_T is None else 0, prec,
                                                     _stream_ptr(self.device.index)))
             if prec != _lib.PREC_FP32:
                 self.last_kernel_ms()
@@ -400,13 +402,14 @@ class LatentDDPM:
         return float(ms.value)
 
     def sample_latents_seeded_host(self, n: int, seed: int, steps: int = DDPM_STEPS, x_T: np.ndarray | None = None,
-                                   precision: str | None = None) -> np.ndarray:
+                                   precision: str | None = None, first_latent: int = 0) -> np.ndarray:
         """Host-buffer form of the seeded sampler: only x_T (optional) goes in and x_0 comes out."""
         prec = _prec(precision or self.precision)
         x = np.empty((n, LATENT), np.float32) if x_T is None else np.ascontiguousarray(np.asarray(x_T, dtype=np.float32)).copy()
         if x.shape != (n, LATENT):
             raise ValueError("x_T must be [n,256]")
-        check(self._lib.sdfb_ddpm_sample_philox_host(self._h, x.ctypes.data, int(seed), n, steps, 1 if x_T is None else 0, prec))
+        check(self._lib.sdfb_ddpm_sample_philox_host(self._h, x.ctypes.data, int(seed), int(first_latent), n, steps,
+                                                     1 if x_T is None else 0, prec))
         return x
 
     def sample_latents_host(self, x_T: np.ndarray, noise: np.ndarray, steps: int = DDPM_STEPS,
@@ -430,14 +433,15 @@ def sample_latents(ddpm: LatentDDPM, n: int, **kw):
     return ddpm.sample_latents(n, **kw)
 
 
-def philox_normal(seed: int, n: int, t0: int, t1: int, device="cuda:0") -> torch.Tensor:
-    """The sampler's noise stream: normals of steps [t0, t1) for n latents, [(t1-t0), n, 256]."""
+def philox_normal(seed: int, n: int, t0: int, t1: int, device="cuda:0", first_latent: int = 0) -> torch.Tensor:
+    """The sampler's noise stream: normals of steps [t0, t1) for latents [first_latent, first_latent + n),
+    [(t1-t0), n, 256]."""
     lib = _lib.load()
     dev = torch.device("cuda", _device_index(device))
     out = torch.empty((t1 - t0, n, LATENT), dtype=torch.float32, device=dev)
     if out.numel():
         with torch.cuda.device(dev):
-            check(lib.sdfb_philox_normal(int(seed), n, t0, t1, out.data_ptr(), _stream_ptr(dev.index)))
+            check(lib.sdfb_philox_normal(int(seed), int(first_latent), n, t0, t1, out.data_ptr(), _stream_ptr(dev.index)))
     return out
 
 

@@ -995,7 +995,7 @@ static int denoise_fp32(sdfb_ddpm* d, const float* x, int t, int n, float* eps, 
 // Tensor-core path: `steps` fused denoise+update steps t = t_first, t_first-1, ... in ONE cooperative
 // launch (eps_out != nullptr: a single denoiser evaluation, no update).
 static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps, int t_first, float* eps_out,
-                   bool fp16, cudaStream_t st, bool philox = false, unsigned long long seed = 0) {
+                   bool fp16, cudaStream_t st, bool philox = false, unsigned long long seed = 0, unsigned int first_latent = 0) {
   const int m_pairs = (n + 255) / 256, n_pad = 256 * m_pairs;
   if (d->act_rows < n_pad) {
     cudaFree(d->act); cudaFree(d->counter); d->act = nullptr; d->counter = nullptr; d->act_rows = 0;
@@ -1014,7 +1014,7 @@ static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps,
   DdpmParams p{};
   p.tb0 = d->tb0; p.bias = d->bias_dev; p.coef = d->coef_dev;
   p.eps_mode = eps_out != nullptr ? 1 : 0;
-  p.philox = philox ? 1 : 0; p.seed = seed;
+  p.philox = philox ? 1 : 0; p.seed = seed; p.first_latent = first_latent;
   p.n = n; p.pair_m_tiles = m_pairs; p.steps = steps; p.t_first = t_first;
   p.bn_h = bn_h;
   p.nstages = bn_h == 256 ? 4 : 5;   // 4 x 32 KiB or 5 x 24 KiB of operand ring + 96 KiB of epilogue staging
@@ -1146,33 +1146,37 @@ int sdfb_ddpm_sample(sdfb_ddpm* d, float* x_dev, const float* noise_dev, int n, 
   return SDFB_OK;
 }
 
-int sdfb_philox_normal(uint64_t seed, int n, int t0, int t1, float* out_dev, void* stream) {
+int sdfb_philox_normal(uint64_t seed, int64_t first_latent, int n, int t0, int t1, float* out_dev, void* stream) {
   if (!out_dev) return fail(SDFB_E_INVALID, "null argument");
-  if (n <= 0 || t0 < 0 || t1 < t0) return fail(SDFB_E_INVALID, "bad n or step range");
-  CU_TRY(launch_philox_normal(seed, n, t0, t1, out_dev, static_cast<cudaStream_t>(stream)));
+  if (n <= 0 || t0 < 0 || t1 < t0 || first_latent < 0 || first_latent + n > 0xFFFFFFFFll)
+    return fail(SDFB_E_INVALID, "bad n, latent range or step range");
+  CU_TRY(launch_philox_normal(seed, static_cast<unsigned int>(first_latent), n, t0, t1, out_dev, static_cast<cudaStream_t>(stream)));
   return SDFB_OK;
 }
 
-int sdfb_ddpm_sample_philox(sdfb_ddpm* d, float* x_dev, uint64_t seed, int n, int steps, int gen_xT, int precision,
-                            void* stream) {
+int sdfb_ddpm_sample_philox(sdfb_ddpm* d, float* x_dev, uint64_t seed, int64_t first_latent, int n, int steps, int gen_xT,
+                            int precision, void* stream) {
   if (!d || !x_dev) return fail(SDFB_E_INVALID, "null argument");
   if (n <= 0 || steps < 1 || steps > kDdpmT) return fail(SDFB_E_INVALID, "bad n or steps");
+  if (first_latent < 0 || first_latent + n > 0xFFFFFFFFll) return fail(SDFB_E_INVALID, "latent range outside [0, 2^32)");
+  const unsigned int f0 = static_cast<unsigned int>(first_latent);
   if (precision != SDFB_PREC_FP32 && precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16)
     return fail(SDFB_E_INVALID, "unknown precision %d", precision);
   DeviceGuard g(d->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (gen_xT) CU_TRY(launch_philox_normal(seed, n, steps, steps + 1, x_dev, st));      // x_T = row t = steps of the stream
+  if (gen_xT) CU_TRY(launch_philox_normal(seed, f0, n, steps, steps + 1, x_dev, st));  // x_T = row t = steps of the stream
   if (precision != SDFB_PREC_FP32)
-    return ddpm_tc(d, x_dev, nullptr, n, steps, steps - 1, nullptr, precision == SDFB_PREC_FP16, st, true, seed);
+    return ddpm_tc(d, x_dev, nullptr, n, steps, steps - 1, nullptr, precision == SDFB_PREC_FP16, st, true, seed, f0);
   // fp32 path: materialise the same stream (bit for bit the in-kernel one) and run the FFMA sampler on it
   const size_t cnt = static_cast<size_t>(n) * kDdpmLatent;
   int rc = ensure_stage(nullptr, nullptr, &d->nstage, &d->nstage_bytes, 0, static_cast<size_t>(steps) * cnt * sizeof(float));
   if (rc) return rc;
-  CU_TRY(launch_philox_normal(seed, n, 0, steps, static_cast<float*>(d->nstage), st));
+  CU_TRY(launch_philox_normal(seed, f0, n, 0, steps, static_cast<float*>(d->nstage), st));
   return sdfb_ddpm_sample(d, x_dev, static_cast<float*>(d->nstage), n, steps, precision, stream);
 }
 
-int sdfb_ddpm_sample_philox_host(sdfb_ddpm* d, float* x_host, uint64_t seed, int n, int steps, int gen_xT, int precision) {
+int sdfb_ddpm_sample_philox_host(sdfb_ddpm* d, float* x_host, uint64_t seed, int64_t first_latent, int n, int steps, int gen_xT,
+                                 int precision) {
   if (!d || !x_host) return fail(SDFB_E_INVALID, "null argument");
   if (n <= 0 || steps < 1 || steps > kDdpmT) return fail(SDFB_E_INVALID, "bad n or steps");
   DeviceGuard g(d->device);
@@ -1181,7 +1185,7 @@ int sdfb_ddpm_sample_philox_host(sdfb_ddpm* d, float* x_host, uint64_t seed, int
   if (rc) return rc;
   float* x = static_cast<float*>(d->dstage);
   if (!gen_xT) CU_TRY(cudaMemcpyAsync(x, x_host, cnt * sizeof(float), cudaMemcpyHostToDevice, 0));
-  rc = sdfb_ddpm_sample_philox(d, x, seed, n, steps, gen_xT, precision, nullptr);
+  rc = sdfb_ddpm_sample_philox(d, x, seed, first_latent, n, steps, gen_xT, precision, nullptr);
   if (rc) return rc;
   CU_TRY(cudaMemcpyAsync(x_host, x, cnt * sizeof(float), cudaMemcpyDeviceToHost, 0));
   CU_TRY(cudaStreamSynchronize(0));

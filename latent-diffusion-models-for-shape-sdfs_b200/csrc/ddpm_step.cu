@@ -451,7 +451,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
 #pragma unroll 2
             for (int u = 0; u < 8; ++u)
               st_shared_f4(nrow_w + ((static_cast<uint32_t>(u) ^ row7) << 4),
-                           philox_normal4(static_cast<uint32_t>(j * 16 + set * 8 + u), static_cast<uint32_t>(g_row + row),
+                           philox_normal4(static_cast<uint32_t>(j * 16 + set * 8 + u), static_cast<uint32_t>(p.first_latent + g_row + row),
                                           static_cast<uint32_t>(t), key));
           }
           if (!mbar_wait(bars + 8 * (kBarAccFull + b), (acc_phase >> b) & 1u, wd, kErrAccFull, b)) goto done;
@@ -636,14 +636,15 @@ __global__ void ddpm_split_kernel(const float* __restrict__ x, int n, int n_pad,
 }
 
 // noise rows [t0, t1) of n latents -> out [(t1 - t0)][n][256] (what the sampler generates in-kernel)
-__global__ void philox_normal_kernel(unsigned long long seed, int n, int t0, int t1, float* __restrict__ out) {
+__global__ void philox_normal_kernel(unsigned long long seed, unsigned int first_latent, int n, int t0, int t1,
+                                     float* __restrict__ out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // (t, row, column group)
   const long long total = static_cast<long long>(t1 - t0) * n * 64;
   if (i >= total) return;
   const uint32_t g = static_cast<uint32_t>(i & 63);
   const long long rt = i >> 6;
   const uint32_t row = static_cast<uint32_t>(rt % n), t = static_cast<uint32_t>(t0 + rt / n);
-  const float4 z = philox_normal4(g, row, t, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  const float4 z = philox_normal4(g, first_latent + row, t, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
   reinterpret_cast<float4*>(out)[i] = z;
 }
 
@@ -683,10 +684,11 @@ cudaError_t make_tensor_map(void* tmap_out, const void* base, int elem_bytes, in
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-cudaError_t launch_philox_normal(unsigned long long seed, int n, int t0, int t1, float* out, cudaStream_t stream) {
+cudaError_t launch_philox_normal(unsigned long long seed, unsigned int first_latent, int n, int t0, int t1, float* out,
+                                 cudaStream_t stream) {
   const long long total = static_cast<long long>(t1 - t0) * n * 64;
   if (total <= 0) return cudaSuccess;
-  philox_normal_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(seed, n, t0, t1, out);
+  philox_normal_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(seed, first_latent, n, t0, t1, out);
   return cudaGetLastError();
 }
 

@@ -119,6 +119,7 @@ struct DdpmParams {
   int nstages;
   int philox;              // 1: noise[t] is generated in the kernel (Philox4x32-10, csrc/philox.cuh) instead of read through tm_nz
   unsigned long long seed;
+  unsigned int first_latent;   // global index of latent 0 of this call in the Philox counters (sharded sampling)
   unsigned int flags;      // experiments: bit0 no consumer-side proxy fence, bit1 relaxed (not release) barrier arrival
   unsigned int* counter;   // [pair_m_tiles] barrier counters, one per group of pair tiles that share 256 latents (zeroed before the launch)
   unsigned int* status;
@@ -142,8 +143,9 @@ cudaError_t make_tensor_map(void* tmap_out, const void* base, int elem_bytes, in
 // x [n][256] fp32 -> [x_hi | x_lo] columns of the activation buffer (rows >= n zero)
 cudaError_t launch_ddpm_split(const float* x, int n, int n_pad, uint16_t* act, bool fp16, cudaStream_t stream);
 cudaError_t launch_ddpm_sample(const DdpmParams& p, const DdpmMaps& maps, bool fp16, int num_sms, cudaStream_t stream);
-// Philox normals of steps [t0, t1) for n latents -> out [(t1 - t0)][n][256]
-cudaError_t launch_philox_normal(unsigned long long seed, int n, int t0, int t1, float* out, cudaStream_t stream);
+// Philox normals of steps [t0, t1) for latents [first_latent, first_latent + n) -> out [(t1 - t0)][n][256]
+cudaError_t launch_philox_normal(unsigned long long seed, unsigned int first_latent, int n, int t0, int t1, float* out,
+                                 cudaStream_t stream);
 
 // ---- fp32 SIMT kernels (fp32_kernels.cu) -----------------------------------
 // C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); row-major, leading dims in elements.

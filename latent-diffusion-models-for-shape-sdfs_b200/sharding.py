@@ -81,3 +81,24 @@ def decode_batch_sharded(decoder, latents: torch.Tensor, res: int, precision=Non
     for j, i in enumerate(range(i0, i1)):
         decoder.decode_grid(latents[i], res, precision=precision, out=out[j])
     return i0, out
+
+
+def sample_latents_sharded(sampler, n: int, seed: int = 0, steps: int = 1000, precision=None, group=None, gather: bool = False):
+    """Config 4's sampling phase: the batch of n latents is split across ranks; every rank samples its share with
+    the in-kernel noise addressed by GLOBAL latent index, so the union equals what one rank sampling all n would
+    draw.  No communication unless ``gather``.  Returns (i0, x [i1-i0, 256]) or the gathered [n, 256]."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    i0, i1 = batch_range(n, rank, world)
+    if i1 > i0:
+        x = sampler.sample_latents(i1 - i0, steps=steps, seed=seed, precision=precision, first_latent=i0)
+    else:
+        x = torch.empty((0, 256), dtype=torch.float32, device=sampler.device)
+    if not gather:
+        return i0, x
+    per = -(-n // world)
+    pad = torch.zeros((per, 256), dtype=torch.float32, device=x.device)
+    pad[: x.shape[0]] = x
+    full = torch.empty((world * per, 256), dtype=torch.float32, device=x.device)
+    dist.all_gather_into_tensor(full, pad, group=group)
+    sizes = [batch_range(n, r, world) for r in range(world)]
+    return torch.cat([full[r * per: r * per + (b - a)] for r, (a, b) in enumerate(sizes)])

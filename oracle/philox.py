@@ -51,11 +51,11 @@ def _box_muller(ra, rb):
     return (rad * np.cos(ang).astype(np.float32)).astype(np.float32), (rad * np.sin(ang).astype(np.float32)).astype(np.float32)
 
 
-def philox_normal_rows(seed: int, n: int, t0: int, t1: int, width: int = 256) -> np.ndarray:
-    """Normals [t1 - t0, n, width] float32 for steps t in [t0, t1) of `n` latents."""
+def philox_normal_rows(seed: int, n: int, t0: int, t1: int, width: int = 256, first_latent: int = 0) -> np.ndarray:
+    """Normals [t1 - t0, n, width] float32 for steps t in [t0, t1) of latents [first_latent, first_latent + n)."""
     key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     t = np.arange(t0, t1, dtype=np.uint32)[:, None, None]
-    i = np.arange(n, dtype=np.uint32)[None, :, None]
+    i = (np.arange(n, dtype=np.uint64) + np.uint64(first_latent)).astype(np.uint32)[None, :, None]
     g = np.arange(width // 4, dtype=np.uint32)[None, None, :]
     shape = (t1 - t0, n, width // 4)
     ctr = np.stack([np.broadcast_to(g, shape), np.broadcast_to(i, shape), np.broadcast_to(t, shape),

@@ -162,3 +162,20 @@ def test_seeded_sampler_equals_explicit_stream(cuda_ddpm, pkg, monkeypatch):
     err = np.abs(x32 - ref).max()
     print(f"seeded fp32 sampler vs oracle with oracle Philox: {err:.2e}")
     assert err < 1e-4
+
+
+def test_seeded_sampler_is_addressed_by_global_latent_index(cuda_ddpm, pkg, monkeypatch):
+    """Shares of one batch sampled separately (first_latent = global index) equal the single call: this is what
+    makes multi-GPU sampling independent of the number of ranks."""
+    monkeypatch.setenv("SDFB_DDPM_BN", "128")
+    n, steps, seed = 600, 15, 99
+    whole = cuda_ddpm.sample_latents(n, steps=steps, seed=seed, precision="bf16")
+    a = cuda_ddpm.sample_latents(256, steps=steps, seed=seed, precision="bf16", first_latent=0)
+    b = cuda_ddpm.sample_latents(n - 256, steps=steps, seed=seed, precision="bf16", first_latent=256)
+    assert torch.equal(torch.cat([a, b]), whole)
+    dev = pkg.philox_normal(seed, 10, 2, 4, first_latent=300).cpu().numpy()
+    assert np.array_equal(dev, pkg.philox_normal(seed, 400, 2, 4).cpu().numpy()[:, 300:310])
+    assert np.abs(dev - oracle.philox_normal_rows(seed, 10, 2, 4, first_latent=300)).max() < 5e-6
+    w32 = cuda_ddpm.sample_latents(40, steps=steps, seed=seed, precision="fp32")
+    p32 = cuda_ddpm.sample_latents(30, steps=steps, seed=seed, precision="fp32", first_latent=10)
+    assert torch.equal(p32, w32[10:])

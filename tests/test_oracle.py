@@ -143,6 +143,7 @@ def test_philox_known_answers_and_normals():
     assert abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1.0) < 0.01 and np.isfinite(z).all()
     # rows are addressed by (t, latent): a sub-range reproduces the same numbers
     assert np.array_equal(oracle.philox_normal_rows(7, 64, 3, 5), z[3:5])
+    assert np.array_equal(oracle.philox_normal_rows(7, 10, 3, 5, first_latent=20), z[3:5, 20:30])   # addressed by global latent index
     x_T, noise = oracle.philox_sampler_inputs(7, 64, 8)
     assert np.array_equal(noise, z) and x_T.shape == (64, 256) and not np.array_equal(x_T, z[0])
 

@@ -55,6 +55,16 @@ class _OracleDecoder:
         return sdf[: z1 - z0], m
 
 
+class _OracleSampler:
+    """Stands in for pkg.LatentDDPM on CPU: seeded sampling addressed by global latent index."""
+    device = torch.device("cpu")
+
+    def sample_latents(self, n, steps=1000, seed=0, precision=None, first_latent=0):
+        noise = oracle.philox_normal_rows(seed, n, 0, steps, first_latent=first_latent)
+        x_T = oracle.philox_normal_rows(seed, n, steps, steps + 1, first_latent=first_latent)[0]
+        return torch.from_numpy(oracle.sample_latents(n, x_T, noise, steps=steps))
+
+
 def _worker(rank, world, port, res, field, out_q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -66,6 +76,11 @@ def _worker(rank, world, port, res, field, out_q):
         sdf, m = pkg.decode_grid_sharded(dec, None, res, mask=True)
         ok = bool(np.array_equal(sdf.numpy(), field)) and bool(np.array_equal(m.numpy(), oracle.sign_change_mask(field)))
         i0, i1 = pkg.batch_range(5, rank, world)
+        # sharded sampling: a stand-in sampler (oracle sampler on the oracle's Philox stream, 3 steps) per rank;
+        # the gathered batch must equal one process sampling all latents
+        full = pkg.sample_latents_sharded(_OracleSampler(), 5, seed=77, steps=3, gather=True)
+        x_T, noise = oracle.philox_sampler_inputs(77, 5, 3)
+        ok = ok and bool(np.array_equal(full.numpy(), oracle.sample_latents(5, x_T, noise, steps=3)))
         out_q.put((rank, ok, (i0, i1)))
     finally:
         dist.destroy_process_group()
