@@ -93,16 +93,19 @@ __device__ __forceinline__ Geo layer_geo(const DdpmParams& p, int l) {
 // Own chunks.  With one tile per pair and layer, the k-chunks a pair produced in the previous layer are
 // still in its staging buffer in operand layout: the next layer starts on them at once (weights come
 // through the ring, A straight from staging) while the peers' chunks travel through L2.
-//   layers 1-3: the bn_h / 64 chunks [j bn_h / 64, ...) in staging slots 0..   (L4 reuses those slots for x / noise: no own chunks)
+//   layers 1-3: the bn_h / 64 chunks [j bn_h / 64, ...) in staging slots round * bn_h / 64 ..   (L4 reuses those slots for x / noise: no own chunks)
 //   layer 0   : x_hi chunk j and x_lo chunk 4 + j in slots 4, 5 (needs the same tile index in L4 and L0: bn_h = 256)
 struct Own { int n, kc0, kstride, slot0; };
-__device__ __forceinline__ Own own_chunks(const DdpmParams& p, int s, int l, int j, bool single_round) {
+// `rounds` = tiles per pair and hidden layer, `round` = which of them this tile is.  The four staging slots hold the
+// hidden outputs of all of a pair's tiles of one layer, so own chunks need rounds * (bn_h / 64) <= 4.
+__device__ __forceinline__ Own own_chunks(const DdpmParams& p, int s, int l, int j, int round, int rounds) {
   Own o{0, 0, 1, 0};
-  if (!single_round) return o;
+  const int nch = p.bn_h >> 6;
+  if (rounds * nch > 4) return o;
   if (l == 0) {
     if (s > 0 && p.bn_h == 256) { o.n = 2; o.kc0 = j; o.kstride = 4; o.slot0 = 4; }
   } else if (l < 4) {
-    o.n = p.bn_h >> 6; o.kc0 = j * o.n; o.slot0 = 0;
+    o.n = nch; o.kc0 = j * nch; o.slot0 = round * nch;
   }
   return o;
 }
@@ -279,12 +282,12 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
           const bool need_sync = !(s == 0 && l == 0);      // the operand of the very first layer was written by an earlier kernel
           const uint32_t target = static_cast<uint32_t>(s) * arr_step + static_cast<uint32_t>(l) * arr_h;
           const int T = p.pair_m_tiles * g.ntn;
-          const bool single_round = p.pair_m_tiles * (kDdpmHid / p.bn_h) <= npairs;
-          for (int tile = pidx; tile < T; tile += npairs) {
+          const int rounds = (p.pair_m_tiles * (kDdpmHid / p.bn_h) + npairs - 1) / npairs;
+          for (int tile = pidx, round = 0; tile < T; tile += npairs, ++round) {
             const int pm = tile / g.ntn, j = tile - pm * g.ntn;
             const int a_row = (2 * pm + static_cast<int>(rank)) * 128;
             const int w_row = g.w_row0 + j * g.bn + static_cast<int>(rank) * (g.bn >> 1);
-            const Own o = own_chunks(p, s, l, j, single_round);
+            const Own o = own_chunks(p, s, l, j, round, rounds);
             int i = 0;
             // own chunks: only their weights travel
             for (; i < o.n; ++i) {
@@ -345,7 +348,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
       const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
       const uint32_t nst = static_cast<uint32_t>(p.nstages);
       uint32_t stage = 0, phase = 0, ephase = 0, gt = 0, prev_stage = 0, own_phase = 0, own_pending = 0;
-      const bool single_round = p.pair_m_tiles * (kDdpmHid / p.bn_h) <= npairs;
+      const int rounds = (p.pair_m_tiles * (kDdpmHid / p.bn_h) + npairs - 1) / npairs;
       const uint32_t stg_lo = ((smem0 + o_stage) & 0x3FFFFu) >> 4;
       for (int s = 0; s < p.steps; ++s) {
         for (int l = 0; l < kLayers; ++l) {
@@ -354,13 +357,14 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
           const int ntn = l == 4 ? kDdpmLatent / kDdpmOutTile : kDdpmHid / p.bn_h;
           const int T = p.pair_m_tiles * ntn;
           // staging slots this pair's epilogue fills in this layer (one barrier phase each per tile)
-          const uint32_t my_slots = l == 4 ? (p.eps_mode ? 0u : 0x30u) : ((1u << (p.bn_h >> 6)) - 1u);
-          bool had_tile = false;
-          for (int tile = pidx; tile < T; tile += npairs, ++gt) {
-            had_tile = true;
+          uint32_t my_slots = 0;
+          int round = 0;
+          for (int tile = pidx; tile < T; tile += npairs, ++gt, ++round) {
+            // staging slots this tile's epilogue fills (one barrier phase each)
+            my_slots |= l == 4 ? (p.eps_mode ? 0u : 0x30u) : ((((1u << (p.bn_h >> 6)) - 1u) << (round * (p.bn_h >> 6))) & 0xFu);
             const uint32_t b = gt & 1u;
             const uint32_t d_tmem = tmem_base + b * 256;
-            const Own o = own_chunks(p, s, l, tile % ntn, single_round);
+            const Own o = own_chunks(p, s, l, tile % ntn, round, rounds);
             if (!mbar_wait(bars + 8 * (kBarAccEmpty + b), ((ephase >> b) & 1u) ^ 1u, wd, kErrAccEmpty, b)) goto done;
             ephase ^= 1u << b;
 #pragma unroll 1
@@ -394,10 +398,11 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               if (++stage == nst) { stage = 0; phase ^= 1u; }
             }
           }
-          // (single-round launches: at most one tile per pair and layer.)  The phases the previous layer's
-          // epilogue completed are behind us now, whether or not they were waited for.
+          // The phases the previous layer's epilogues completed are behind us now, whether or not they were waited
+          // for.  (With more tiles per layer than staging slots, slots are rewritten within a layer and own chunks
+          // are off: the tracking is then unused.)
           own_phase ^= own_pending;
-          own_pending = had_tile ? my_slots : 0u;
+          own_pending = my_slots;
         }
       }
     }
@@ -418,9 +423,13 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
         const float* bias = l == 0 ? p.tb0 + static_cast<long long>(t) * kDdpmHid
                                    : (l < 4 ? p.bias + (l - 1) * kDdpmHid : p.bias + 3 * kDdpmHid);
         const int T = p.pair_m_tiles * g.ntn;
-        for (int tile = pidx; tile < T; tile += npairs, ++gt) {
+        const int rounds = (p.pair_m_tiles * (kDdpmHid / p.bn_h) + npairs - 1) / npairs;
+        for (int tile = pidx, round = 0; tile < T; tile += npairs, ++gt, ++round) {
           const int pm = tile / g.ntn, j = tile - pm * g.ntn;
           const int g_row = (2 * pm + static_cast<int>(rank)) * 128;             // first latent of this CTA's half tile
+          // staging slots of this tile's hidden output: one set per round while they all fit (they are then the
+          // next layer's own chunks), else slots 0.. are simply reused
+          const int slot0 = (l < 4 && rounds * (g.bn >> 6) <= 4) ? round * (g.bn >> 6) : 0;
           const uint32_t b = gt & 1u;
           const uint32_t tbase = tmem_row + b * 256;
           // The tile's bias slice -> shared memory, off the critical path (the producer's gpu-scope
@@ -467,7 +476,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               uint32_t v[2][32];
               tmem_ld32(tbase + c * 64, v[0]);
               tmem_ld32(tbase + c * 64 + 32, v[1]);
-              const uint32_t srow = stg + c * kChunk + row * 128u;
+              const uint32_t srow = stg + (slot0 + c) * kChunk + row * 128u;
               tmem_ld_wait();
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
@@ -490,11 +499,11 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               }
               fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0) arrive_on_leader(bars + 8 * (kBarOwn + c), 1);     // the pair's next layer may start on this chunk
+              if (lane == 0) arrive_on_leader(bars + 8 * (kBarOwn + slot0 + c), 1);   // the pair's next layer may start on this chunk
               named_bar_sync(2 + set, kEpiThreads / 2);
               if (set_leader) {
                 if (c == 0) SDFB_TRACE(3);
-                tma_store_2d(&tm_act, g.o_col0 + j * g.bn + c * 64, g_row, stg + c * kChunk);
+                tma_store_2d(&tm_act, g.o_col0 + j * g.bn + c * 64, g_row, stg + (slot0 + c) * kChunk);
                 bulk_commit_group();
               }
             }
