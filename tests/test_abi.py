@@ -62,3 +62,19 @@ def test_argument_validation_without_device(pkg):
     assert lib.sdfb_ddpm_create(bad.ctypes.data, bad.size, 0, C.byref(h)) == -1
     assert lib.sdfb_decoder_destroy(None) == 0
     assert lib.sdfb_ddpm_destroy(None) == 0
+
+
+def test_workspace_queries_and_validation_of_the_extraction_entry_points(pkg):
+    """Size queries need no device; bad shapes / null pointers are refused before anything is launched."""
+    lib = pkg.load_library()
+    b = C.c_size_t()
+    assert lib.sdfb_mc_workspace_bytes(64, 64, 64, C.byref(b)) == 0 and b.value >= 64 ** 3 // 8
+    assert lib.sdfb_mc_workspace_bytes(1, 64, 64, C.byref(b)) == -1
+    assert lib.sdfb_sparse_select_workspace_bytes(256, 8, C.byref(b)) == 0 and b.value > 32 ** 3
+    assert lib.sdfb_sparse_select_workspace_bytes(256, 0, C.byref(b)) == -1
+    assert lib.sdfb_mc_blocks_workspace_bytes(8, 1000, C.byref(b)) == 0 and b.value > 1000 * 729 // 8
+    n = C.c_int64()
+    assert lib.sdfb_mc_count(None, None, 4, 4, 4, None, 0, C.byref(n), None) == -1
+    assert lib.sdfb_decoder_vjp_latent(None, None, None, 0, None, None, None, None) == -1
+    assert lib.sdfb_philox_normal(1, -1, 4, 0, 1, None, None) == -1
+    assert lib.sdfb_ddpm_sample_philox(None, None, 0, 0, 4, 10, 1, 1, None) == -1
