@@ -7,13 +7,12 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from __graft_entry__ import load_package
-import oracle
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 pkg = load_package()
-m = pkg.LatentDDPM(oracle.flatten_params(oracle.ddpm_weights()), device="cuda:0", precision="bf16")
+m = pkg.LatentDDPM(pkg.synthetic.ddpm_params(), device="cuda:0", precision="bf16")
 g = torch.Generator(device="cuda").manual_seed(0)
 x_T = torch.randn((n, 256), generator=g, device="cuda")
 noise = torch.randn((steps, n, 256), generator=g, device="cuda")

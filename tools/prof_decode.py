@@ -7,15 +7,14 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
-import oracle  # noqa: E402
 from __graft_entry__ import load_package  # noqa: E402
 
 res = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 pkg = load_package()
-dec = pkg.Decoder(oracle.flatten_params(oracle.decoder_weights()), precision=prec)
-z = torch.from_numpy(oracle.default_latent()).cuda()
+dec = pkg.Decoder(pkg.synthetic.decoder_params(), precision=prec)
+z = torch.from_numpy(pkg.synthetic.latent(0)).cuda()
 out = torch.empty((res, res, res), device="cuda")
 for i in range(reps):
     dec.decode_grid(z, res, out=out)
