@@ -60,9 +60,10 @@ def _stats(d):
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
-@pytest.mark.parametrize("n,bn", [(37, 0), (300, 256), (300, 128), (2400, 128)])
+@pytest.mark.parametrize("n,bn", [(37, 0), (300, 256), (300, 128), (2400, 128), (5000, 256)])
 def test_denoiser_single_step_tensor_core(cuda_ddpm, monkeypatch, prec, n, bn):
-    """One denoiser evaluation; ragged n, every tile width, and more pair tiles than CTA pairs."""
+    """One denoiser evaluation; ragged n, every tile width, and more pair tiles than CTA pairs: (2400, 128) = two
+    tiles per pair with own chunks kept per round, (5000, 256) = two tiles per pair without own chunks."""
     if bn:
         monkeypatch.setenv("SDFB_DDPM_BN", str(bn))
     rs = np.random.RandomState(n)
@@ -96,7 +97,7 @@ def test_sample_latents_tensor_core_golden(cuda_ddpm, golden, prec):
     assert np.array_equal(xh, x)            # deterministic, and the host entry point is the same path
 
 
-@pytest.mark.parametrize("n,bn,steps", [(300, 256, 12), (2400, 128, 6), (515, 0, 12)])
+@pytest.mark.parametrize("n,bn,steps", [(300, 256, 12), (2400, 128, 6), (515, 0, 12), (5000, 256, 4)])
 def test_sample_latents_tensor_core_short_runs(cuda_ddpm, monkeypatch, n, bn, steps):
     if bn:
         monkeypatch.setenv("SDFB_DDPM_BN", str(bn))
