@@ -145,6 +145,7 @@ struct sdfb_decoder {
   float* bias4f = nullptr;
   unsigned int* status = nullptr;
   unsigned int* signs = nullptr; long long sign_words = 0;   // sign bit-planes of the last masked decode (lazy)
+  unsigned int* rowmask = nullptr; size_t rowmask_words = 0; // row-aligned packed mask scratch (lazy)
   // backward workspace (lazy): stored activations of one chunk, two delta buffers, column-sum partials
   float* bw_act[8] = {}; float *bw_d0 = nullptr, *bw_d1 = nullptr, *bw_y = nullptr, *bw_partial = nullptr;
   long long bw_rows = 0, bw_blocks = 0;
@@ -284,8 +285,17 @@ int decode_any(sdfb_decoder* d, const float* z, const float* xyz, int res, long 
 int ensure_signs(sdfb_decoder* d, long long words) {
   if (d->sign_words >= words) return SDFB_OK;
   cudaFree(d->signs); d->signs = nullptr; d->sign_words = 0;
-  CU_TRY(cudaMalloc(&d->signs, static_cast<size_t>(words) * sizeof(unsigned int)));
+  CU_TRY(cudaMalloc(&d->signs, static_cast<size_t>(words + 1) * sizeof(unsigned int)));   // + 1: the mask kernel reads word pairs
+  CU_TRY(cudaMemset(d->signs, 0, static_cast<size_t>(words + 1) * sizeof(unsigned int)));
   d->sign_words = words;
+  return SDFB_OK;
+}
+
+int ensure_rowmask(sdfb_decoder* d, size_t words) {
+  if (d->rowmask_words >= words) return SDFB_OK;
+  cudaFree(d->rowmask); d->rowmask = nullptr; d->rowmask_words = 0;
+  CU_TRY(cudaMalloc(&d->rowmask, words * sizeof(unsigned int)));
+  d->rowmask_words = words;
   return SDFB_OK;
 }
 
@@ -408,7 +418,7 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
   cudaDeviceSynchronize();
   cudaFree(d->params); cudaFree(d->w4s); cudaFree(d->wstream[0]); cudaFree(d->wstream[1]);
   cudaFree(d->consts); cudaFree(d->bias0f); cudaFree(d->bias4f); cudaFree(d->status);
-  cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x); cudaFree(d->prof); cudaFree(d->signs);
+  cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x); cudaFree(d->prof); cudaFree(d->signs); cudaFree(d->rowmask);
   for (float* a : d->bw_act) cudaFree(a);
   cudaFree(d->bw_d0); cudaFree(d->bw_d1); cudaFree(d->bw_y); cudaFree(d->bw_partial);
   if (d->pin) cudaFreeHost(d->pin);
@@ -438,9 +448,11 @@ int sdfb_decode_grid(sdfb_decoder* d, const float* latent_dev, int res, int z0, 
   // (1/32 of the field's bytes) instead of a second pass over the fp32 field
   int rc = ensure_signs(d, (M + 31) >> 5);
   if (rc) return rc;
+  if (rc == SDFB_OK) rc = ensure_rowmask(d, mask_rows_words(zend - z0, res, res));
+  if (rc) return rc;
   rc = decode_any(d, latent_dev, nullptr, res, z0 * plane, M, sdf_dev, precision, st, d->signs);
   if (rc) return rc;
-  CU_TRY(launch_mask_from_bits(d->signs, zend - z0, res, res, mask_dev, nullptr, st));
+  CU_TRY(launch_mask_from_bits(d->signs, zend - z0, res, res, mask_dev, nullptr, d->rowmask, st));
   return SDFB_OK;
 }
 
@@ -455,10 +467,16 @@ int sdfb_decode_grid_bits(sdfb_decoder* d, const float* latent_dev, int res, int
   int zend = z1;
   if (mask_bits_dev != nullptr && z1 < res && z1 > z0) zend = z1 + 1;
   const long long M = (zend - z0) * plane;
-  int rc = decode_any(d, latent_dev, nullptr, res, z0 * plane, M, sdf_dev, precision, st, sign_bits_dev);
+  // the decoder writes into the context's own bit-plane buffer (it has the padding word the mask kernel reads);
+  // the caller's copy is made from it
+  int rc = ensure_signs(d, (M + 31) >> 5);
+  if (rc == SDFB_OK && mask_bits_dev != nullptr && zend - z0 >= 2) rc = ensure_rowmask(d, mask_rows_words(zend - z0, res, res));
   if (rc) return rc;
+  rc = decode_any(d, latent_dev, nullptr, res, z0 * plane, M, sdf_dev, precision, st, d->signs);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(sign_bits_dev, d->signs, static_cast<size_t>((M + 31) >> 5) * 4, cudaMemcpyDeviceToDevice, st));
   if (mask_bits_dev != nullptr && zend - z0 >= 2)
-    CU_TRY(launch_mask_from_bits(sign_bits_dev, zend - z0, res, res, nullptr, mask_bits_dev, st));
+    CU_TRY(launch_mask_from_bits(d->signs, zend - z0, res, res, nullptr, mask_bits_dev, d->rowmask, st));
   return SDFB_OK;
 }
 

@@ -250,38 +250,68 @@ __global__ void sign_bits_kernel(const float* __restrict__ sdf, long long M, uns
   }
 }
 
-// A4 from sign bits.  A warp owns 32 consecutive cells; every lane reads the 8 corner bits of its cell.
-// IdxT = unsigned int when every index fits 32 bits (grids up to 1290^3): 64-bit div/mod per cell
-// was most of this kernel's time.
-template <typename IdxT>
-__global__ void mask_from_bits_kernel(const unsigned int* __restrict__ bits, int nz, int ny, int nx,
-                                      unsigned char* __restrict__ mask_u8, unsigned int* __restrict__ mask_bits) {
-  const IdxT cx = nx - 1, cy = ny - 1, cz = nz - 1;
-  const IdxT total = cx * cy * cz;
-  const IdxT groups = (total + 31) >> 5;
-  const IdxT lane = threadIdx.x & 31;
-  const IdxT sy = nx, sz = static_cast<IdxT>(nx) * ny;
-  const IdxT stride = (static_cast<IdxT>(gridDim.x) * blockDim.x) >> 5;
-  for (IdxT gidx = (static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; gidx < groups; gidx += stride) {
-    const IdxT c = (gidx << 5) + lane;
-    bool active = false;
-    if (c < total) {
-      const IdxT t = c / cx;
-      const IdxT x = c - t * cx;
-      const IdxT z = t / cy;
-      const IdxT y = t - z * cy;
-      const IdxT q = (z * ny + y) * nx + x;
-      unsigned int n_in = 0;
+// A4 from sign bits, word-parallel.  Pass 1: one thread per 32 consecutive cells of an x-row: the 33 node bits of
+// each of the four node rows around it are pulled out with one funnel shift, any / all over the 8 corners are
+// plain bitwise ops -> one word per thread in a row-aligned packed mask [(cz cy)][wpr].  Pass 2 turns that into
+// the API's layouts with coalesced stores: one byte per cell, or the linear packing (cell c -> bit c & 31 of
+// word c >> 5).  (The first version gathered 8 single bits per cell with 64-bit div/mod: 1.2 ms at 512^3.)
+__device__ __forceinline__ unsigned long long bits33(const unsigned int* __restrict__ bits, long long q) {
+  const long long w = q >> 5;
+  const unsigned int sh = static_cast<unsigned int>(q & 31);
+  const unsigned long long lo = bits[w], hi = bits[w + 1];     // the bit-plane buffer carries one padding word
+  return ((lo | (hi << 32)) >> sh) & 0x1FFFFFFFFull;
+}
+
+__global__ void mask_rows_kernel(const unsigned int* __restrict__ bits, int nz, int ny, int nx,
+                                 unsigned int* __restrict__ rowmask, int wpr) {
+  const long long rows = static_cast<long long>(nz - 1) * (ny - 1);
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * wpr) return;
+  const long long r = i / wpr;
+  const int g = static_cast<int>(i - r * wpr);
+  const int z = static_cast<int>(r / (ny - 1)), y = static_cast<int>(r - static_cast<long long>(z) * (ny - 1));
+  const int x0 = g * 32;
+  const int cx = nx - 1;
+  unsigned int any = 0, all = 0xFFFFFFFFu;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const IdxT qq = q + (k & 1) + ((k >> 1) & 1) * sy + (k >> 2) * sz;
-        n_in += (bits[qq >> 5] >> (qq & 31)) & 1u;
-      }
-      active = n_in != 0 && n_in != 8;
-      if (mask_u8 != nullptr) mask_u8[c] = active ? 1 : 0;
+  for (int k = 0; k < 4; ++k) {
+    const long long q = (static_cast<long long>(z + (k >> 1)) * ny + (y + (k & 1))) * nx + x0;
+    // nodes x0 .. x0 + 32 of this node row (bits past the row's end belong to the next row: masked off below)
+    const unsigned long long a = bits33(bits, q);
+    const unsigned int n0 = static_cast<unsigned int>(a), n1 = static_cast<unsigned int>(a >> 1);
+    any |= n0 | n1;
+    all &= n0 & n1;
+  }
+  const int valid = cx - x0;                                       // cells of this word that exist
+  const unsigned int vm = valid >= 32 ? 0xFFFFFFFFu : ((1u << valid) - 1u);
+  rowmask[i] = any & ~all & vm;
+}
+
+__global__ void mask_expand_u8_kernel(const unsigned int* __restrict__ rowmask, long long total, int cx, int wpr,
+                                      unsigned char* __restrict__ mask_u8) {
+  for (long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; c < total;
+       c += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = c / cx;
+    const int x = static_cast<int>(c - r * cx);
+    mask_u8[c] = (rowmask[r * wpr + (x >> 5)] >> (x & 31)) & 1u;
+  }
+}
+
+__global__ void mask_pack_linear_kernel(const unsigned int* __restrict__ rowmask, long long total, int cx, int wpr,
+                                        unsigned int* __restrict__ mask_bits) {
+  const long long words = (total + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < words;
+       w += (static_cast<long long>(gridDim.x) * blockDim.x) >> 5) {
+    const long long c = (w << 5) + lane;
+    bool a = false;
+    if (c < total) {
+      const long long r = c / cx;
+      const int x = static_cast<int>(c - r * cx);
+      a = (rowmask[r * wpr + (x >> 5)] >> (x & 31)) & 1u;
     }
-    const unsigned int w = __ballot_sync(0xffffffffu, active);
-    if (mask_bits != nullptr && lane == 0) mask_bits[gidx] = w;
+    const unsigned int v = __ballot_sync(0xffffffffu, a);
+    if (lane == 0) mask_bits[w] = v;
   }
 }
 
@@ -384,18 +414,32 @@ cudaError_t launch_sign_bits(const float* sdf, long long M, unsigned int* bits, 
   return cudaGetLastError();
 }
 
+size_t mask_rows_words(int nz, int ny, int nx) {
+  return static_cast<size_t>(nz - 1) * (ny - 1) * ((nx - 1 + 31) / 32);
+}
+
+// `rowmask` = scratch of mask_rows_words(nz, ny, nx) words; `bits` must be readable one word past its last word.
 cudaError_t launch_mask_from_bits(const unsigned int* bits, int nz, int ny, int nx, unsigned char* mask_u8,
-                                  unsigned int* mask_bits, cudaStream_t stream) {
+                                  unsigned int* mask_bits, unsigned int* rowmask, cudaStream_t stream) {
   const long long total = static_cast<long long>(nx - 1) * (ny - 1) * (nz - 1);
   if (total <= 0) return cudaSuccess;
-  long long blocks = (((total + 31) >> 5) * 32 + 255) / 256;
-  if (blocks > 148LL * 32) blocks = 148LL * 32;
-  const long long nodes = static_cast<long long>(nx) * ny * nz;
-  if (nodes + 64 < (1LL << 31))
-    mask_from_bits_kernel<unsigned int><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(bits, nz, ny, nx, mask_u8, mask_bits);
-  else
-    mask_from_bits_kernel<unsigned long long><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(bits, nz, ny, nx, mask_u8, mask_bits);
-  return cudaGetLastError();
+  const int wpr = (nx - 1 + 31) / 32;
+  const long long n1 = static_cast<long long>(nz - 1) * (ny - 1) * wpr;
+  mask_rows_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, stream>>>(bits, nz, ny, nx, rowmask, wpr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  if (mask_u8 != nullptr) {
+    mask_expand_u8_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(rowmask, total, nx - 1, wpr, mask_u8);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  if (mask_bits != nullptr) {
+    mask_pack_linear_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(rowmask, total, nx - 1, wpr, mask_bits);
+    e = cudaGetLastError();
+  }
+  return e;
 }
 
 cudaError_t launch_ddpm_update(float* x, const float* eps, const float* noise, long long count,

@@ -177,8 +177,10 @@ cudaError_t launch_sign_change_mask(const float* sdf, int nz, int ny, int nx, un
 // bits[m >> 5] bit (m & 31) = (sdf[m] < 0), m < M   (the fused decoder writes the same words itself)
 cudaError_t launch_sign_bits(const float* sdf, long long M, unsigned int* bits, cudaStream_t stream);
 // A4 from the sign bits of an [nz][ny][nx] field: uint8 per cell and / or packed (cell c -> bit c & 31 of word c >> 5)
+// (`rowmask`: scratch of mask_rows_words() words; `bits` must be readable one word past its last word)
+size_t mask_rows_words(int nz, int ny, int nx);
 cudaError_t launch_mask_from_bits(const unsigned int* bits, int nz, int ny, int nx, unsigned char* mask_u8,
-                                  unsigned int* mask_bits, cudaStream_t stream);
+                                  unsigned int* mask_bits, unsigned int* rowmask, cudaStream_t stream);
 // x <- c1*clamp(sra*x - srm1*eps, -1, 1) + c2*x + sigma*noise   (noise may be null)
 cudaError_t launch_ddpm_update(float* x, const float* eps, const float* noise, long long count,
                                float sra, float srm1, float c1, float c2, float sigma,
