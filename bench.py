@@ -35,7 +35,7 @@ FLOP_TENSOR_PER_QUERY = 2 * 6 * 512 * 512          # 3,145,728
 FLOP_DENSE_PER_QUERY = 3_671_040
 DDPM_LATENTS = 4096
 DDPM_FLOP_PER_LATENT_STEP = 2 * (512 * 1024 + 3 * 1024 * 1024 + 1024 * 256)   # 7,864,320 executed (hi/lo split of x: K = 512)
-NCU_DRAM_BYTES_PER_LAUNCH = 3445504 + 13815552      # profiles/r1_fused_decoder_ncu_full.csv
+NCU_DRAM_BYTES_PER_LAUNCH = 3400192 + 14253312      # profiles/r1_fused_decoder_ncu_full.csv (dram__bytes_read + write)
 METRIC = "sdf_decoder_queries_per_s"
 UNIT = "queries/s"
 
