@@ -301,11 +301,17 @@ class Decoder:
                                               m.ctypes.data if (m is not None and m.size) else None, prec))
         return (sdf, m) if mask else sdf
 
-    def decode_points_host(self, latent: np.ndarray, xyz: np.ndarray, precision: str | None = None) -> np.ndarray:
+    def decode_points_host(self, latent: np.ndarray, xyz: np.ndarray, precision: str | None = None,
+                           out: np.ndarray | None = None) -> np.ndarray:
+        """Decoder(latent, xyz) with numpy arrays: chunks are copied in, decoded and copied out on three streams.
+        ``out`` (optional): a caller-owned, ideally pinned, float32 array of M elements."""
         prec = _prec(precision or self.precision)
         lat = np.ascontiguousarray(np.asarray(latent, dtype=np.float32).reshape(LATENT))
         pts = np.ascontiguousarray(np.asarray(xyz, dtype=np.float32).reshape(-1, 3))
-        out = np.empty(pts.shape[0], dtype=np.float32)
+        if out is None:
+            out = np.empty(pts.shape[0], dtype=np.float32)
+        elif out.dtype != np.float32 or not out.flags.c_contiguous or out.size != pts.shape[0]:
+            raise ValueError("out must be a C-contiguous float32 array with one element per point")
         check(self._lib.sdfb_decode_points_host(self._h, lat.ctypes.data, pts.ctypes.data, pts.shape[0],
                                                 out.ctypes.data, prec))
         return out

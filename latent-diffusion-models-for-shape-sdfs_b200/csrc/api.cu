@@ -158,8 +158,8 @@ struct sdfb_decoder {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   // *_host calls: compute and copy-out streams, one event per z-chunk (the D2H copy of a chunk overlaps the next chunk's kernel)
-  cudaStream_t st_compute = nullptr, st_copy = nullptr;
-  cudaEvent_t chunk_ev[17] = {};
+  cudaStream_t st_compute = nullptr, st_copy = nullptr, st_in = nullptr;
+  cudaEvent_t chunk_ev[17] = {}, in_ev[17] = {};
   unsigned long long timeout_ns = 2000000000ull;
   unsigned int debug_flags = 0;
   long long* prof = nullptr;     // wait profile buffer (allocated when SDFB_PROF is set)
@@ -407,6 +407,7 @@ int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, s
   CU_TRY_D(cudaStreamCreateWithFlags(&d->st_compute, cudaStreamNonBlocking));
   CU_TRY_D(cudaStreamCreateWithFlags(&d->st_copy, cudaStreamNonBlocking));
   for (cudaEvent_t& e : d->chunk_ev) CU_TRY_D(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (cudaEvent_t& e : d->in_ev) CU_TRY_D(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 #undef CU_TRY_D
   *out = d;
   return SDFB_OK;
@@ -426,6 +427,8 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
   for (cudaEvent_t e : d->chunk_ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : d->in_ev) if (e) cudaEventDestroy(e);
+  if (d->st_in) cudaStreamDestroy(d->st_in);
   if (d->st_compute) cudaStreamDestroy(d->st_compute);
   if (d->st_copy) cudaStreamDestroy(d->st_copy);
   delete d;
@@ -620,15 +623,31 @@ int sdfb_decode_points_host(sdfb_decoder* d, const float* latent_host, const flo
   const size_t off_xyz = 1024, off_sdf = off_xyz + ((M * 12 + 255) / 256) * 256;
   int rc = ensure_stage(&d->pin, &d->pin_bytes, &d->dstage, &d->dstage_bytes, 1024, off_sdf + M * 4);
   if (rc) return rc;
+  if (d->st_in == nullptr) CU_TRY(cudaStreamCreateWithFlags(&d->st_in, cudaStreamNonBlocking));
   uint8_t* base = static_cast<uint8_t*>(d->dstage);
+  float* lat_dev = reinterpret_cast<float*>(base);
+  float* xyz_dev = reinterpret_cast<float*>(base + off_xyz);
+  float* sdf_dev = reinterpret_cast<float*>(base + off_sdf);
   std::memcpy(d->pin, latent_host, kLatent * sizeof(float));
-  CU_TRY(cudaMemcpyAsync(base, d->pin, kLatent * sizeof(float), cudaMemcpyHostToDevice, 0));
-  CU_TRY(cudaMemcpyAsync(base + off_xyz, xyz_host, M * 12, cudaMemcpyHostToDevice, 0));
-  rc = sdfb_decode_points(d, reinterpret_cast<float*>(base), reinterpret_cast<float*>(base + off_xyz), M,
-                          reinterpret_cast<float*>(base + off_sdf), precision, nullptr);
-  if (rc) return rc;
-  CU_TRY(cudaMemcpyAsync(sdf_host, base + off_sdf, M * 4, cudaMemcpyDeviceToHost, 0));
-  CU_TRY(cudaStreamSynchronize(0));
+  CU_TRY(cudaMemcpyAsync(lat_dev, d->pin, kLatent * sizeof(float), cudaMemcpyHostToDevice, d->st_compute));
+  // three-stage pipeline over chunks of points: copy-in (st_in) | decode (st_compute) | copy-out (st_copy)
+  long long per = 2097152;
+  if (per * 16 < M) per = (M + 15) / 16;
+  int c = 0;
+  for (long long m0 = 0; m0 < M; m0 += per, ++c) {
+    const long long m = (M - m0) < per ? (M - m0) : per;
+    CU_TRY(cudaMemcpyAsync(xyz_dev + 3 * m0, xyz_host + 3 * m0, m * 12, cudaMemcpyHostToDevice, d->st_in));
+    CU_TRY(cudaEventRecord(d->in_ev[c], d->st_in));
+    CU_TRY(cudaStreamWaitEvent(d->st_compute, d->in_ev[c], 0));
+    rc = decode_any(d, lat_dev, xyz_dev + 3 * m0, 0, 0, m, sdf_dev + m0, precision, d->st_compute);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(d->chunk_ev[c], d->st_compute));
+    CU_TRY(cudaStreamWaitEvent(d->st_copy, d->chunk_ev[c], 0));
+    CU_TRY(cudaMemcpyAsync(sdf_host + m0, sdf_dev + m0, m * sizeof(float), cudaMemcpyDeviceToHost, d->st_copy));
+  }
+  CU_TRY(cudaStreamSynchronize(d->st_in));
+  CU_TRY(cudaStreamSynchronize(d->st_compute));
+  CU_TRY(cudaStreamSynchronize(d->st_copy));
   return precision == SDFB_PREC_FP32 ? SDFB_OK : kernel_status(d);
 }
 

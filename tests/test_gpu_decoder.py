@@ -258,3 +258,14 @@ def test_torch_mask_helper_matches_oracle():
     rs = np.random.RandomState(0)
     f = rs.standard_normal((9, 7, 8)).astype(np.float32)
     assert np.array_equal(torch_mask(torch.from_numpy(f).cuda()).cpu().numpy(), oracle.sign_change_mask(f))
+
+
+def test_points_host_entry_point_pipelined(cuda_decoder):
+    """decode_points_host streams chunks (copy-in | decode | copy-out): same bits as the device call, ragged chunk sizes."""
+    rs = np.random.RandomState(9)
+    z = oracle.default_latent(3)
+    for M in (5, 2097152 + 77, 3 * 2097152):
+        xyz = (rs.rand(M, 3) * 2 - 1).astype(np.float32)
+        got = cuda_decoder.decode_points_host(z, xyz, precision="bf16")
+        want = cuda_decoder(z, xyz, precision="bf16").cpu().numpy()
+        assert np.array_equal(got, want)
