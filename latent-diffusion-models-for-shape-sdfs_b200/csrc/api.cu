@@ -1054,7 +1054,7 @@ static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps,
   p.philox = philox ? 1 : 0; p.seed = seed; p.first_latent = first_latent;
   p.n = n; p.pair_m_tiles = m_pairs; p.steps = steps; p.t_first = t_first;
   p.bn_h = bn_h;
-  p.nstages = bn_h == 256 ? 4 : 5;   // 4 x 32 KiB or 5 x 24 KiB of operand ring + 96 KiB of epilogue staging
+  p.nstages = bn_h == 256 ? 5 : 6;   // 5 x 32 KiB or 6 x 24 KiB of operand ring + 64 KiB of epilogue staging
   if (const char* e = std::getenv("SDFB_DDPM_STAGES")) {   // diagnostics: a shallower ring (leaves shared memory to a profiler)
     const int v = std::atoi(e);
     if (v >= 2 && v < p.nstages) p.nstages = v;

@@ -44,7 +44,8 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 64;
 constexpr int kLayers = 5;
-constexpr uint32_t kStagingBytes = 96 * 1024;   // hidden: bn_h / 64 chunk images | last layer: x (32K), noise (32K), x_hi, x_lo (16K each)
+constexpr uint32_t kStagingBytes = 64 * 1024;   // four 16 KiB slots.  hidden: the tile's chunk images | last layer: x boxes in slots 0, 1,
+                                                // noise boxes in slots 2, 3, later overwritten by the x_hi / x_lo images
 constexpr uint32_t kChunk = 16384;
 
 constexpr int kBarFull = 0;
@@ -94,7 +95,7 @@ __device__ __forceinline__ Geo layer_geo(const DdpmParams& p, int l) {
 // still in its staging buffer in operand layout: the next layer starts on them at once (weights come
 // through the ring, A straight from staging) while the peers' chunks travel through L2.
 //   layers 1-3: the bn_h / 64 chunks [j bn_h / 64, ...) in staging slots round * bn_h / 64 ..   (L4 reuses those slots for x / noise: no own chunks)
-//   layer 0   : x_hi chunk j and x_lo chunk 4 + j in slots 4, 5 (needs the same tile index in L4 and L0: bn_h = 256)
+//   layer 0   : x_hi chunk j and x_lo chunk 4 + j in slots 2, 3 (needs the same tile index in L4 and L0: bn_h = 256)
 struct Own { int n, kc0, kstride, slot0; };
 // `rounds` = tiles per pair and hidden layer, `round` = which of them this tile is.  The four staging slots hold the
 // hidden outputs of all of a pair's tiles of one layer, so own chunks need rounds * (bn_h / 64) <= 4.
@@ -103,7 +104,7 @@ __device__ __forceinline__ Own own_chunks(const DdpmParams& p, int s, int l, int
   const int nch = p.bn_h >> 6;
   if (rounds * nch > 4) return o;
   if (l == 0) {
-    if (s > 0 && p.bn_h == 256) { o.n = 2; o.kc0 = j; o.kstride = 4; o.slot0 = 4; }
+    if (s > 0 && p.bn_h == 256) { o.n = 2; o.kc0 = j; o.kstride = 4; o.slot0 = 2; }
   } else if (l < 4) {
     o.n = nch; o.kc0 = j * nch; o.slot0 = round * nch;
   }
@@ -253,7 +254,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
       mbar_init(bars + 8 * (kBarAccEmpty + b), 2 * kEpiWarps);
     }
     mbar_init(bars + 8 * kBarXn, 1);
-    for (int c = 0; c < 6; ++c) mbar_init(bars + 8 * (kBarOwn + c), c < 4 ? kEpiWarps : 2 * kEpiWarps);   // one warp set | both, x 2 CTAs
+    for (int c = 0; c < 6; ++c) mbar_init(bars + 8 * (kBarOwn + c), kEpiWarps);   // one warp set x 2 CTAs arrive per phase
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -361,7 +362,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
           int round = 0;
           for (int tile = pidx; tile < T; tile += npairs, ++gt, ++round) {
             // staging slots this tile's epilogue fills (one barrier phase each)
-            my_slots |= l == 4 ? (p.eps_mode ? 0u : 0x30u) : ((((1u << (p.bn_h >> 6)) - 1u) << (round * (p.bn_h >> 6))) & 0xFu);
+            my_slots |= l == 4 ? (p.eps_mode ? 0u : 0xCu) : ((((1u << (p.bn_h >> 6)) - 1u) << (round * (p.bn_h >> 6))) & 0xFu);
             const uint32_t b = gt & 1u;
             const uint32_t d_tmem = tmem_base + b * 256;
             const Own o = own_chunks(p, s, l, tile % ntn, round, rounds);
@@ -535,7 +536,19 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             if (threadIdx.x == 0) SDFB_TRACE(10);
             const uint32_t xrow = stg + set * kChunk + row * 128u;             // this thread's 32 floats of x (swizzled 16-byte units)
             const uint32_t nrow = xrow + 2 * kChunk;
-            const uint32_t hrow = stg + 4 * kChunk + row * 128u, lrow = hrow + kChunk;
+            const uint32_t hrow = stg + 2 * kChunk + row * 128u, lrow = hrow + kChunk;   // x_hi / x_lo images: OVER the noise boxes
+            // everything this thread needs from shared memory -> registers, then a barrier: after it the noise boxes
+            // (read by their own warp set only) may be overwritten by the operand images (written by both sets)
+            float4 xq[8], nq[8];
+            if (!p.eps_mode) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const uint32_t off = (static_cast<uint32_t>(u) ^ row7) << 4;
+                xq[u] = ld_shared_f4(xrow + off);
+                nq[u] = t > 0 ? ld_shared_f4(nrow + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+            named_bar_sync(1, kEpiThreads);
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -547,12 +560,9 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               if (p.eps_mode) {
                 o = make_float4(e0, e1, e2, e3);
               } else {
-                const float4 xv = ld_shared_f4(xrow + off);
-                float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t > 0) nz = ld_shared_f4(nrow + off);
                 const float ev[4] = {e0, e1, e2, e3};
-                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-                const float ns[4] = {nz.x, nz.y, nz.z, nz.w};
+                const float xs[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
+                const float ns[4] = {nq[u].x, nq[u].y, nq[u].z, nq[u].w};
                 float r[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -574,18 +584,16 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             }
             if (threadIdx.x == 0) SDFB_TRACE(11);
             fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0 && !p.eps_mode) {   // x_hi / x_lo chunks of this tile: own chunks of the next step's layer 0
-              arrive_on_leader(bars + 8 * (kBarOwn + 4), 1);
-              arrive_on_leader(bars + 8 * (kBarOwn + 5), 1);
-            }
             named_bar_sync(1, kEpiThreads);
+            // both sets wrote both images: only now are they complete.  x_hi (slot 2) / x_lo (slot 3) are the own
+            // chunks of the next step's layer 0; one warp set arrives per slot, as for the hidden layers' slots.
+            if (lane == 0 && !p.eps_mode) arrive_on_leader(bars + 8 * (kBarOwn + 2 + set), 1);
             if (threadIdx.x == 0) {
               tma_store_2d(&tm_x, j * 64, g_row, stg);                          // rows >= n are clipped by the TMA unit
               tma_store_2d(&tm_x, j * 64 + 32, g_row, stg + kChunk);
               if (!p.eps_mode) {
-                tma_store_2d(&tm_act, j * 64, g_row, stg + 4 * kChunk);
-                tma_store_2d(&tm_act, 256 + j * 64, g_row, stg + 5 * kChunk);
+                tma_store_2d(&tm_act, j * 64, g_row, stg + 2 * kChunk);
+                tma_store_2d(&tm_act, 256 + j * 64, g_row, stg + 3 * kChunk);
               }
               bulk_commit_group();
               SDFB_TRACE(4);
@@ -668,7 +676,7 @@ uint32_t smem_bytes_for(int bn_h, int nstages) {
 }  // namespace
 
 cudaError_t ddpm_step_init() {
-  const int max_smem = static_cast<int>(smem_bytes_for(256, 4));   // = smem_bytes_for(128, 5) + 8 KiB: the largest configuration
+  const int max_smem = static_cast<int>(smem_bytes_for(256, 5));   // 5 x 32 KiB ring + 64 KiB staging: the largest configuration
   cudaError_t e = cudaFuncSetAttribute(ddpm_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(ddpm_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
