@@ -51,12 +51,21 @@ def main():
     lat = torch.stack([torch.from_numpy(oracle.default_latent(i)) for i in range(B)]).to(dev)
     i0, part = pkg.decode_batch_sharded(dec, lat, bres)
     ok_batch = all(bool(torch.equal(part[k], dec.decode_grid(lat[i0 + k], bres))) for k in range(part.shape[0]))
+    # config 4's sampling phase: shares of one seeded batch sampled per rank == the whole batch sampled by one GPU
+    ddpm = pkg.LatentDDPM(oracle.flatten_params(oracle.ddpm_weights()), device=dev, precision="bf16")
+    os.environ["SDFB_DDPM_BN"] = "128"          # the tile width fixes the fp32 summation order: same for shares and whole
+    n_lat, steps = 150 * world + 7, 12
+    gathered = pkg.sample_latents_sharded(ddpm, n_lat, seed=31, steps=steps, gather=True)
+    whole = ddpm.sample_latents(n_lat, steps=steps, seed=31)
+    ok_sample = bool(torch.equal(gathered, whole))
+    ok_batch = ok_batch and ok_sample
+
     counts = torch.tensor([part.shape[0]], device=dev)
     dist.all_reduce(counts)
     ok = torch.tensor([int(ok_sdf and ok_mask and ok_batch and int(counts.item()) == B)], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"world": world, "res": res, "sdf_equal": ok_sdf, "mask_equal": ok_mask, "batch_equal": ok_batch,
+        print(json.dumps({"world": world, "res": res, "sdf_equal": ok_sdf, "mask_equal": ok_mask, "batch_equal": ok_batch, "sharded_sampling_equal": ok_sample,
                           "all_ranks_ok": bool(ok.item()), "sharded_decode_mask_gather_ms": float(ms.item()),
                           "queries_per_s": res ** 3 / (float(ms.item()) * 1e-3)}))
     dist.barrier()
