@@ -123,8 +123,10 @@ int sdfb_sign_change_mask(const float* sdf_dev, int nz, int ny, int nx, uint8_t*
 int sdfb_mc_workspace_bytes(int nz, int ny, int nx, size_t* bytes);
 int sdfb_mc_count(const float* sdf_dev, const uint32_t* sign_bits_dev, int nz, int ny, int nx, void* workspace_dev,
                   size_t workspace_bytes, int64_t* n_triangles_host, void* stream);
+/* edge_keys_dev (optional, int64 [n][3]): the grid edge each vertex sits on, ((z*res + y)*res + x)*3 + axis of
+ * the edge's lower node - equal for every cell sharing the edge, so unique(keys) welds the soup into an indexed mesh. */
 int sdfb_mc_generate(const float* sdf_dev, int nz, int ny, int nx, int res, int z0, const void* workspace_dev,
-                     float* triangles_dev, void* stream);
+                     float* triangles_dev, int64_t* edge_keys_dev, void* stream);
 
 /* ---- sparse extraction: decode only near the surface ---------------------------
  * The res^3 grid is cut into blocks of `block`^3 cells (nb = ceil((res-1)/block) per axis; the last block
@@ -145,7 +147,7 @@ int sdfb_mc_blocks_workspace_bytes(int block, int64_t n_blocks, size_t* bytes);
 int sdfb_mc_blocks_count(const float* fields_dev, const int32_t* block_ids_dev, int64_t n_blocks, int res, int block,
                          void* workspace_dev, size_t workspace_bytes, int64_t* n_triangles_host, void* stream);
 int sdfb_mc_blocks_generate(const float* fields_dev, const int32_t* block_ids_dev, int64_t n_blocks, int res, int block,
-                            const void* workspace_dev, float* triangles_dev, void* stream);
+                            const void* workspace_dev, float* triangles_dev, int64_t* edge_keys_dev, void* stream);
 
 /* Debug/diagnostic: pre-activation (accumulator + bias, before ReLU) of
  * tensor-core pass `pass` (0..12) for the first 128 queries of a grid decode,

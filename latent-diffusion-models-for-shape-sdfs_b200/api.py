@@ -210,14 +210,14 @@ class Decoder:
         del ones
         return z, loss
 
-    def extract_surface(self, latent, res: int, precision: str | None = None) -> torch.Tensor:
+    def extract_surface(self, latent, res: int, precision: str | None = None, indexed: bool = False):
         """decode_grid + marching cubes: triangles [n,3,3] of the zero level set on the res^3 grid
-        (the decoder's own sign bit-planes classify the cells)."""
+        (the decoder's own sign bit-planes classify the cells); ``indexed=True``: (vertices, faces)."""
         sdf, signs, _ = self.decode_grid_bits(latent, res, mask=False, precision=precision)
-        return extract_surface(sdf, res, 0, sign_words=signs)
+        return extract_surface(sdf, res, 0, sign_words=signs, indexed=indexed)
 
     def extract_surface_sparse(self, latent, res: int, block: int = 8, lipschitz: float | None = None,
-                               precision: str | None = None, return_stats: bool = False):
+                               precision: str | None = None, return_stats: bool = False, indexed: bool = False):
         """The zero level set on the res^3 grid WITHOUT decoding the whole grid: decode the corners of
         `block`^3-cell blocks, keep the blocks whose corners straddle zero or come within
         tau = L * block * h * sqrt(3) / 2 of it (h = 2 / (res - 1)), decode only their nodes and run marching
@@ -248,6 +248,7 @@ class Decoder:
             n = nblk.value
             per = (block + 1) ** 3
             tris = torch.empty((0, 3, 3), dtype=torch.float32, device=self.device)
+            keys = torch.empty((0, 3), dtype=torch.int64, device=self.device)
             if n:
                 pts = torch.empty((n * per, 3), dtype=torch.float32, device=self.device)
                 check(lib.sdfb_sparse_block_points(res, block, ids.data_ptr(), n, pts.data_ptr(), st))
@@ -258,9 +259,12 @@ class Decoder:
                 check(lib.sdfb_mc_blocks_count(fields.data_ptr(), ids.data_ptr(), n, res, block, ws2.data_ptr(), nbytes.value,
                                                C.byref(ntri), st))
                 tris = torch.empty((ntri.value, 3, 3), dtype=torch.float32, device=self.device)
+                keys = torch.empty((ntri.value, 3), dtype=torch.int64, device=self.device)
                 if ntri.value:
                     check(lib.sdfb_mc_blocks_generate(fields.data_ptr(), ids.data_ptr(), n, res, block, ws2.data_ptr(),
-                                                      tris.data_ptr(), st))
+                                                      tris.data_ptr(), keys.data_ptr() if indexed else None, st))
+        if indexed:
+            tris = weld(tris, keys)
         if return_stats:
             return tris, {"blocks": n, "blocks_total": nb ** 3, "queries": (nb + 1) ** 3 + n * per, "dense_queries": res ** 3,
                           "tau": tau, "lipschitz": float(lipschitz)}
@@ -451,10 +455,20 @@ def philox_normal(seed: int, n: int, t0: int, t1: int, device="cuda:0", first_la
     return out
 
 
-def extract_surface(sdf: torch.Tensor, res: int | None = None, z0: int = 0, sign_words: torch.Tensor | None = None) -> torch.Tensor:
+def weld(tris: torch.Tensor, keys: torch.Tensor):
+    """Triangle soup [n,3,3] + grid-edge keys [n,3] -> indexed mesh (vertices [V,3], faces [n,3] int64)."""
+    uniq, inv = torch.unique(keys.reshape(-1), return_inverse=True)
+    verts = torch.empty((uniq.numel(), 3), dtype=tris.dtype, device=tris.device)
+    verts[inv] = tris.reshape(-1, 3)          # every occurrence of a key carries the same bits
+    return verts, inv.reshape(-1, 3)
+
+
+def extract_surface(sdf: torch.Tensor, res: int | None = None, z0: int = 0, sign_words: torch.Tensor | None = None,
+                    indexed: bool = False):
     """Marching cubes on a [nz,ny,nx] float32 CUDA field -> triangles [n,3,3] (x,y,z), cell order, normals
     from inside (sdf < 0) to outside.  ``res``/``z0`` place a slab in the res^3 grid of rule A1 (default:
-    the field is the whole grid); ``sign_words`` are the bit-planes from ``Decoder.decode_grid_bits``."""
+    the field is the whole grid); ``sign_words`` are the bit-planes from ``Decoder.decode_grid_bits``.
+    ``indexed=True`` returns (vertices [V,3], faces [n,3]) instead: vertices on the same grid edge are merged."""
     lib = _lib.load()
     if sdf.ndim != 3 or sdf.dtype != torch.float32 or not sdf.is_cuda:
         raise ValueError("sdf must be a 3-D float32 CUDA tensor")
@@ -462,7 +476,8 @@ def extract_surface(sdf: torch.Tensor, res: int | None = None, z0: int = 0, sign
     nz, ny, nx = s.shape
     res = nx if res is None else res
     if min(nz, ny, nx) < 2:
-        return torch.empty((0, 3, 3), dtype=torch.float32, device=s.device)
+        empty = torch.empty((0, 3, 3), dtype=torch.float32, device=s.device)
+        return (empty.reshape(0, 3), torch.empty((0, 3), dtype=torch.int64, device=s.device)) if indexed else empty
     with torch.cuda.device(s.device):
         nbytes = C.c_size_t()
         check(lib.sdfb_mc_workspace_bytes(nz, ny, nx, C.byref(nbytes)))
@@ -472,9 +487,11 @@ def extract_surface(sdf: torch.Tensor, res: int | None = None, z0: int = 0, sign
         check(lib.sdfb_mc_count(s.data_ptr(), sign_words.data_ptr() if sign_words is not None else None, nz, ny, nx,
                                 ws.data_ptr(), nbytes.value, C.byref(n), st))
         tris = torch.empty((n.value, 3, 3), dtype=torch.float32, device=s.device)
+        keys = torch.empty((n.value, 3), dtype=torch.int64, device=s.device) if indexed else None
         if n.value:
-            check(lib.sdfb_mc_generate(s.data_ptr(), nz, ny, nx, res, z0, ws.data_ptr(), tris.data_ptr(), st))
-    return tris
+            check(lib.sdfb_mc_generate(s.data_ptr(), nz, ny, nx, res, z0, ws.data_ptr(), tris.data_ptr(),
+                                       keys.data_ptr() if indexed else None, st))
+    return weld(tris, keys) if indexed else tris
 
 
 def grid_points(res: int, z0: int = 0, z1: int | None = None, device="cuda:0") -> torch.Tensor:

@@ -701,11 +701,12 @@ int mc_count_impl(const float* sdf_dev, const uint32_t* sign_bits_dev, const McG
   return SDFB_OK;
 }
 
-int mc_generate_impl(const float* sdf_dev, const McGeom& g, const void* workspace_dev, float* triangles_dev, cudaStream_t st) {
+int mc_generate_impl(const float* sdf_dev, const McGeom& g, const void* workspace_dev, float* triangles_dev, long long* keys_dev,
+                     cudaStream_t st) {
   const McLayout L = mc_layout(g.total_nodes, g.total_cells);
   const uint8_t* ws = static_cast<const uint8_t*>(workspace_dev);
   CU_TRY(launch_mc_generate(sdf_dev, reinterpret_cast<const unsigned int*>(ws + L.off_bits),
-                            reinterpret_cast<const unsigned int*>(ws + L.off_groups), g, triangles_dev, st));
+                            reinterpret_cast<const unsigned int*>(ws + L.off_groups), g, triangles_dev, keys_dev, st));
   return SDFB_OK;
 }
 }  // namespace
@@ -727,10 +728,11 @@ int sdfb_mc_count(const float* sdf_dev, const uint32_t* sign_bits_dev, int nz, i
 }
 
 int sdfb_mc_generate(const float* sdf_dev, int nz, int ny, int nx, int res, int z0, const void* workspace_dev,
-                     float* triangles_dev, void* stream) {
+                     float* triangles_dev, int64_t* edge_keys_dev, void* stream) {
   if (!sdf_dev || !workspace_dev || !triangles_dev) return fail(SDFB_E_INVALID, "null argument");
   if (nz < 2 || ny < 2 || nx < 2 || res < 2 || z0 < 0) return fail(SDFB_E_INVALID, "bad field shape");
-  return mc_generate_impl(sdf_dev, mc_dense_geom(nz, ny, nx, res, z0), workspace_dev, triangles_dev, static_cast<cudaStream_t>(stream));
+  return mc_generate_impl(sdf_dev, mc_dense_geom(nz, ny, nx, res, z0), workspace_dev, triangles_dev,
+                          reinterpret_cast<long long*>(edge_keys_dev), static_cast<cudaStream_t>(stream));
 }
 
 // ---- sparse extraction: coarse block corners -> block selection -> nodes of the selected blocks -> marching cubes ----
@@ -800,13 +802,13 @@ int sdfb_mc_blocks_count(const float* fields_dev, const int32_t* block_ids_dev, 
 }
 
 int sdfb_mc_blocks_generate(const float* fields_dev, const int32_t* block_ids_dev, int64_t n_blocks, int res, int block,
-                            const void* workspace_dev, float* triangles_dev, void* stream) {
+                            const void* workspace_dev, float* triangles_dev, int64_t* edge_keys_dev, void* stream) {
   if (n_blocks == 0) return SDFB_OK;
   if (!fields_dev || !block_ids_dev || !workspace_dev || !triangles_dev) return fail(SDFB_E_INVALID, "null argument");
   if (res < 2 || block < 1 || block > 64 || n_blocks < 0) return fail(SDFB_E_INVALID, "bad arguments");
   const int nb = (res - 1 + block - 1) / block;
   return mc_generate_impl(fields_dev, mc_block_geom(res, block, nb, block_ids_dev, n_blocks), workspace_dev, triangles_dev,
-                          static_cast<cudaStream_t>(stream));
+                          reinterpret_cast<long long*>(edge_keys_dev), static_cast<cudaStream_t>(stream));
 }
 
 int sdfb_decode_debug_pass(sdfb_decoder* d, const float* latent_dev, int res, int pass, float* dump_dev,

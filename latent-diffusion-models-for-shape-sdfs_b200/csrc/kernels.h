@@ -206,8 +206,9 @@ inline McGeom mc_block_geom(int res, int B, int nb, const int* blocks, long long
 size_t mc_scan_temp_bytes(long long groups);
 cudaError_t launch_mc_count_scan(const unsigned int* bits, const McGeom& g, unsigned int* group_tris, void* temp,
                                  size_t temp_bytes, cudaStream_t stream);
+// keys (optional, [n_tri * 3]): the grid edge of every emitted vertex, ((z res + y) res + x) * 3 + axis of its lower node
 cudaError_t launch_mc_generate(const float* sdf, const unsigned int* bits, const unsigned int* group_first, const McGeom& g,
-                               float* tris, cudaStream_t stream);
+                               float* tris, long long* keys, cudaStream_t stream);
 // sparse extractor: block corners, block selection (ascending ids, count on the device), nodes of the selected blocks
 cudaError_t launch_block_corner_points(int res, int B, int nb, float* xyz, cudaStream_t stream);
 size_t block_select_temp_bytes(long long nblocks);

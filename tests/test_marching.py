@@ -117,3 +117,25 @@ def test_sparse_extraction_equals_dense(cuda_decoder, res, block):
     assert np.array_equal(_sorted_tris(sparse.cpu().numpy()), _sorted_tris(dense))
     if res >= 256:        # the criterion is exact (Lipschitz band), hence conservative: the saving grows with the resolution
         assert st["queries"] < st["dense_queries"] * (0.5 if res >= 512 else 0.75)
+
+
+@pytest.mark.gpu
+def test_indexed_mesh_welding(pkg, cuda_decoder):
+    """indexed=True merges vertices by grid edge: the faces index exactly the soup's vertices, a closed surface
+    has Euler characteristic 2, and the sparse extractor welds to the same vertex set."""
+    f = torch.from_numpy(_sphere(40)).cuda()
+    soup = pkg.extract_surface(f)
+    verts, faces = pkg.extract_surface(f, indexed=True)
+    assert faces.shape == (soup.shape[0], 3) and faces.dtype == torch.int64
+    assert torch.equal(verts[faces], soup)                                   # same geometry, bit for bit
+    uniq = np.unique(soup.cpu().numpy().reshape(-1, 3).view(np.uint32), axis=0).shape[0]
+    assert verts.shape[0] == uniq                                            # one vertex per crossed edge
+    fa = faces.cpu().numpy()
+    e = np.sort(np.concatenate([fa[:, [0, 1]], fa[:, [1, 2]], fa[:, [2, 0]]]), axis=1)
+    n_edges = np.unique(e, axis=0).shape[0]
+    assert verts.shape[0] - n_edges + fa.shape[0] == 2                       # a sphere
+    z = oracle.default_latent()
+    v1, f1 = cuda_decoder.extract_surface(z, 97, indexed=True)
+    v2, f2 = cuda_decoder.extract_surface_sparse(z, 97, block=8, indexed=True)
+    assert v1.shape == v2.shape and torch.equal(v1, v2)                      # unique() sorts by edge key: identical vertex arrays
+    assert f1.shape == f2.shape

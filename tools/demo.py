@@ -17,16 +17,11 @@ import torch
 from __graft_entry__ import load_package
 
 
-def write_obj(path, tris):
-    """Triangle soup [n,3,3] -> indexed OBJ (bit-identical vertices are merged)."""
-    v = tris.reshape(-1, 3)
-    uniq, inv = np.unique(v.view(np.uint32).reshape(-1, 3), axis=0, return_inverse=True)
-    verts = uniq.view(np.float32).reshape(-1, 3)
-    faces = inv.reshape(-1, 3) + 1
+def write_obj(path, verts, faces):
     with open(path, "w") as f:
         f.write(f"# {verts.shape[0]} vertices, {faces.shape[0]} triangles\n")
         np.savetxt(f, verts, fmt="v %.7g %.7g %.7g")
-        np.savetxt(f, faces, fmt="f %d %d %d")
+        np.savetxt(f, faces + 1, fmt="f %d %d %d")
     return verts.shape[0], faces.shape[0]
 
 
@@ -48,10 +43,14 @@ def main():
         z = torch.from_numpy(pkg.synthetic.latent(0)).cuda()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    tris = dec.extract_surface_sparse(z, args.res) if args.sparse else dec.extract_surface(z, args.res)
+    if args.sparse:
+        verts, faces = dec.extract_surface_sparse(z, args.res, indexed=True)
+    else:
+        verts, faces = dec.extract_surface(z, args.res, indexed=True)
     torch.cuda.synchronize()
-    print(f"{'sparse' if args.sparse else 'dense'} extraction at {args.res}^3: {tris.shape[0]} triangles in {1e3 * (time.perf_counter() - t0):.1f} ms")
-    nv, nf = write_obj(args.out, tris.cpu().numpy())
+    print(f"{'sparse' if args.sparse else 'dense'} extraction at {args.res}^3: {faces.shape[0]} triangles, {verts.shape[0]} vertices "
+          f"(welded on the GPU) in {1e3 * (time.perf_counter() - t0):.1f} ms")
+    nv, nf = write_obj(args.out, verts.cpu().numpy(), faces.cpu().numpy())
     print(f"wrote {args.out}: {nv} vertices, {nf} faces")
 
 
