@@ -373,6 +373,8 @@ class LatentDDPM:
         eps = torch.empty_like(xt)
         check(self._lib.sdfb_ddpm_denoise(self._h, xt.data_ptr(), int(t), xt.shape[0], eps.data_ptr(), prec,
                                           _stream_ptr(self.device.index)))
+        if prec != _lib.PREC_FP32:
+            self.last_kernel_ms()       # raises if the fused kernel's watchdog tripped
         return eps
 
     def sample_latents(self, n: int, x_T=None, noise=None, steps: int = DDPM_STEPS, seed: int = 0,
