@@ -165,6 +165,9 @@ struct sdfb_decoder {
   long long* prof = nullptr;     // wait profile buffer (allocated when SDFB_PROF is set)
 };
 
+// row-major activations [act_rows][kDdpmActCols] (16-bit) and one barrier counter per 256-latent group
+struct DdpmLane { uint16_t* act = nullptr; int act_rows = 0; unsigned int* counter = nullptr; };
+
 struct sdfb_ddpm {
   int device = 0, num_sms = 0;
   float* params = nullptr;
@@ -179,13 +182,14 @@ struct sdfb_ddpm {
   uint8_t* wpack[2] = {nullptr, nullptr};     // [0] bf16, [1] fp16: kDdpmWRows rows of 128 B
   float* bias_dev = nullptr;                  // [3][1024] + [256]
   float* coef_dev = nullptr;                  // [1000][8]
-  uint16_t* act = nullptr; int act_rows = 0;  // row-major activations [act_rows][kDdpmActCols], 16-bit
-  unsigned int* counter = nullptr;            // [act_rows / 256] barrier counters (one per 256-latent group)
+  DdpmLane lane[2];                           // workspaces of the (at most two) concurrent launches of a call
+  cudaStream_t st_b = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   unsigned int* status = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   unsigned long long timeout_ns = 4000000000ull;
   long long* prof = nullptr;                  // wait profile buffer (allocated when SDFB_PROF is set)
+  int max_clusters8[2] = {-1, -1};            // resident 8-CTA clusters of the sampler kernel (queried once), [bf16, fp16]
 };
 
 namespace {
@@ -997,8 +1001,12 @@ int sdfb_ddpm_destroy(sdfb_ddpm* d) {
   DeviceGuard g(d->device);
   cudaDeviceSynchronize();
   cudaFree(d->params); cudaFree(d->tb0); cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->eps); cudaFree(d->dstage);
-  cudaFree(d->wpack[0]); cudaFree(d->wpack[1]); cudaFree(d->bias_dev); cudaFree(d->coef_dev); cudaFree(d->act);
-  cudaFree(d->counter); cudaFree(d->status); cudaFree(d->prof); cudaFree(d->nstage);
+  cudaFree(d->wpack[0]); cudaFree(d->wpack[1]); cudaFree(d->bias_dev); cudaFree(d->coef_dev);
+  for (DdpmLane& L : d->lane) { cudaFree(L.act); cudaFree(L.counter); }
+  if (d->st_b) cudaStreamDestroy(d->st_b);
+  if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+  if (d->ev_join) cudaEventDestroy(d->ev_join);
+  cudaFree(d->status); cudaFree(d->prof); cudaFree(d->nstage);
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
   delete d;
@@ -1033,19 +1041,24 @@ static int denoise_fp32(sdfb_ddpm* d, const float* x, int t, int n, float* eps, 
 
 // Tensor-core path: `steps` fused denoise+update steps t = t_first, t_first-1, ... in ONE cooperative
 // launch (eps_out != nullptr: a single denoiser evaluation, no update).
-static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps, int t_first, float* eps_out,
-                   bool fp16, cudaStream_t st, bool philox = false, unsigned long long seed = 0, unsigned int first_latent = 0) {
+// One launch of the fused sampler over latents [0, n) of (x, noise) with workspace `lane`.  `noise_batch` is the
+// latent count of the noise tensor's step stride (> n when this launch covers a share of a batch); bn_force = 0: auto.
+static int ddpm_tc_lane(sdfb_ddpm* d, int lane, float* x, const float* noise, long long noise_batch, int n, int steps, int t_first,
+                        float* eps_out, bool fp16, cudaStream_t st, bool philox, unsigned long long seed, unsigned int first_latent,
+                        int bn_force, bool time_it) {
+  DdpmLane& L = d->lane[lane];
   const int m_pairs = (n + 255) / 256, n_pad = 256 * m_pairs;
-  if (d->act_rows < n_pad) {
-    cudaFree(d->act); cudaFree(d->counter); d->act = nullptr; d->counter = nullptr; d->act_rows = 0;
-    CU_TRY(cudaMalloc(&d->counter, static_cast<size_t>(m_pairs) * sizeof(unsigned int)));
-    CU_TRY(cudaMalloc(&d->act, static_cast<size_t>(n_pad) * kDdpmActCols * 2));
-    CU_TRY(cudaMemset(d->act, 0, static_cast<size_t>(n_pad) * kDdpmActCols * 2));
-    d->act_rows = n_pad;
+  if (L.act_rows < n_pad) {
+    cudaFree(L.act); cudaFree(L.counter); L.act = nullptr; L.counter = nullptr; L.act_rows = 0;
+    CU_TRY(cudaMalloc(&L.counter, static_cast<size_t>(m_pairs) * sizeof(unsigned int)));
+    CU_TRY(cudaMalloc(&L.act, static_cast<size_t>(n_pad) * kDdpmActCols * 2));
+    CU_TRY(cudaMemset(L.act, 0, static_cast<size_t>(n_pad) * kDdpmActCols * 2));
+    L.act_rows = n_pad;
   }
   // tile width of the hidden layers: 256 if that still gives about one pair tile per CTA pair
   const int max_pairs = d->num_sms / 2;
   int bn_h = (m_pairs * (kDdpmHid / 256) * 4 >= max_pairs * 3) ? 256 : 128;
+  if (bn_force) bn_h = bn_force;
   if (const char* e = std::getenv("SDFB_DDPM_BN")) {
     const int v = std::atoi(e);
     if (v == 128 || v == 256) bn_h = v;
@@ -1057,18 +1070,29 @@ static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps,
   p.n = n; p.pair_m_tiles = m_pairs; p.steps = steps; p.t_first = t_first;
   p.bn_h = bn_h;
   p.nstages = bn_h == 256 ? 5 : 6;   // 5 x 32 KiB or 6 x 24 KiB of operand ring + 64 KiB of epilogue staging
+  // the four pair tiles of a latent group as ONE cluster of 8 CTAs (cluster-scope group barrier) when every pair has
+  // exactly one tile per layer and that many clusters can be resident
+  if (bn_h == 256 && m_pairs * 4 <= max_pairs) {
+    if (d->max_clusters8[fp16 ? 1 : 0] < 0) d->max_clusters8[fp16 ? 1 : 0] = ddpm_max_clusters8(256, p.nstages, fp16);
+    p.cluster8 = m_pairs <= d->max_clusters8[fp16 ? 1 : 0] ? 1 : 0;
+  }
+  if (const char* e = std::getenv("SDFB_DDPM_CLUSTER8")) p.cluster8 = (p.cluster8 && std::atoi(e) != 0) ? 1 : 0;
+  if (lane != 0) p.cluster8 = 0;     // the second launch runs beside a full house of 8-CTA clusters: plain pairs only
+  if (d->prof != nullptr)
+    std::fprintf(stderr, "[sdfb ddpm prof] lane %d: n=%d bn_h=%d stages=%d cluster8=%d (resident 8-CTA clusters: %d)\n", lane, n, bn_h,
+                 p.nstages, p.cluster8, d->max_clusters8[fp16 ? 1 : 0]);
   if (const char* e = std::getenv("SDFB_DDPM_STAGES")) {   // diagnostics: a shallower ring (leaves shared memory to a profiler)
     const int v = std::atoi(e);
     if (v >= 2 && v < p.nstages) p.nstages = v;
   }
-  p.counter = d->counter; p.status = d->status; p.timeout_ns = d->timeout_ns; p.prof = d->prof;
+  p.counter = L.counter; p.status = d->status; p.timeout_ns = d->timeout_ns; p.prof = lane == 0 ? d->prof : nullptr;
   if (const char* e = std::getenv("SDFB_DDPM_FLAGS")) p.flags = static_cast<unsigned int>(std::strtoul(e, nullptr, 0));
   DdpmMaps maps;
   {
-    const unsigned long long a_dims[2] = {kDdpmActCols, static_cast<unsigned long long>(d->act_rows)};
+    const unsigned long long a_dims[2] = {kDdpmActCols, static_cast<unsigned long long>(L.act_rows)};
     const unsigned long long a_str[1] = {kDdpmActCols * 2ull};
     const unsigned a_box[2] = {64, 128};
-    CU_TRY(make_tensor_map(maps.act, d->act, 2, 2, a_dims, a_str, a_box, true));
+    CU_TRY(make_tensor_map(maps.act, L.act, 2, 2, a_dims, a_str, a_box, true));
     const unsigned long long w_dims[2] = {64, kDdpmWRows};
     const unsigned long long w_str[1] = {128};
     const unsigned wh_box[2] = {64, static_cast<unsigned>(bn_h / 2)}, wo_box[2] = {64, kDdpmOutTile / 2};
@@ -1080,18 +1104,63 @@ static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps,
     CU_TRY(make_tensor_map(maps.x, eps_out != nullptr ? eps_out : x, 4, 2, x_dims, x_str, x_box, true));
     if (noise != nullptr && eps_out == nullptr) {
       const unsigned long long n_dims[3] = {kDdpmLatent, static_cast<unsigned long long>(n), static_cast<unsigned long long>(t_first + 1)};
-      const unsigned long long n_str[2] = {kDdpmLatent * 4ull, static_cast<unsigned long long>(n) * kDdpmLatent * 4ull};
+      const unsigned long long n_str[2] = {kDdpmLatent * 4ull, static_cast<unsigned long long>(noise_batch) * kDdpmLatent * 4ull};
       const unsigned n_box[3] = {32, 128, 1};
       CU_TRY(make_tensor_map(maps.nz, noise, 4, 3, n_dims, n_str, n_box, true));
     } else {
       std::memcpy(maps.nz, maps.x, 128);   // never dereferenced (t_first == 0 or eps_mode)
     }
   }
-  CU_TRY(launch_ddpm_split(x, n, n_pad, d->act, fp16, st));
-  CU_TRY(cudaMemsetAsync(d->counter, 0, static_cast<size_t>(m_pairs) * sizeof(unsigned int), st));
-  if (d->prof) CU_TRY(cudaMemsetAsync(d->prof, 0, (static_cast<size_t>(148) * 24 + 96) * sizeof(long long), st));
-  CU_TRY(cudaEventRecord(d->ev0, st));
+  CU_TRY(launch_ddpm_split(x, n, n_pad, L.act, fp16, st));
+  CU_TRY(cudaMemsetAsync(L.counter, 0, static_cast<size_t>(m_pairs) * sizeof(unsigned int), st));
+  if (p.prof) CU_TRY(cudaMemsetAsync(d->prof, 0, (static_cast<size_t>(148) * 24 + 96) * sizeof(long long), st));
+  if (time_it) CU_TRY(cudaEventRecord(d->ev0, st));
   CU_TRY(launch_ddpm_sample(p, maps, fp16, d->num_sms, st));
+  return SDFB_OK;
+}
+
+// Tensor-core path: `steps` fused denoise+update steps t = t_first, t_first-1, ... in ONE cooperative launch
+// (eps_out != nullptr: a single denoiser evaluation, no update) - or in TWO concurrent launches when the batch has
+// one to three latent groups more than fit the 8-CTA-cluster mode: the groups that fit run in that mode (they have no
+// dependency outside their cluster), the rest as plain CTA pairs on the SMs that are left, on a second stream.
+static int ddpm_tc(sdfb_ddpm* d, float* x, const float* noise, int n, int steps, int t_first, float* eps_out,
+                   bool fp16, cudaStream_t st, bool philox = false, unsigned long long seed = 0, unsigned int first_latent = 0) {
+  const int m_pairs = (n + 255) / 256;
+  const int f = fp16 ? 1 : 0;
+  if (d->max_clusters8[f] < 0) d->max_clusters8[f] = ddpm_max_clusters8(256, 5, fp16);
+  const int c8 = d->max_clusters8[f];
+  bool split = eps_out == nullptr && c8 > 0 && m_pairs > c8 && m_pairs * 4 <= d->num_sms / 2 &&
+               std::getenv("SDFB_DDPM_BN") == nullptr && std::getenv("SDFB_DDPM_CLUSTER8") == nullptr &&
+               std::getenv("SDFB_DDPM_NO_SPLIT") == nullptr;
+  int bn_b = 0;
+  if (split) {
+    const int groups_b = m_pairs - c8;
+    bn_b = groups_b == 1 ? 128 : 256;
+    if (2 * groups_b * (kDdpmHid / bn_b) > d->num_sms - 8 * c8) split = false;    // the rest must be resident beside the clusters
+  }
+  if (!split) {
+    int rc = ddpm_tc_lane(d, 0, x, noise, n, n, steps, t_first, eps_out, fp16, st, philox, seed, first_latent, 0, true);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(d->ev1, st));
+    d->timed = true;
+    return SDFB_OK;
+  }
+  const int n_a = 256 * c8, n_b = n - n_a;
+  if (d->st_b == nullptr) {
+    CU_TRY(cudaStreamCreateWithFlags(&d->st_b, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
+  }
+  CU_TRY(cudaEventRecord(d->ev0, st));
+  CU_TRY(cudaEventRecord(d->ev_fork, st));
+  CU_TRY(cudaStreamWaitEvent(d->st_b, d->ev_fork, 0));
+  int rc = ddpm_tc_lane(d, 0, x, noise, n, n_a, steps, t_first, nullptr, fp16, st, philox, seed, first_latent, 256, false);
+  if (rc) return rc;
+  rc = ddpm_tc_lane(d, 1, x + static_cast<size_t>(n_a) * kDdpmLatent, noise ? noise + static_cast<size_t>(n_a) * kDdpmLatent : nullptr, n,
+                    n_b, steps, t_first, nullptr, fp16, d->st_b, philox, seed, first_latent + static_cast<unsigned int>(n_a), bn_b, false);
+  if (rc) return rc;
+  CU_TRY(cudaEventRecord(d->ev_join, d->st_b));
+  CU_TRY(cudaStreamWaitEvent(st, d->ev_join, 0));
   CU_TRY(cudaEventRecord(d->ev1, st));
   d->timed = true;
   return SDFB_OK;

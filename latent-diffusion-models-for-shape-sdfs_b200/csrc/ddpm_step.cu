@@ -54,7 +54,8 @@ constexpr int kBarAccFull = kBarEmpty + kDdpmMaxStages;
 constexpr int kBarAccEmpty = kBarAccFull + 2;
 constexpr int kBarXn = kBarAccEmpty + 2;
 constexpr int kBarOwn = kBarXn + 1;          // staging slot s holds a finished operand chunk (6 slots)
-constexpr int kNumBars = kBarOwn + 6;
+constexpr int kBarGroup = kBarOwn + 6;        // cluster8 mode: every warp set of the latent group's 8 CTAs has stored its output
+constexpr int kNumBars = kBarGroup + 1;
 constexpr uint32_t kBarBytes = (kNumBars * 8 + 15) & ~15u;   // keeps what follows 16-byte aligned
 
 // wait sites (status codes); (site >> 4) & 7 is the class under which blocked cycles are profiled
@@ -235,7 +236,11 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
   float* sbias = reinterpret_cast<float*>(smem_raw + o_bar + kBarBytes + 16);                    // 2 x 256 floats: the tile's bias slice
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  // The cluster is one CTA pair, or (cluster8 mode) the four pairs that share 256 latents.
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1u;                    // rank inside the pair
+  const uint32_t lrank = crank & ~1u;                  // cluster rank of this pair's leader CTA
+  const uint16_t pmask = static_cast<uint16_t>(3u << lrank);
   const bool leader = rank == 0;
   const int npairs = gridDim.x >> 1, pidx = blockIdx.x >> 1;
   // Barrier arithmetic: a pair tile contributes 4 arrivals (2 CTAs x 2 warp sets) to the counter of its
@@ -255,6 +260,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
     }
     mbar_init(bars + 8 * kBarXn, 1);
     for (int c = 0; c < 6; ++c) mbar_init(bars + 8 * (kBarOwn + c), kEpiWarps);   // one warp set x 2 CTAs arrive per phase
+    mbar_init(bars + 8 * kBarGroup, 16);                                        // 8 CTAs x 2 warp sets
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -273,7 +279,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
   if (warp == 8) {
     // ===================== producer =====================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, gphase = 0;
       const uint32_t nst = static_cast<uint32_t>(p.nstages);
       for (int s = 0; s < p.steps; ++s) {
         for (int l = 0; l < kLayers; ++l) {
@@ -296,7 +302,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               const uint32_t full = bars + 8 * (kBarFull + stage);
               if (leader) mbar_arrive_expect_tx(full, static_cast<uint32_t>(g.bn) * 128u);
               const int kc = kc_of(o, i), wk = l == 0 ? (kc & 3) : kc;
-              tma_load_2d_pair(smem0 + stage * stage_bytes + kChunk, tmw, 0, w_row + wk * g.n_total, map_to_cta(full, 0));
+              tma_load_2d_pair(smem0 + stage * stage_bytes + kChunk, tmw, 0, w_row + wk * g.n_total, map_to_cta(full, lrank));
               if (++stage == nst) { stage = 0; phase ^= 1u; }
             }
             if (need_sync) {
@@ -309,17 +315,22 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
                 const uint32_t full = bars + 8 * (kBarFull + st);
                 if (leader) mbar_arrive_expect_tx(full, tx);
                 const int kc = kc_of(o, i + k), wk = l == 0 ? (kc & 3) : kc;
-                tma_load_2d_pair(smem0 + st * stage_bytes + kChunk, tmw, 0, w_row + wk * g.n_total, map_to_cta(full, 0));
+                tma_load_2d_pair(smem0 + st * stage_bytes + kChunk, tmw, 0, w_row + wk * g.n_total, map_to_cta(full, lrank));
                 if (++st == nst) { st = 0; ph ^= 1u; }
               }
               SDFB_TRACE(7);
-              if (!grid_wait(p, p.counter + pm, target, wd)) goto done;
+              if (p.cluster8) {
+                if (!mbar_wait_cluster(bars + 8 * kBarGroup, gphase, wd, kErrGrid)) goto done;
+                gphase ^= 1u;
+              } else {
+                if (!grid_wait(p, p.counter + pm, target, wd)) goto done;
+              }
               SDFB_TRACE(8);
               if (!(p.flags & 1u)) fence_proxy_async_global();
               st = stage;
               for (int k = 0; k < pre; ++k) {
                 tma_load_2d_pair(smem0 + st * stage_bytes, &tm_act, g.a_col0 + kc_of(o, i + k) * 64, a_row,
-                                 map_to_cta(bars + 8 * (kBarFull + st), 0));
+                                 map_to_cta(bars + 8 * (kBarFull + st), lrank));
                 if (++st == nst) st = 0;
               }
               SDFB_TRACE(9);
@@ -332,7 +343,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               const uint32_t full = bars + 8 * (kBarFull + stage);
               if (leader) mbar_arrive_expect_tx(full, tx);
               const int kc = kc_of(o, i), wk = l == 0 ? (kc & 3) : kc;
-              const uint32_t full_l = map_to_cta(full, 0);
+              const uint32_t full_l = map_to_cta(full, lrank);
               tma_load_2d_pair(smem0 + stage * stage_bytes + kChunk, tmw, 0, w_row + wk * g.n_total, full_l);
               tma_load_2d_pair(smem0 + stage * stage_bytes, &tm_act, g.a_col0 + kc * 64, a_row, full_l);
               if (++stage == nst) { stage = 0; phase ^= 1u; }
@@ -388,9 +399,9 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) umma_ss<2>(d_tmem, adesc + 2 * jj, bdesc + 2 * jj, idesc, (k | jj) != 0 ? 1u : 0u);
                 if (k & 1) {   // one commit point per pair of chunks
-                  umma_commit<2>(bars + 8 * (kBarEmpty + prev_stage));
-                  umma_commit<2>(bars + 8 * (kBarEmpty + stage));
-                  if (k == nk - 1) umma_commit<2>(bars + 8 * (kBarAccFull + b));
+                  umma_commit<2>(bars + 8 * (kBarEmpty + prev_stage), pmask);
+                  umma_commit<2>(bars + 8 * (kBarEmpty + stage), pmask);
+                  if (k == nk - 1) umma_commit<2>(bars + 8 * (kBarAccFull + b), pmask);
                 }
               }
               __syncwarp();
@@ -496,11 +507,11 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               if (c + 2 >= nch) {      // every column this warp owns has been read: hand the accumulator back
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1);
+                if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1, lrank);
               }
               fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0) arrive_on_leader(bars + 8 * (kBarOwn + slot0 + c), 1);   // the pair's next layer may start on this chunk
+              if (lane == 0) arrive_on_leader(bars + 8 * (kBarOwn + slot0 + c), 1, lrank);   // the pair's next layer may start on this chunk
               named_bar_sync(2 + set, kEpiThreads / 2);
               if (set_leader) {
                 if (c == 0) SDFB_TRACE(3);
@@ -512,7 +523,13 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             if (set_leader) {          // stores complete -> arrive on the barrier of this latent group
               bulk_wait_group0();
               if (threadIdx.x == 0) SDFB_TRACE(5);
-              if (p.flags & 2u) {
+              if (p.cluster8) {
+                // the latent group IS the cluster: one arrival on every member's group barrier instead of a counter in L2
+                fence_proxy_async_global();
+                fence_acq_rel_cluster();
+#pragma unroll
+                for (uint32_t r = 0; r < 8; ++r) mbar_arrive_remote_relaxed(bars + 8 * kBarGroup, r, 1u);
+              } else if (p.flags & 2u) {
                 red_relaxed_gpu_add(p.counter + pm, 1u);
               } else {
                 fence_proxy_async_global();
@@ -532,7 +549,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1);
+            if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1, lrank);
             if (threadIdx.x == 0) SDFB_TRACE(10);
             const uint32_t xrow = stg + set * kChunk + row * 128u;             // this thread's 32 floats of x (swizzled 16-byte units)
             const uint32_t nrow = xrow + 2 * kChunk;
@@ -587,7 +604,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             named_bar_sync(1, kEpiThreads);
             // both sets wrote both images: only now are they complete.  x_hi (slot 2) / x_lo (slot 3) are the own
             // chunks of the next step's layer 0; one warp set arrives per slot, as for the hidden layers' slots.
-            if (lane == 0 && !p.eps_mode) arrive_on_leader(bars + 8 * (kBarOwn + 2 + set), 1);
+            if (lane == 0 && !p.eps_mode) arrive_on_leader(bars + 8 * (kBarOwn + 2 + set), 1, lrank);
             if (threadIdx.x == 0) {
               tma_store_2d(&tm_x, j * 64, g_row, stg);                          // rows >= n are clipped by the TMA unit
               tma_store_2d(&tm_x, j * 64 + 32, g_row, stg + kChunk);
@@ -599,7 +616,12 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               SDFB_TRACE(4);
               bulk_wait_group0();
               SDFB_TRACE(5);
-              if (p.flags & 2u) {
+              if (p.cluster8) {
+                fence_proxy_async_global();
+                fence_acq_rel_cluster();
+#pragma unroll
+                for (uint32_t r = 0; r < 8; ++r) mbar_arrive_remote_relaxed(bars + 8 * kBarGroup, r, 2u);
+              } else if (p.flags & 2u) {
                 red_relaxed_gpu_add(p.counter + pm, 2u);
               } else {
                 fence_proxy_async_global();
@@ -709,6 +731,25 @@ cudaError_t launch_philox_normal(unsigned long long seed, unsigned int first_lat
   return cudaGetLastError();
 }
 
+int ddpm_max_clusters8(int bn_h, int nstages, bool fp16) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(8 * 18);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes_for(bn_h, nstages);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 8;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e = fp16 ? cudaOccupancyMaxActiveClusters(&n, ddpm_sample_kernel<true>, &cfg)
+                       : cudaOccupancyMaxActiveClusters(&n, ddpm_sample_kernel<false>, &cfg);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 cudaError_t launch_ddpm_split(const float* x, int n, int n_pad, uint16_t* act, bool fp16, cudaStream_t stream) {
   const long long total = static_cast<long long>(n_pad) * 32;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
@@ -729,7 +770,7 @@ cudaError_t launch_ddpm_sample(const DdpmParams& p, const DdpmMaps& maps, bool f
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = p.cluster8 ? 8 : 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeCooperative;           // every CTA must be resident: they wait on one another
@@ -737,7 +778,8 @@ cudaError_t launch_ddpm_sample(const DdpmParams& p, const DdpmMaps& maps, bool f
   cfg.attrs = attr;
   // SDFB_DDPM_NO_COOP=1 (profiling only): drop the co-residency guarantee - ncu cannot launch a cooperative
   // cluster kernel; on an otherwise idle GPU the grid (<= 1 CTA per SM) is resident anyway.
-  cfg.numAttrs = std::getenv("SDFB_DDPM_NO_COOP") != nullptr ? 1 : 2;
+  // (In cluster8 mode nothing waits across clusters, and the hardware co-schedules a cluster's CTAs: no guarantee needed.)
+  cfg.numAttrs = (p.cluster8 || std::getenv("SDFB_DDPM_NO_COOP") != nullptr) ? 1 : 2;
   const CUtensorMap* a = reinterpret_cast<const CUtensorMap*>(maps.act);
   const CUtensorMap* wh = reinterpret_cast<const CUtensorMap*>(maps.wh);
   const CUtensorMap* wo = reinterpret_cast<const CUtensorMap*>(maps.wo);

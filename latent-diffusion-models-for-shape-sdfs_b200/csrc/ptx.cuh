@@ -124,6 +124,14 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, const W
   }
 }
 
+// one arrival (count `count`) on the barrier at the same offset in CTA `rank` of the cluster; ordering is supplied by
+// the caller's fence_acq_rel_cluster()
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t local_bar, uint32_t rank, uint32_t count) {
+  const uint32_t remote = map_to_cta(local_bar, rank);
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+
 // ------------------------------------------------------------ async proxy ---
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -223,8 +231,9 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_
 
 // All previously issued MMAs of this thread arrive on `bar` when complete.
 // CG==2: the arrive is multicast to the same barrier offset in both CTAs of the pair.
+// `pair_mask`: the cluster ranks of the pair's two CTAs (3 for a cluster that is just the pair).
 template <int CG>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint16_t pair_mask = 3) {
   if constexpr (CG == 1)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
@@ -232,7 +241,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
         "[%0], %1;" ::"r"(bar),
-        "h"(static_cast<uint16_t>(3))
+        "h"(pair_mask)
         : "memory");
 }
 
@@ -321,8 +330,8 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity,
 // costs a MEMBAR of several hundred cycles per arrival (30% of all epilogue stall samples when it
 // was tried).  The data being published was made visible to the async proxy by each lane's
 // fence.proxy.async and ordered before this arrive by __syncwarp().
-__device__ __forceinline__ void arrive_on_leader(uint32_t local_bar, uint32_t count) {
-  const uint32_t remote = map_to_cta(local_bar, 0);
+__device__ __forceinline__ void arrive_on_leader(uint32_t local_bar, uint32_t count, uint32_t leader_rank = 0) {
+  const uint32_t remote = map_to_cta(local_bar, leader_rank);
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(count) : "memory");
 }
 // Rows [row0, row0 + box rows) of a [rows][64] 16-bit tensor map -> local shared memory; the
