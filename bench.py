@@ -272,112 +272,124 @@ def main():
     # z-slab per rank, fused-path decode + sign-change mask (halo plane recomputed locally) + in-place NCCL all-gather
     cfg5 = None
     if world > 1 and not args.no_config5:
-        res5 = 512
-        z5 = torch.from_numpy(pkg.synthetic.latent(0)).to(dev)
-        del out, flush
-        for _ in range(2):
-            s5, m5 = pkg.decode_grid_sharded(dec, z5, res5, mask=True)
-        t5 = []
-        for _ in range(5):
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            s5, m5 = pkg.decode_grid_sharded(dec, z5, res5, mask=True)
-            b.record()
-            b.synchronize()
-            t5.append(a.elapsed_time(b))
-        t5 = torch.tensor([statistics.median(t5)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
-        ms5 = float(t5.item())
-        per_gpu_tflops = (res5 ** 3 / world) * FLOP_TENSOR_PER_QUERY / (ms5 * 1e-3) / 1e12
-        cfg5 = {"workload": f"decode_grid_sharded(z, 512, mask=True) on {world} GPUs: z-slabs, mask with locally recomputed halo plane, "
-                            "in-place NCCL all-gather of the sdf slabs and gather of the mask slabs; median of 5, max over ranks",
-                "ms": ms5, "queries_per_s": res5 ** 3 / (ms5 * 1e-3), "tflops_per_gpu_incl_mask_and_gather": per_gpu_tflops,
-                "active_cells": int(m5.sum().item()), "sdf_checksum": float(s5[::32, ::32, ::32].double().sum().item())}
-        del s5, m5
+        try:
+            res5 = 512
+            z5 = torch.from_numpy(pkg.synthetic.latent(0)).to(dev)
+            del out, flush
+            for _ in range(2):
+                s5, m5 = pkg.decode_grid_sharded(dec, z5, res5, mask=True)
+            t5 = []
+            for _ in range(5):
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                s5, m5 = pkg.decode_grid_sharded(dec, z5, res5, mask=True)
+                b.record()
+                b.synchronize()
+                t5.append(a.elapsed_time(b))
+            t5 = torch.tensor([statistics.median(t5)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            ms5 = float(t5.item())
+            per_gpu_tflops = (res5 ** 3 / world) * FLOP_TENSOR_PER_QUERY / (ms5 * 1e-3) / 1e12
+            cfg5 = {"workload": f"decode_grid_sharded(z, 512, mask=True) on {world} GPUs: z-slabs, mask with locally recomputed halo plane, "
+                                "in-place NCCL all-gather of the sdf slabs and gather of the mask slabs; median of 5, max over ranks",
+                    "ms": ms5, "queries_per_s": res5 ** 3 / (ms5 * 1e-3), "tflops_per_gpu_incl_mask_and_gather": per_gpu_tflops,
+                    "active_cells": int(m5.sum().item()), "sdf_checksum": float(s5[::32, ::32, ::32].double().sum().item())}
+            del s5, m5
+        except Exception as exc:                     # an optional leg must never cost the headline line
+            cfg5 = {"error": repr(exc)}
+            print(f"bench.py: optional leg failed: {exc!r}", file=sys.stderr)
 
     # ---- second half of the metric: latent-DDPM latents/s (BASELINE configs[3]: 4096 latents, 1000 steps) ----
     ddpm_line = None
     if not args.no_ddpm:
-        n_lat, T = DDPM_LATENTS, 1000
-        sampler = pkg.LatentDDPM(pkg.synthetic.ddpm_params(), device=dev, precision=args.precision)
-        g = torch.Generator(device=dev).manual_seed(100 + rank)
-        x_T = torch.randn((n_lat, 256), generator=g, device=dev)
-        noise = torch.randn((T, n_lat, 256), generator=g, device=dev)           # 4.2 GB explicit noise stream in HBM
-        dd_ms = []
-        for i in range(1 + 3):                                                   # 1 warm-up + 3 timed full samplings
+        try:
+            n_lat, T = DDPM_LATENTS, 1000
+            sampler = pkg.LatentDDPM(pkg.synthetic.ddpm_params(), device=dev, precision=args.precision)
+            g = torch.Generator(device=dev).manual_seed(100 + rank)
+            x_T = torch.randn((n_lat, 256), generator=g, device=dev)
+            noise = torch.randn((T, n_lat, 256), generator=g, device=dev)           # 4.2 GB explicit noise stream in HBM
+            dd_ms = []
+            for i in range(1 + 3):                                                   # 1 warm-up + 3 timed full samplings
+                barrier()
+                x0 = sampler.sample_latents(n_lat, x_T=x_T, noise=noise, steps=T)
+                if i:
+                    dd_ms.append(sampler.last_kernel_ms())
+            dd = torch.tensor([statistics.mean(dd_ms)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dd, op=dist.ReduceOp.MAX)
+            dd_ms_max = float(dd.item())
+            flop = n_lat * T * DDPM_FLOP_PER_LATENT_STEP
+            ddpm_line = {"metric": "ddpm_latents_per_s", "value": world * n_lat / (dd_ms_max * 1e-3), "unit": "latents/s",
+                         "workload": f"sample_latents({n_lat}) per GPU: MLP denoiser 4x1024, latent 256, {T} steps, explicit noise "
+                                     "stream resident in HBM; ONE persistent cooperative kernel per call",
+                         "ms_per_sampling": dd_ms_max, "us_per_step": dd_ms_max * 1e3 / T,
+                         "kernel": "ddpm_sample_kernel", "achieved_tflops": flop / (dd_ms_max * 1e-3) / 1e12,
+                         "flop_per_latent_step": DDPM_FLOP_PER_LATENT_STEP, "gpu_launches_per_sampling": 2,
+                         "x0_abs_max": float(x0.abs().max().item())}
+            # sample_latents(n) as the north star spells it - no stream argument: noise generated in the kernel
+            # (Philox4x32-10), device-timed, then end to end through the host-buffer call (x_0 [n,256] comes back)
+            sd_ms = []
+            for i in range(1 + 3):
+                barrier()
+                xs0 = sampler.sample_latents(n_lat, steps=T, seed=7 + rank)
+                if i:
+                    sd_ms.append(sampler.last_kernel_ms())
+            sd = torch.tensor([statistics.mean(sd_ms)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(sd, op=dist.ReduceOp.MAX)
+            ddpm_line["seeded"] = {"value": world * n_lat / (float(sd.item()) * 1e-3), "unit": "latents/s", "ms_per_sampling": float(sd.item()),
+                                   "noise": "generated in the update epilogue (Philox4x32-10 + Box-Muller), no noise stream in memory",
+                                   "x0_abs_max": float(xs0.abs().max().item())}
+            sampler.sample_latents_seeded_host(n_lat, 7 + rank, steps=T)
             barrier()
-            x0 = sampler.sample_latents(n_lat, x_T=x_T, noise=noise, steps=T)
-            if i:
-                dd_ms.append(sampler.last_kernel_ms())
-        dd = torch.tensor([statistics.mean(dd_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dd, op=dist.ReduceOp.MAX)
-        dd_ms_max = float(dd.item())
-        flop = n_lat * T * DDPM_FLOP_PER_LATENT_STEP
-        ddpm_line = {"metric": "ddpm_latents_per_s", "value": world * n_lat / (dd_ms_max * 1e-3), "unit": "latents/s",
-                     "workload": f"sample_latents({n_lat}) per GPU: MLP denoiser 4x1024, latent 256, {T} steps, explicit noise "
-                                 "stream resident in HBM; ONE persistent cooperative kernel per call",
-                     "ms_per_sampling": dd_ms_max, "us_per_step": dd_ms_max * 1e3 / T,
-                     "kernel": "ddpm_sample_kernel", "achieved_tflops": flop / (dd_ms_max * 1e-3) / 1e12,
-                     "flop_per_latent_step": DDPM_FLOP_PER_LATENT_STEP, "gpu_launches_per_sampling": 2,
-                     "x0_abs_max": float(x0.abs().max().item())}
-        # sample_latents(n) as the north star spells it - no stream argument: noise generated in the kernel
-        # (Philox4x32-10), device-timed, then end to end through the host-buffer call (x_0 [n,256] comes back)
-        sd_ms = []
-        for i in range(1 + 3):
-            barrier()
-            xs0 = sampler.sample_latents(n_lat, steps=T, seed=7 + rank)
-            if i:
-                sd_ms.append(sampler.last_kernel_ms())
-        sd = torch.tensor([statistics.mean(sd_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(sd, op=dist.ReduceOp.MAX)
-        ddpm_line["seeded"] = {"value": world * n_lat / (float(sd.item()) * 1e-3), "unit": "latents/s", "ms_per_sampling": float(sd.item()),
-                               "noise": "generated in the update epilogue (Philox4x32-10 + Box-Muller), no noise stream in memory",
-                               "x0_abs_max": float(xs0.abs().max().item())}
-        sampler.sample_latents_seeded_host(n_lat, 7 + rank, steps=T)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            xh = sampler.sample_latents_seeded_host(n_lat, 7 + rank, steps=T)
-        e2 = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e2, op=dist.ReduceOp.MAX)
-        ddpm_line["e2e"] = {"value": world * n_lat / float(e2.item()), "unit": "latents/s", "h2d_bytes_per_step": 0,
-                            "d2h_bytes_per_step": int(xh.nbytes),
-                            "api": "LatentDDPM.sample_latents_seeded_host -> sdfb_ddpm_sample_philox_host (x_T and noise generated on the device, x_0 returned to the host)"}
-        del noise, sampler
+            t0 = time.perf_counter()
+            for _ in range(3):
+                xh = sampler.sample_latents_seeded_host(n_lat, 7 + rank, steps=T)
+            e2 = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+            ddpm_line["e2e"] = {"value": world * n_lat / float(e2.item()), "unit": "latents/s", "h2d_bytes_per_step": 0,
+                                "d2h_bytes_per_step": int(xh.nbytes),
+                                "api": "LatentDDPM.sample_latents_seeded_host -> sdfb_ddpm_sample_philox_host (x_T and noise generated on the device, x_0 returned to the host)"}
+            del noise, sampler
+        except Exception as exc:                     # an optional leg must never cost the headline line
+            ddpm_line = {"error": repr(exc)}
+            print(f"bench.py: optional leg failed: {exc!r}", file=sys.stderr)
 
     # ---- BASELINE configs[3], one GPU's share when it is spread over 8: 512 of the 4096 latents are sampled (1000 steps,
     # noise generated in the kernel) and each is decoded on a 128^3 grid (64 shapes per call into a reused buffer; 34 GB of
     # sdf in total for the full config, so the fields are consumed / discarded as they are produced)
     cfg4 = None
     if not args.no_config4:
-        n4, res4 = 512, 128
-        smp = pkg.LatentDDPM(pkg.synthetic.ddpm_params(), device=dev, precision=args.precision)
-        buf4 = torch.empty((64, res4, res4, res4), dtype=torch.float32, device=dev)
-        lat4 = smp.sample_latents(n4, seed=1000 + rank)
-        dec.decode_grid_batch(lat4[:64], res4, out=buf4)
-        barrier()
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record()
-        lat4 = smp.sample_latents(n4, seed=1000 + rank)
-        b.record()
-        for i0 in range(0, n4, 64):
-            dec.decode_grid_batch(lat4[i0:i0 + 64], res4, out=buf4)
-        c.record()
-        c.synchronize()
-        t4 = torch.tensor([a.elapsed_time(b), b.elapsed_time(c)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
-        q4 = n4 * res4 ** 3
-        cfg4 = {"workload": f"per GPU: sample_latents({n4}) (1000 steps, in-kernel noise) then decode_grid_batch of the {n4} samples at "
-                            f"{res4}^3 (64 per call); {world} GPUs cover {world * n4} latents (BASELINE configs[3] = 4096 latents on 8 GPUs)",
-                "ddpm_ms": float(t4[0].item()), "decode_ms": float(t4[1].item()), "total_ms": float(t4.sum().item()),
-                "decode_queries_per_s": world * q4 / (float(t4[1].item()) * 1e-3),
-                "decode_tflops_per_gpu": q4 * FLOP_TENSOR_PER_QUERY / (float(t4[1].item()) * 1e-3) / 1e12}
-        del buf4, smp, lat4
+        try:
+            n4, res4 = 512, 128
+            smp = pkg.LatentDDPM(pkg.synthetic.ddpm_params(), device=dev, precision=args.precision)
+            buf4 = torch.empty((64, res4, res4, res4), dtype=torch.float32, device=dev)
+            lat4 = smp.sample_latents(n4, seed=1000 + rank)
+            dec.decode_grid_batch(lat4[:64], res4, out=buf4)
+            barrier()
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            lat4 = smp.sample_latents(n4, seed=1000 + rank)
+            b.record()
+            for i0 in range(0, n4, 64):
+                dec.decode_grid_batch(lat4[i0:i0 + 64], res4, out=buf4)
+            c.record()
+            c.synchronize()
+            t4 = torch.tensor([a.elapsed_time(b), b.elapsed_time(c)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+            q4 = n4 * res4 ** 3
+            cfg4 = {"workload": f"per GPU: sample_latents({n4}) (1000 steps, in-kernel noise) then decode_grid_batch of the {n4} samples at "
+                                f"{res4}^3 (64 per call); {world} GPUs cover {world * n4} latents (BASELINE configs[3] = 4096 latents on 8 GPUs)",
+                    "ddpm_ms": float(t4[0].item()), "decode_ms": float(t4[1].item()), "total_ms": float(t4.sum().item()),
+                    "decode_queries_per_s": world * q4 / (float(t4[1].item()) * 1e-3),
+                    "decode_tflops_per_gpu": q4 * FLOP_TENSOR_PER_QUERY / (float(t4[1].item()) * 1e-3) / 1e12}
+            del buf4, smp, lat4
+        except Exception as exc:                     # an optional leg must never cost the headline line
+            cfg4 = {"error": repr(exc)}
+            print(f"bench.py: optional leg failed: {exc!r}", file=sys.stderr)
 
     if rank == 0:
         peaks = read_peaks()
@@ -410,16 +422,18 @@ def main():
             "wall_s_timed_region": t_wall,
         }
         if cfg5 is not None:
-            cfg5["frac_of_burst_peak_per_gpu"] = cfg5["tflops_per_gpu_incl_mask_and_gather"] / peaks["burst"]
+            if "error" not in cfg5:
+                cfg5["frac_of_burst_peak_per_gpu"] = cfg5["tflops_per_gpu_incl_mask_and_gather"] / peaks["burst"]
             line["config5_512cubed_sharded"] = cfg5
         if cfg4 is not None:
             line["config4_sample_then_decode"] = cfg4
         if ddpm_line is not None:
-            ddpm_line["frac_of_burst_peak"] = ddpm_line["achieved_tflops"] / peaks["burst"]
+            if "achieved_tflops" in ddpm_line:
+                ddpm_line["frac_of_burst_peak"] = ddpm_line["achieved_tflops"] / peaks["burst"]
             line["ddpm"] = ddpm_line
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_oracle_rate()
-            if ddpm_line is not None:
+            if ddpm_line is not None and "error" not in ddpm_line:
                 line["ddpm"]["cpu_baseline"] = cpu_ddpm_rate()
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
