@@ -78,3 +78,21 @@ def test_workspace_queries_and_validation_of_the_extraction_entry_points(pkg):
     assert lib.sdfb_decoder_vjp_latent(None, None, None, 0, None, None, None, None) == -1
     assert lib.sdfb_philox_normal(1, -1, 4, 0, 1, None, None) == -1
     assert lib.sdfb_ddpm_sample_philox(None, None, 0, 0, 4, 10, 1, 1, None) == -1
+
+
+def test_header_is_valid_c_and_links_from_a_c_program(pkg, tmp_path):
+    """include/sdfb200.h compiled as C99 with -Wall -Werror, linked against libsdfb200.so, run without a device."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not found")
+    lib = os.path.join(ROOT, "latent-diffusion-models-for-shape-sdfs_b200", "libsdfb200.so")
+    exe = str(tmp_path / "abi_smoke")
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "sdfb C ABI ok" in run.stdout
