@@ -104,3 +104,32 @@ def test_sharded_decode_gloo_world2(res):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in results)
     assert sorted(r[2] for r in results) == [(0, 3), (3, 5)]
+
+
+def test_partition_properties_hypothesis(pkg):
+    """slab_range / batch_range: disjoint, ordered, covering, balanced - for arbitrary sizes."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(2, 4096), st.integers(1, 64))
+    def slabs(res, world):
+        prev = 0
+        for r in range(world):
+            z0, z1 = pkg.slab_range(res, r, world)
+            assert z0 == min(prev, res) and z0 <= z1 <= res
+            prev = z1
+        assert prev == res
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 100000), st.integers(1, 64))
+    def batches(n, world):
+        prev, sizes = 0, []
+        for r in range(world):
+            i0, i1 = pkg.batch_range(n, r, world)
+            assert i0 == prev and i1 >= i0
+            prev = i1
+            sizes.append(i1 - i0)
+        assert prev == n and max(sizes) - min(sizes) <= 1
+
+    slabs()
+    batches()
