@@ -286,11 +286,12 @@ int decode_any(sdfb_decoder* d, const float* z, const float* xyz, int res, long 
   }
 }
 
-int ensure_signs(sdfb_decoder* d, long long words) {
+int ensure_signs(sdfb_decoder* d, long long words, cudaStream_t st) {
   if (d->sign_words >= words) return SDFB_OK;
   cudaFree(d->signs); d->signs = nullptr; d->sign_words = 0;
   CU_TRY(cudaMalloc(&d->signs, static_cast<size_t>(words + 1) * sizeof(unsigned int)));   // + 1: the mask kernel reads word pairs
-  CU_TRY(cudaMemset(d->signs, 0, static_cast<size_t>(words + 1) * sizeof(unsigned int)));
+  // (on the caller's stream: a legacy-stream memset is not ordered with a non-blocking stream)
+  CU_TRY(cudaMemsetAsync(d->signs, 0, static_cast<size_t>(words + 1) * sizeof(unsigned int), st));
   d->sign_words = words;
   return SDFB_OK;
 }
@@ -412,6 +413,7 @@ int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, s
   CU_TRY_D(cudaStreamCreateWithFlags(&d->st_copy, cudaStreamNonBlocking));
   for (cudaEvent_t& e : d->chunk_ev) CU_TRY_D(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (cudaEvent_t& e : d->in_ev) CU_TRY_D(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CU_TRY_D(cudaDeviceSynchronize());   // the set-up copies and memsets above are done before any caller stream can touch the context
 #undef CU_TRY_D
   *out = d;
   return SDFB_OK;
@@ -453,7 +455,7 @@ int sdfb_decode_grid(sdfb_decoder* d, const float* latent_dev, int res, int z0, 
   if (mask_dev == nullptr || zend - z0 < 2) return decode_any(d, latent_dev, nullptr, res, z0 * plane, M, sdf_dev, precision, st);
   // the decoder emits the sign bit of every value it stores; the cell mask is a combine of those bit-planes
   // (1/32 of the field's bytes) instead of a second pass over the fp32 field
-  int rc = ensure_signs(d, (M + 31) >> 5);
+  int rc = ensure_signs(d, (M + 31) >> 5, st);
   if (rc) return rc;
   if (rc == SDFB_OK) rc = ensure_rowmask(d, mask_rows_words(zend - z0, res, res));
   if (rc) return rc;
@@ -476,7 +478,7 @@ int sdfb_decode_grid_bits(sdfb_decoder* d, const float* latent_dev, int res, int
   const long long M = (zend - z0) * plane;
   // the decoder writes into the context's own bit-plane buffer (it has the padding word the mask kernel reads);
   // the caller's copy is made from it
-  int rc = ensure_signs(d, (M + 31) >> 5);
+  int rc = ensure_signs(d, (M + 31) >> 5, st);
   if (rc == SDFB_OK && mask_bits_dev != nullptr && zend - z0 >= 2) rc = ensure_rowmask(d, mask_rows_words(zend - z0, res, res));
   if (rc) return rc;
   rc = decode_any(d, latent_dev, nullptr, res, z0 * plane, M, sdf_dev, precision, st, d->signs);
@@ -991,6 +993,7 @@ int sdfb_ddpm_create(const float* params_host, size_t n_floats, int device, sdfb
   }
   CU_TRY_D(cudaEventCreate(&d->ev0));
   CU_TRY_D(cudaEventCreate(&d->ev1));
+  CU_TRY_D(cudaDeviceSynchronize());   // the set-up copies and memsets above are done before any caller stream can touch the context
 #undef CU_TRY_D
   *out = d;
   return SDFB_OK;
@@ -1052,7 +1055,9 @@ static int ddpm_tc_lane(sdfb_ddpm* d, int lane, float* x, const float* noise, lo
     cudaFree(L.act); cudaFree(L.counter); L.act = nullptr; L.counter = nullptr; L.act_rows = 0;
     CU_TRY(cudaMalloc(&L.counter, static_cast<size_t>(m_pairs) * sizeof(unsigned int)));
     CU_TRY(cudaMalloc(&L.act, static_cast<size_t>(n_pad) * kDdpmActCols * 2));
-    CU_TRY(cudaMemset(L.act, 0, static_cast<size_t>(n_pad) * kDdpmActCols * 2));
+    // on the lane's own stream: a legacy-stream memset is not ordered with a non-blocking stream and could land after
+    // the kernels below have started to fill the buffer
+    CU_TRY(cudaMemsetAsync(L.act, 0, static_cast<size_t>(n_pad) * kDdpmActCols * 2, st));
     L.act_rows = n_pad;
   }
   // tile width of the hidden layers: 256 if that still gives about one pair tile per CTA pair

@@ -182,20 +182,27 @@ def test_seeded_sampler_is_addressed_by_global_latent_index(cuda_ddpm, pkg, monk
     assert torch.equal(p32, w32[10:])
 
 
-def test_batch_split_over_two_concurrent_launches(cuda_ddpm):
-    """4096 latents = 16 latent groups, one more than fit the 8-CTA-cluster mode: the call runs 15 groups in that mode
-    and the 16th as plain CTA pairs on a second stream.  Same numbers as sampling the two shares separately."""
+def test_batch_split_over_two_concurrent_launches(cuda_ddpm, monkeypatch):
+    """4096 latents = 16 latent groups.  If only 15 eight-CTA clusters fit this GPU (it depends on the chip's GPC
+    configuration), the call runs 15 groups in that mode and the 16th as plain CTA pairs (tile width 128) on a second
+    stream; if 16 fit, all groups run in cluster mode (tile width 256).  Either way the numbers are those of sampling
+    the shares separately with the matching tile width."""
     steps, seed = 25, 5
     whole = cuda_ddpm.sample_latents(4096, steps=steps, seed=seed, precision="bf16")
     ms = cuda_ddpm.last_kernel_ms()
     a = cuda_ddpm.sample_latents(3840, steps=steps, seed=seed, precision="bf16", first_latent=0)
-    b = cuda_ddpm.sample_latents(256, steps=steps, seed=seed, precision="bf16", first_latent=3840)
-    print(f"4096 latents x {steps} steps: {ms * 1e3 / steps:.1f} us/step")
-    assert torch.equal(whole[:3840], a)
-    assert torch.equal(whole[3840:], b)
+    b128 = cuda_ddpm.sample_latents(256, steps=steps, seed=seed, precision="bf16", first_latent=3840)
     g = torch.Generator(device="cuda").manual_seed(8)
     x_T = torch.randn((4096, 256), generator=g, device="cuda")
     noise = torch.randn((steps, 4096, 256), generator=g, device="cuda")
     we = cuda_ddpm.sample_latents(4096, x_T=x_T, noise=noise, steps=steps, precision="bf16")      # explicit stream, strided share
-    be = cuda_ddpm.sample_latents(256, x_T=x_T[3840:], noise=noise[:, 3840:].contiguous(), steps=steps, precision="bf16")
-    assert torch.equal(we[3840:], be)
+    tail_noise = noise[:, 3840:].contiguous()
+    be128 = cuda_ddpm.sample_latents(256, x_T=x_T[3840:], noise=tail_noise, steps=steps, precision="bf16")
+    monkeypatch.setenv("SDFB_DDPM_BN", "256")
+    b256 = cuda_ddpm.sample_latents(256, steps=steps, seed=seed, precision="bf16", first_latent=3840)
+    be256 = cuda_ddpm.sample_latents(256, x_T=x_T[3840:], noise=tail_noise, steps=steps, precision="bf16")
+    split = torch.equal(whole[3840:], b128)
+    print(f"4096 latents x {steps} steps: {ms * 1e3 / steps:.1f} us/step ({'15 clusters + plain pairs' if split else '16 clusters'})")
+    assert torch.equal(whole[:3840], a)
+    assert split or torch.equal(whole[3840:], b256)
+    assert torch.equal(we[3840:], be128 if split else be256)
