@@ -62,3 +62,31 @@ def test_config4_sample_then_decode(cuda_decoder, cuda_ddpm, golden):
         print(f"sampled latent {b}: |bf16 kernel - bf16 oracle| p90 {np.quantile(d, 0.9):.2e} max {d.max():.2e}; "
               f"inside fraction {float((g < 0).mean()):.3f}")
         assert d.max() < 5e-2 and np.quantile(d, 0.9) < 1e-3
+
+
+def test_first_calls_on_a_side_stream(pkg):
+    """Fresh contexts, first call issued on a non-blocking (non-default) torch stream: lazily allocated workspaces
+    must be initialised in stream order (a legacy-stream memset is not ordered with such a stream)."""
+    z = torch.from_numpy(oracle.default_latent()).cuda()
+    ref_dec = pkg.Decoder(oracle.flatten_params(oracle.decoder_weights()), device="cuda:0")
+    ref_sdf, ref_mask = ref_dec.decode_grid(z, 96, mask=True)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        dec = pkg.Decoder(oracle.flatten_params(oracle.decoder_weights()), device="cuda:0")
+        with torch.cuda.stream(side):
+            sdf, mask = dec.decode_grid(z, 96, mask=True)          # first call of this context
+            side.synchronize()
+        assert torch.equal(sdf, ref_sdf) and torch.equal(mask, ref_mask)
+        dec.close()
+    ref = pkg.LatentDDPM(oracle.flatten_params(oracle.ddpm_weights()), device="cuda:0", precision="bf16")
+    want = ref.sample_latents(4096, steps=6, seed=3)
+    want2 = ref.sample_latents(4096, steps=6, seed=3)
+    assert torch.equal(want, want2)
+    for _ in range(2):
+        smp = pkg.LatentDDPM(oracle.flatten_params(oracle.ddpm_weights()), device="cuda:0", precision="bf16")
+        with torch.cuda.stream(side):
+            got = smp.sample_latents(4096, steps=6, seed=3)        # first call: may split into two concurrent launches
+            side.synchronize()
+        assert torch.equal(got, want)
+        smp.close()
