@@ -98,6 +98,14 @@ int sdfb_decode_points(sdfb_decoder* dec, const float* latent_dev, const float* 
 int sdfb_decoder_vjp_latent(sdfb_decoder* dec, const float* latent_dev, const float* xyz_dev, int64_t M,
                             const float* dLdy_dev, float* grad_latent_dev, float* sdf_dev, void* stream);
 
+/* The same product on the tensor pipe (precision SDFB_PREC_BF16 or SDFB_PREC_FP16): one launch of the
+ * forward + backward instance of the fused decoder kernel - 16-bit operands, fp32 accumulation, the
+ * column sums the latent sees kept in fp32 (oracle: decoder_vjp_latent_lowp).  sdf_dev (optional)
+ * receives exactly what sdfb_decode_points returns at that precision. */
+int sdfb_decoder_vjp_latent_tc(sdfb_decoder* dec, const float* latent_dev, const float* xyz_dev, int64_t M,
+                               const float* dLdy_dev, float* grad_latent_dev, float* sdf_dev, int precision,
+                               void* stream);
+
 /* Host-buffer forms (what a plugin caller with CPU arrays uses): stage through
  * pinned memory owned by the context, run, copy back, synchronise. */
 int sdfb_decode_grid_host(sdfb_decoder* dec, const float* latent_host, int res, int z0, int z1,

@@ -167,8 +167,11 @@ class Decoder:
         return buf[: z1 - z0], signs, mw
 
     # ---- gradient w.r.t. the latent (auto-decoder fitting) ----------------------------------------
-    def latent_vjp(self, latent, xyz, dLdy):
-        """(grad [256], sdf [M]): grad = sum_m dLdy[m] * d sdf(latent, xyz_m) / d latent, fp32 path."""
+    def latent_vjp(self, latent, xyz, dLdy, precision: str = "fp32"):
+        """(grad [256], sdf [M]): grad = sum_m dLdy[m] * d sdf(latent, xyz_m) / d latent.
+        ``precision="fp32"``: FFMA path; ``"bf16"`` / ``"fp16"``: one launch of the forward + backward instance of
+        the fused tensor-core kernel (sdf is then what ``Decoder(latent, xyz)`` returns at that precision)."""
+        prec = PRECISIONS[precision]
         lat = _as_dev_f32(latent, self.device, (LATENT,))
         pts = _as_dev_f32(xyz, self.device)
         up = _as_dev_f32(dLdy, self.device)
@@ -177,15 +180,22 @@ class Decoder:
         M = pts.shape[0]
         grad = torch.empty(LATENT, dtype=torch.float32, device=self.device)
         sdf = torch.empty(M, dtype=torch.float32, device=self.device)
-        check(self._lib.sdfb_decoder_vjp_latent(self._h, lat.data_ptr(), pts.data_ptr() if M else None, M,
-                                                up.data_ptr() if M else None, grad.data_ptr(),
-                                                sdf.data_ptr() if M else None, _stream_ptr(self.device.index)))
+        if prec == PRECISIONS["fp32"]:
+            check(self._lib.sdfb_decoder_vjp_latent(self._h, lat.data_ptr(), pts.data_ptr() if M else None, M,
+                                                    up.data_ptr() if M else None, grad.data_ptr(),
+                                                    sdf.data_ptr() if M else None, _stream_ptr(self.device.index)))
+        else:
+            check(self._lib.sdfb_decoder_vjp_latent_tc(self._h, lat.data_ptr(), pts.data_ptr() if M else None, M,
+                                                       up.data_ptr() if M else None, grad.data_ptr(),
+                                                       sdf.data_ptr() if M else None, prec,
+                                                       _stream_ptr(self.device.index)))
         return grad, sdf
 
     def fit_latent(self, xyz, sdf_target, steps: int = 300, lr: float = 5e-3, clamp: float = 0.1, reg: float = 1e-4,
-                   init=None):
+                   init=None, precision: str = "fp32"):
         """Auto-decoder inference (DeepSDF's reconstruction step): Adam on the latent so that the decoded
         field matches ``sdf_target`` at ``xyz``; loss = mean |clamp(y) - clamp(s)| + reg |z|^2.
+        ``precision``: arithmetic of the forward and backward passes ("bf16" / "fp16": tensor pipe).
         Returns (latent [256], last loss)."""
         pts = _as_dev_f32(xyz, self.device)
         tgt = torch.clamp(_as_dev_f32(sdf_target, self.device), -clamp, clamp)
@@ -197,16 +207,16 @@ class Decoder:
         loss = float("nan")
         for it in range(1, steps + 1):
             if it == 1:
-                y = self(z, pts, precision="fp32")
+                y = self(z, pts, precision=precision)
             inside = (y > -clamp) & (y < clamp)
             dLdy = torch.sign(torch.clamp(y, -clamp, clamp) - tgt) * inside / M
-            g, y_chk = self.latent_vjp(z, pts, dLdy)
+            g, y_chk = self.latent_vjp(z, pts, dLdy, precision=precision)
             loss = float((torch.clamp(y_chk, -clamp, clamp) - tgt).abs().mean() + reg * (z * z).sum())
             g = g + 2 * reg * z
             m = 0.9 * m + 0.1 * g
             v = 0.999 * v + 0.001 * g * g
             z = z - lr * (m / (1 - 0.9 ** it)) / ((v / (1 - 0.999 ** it)).sqrt() + 1e-8)
-            y = self(z, pts, precision="fp32")
+            y = self(z, pts, precision=precision)
         del ones
         return z, loss
 

@@ -82,9 +82,10 @@ void decoder_offsets(LayerOff off[9]) {
   }
 }
 
-// The 96-block weight stream of kernels.h, as 128B-swizzled shared-memory images.
+// The weight stream of kernels.h (96 forward blocks, then the 96 transposed blocks of the backward
+// passes), as 128B-swizzled shared-memory images.
 void pack_wstream(const float* P, const LayerOff off[9], bool fp16, std::vector<uint16_t>& out) {
-  out.assign(static_cast<size_t>(kBlocksPerTile) * kBlockBytes / 2, 0);
+  out.assign(static_cast<size_t>(kBlocksPerTileBwd) * kBlockBytes / 2, 0);
   static const int pass_layer[kPasses] = {1, 1, 2, 2, 3, 4, 4, 5, 5, 6, 6, 7, 7};
   static const int pass_half[kPasses] = {0, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 0, 1};
   size_t blk = 0;
@@ -104,6 +105,30 @@ void pack_wstream(const float* P, const LayerOff off[9], bool fp16, std::vector<
             const int kk = k * 64 + u * 8 + e;
             const int src = (L == 4 && kk >= kSkipOut) ? kk + kLatent : kk;
             const float v = (n < fout) ? W[static_cast<long long>(n) * fin + src] : 0.f;
+            d[e] = to_lowp(v, fp16);
+          }
+        }
+      }
+    }
+  }
+  // backward: block rows = INPUT features n of layer L, k = its OUTPUT features: W_L[k][n]
+  static const int bpass_layer[kPassesBwd - kPasses] = {7, 7, 6, 6, 5, 5, 4, 3, 3, 2, 2, 1, 1};
+  static const int bpass_half[kPassesBwd - kPasses] = {0, 1, 0, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1};
+  for (int p = 0; p < kPassesBwd - kPasses; ++p) {
+    const int L = bpass_layer[p], h = bpass_half[p];
+    const int nk = (L == 3) ? 4 : 8;                       // layer 3 has 253 outputs: K = 256
+    const float* W = P + off[L].w;
+    const int fin = off[L].fin, fout = off[L].fout;
+    const int n_valid = (L == 4) ? kSkipOut : fin;         // the skip layer hands back its 253 hidden columns only
+    for (int k = 0; k < nk; ++k, ++blk) {
+      uint16_t* dst = out.data() + blk * (kBlockBytes / 2);
+      for (int r = 0; r < kBlockRows; ++r) {
+        const int n = h * 256 + r;
+        for (int u = 0; u < 8; ++u) {
+          uint16_t* d = dst + r * 64 + ((u ^ (r & 7)) * 8);
+          for (int e = 0; e < 8; ++e) {
+            const int kk = k * 64 + u * 8 + e;
+            const float v = (n < n_valid && kk < fout) ? W[static_cast<long long>(kk) * fin + n] : 0.f;
             d[e] = to_lowp(v, fp16);
           }
         }
@@ -149,6 +174,9 @@ struct sdfb_decoder {
   // backward workspace (lazy): stored activations of one chunk, two delta buffers, column-sum partials
   float* bw_act[8] = {}; float *bw_d0 = nullptr, *bw_d1 = nullptr, *bw_y = nullptr, *bw_partial = nullptr;
   long long bw_rows = 0, bw_blocks = 0;
+  uint32_t* bw_masks = nullptr;   // tensor-core backward: ReLU-mask scratch [num_sms][6][16][128]
+  float* bw_colsum = nullptr;     //                       column sums [num_sms * 4][1024]
+  unsigned int* bw_amax = nullptr;   //                    bits of max |dLdy|
   // fp32 workspace (lazy)
   long long ws_rows = 0;
   float *h0 = nullptr, *h1 = nullptr, *s = nullptr, *x = nullptr;
@@ -428,6 +456,7 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
   cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x); cudaFree(d->prof); cudaFree(d->signs); cudaFree(d->rowmask);
   for (float* a : d->bw_act) cudaFree(a);
   cudaFree(d->bw_d0); cudaFree(d->bw_d1); cudaFree(d->bw_y); cudaFree(d->bw_partial);
+  cudaFree(d->bw_masks); cudaFree(d->bw_colsum); cudaFree(d->bw_amax);
   if (d->pin) cudaFreeHost(d->pin);
   cudaFree(d->dstage);
   if (d->ev0) cudaEventDestroy(d->ev0);
@@ -573,6 +602,53 @@ int sdfb_decoder_vjp_latent(sdfb_decoder* d, const float* latent_dev, const floa
     blk += (m + 255) / 256;
   }
   CU_TRY(launch_vjp_finish(d->bw_partial, static_cast<int>(blk), P + o[0].w, P + o[4].w, grad_latent_dev, st));
+  return SDFB_OK;
+}
+
+// The same gradient on the tensor pipe: ONE launch of the forward + backward instance of the fused kernel (every
+// tile is decoded, then run backwards through the transposed weight blocks while it is still in shared memory),
+// then the small contraction of the two column sums with the fp32 latent columns of W0 and W4.
+int sdfb_decoder_vjp_latent_tc(sdfb_decoder* d, const float* latent_dev, const float* xyz_dev, int64_t M, const float* dLdy_dev,
+                               float* grad_latent_dev, float* sdf_dev, int precision, void* stream) {
+  if (!d || !latent_dev || !grad_latent_dev || (M > 0 && (!xyz_dev || !dLdy_dev))) return fail(SDFB_E_INVALID, "null argument");
+  if (M < 0) return fail(SDFB_E_INVALID, "negative point count");
+  if (precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16)
+    return fail(SDFB_E_INVALID, "the tensor-core gradient runs in bf16 or fp16 (precision %d); fp32: sdfb_decoder_vjp_latent", precision);
+  DeviceGuard g(d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M == 0) { CU_TRY(cudaMemsetAsync(grad_latent_dev, 0, kLatent * sizeof(float), st)); return SDFB_OK; }
+  if (d->bw_masks == nullptr) {
+    CU_TRY(cudaMalloc(&d->bw_masks, static_cast<size_t>(d->num_sms) * 6 * 16 * kTileM * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&d->bw_colsum, static_cast<size_t>(d->num_sms) * 4 * 1024 * sizeof(float)));
+    CU_TRY(cudaMalloc(&d->bw_amax, sizeof(unsigned int)));
+  }
+  CU_TRY(launch_abs_max(dLdy_dev, M, d->bw_amax, st));
+  const bool fp16 = precision == SDFB_PREC_FP16;
+  const float* P = d->params;
+  const LayerOff* o = d->off;
+  CU_TRY(launch_fold_latent(P + o[0].w, P + o[0].b, P + o[4].w, P + o[4].b, latent_dev, d->consts, st));
+  DecodeParams p{};
+  p.wstream = d->wstream[fp16 ? 1 : 0];
+  p.consts = d->consts;
+  p.xyz = xyz_dev;
+  p.out = sdf_dev;
+  p.M = M;
+  p.status = d->status;
+  p.dump_pass = -1;
+  p.timeout_ns = d->timeout_ns;
+  p.debug_flags = d->debug_flags;
+  p.dLdy = dLdy_dev;
+  p.dLdy_amax = d->bw_amax;
+  p.mask_scratch = d->bw_masks;
+  p.colsum = d->bw_colsum;
+  CU_TRY(cudaEventRecord(d->ev0, st));
+  CU_TRY(launch_fused_decoder(p, d->tmap[fp16 ? 1 : 0], fp16, d->num_sms, st));
+  CU_TRY(cudaEventRecord(d->ev1, st));
+  d->timed = true;
+  const long long tiles = (M + 2 * kTileM - 1) / (2 * kTileM);
+  const long long pairs = tiles < d->num_sms / 2 ? tiles : d->num_sms / 2;
+  CU_TRY(launch_vjp_finish(d->bw_colsum, static_cast<int>(2 * pairs * 4), P + o[0].w, P + o[4].w, grad_latent_dev, st,
+                           d->bw_amax));
   return SDFB_OK;
 }
 

@@ -149,8 +149,22 @@ __global__ void colsum_f32_kernel(const float* __restrict__ D, long long M, floa
 }
 
 // grad[k] = sum_n s0[n] W0[n][k] + sum_n s4[n] W4[n][253 + k], s0 / s4 = column sums over all partial blocks
+// max |v| as float bits (non-negative floats order like unsigned integers); `out` starts at zero
+__global__ void abs_max_kernel(const float* __restrict__ v, long long M, unsigned int* __restrict__ out) {
+  float a = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < M;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    a = fmaxf(a, fabsf(v[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+  if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(out, __float_as_uint(a));
+}
+
+// `amax_bits` (tensor-core path): the kernel ran on dLdy * 2^-e with 2^e the power of two just above
+// max |dLdy| (vjp_scale_exponent): undo it here, exactly.
 __global__ void vjp_finish_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ W0,
-                                  const float* __restrict__ W4, float* __restrict__ grad) {
+                                  const float* __restrict__ W4, float* __restrict__ grad,
+                                  const unsigned int* __restrict__ amax_bits) {
   __shared__ float s[1024];
   for (int c = threadIdx.x; c < 1024; c += blockDim.x) {
     float a = 0.f;
@@ -163,6 +177,7 @@ __global__ void vjp_finish_kernel(const float* __restrict__ partial, int nblk, c
     float g = 0.f;
     for (int n = 0; n < 512; ++n) g = fmaf(s[n], W0[n * 259 + k], g);
     for (int n = 0; n < 512; ++n) g = fmaf(s[512 + n], W4[n * 512 + 253 + k], g);
+    if (amax_bits != nullptr) g = ldexpf(g, vjp_scale_exponent(__uint_as_float(*amax_bits)));
     grad[k] = g;
   }
 }
@@ -364,8 +379,17 @@ cudaError_t launch_colsum_f32(const float* D, long long M, float* partial, int h
 }
 
 cudaError_t launch_vjp_finish(const float* partial, int nblk, const float* W0, const float* W4, float* grad,
-                              cudaStream_t stream) {
-  vjp_finish_kernel<<<1, 256, 0, stream>>>(partial, nblk, W0, W4, grad);
+                              cudaStream_t stream, const unsigned int* amax_bits) {
+  vjp_finish_kernel<<<1, 256, 0, stream>>>(partial, nblk, W0, W4, grad, amax_bits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_abs_max(const float* v, long long M, unsigned int* out, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess || M <= 0) return e;
+  long long blocks = (M + 1023) / 1024;
+  if (blocks > 592) blocks = 592;
+  abs_max_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(v, M, out);
   return cudaGetLastError();
 }
 

@@ -30,6 +30,19 @@
 // (tools/umma_rate.py: 189 cycles/MMA instead of 128), after every 8 MMAs nothing.  So the
 // issuer commits once per PAIR of weight blocks and releases both ring slots, both activation
 // chunks and (at the end of a pass) the accumulator at that one point.
+//
+// BWD = true (oracle: oracle/decoder.py decoder_vjp_latent_lowp): the same
+// tile then runs BACKWARDS through the same machinery - 13 more passes against the transposed weight
+// blocks (kernels.h) - to produce what the latent's gradient needs:
+//   g = dLdy (1 - sdf^2);  delta7 = g w8 where h7 > 0 (epilogue, like the first layer);
+//   delta_{l-1} = mask_{l-1} * (delta_l W_l): the accumulator is masked instead of biased + rectified and
+//   written back in place as the next A operand.  The ReLU masks of layers 1-6 are one 32-bit word per
+//   (thread, 32 columns) parked in an L2-resident scratch (48 KiB per CTA, written and read by the same
+//   thread); layer 7's stay in registers, layer 0's are recomputed from the coordinates.
+//   The latent enters through the bias of layers 0 and 4 only, so all it needs are the COLUMN SUMS of
+//   delta0 and delta4 over the queries: a 31-shuffle transpose-reduce per 32 x 32 block leaves lane l
+//   with column l's sum, accumulated in registers over all tiles and written once per warp at the end
+//   (vjp_finish_kernel contracts them with the fp32 latent columns of W0 and W4).
 #include <cuda.h>
 
 #include "kernels.h"
@@ -70,9 +83,19 @@ enum : uint32_t {
   kErrAReady = 0x50, kErrAFree = 0x60,
 };
 
-__device__ __forceinline__ int pass_chunks(int p) { return (p == 5 || p == 6) ? 4 : 8; }
-__device__ __forceinline__ bool pass_first(int p) { return (0x0AB5u >> p) & 1u; }  // {0,2,4,5,7,9,11}
-__device__ __forceinline__ bool pass_last(int p) { return (0x155Au >> p) & 1u; }   // {1,3,4,6,8,10,12}
+// Pass tables (kernels.h).  `first`: the pass is the first reader of a freshly written A operand (waits
+// for its chunks); `last`: the last reader (releases them).  Backward passes 13-25: delta6, delta5, delta4
+// in halves, 19 = delta3 (N = 256), 20/21 = delta2 (K = 256), delta1 and delta0 in halves.
+constexpr uint32_t kFirstFwd = 0x0AB5u;                                           // {0,2,4,5,7,9,11}
+constexpr uint32_t kLastFwd = 0x155Au;                                            // {1,3,4,6,8,10,12}
+constexpr uint32_t kFirstBwd = kFirstFwd | (1u << 13) | (1u << 15) | (1u << 17) | (1u << 19) | (1u << 20) | (1u << 22) | (1u << 24);
+constexpr uint32_t kLastBwd = kLastFwd | (1u << 14) | (1u << 16) | (1u << 18) | (1u << 19) | (1u << 21) | (1u << 23) | (1u << 25);
+template <bool BWD>
+__device__ __forceinline__ int pass_chunks(int p) { return (p == 5 || p == 6 || (BWD && (p == 20 || p == 21))) ? 4 : 8; }
+template <bool BWD>
+__device__ __forceinline__ bool pass_first(int p) { return ((BWD ? kFirstBwd : kFirstFwd) >> p) & 1u; }
+template <bool BWD>
+__device__ __forceinline__ bool pass_last(int p) { return ((BWD ? kLastBwd : kLastFwd) >> p) & 1u; }
 
 struct Query { float x, y, z; };
 
@@ -111,9 +134,11 @@ struct Epi {
 // next layer's MMAs consume them.  The TMEM load of the next chunk is in flight while the
 // current one is converted.  `L3`: this is layer 3, whose last three (padding) columns carry
 // the query coordinates into layer 4.
-template <bool FP16, bool L3, bool WAIT_FREE>
+// `mrow` (BWD kernels only): where this thread parks the ReLU mask of its 32 columns of chunk cc: word
+// (2 cc + set) * 128 of the (layer, half) block, already offset by the row.
+template <bool FP16, bool L3, bool WAIT_FREE, bool MASK = false>
 __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict__ sbias, Query q, int c0, int b,
-                                                const Watchdog& wd, float* dump_row) {
+                                                const Watchdog& wd, float* dump_row, uint32_t* mrow = nullptr) {
   if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
   e.acc_phase ^= 1u << b;
   __syncwarp();
@@ -134,6 +159,7 @@ __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict_
     const uint32_t(&vc)[32] = v[cc & 1];
     const int col = cc * 64 + e.set * 32;
     uint32_t packed[16];
+    uint32_t bits = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 t = *reinterpret_cast<const float4*>(sbias + col + 4 * j);
@@ -145,13 +171,18 @@ __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict_
       }
       packed[2 * j] = pack_relu<FP16>(f0, f1);
       packed[2 * j + 1] = pack_relu<FP16>(f2, f3);
+      if constexpr (MASK)
+        bits |= (f0 > 0.f ? 1u : 0u) << (4 * j) | (f1 > 0.f ? 1u : 0u) << (4 * j + 1) |
+                (f2 > 0.f ? 1u : 0u) << (4 * j + 2) | (f3 > 0.f ? 1u : 0u) << (4 * j + 3);
       if constexpr (L3) {
         if (j == 7 && cc == 3 && e.set == 1) {   // features 252 | x, y | z  (x, y, z unrectified)
           packed[14] = pack_plain<FP16>(fmaxf(f0, 0.f), q.x);
           packed[15] = pack_plain<FP16>(q.y, q.z);
+          if constexpr (MASK) bits &= 0x1FFFFFFFu;   // columns 253-255 are not features: nothing flows back
         }
       }
     }
+    if constexpr (MASK) mrow[(2 * cc + e.set) * kTileM] = bits;
     const int c = c0 + cc;
     // Chunks written by a layer's LAST pass were read for the last time by that very pass, whose
     // completion acc_full already reported: only a first-half pass must wait for the other half's
@@ -173,8 +204,11 @@ __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict_
 }
 
 // Head pass: this warp reduces columns [128*set, 128*set+128) of half `b` of h7 against w8.
+// `hm` (BWD kernels): receives the ReLU mask of the four 32-column groups this thread reduces.
+template <bool MASK = false>
 __device__ __forceinline__ bool epi_head_pass(Epi& e, const float* __restrict__ sbias, const float* __restrict__ shead,
-                                              int b, const Watchdog& wd, float& dot, float* dump_row) {
+                                              int b, const Watchdog& wd, float& dot, float* dump_row,
+                                              uint32_t* hm = nullptr) {
   if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
   e.acc_phase ^= 1u << b;
   __syncwarp();
@@ -194,6 +228,7 @@ __device__ __forceinline__ bool epi_head_pass(Epi& e, const float* __restrict__ 
     }
     const uint32_t(&vc)[32] = v[g & 1];
     const int col = e.set * 128 + g * 32;
+    uint32_t bits = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 t = *reinterpret_cast<const float4*>(sbias + col + 4 * j);
@@ -208,7 +243,154 @@ __device__ __forceinline__ bool epi_head_pass(Epi& e, const float* __restrict__ 
       dot = fmaf(fmaxf(f1, 0.f), h.y, dot);
       dot = fmaf(fmaxf(f2, 0.f), h.z, dot);
       dot = fmaf(fmaxf(f3, 0.f), h.w, dot);
+      if constexpr (MASK)
+        bits |= (f0 > 0.f ? 1u : 0u) << (4 * j) | (f1 > 0.f ? 1u : 0u) << (4 * j + 1) |
+                (f2 > 0.f ? 1u : 0u) << (4 * j + 2) | (f3 > 0.f ? 1u : 0u) << (4 * j + 3);
     }
+    if constexpr (MASK) hm[g] = bits;
+  }
+  return true;
+}
+
+// ---- backward epilogues (BWD kernels) ------------------------------------------------------------
+// Transpose-reduce of a 32 (rows = lanes) x 32 (columns = v[]) block in 31 shuffles: on return lane l
+// holds the sum over the warp's 32 rows of column l.  v is destroyed.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      v[i] = (up ? v[i + off] : v[i]) + recv;
+    }
+  }
+  return v[0];
+}
+
+// delta7 = g * w8 where h7's pre-activation was positive: built by the thread that holds the masks (head
+// passes), i.e. set s writes chunks 4b + 2s, 4b + 2s + 1 of its row.  Like the first layer, every chunk
+// must have been released by the last forward pass first.
+template <bool FP16>
+__device__ __forceinline__ bool epi_delta7(Epi& e, const float* __restrict__ shead, float gs, const uint32_t (&hm)[2][4],
+                                           const Watchdog& wd) {
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c = 4 * b + 2 * e.set + (g >> 1);
+      if ((g & 1) == 0) {
+        if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
+      }
+      const int col = 256 * b + 128 * e.set + 32 * g;
+      const uint32_t m = hm[b][g];
+      uint32_t packed[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 h = *reinterpret_cast<const float4*>(shead + col + 4 * j);
+        const float v0 = (m >> (4 * j)) & 1u ? gs * h.x : 0.f, v1 = (m >> (4 * j + 1)) & 1u ? gs * h.y : 0.f;
+        const float v2 = (m >> (4 * j + 2)) & 1u ? gs * h.z : 0.f, v3 = (m >> (4 * j + 3)) & 1u ? gs * h.w : 0.f;
+        packed[2 * j] = pack_plain<FP16>(v0, v1);
+        packed[2 * j + 1] = pack_plain<FP16>(v2, v3);
+      }
+      const uint32_t base = e.a_row_addr + c * kAChunkBytes;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        st_shared_v4(base + (((4 * (g & 1) + u) ^ e.row7) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
+                     packed[4 * u + 3]);
+      if (g & 1) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c), 2);   // 4 warps x 2 = the 8 expected per CTA
+      }
+    }
+  }
+  e.wphase ^= 0xFFu;
+  return true;
+}
+
+// Backward hidden pass: delta = mask * accumulator, rounded and written in place as the next A operand
+// (same thread <-> column mapping as the forward pass that stored the mask words at `mrow`).
+// `cs` != nullptr: also the column sums of the unrounded values (delta4), one column per lane and chunk.
+template <bool FP16, bool WAIT_FREE>
+__device__ __forceinline__ bool epi_bwd_pass(Epi& e, const uint32_t* mrow, int c0, int b, const Watchdog& wd, float* cs) {
+  uint32_t mw[4];
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) mw[cc] = mrow[(2 * cc + e.set) * kTileM];
+  if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
+  e.acc_phase ^= 1u << b;
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t tbase = e.tmem_row + b * 256 + e.set * 32;
+  uint32_t v[2][32];
+  tmem_ld32(tbase, v[0]);
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    tmem_ld_wait();
+    if (cc < 3) {
+      tmem_ld32(tbase + (cc + 1) * 64, v[(cc + 1) & 1]);
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAccEmpty + b), 1);
+    }
+    const uint32_t(&vc)[32] = v[cc & 1];
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = (mw[cc] >> i) & 1u ? __uint_as_float(vc[i]) : 0.f;
+    uint32_t packed[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) packed[k] = pack_plain<FP16>(f[2 * k], f[2 * k + 1]);
+    const int c = c0 + cc;
+    if (WAIT_FREE) {
+      if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
+    }
+    const uint32_t base = e.a_row_addr + c * kAChunkBytes;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      st_shared_v4(base + (((4 * e.set + u) ^ e.row7) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
+                   packed[4 * u + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c), 1);
+    if (cs != nullptr) cs[cc] += warp_colsum32(f, e.lane);
+  }
+  e.wphase ^= 0xFu << c0;
+  return true;
+}
+
+// delta0 is only ever summed over the queries: mask (recomputed from the coordinates with the first
+// layer's own expression) and column sums, nothing written back.  `l0`: consts->l0 + 256 * half.
+__device__ __forceinline__ bool epi_bwd_l0_pass(Epi& e, const float4* __restrict__ l0, Query q, int b, const Watchdog& wd,
+                                                float* cs) {
+  if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
+  e.acc_phase ^= 1u << b;
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t tbase = e.tmem_row + b * 256 + e.set * 32;
+  uint32_t v[2][32];
+  tmem_ld32(tbase, v[0]);
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    tmem_ld_wait();
+    if (cc < 3) {
+      tmem_ld32(tbase + (cc + 1) * 64, v[(cc + 1) & 1]);
+    } else {
+      tc_fence_before();
+      __syncwarp();
+      if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAccEmpty + b), 1);
+    }
+    const uint32_t(&vc)[32] = v[cc & 1];
+    const float4* w = l0 + cc * 64 + e.set * 32;
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float4 wi = __ldg(w + i);
+      const float pre = fmaf(q.z, wi.z, fmaf(q.y, wi.y, fmaf(q.x, wi.x, wi.w)));
+      f[i] = pre > 0.f ? __uint_as_float(vc[i]) : 0.f;
+    }
+    cs[cc] += warp_colsum32(f, e.lane);
   }
   return true;
 }
@@ -247,9 +429,11 @@ __device__ __forceinline__ bool epi_layer0(Epi& e, int warp, const L0Weights (&w
   return true;
 }
 
-template <bool FP16>
+template <bool FP16, bool BWD>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int kNumPasses = BWD ? kPassesBwd : kPasses;
+  constexpr int kNumBlocks = BWD ? kBlocksPerTileBwd : kBlocksPerTile;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem0 = smem_u32(smem_raw);
   uint8_t* gen = smem_raw;
@@ -314,7 +498,7 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
       uint32_t stage = 0, phase = 0;
       for (long long it = 0; it < my_tiles; ++it) {
 #pragma unroll 1
-        for (int blk = 0; blk < kBlocksPerTile; ++blk) {
+        for (int blk = 0; blk < kNumBlocks; ++blk) {
           if (!mbar_wait(bars + 8 * (kBarWEmpty + stage), phase ^ 1u, wd, kErrWEmpty, stage)) goto done;
           const uint32_t full = bars + 8 * (kBarWFull + stage);
           if (leader) mbar_arrive_expect_tx(full, kBlockBytes);          // both halves land on this barrier
@@ -341,9 +525,9 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
       uint32_t stage = 0, phase = 0, rphase = 0, ephase = 0, gpass = 0, prev_stage = 0;
       for (long long it = 0; it < my_tiles; ++it) {
 #pragma unroll 1
-        for (int ps = 0; ps < kPasses; ++ps, ++gpass) {
-          const int nk = pass_chunks(ps);
-          const bool first = pass_first(ps), last = pass_last(ps);
+        for (int ps = 0; ps < kNumPasses; ++ps, ++gpass) {
+          const int nk = pass_chunks<BWD>(ps);
+          const bool first = pass_first<BWD>(ps), last = pass_last<BWD>(ps);
           const uint32_t b = gpass & 1u;
           const uint32_t d_tmem = tmem_base + b * 256;
           if (!mbar_wait(bars + 8 * (kBarAccEmpty + b), ((ephase >> b) & 1u) ^ 1u, wd, kErrAccEmpty, b)) goto done;
@@ -402,6 +586,8 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
     const long long tile_stride = npairs * 2 * kTileM;
     long long row_base = pidx * 2 * kTileM + rank * kTileM;   // first query of this CTA's half tile
     uint32_t gpass = 0;
+    float cs0[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // BWD: column sums of delta0 / delta4 (lane = column)
+    float cs4[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     if (my_tiles > 0) {
       if (e.set == 0) {
         const Query q0 = load_query(p, row_base + row);
@@ -411,6 +597,7 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
       if (!epi_layer0<FP16>(e, warp, wl, sxyz, smem0 + oA, wd)) goto done;
       float4 qv = sxyz[row];
       Query q{qv.x, qv.y, qv.z};
+      if constexpr (!BWD) {
       for (long long it = 0; it < my_tiles; ++it, row_base += tile_stride) {
         const bool dump_tile = p.dump != nullptr && row_base == 0;
 #pragma unroll 1
@@ -460,6 +647,102 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
         }
         q = Query{qv.x, qv.y, qv.z};
       }
+      } else {
+        // ============ forward + backward (latent gradient) ============
+        uint32_t* mbase = p.mask_scratch + static_cast<size_t>(blockIdx.x) * (6 * 16 * kTileM) + row;
+        const float up_scale = ldexpf(1.f, -vjp_scale_exponent(__uint_as_float(__ldg(p.dLdy_amax))));
+        const float4* l0 = cs->l0;
+        for (long long it = 0; it < my_tiles; ++it, row_base += tile_stride) {
+#pragma unroll 1
+          for (int ps = 0; ps < 11; ++ps, ++gpass) {
+            int layer, half;
+            if (ps < 4) { layer = 1 + (ps >> 1); half = ps & 1; }
+            else if (ps == 4) { layer = 3; half = 0; }
+            else { layer = 4 + ((ps - 5) >> 1); half = (ps - 5) & 1; }
+            const float* bias = sbias + (layer - 1) * kHid + half * 256;
+            uint32_t* mrow = mbase + ((layer - 1) * 16 + half * 8) * kTileM;
+            bool ok;
+            if (layer == 3)
+              ok = epi_hidden_pass<FP16, true, false, true>(e, bias, q, 0, gpass & 1u, wd, nullptr, mrow);
+            else if (half == 0)
+              ok = epi_hidden_pass<FP16, false, true, true>(e, bias, q, 0, gpass & 1u, wd, nullptr, mrow);
+            else
+              ok = epi_hidden_pass<FP16, false, false, true>(e, bias, q, 4, gpass & 1u, wd, nullptr, mrow);
+            if (!ok) goto done;
+          }
+          float dot = 0.f;
+          uint32_t hm[2][4];
+          if (!epi_head_pass<true>(e, sbias + 6 * kHid, shead, gpass & 1u, wd, dot, nullptr, hm[0])) goto done;
+          ++gpass;
+          if (!epi_head_pass<true>(e, sbias + 6 * kHid + 256, shead + 256, gpass & 1u, wd, dot, nullptr, hm[1])) goto done;
+          ++gpass;
+          if (e.set == 1) sdot[row] = dot;
+          named_bar_sync(2, kEpiThreads);
+          if (e.set == 0) {
+            const long long m = row_base + row;
+            const float v = tanhf((dot + sdot[row]) + head_b);
+            float gsv = 0.f;
+            if (m < p.M) {
+              if (p.out != nullptr) p.out[m] = v;
+              gsv = (__ldg(p.dLdy + m) * up_scale) * (1.f - v * v);
+            }
+            sdot[row] = gsv;                                     // rows past M carry no gradient
+          }
+          named_bar_sync(2, kEpiThreads);
+          const float gs = sdot[row];
+          if (!epi_delta7<FP16>(e, shead, gs, hm, wd)) goto done;
+#pragma unroll 1
+          for (int ps = 13; ps < kPassesBwd; ++ps, ++gpass) {
+            const uint32_t b = gpass & 1u;
+            bool ok;
+            if (ps >= 24) {
+              if (ps == 25 && it + 1 < my_tiles) {   // first layer of the next tile, behind the last readers of delta1
+                if (e.set == 0) {
+                  const Query qn = load_query(p, row_base + tile_stride + row);
+                  sxyz[row] = make_float4(qn.x, qn.y, qn.z, 0.f);
+                }
+                named_bar_sync(1, kEpiThreads);
+                if (!epi_layer0<FP16>(e, warp, wl, sxyz, smem0 + oA, wd)) goto done;
+                qv = sxyz[row];
+              }
+              float t[4] = {0.f, 0.f, 0.f, 0.f};
+              ok = epi_bwd_l0_pass(e, l0 + (ps - 24) * 256, q, b, wd, t);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (ps == 24) cs0[0][i] += t[i]; else cs0[1][i] += t[i];
+              }
+            } else {
+              int layer, half;
+              if (ps < 19) { layer = 6 - ((ps - 13) >> 1); half = (ps - 13) & 1; }
+              else if (ps == 19) { layer = 3; half = 0; }
+              else { layer = 2 - ((ps - 20) >> 1); half = (ps - 20) & 1; }
+              const uint32_t* mrow = mbase + ((layer - 1) * 16 + half * 8) * kTileM;
+              float t[4] = {0.f, 0.f, 0.f, 0.f};
+              float* tp = layer == 4 ? t : nullptr;
+              if (half == 0 && layer != 3)
+                ok = epi_bwd_pass<FP16, true>(e, mrow, 0, b, wd, tp);
+              else
+                ok = epi_bwd_pass<FP16, false>(e, mrow, half * 4, b, wd, tp);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (half == 0) cs4[0][i] += t[i]; else cs4[1][i] += t[i];
+              }
+            }
+            if (!ok) goto done;
+          }
+          q = Query{qv.x, qv.y, qv.z};
+        }
+      }
+    }
+    if constexpr (BWD) {   // this warp's share of the column sums: [CTA][quadrant][delta0 512 | delta4 512]
+      float* dst = p.colsum + (static_cast<size_t>(blockIdx.x) * 4 + (warp & 3)) * 1024 + e.set * 32 + lane;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          dst[256 * h + 64 * cc] = cs0[h][cc];
+          dst[512 + 256 * h + 64 * cc] = cs4[h][cc];
+        }
     }
   }
 done:
@@ -488,22 +771,26 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 }  // namespace
 
 cudaError_t fused_decoder_init() {
-  cudaError_t e = cudaFuncSetAttribute(fused_decoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kSmemAlloc));
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(fused_decoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              static_cast<int>(kSmemAlloc));
+  const void* fns[4] = {reinterpret_cast<const void*>(fused_decoder_kernel<false, false>),
+                        reinterpret_cast<const void*>(fused_decoder_kernel<true, false>),
+                        reinterpret_cast<const void*>(fused_decoder_kernel<false, true>),
+                        reinterpret_cast<const void*>(fused_decoder_kernel<true, true>)};
+  for (const void* f : fns) {
+    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemAlloc));
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
-// The weight stream viewed as a [96*256 rows][64] 16-bit matrix; box = 128 rows x 64 = one CTA's
-// half of a block.  The stream already holds swizzled shared-memory images, so no TMA swizzle.
+// The weight stream (forward blocks, then the backward ones) viewed as a [192*256 rows][64] 16-bit matrix;
+// box = 128 rows x 64 = one CTA's half of a block.  The stream already holds swizzled shared-memory images, so no TMA swizzle.
 cudaError_t make_wstream_tensor_map(const void* wstream, void* tmap_out) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess) return e;
   if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kChunkK), static_cast<cuuint64_t>(kBlocksPerTile) * kBlockRows};
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kChunkK), static_cast<cuuint64_t>(kBlocksPerTileBwd) * kBlockRows};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(kChunkK) * 2};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), 128u};
   const cuuint32_t estr[2] = {1u, 1u};
@@ -532,8 +819,13 @@ cudaError_t launch_fused_decoder(const DecodeParams& p, const void* tmap, bool f
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const CUtensorMap* tm = static_cast<const CUtensorMap*>(tmap);
-  if (fp16) return cudaLaunchKernelEx(&cfg, fused_decoder_kernel<true>, p, *tm);
-  return cudaLaunchKernelEx(&cfg, fused_decoder_kernel<false>, p, *tm);
+  if (p.dLdy != nullptr) {   // forward + backward: needs the mask scratch and the column-sum rows of every CTA
+    if (p.mask_scratch == nullptr || p.colsum == nullptr || p.dLdy_amax == nullptr) return cudaErrorInvalidValue;
+    if (fp16) return cudaLaunchKernelEx(&cfg, fused_decoder_kernel<true, true>, p, *tm);
+    return cudaLaunchKernelEx(&cfg, fused_decoder_kernel<false, true>, p, *tm);
+  }
+  if (fp16) return cudaLaunchKernelEx(&cfg, fused_decoder_kernel<true, false>, p, *tm);
+  return cudaLaunchKernelEx(&cfg, fused_decoder_kernel<false, false>, p, *tm);
 }
 
 }  // namespace sdfb

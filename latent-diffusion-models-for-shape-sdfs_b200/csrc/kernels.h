@@ -40,6 +40,13 @@ constexpr int kBlockRows = 256;
 constexpr int kBlockBytes = kBlockRows * kChunkK * 2;   // 32 KiB
 constexpr int kPasses = 13;
 constexpr int kBlocksPerTile = 96;
+// Forward + backward (latent gradient) kernel: 13 more passes against the TRANSPOSED weights (block rows =
+// the layer's INPUT features, k = its OUTPUT features), appended to the same stream:
+//   pass 13, 14 : delta6 = delta7 W7 (halves)   pass 19     : delta3 = delta4 W4[:, :253] (N = 253 -> 256)
+//   pass 15, 16 : delta5 = delta6 W6            pass 20, 21 : delta2 = delta3 W3 (K = 253 -> 256: 4 chunks)
+//   pass 17, 18 : delta4 = delta5 W5            pass 22, 23 : delta1;   pass 24, 25 : delta0 (column sums only)
+constexpr int kPassesBwd = 26;
+constexpr int kBlocksPerTileBwd = 192;
 constexpr int kAChunkBytes = kTileM * kChunkK * 2;      // 16 KiB: one 64-wide slice of activations
 constexpr int kAChunks = 8;
 
@@ -67,6 +74,11 @@ struct DecodeParams {
   unsigned long long timeout_ns;
   long long* prof;             // optional [grid][3 roles][8]: blocked cycles per wait class (diagnostics)
   unsigned int debug_flags;    // bit0: producer skips the weight copies (timing experiment; results are garbage)
+  // forward + backward kernel only (dLdy != nullptr selects it; `out` is then optional, `signs` unused)
+  const float* dLdy;           // [M] upstream gradient d loss / d sdf
+  const unsigned int* dLdy_amax;   // bits of max |dLdy| (launch_abs_max): the kernel works on dLdy * 2^-vjp_scale_exponent
+  uint32_t* mask_scratch;      // [grid][6 layers][16 words][128 rows]: ReLU masks of the tile in flight
+  float* colsum;               // [grid * 4][1024]: per-warp-quadrant column sums of delta0 (512) | delta4 (512)
 };
 
 cudaError_t fused_decoder_init();   // opt in to the large dynamic shared memory carve-out
@@ -167,7 +179,18 @@ cudaError_t launch_head_bwd_f32(const float* dLdy, const float* y, const float* 
                                 cudaStream_t stream);
 cudaError_t launch_colsum_f32(const float* D, long long M, float* partial, int half, cudaStream_t stream);
 cudaError_t launch_vjp_finish(const float* partial, int nblk, const float* W0, const float* W4, float* grad,
-                              cudaStream_t stream);
+                              cudaStream_t stream, const unsigned int* amax_bits = nullptr);
+// out[0] = bits of max |v[i]| (0 for an empty or all-zero v)
+cudaError_t launch_abs_max(const float* v, long long M, unsigned int* out, cudaStream_t stream);
+// Tensor-core backward: the upstream gradient is scaled by 2^-e, e = vjp_scale_exponent(max |dLdy|), so that the
+// deltas sit in the same range whatever the caller's loss scale (fp16 deltas would otherwise underflow), and the
+// result is scaled back by 2^e.  amax = m 2^e with m in [0.5, 1); 0 for amax = 0 or non-finite.
+__host__ __device__ inline int vjp_scale_exponent(float amax) {
+  if (!(amax > 0.f) || amax > 3.0e38f) return 0;
+  int e = 0;
+  frexpf(amax, &e);
+  return e < -100 ? -100 : (e > 100 ? 100 : e);
+}
 // xyz of queries [q0, q0+M) of the res^3 grid -> X[M,3] and (optionally) cols 253..255 of S[M,256]
 cudaError_t launch_grid_xyz(int res, long long q0, long long M, float* X, float* S,
                             cudaStream_t stream);

@@ -147,3 +147,56 @@ def decoder_vjp_latent(latent, xyz, dLdy, params=None, dtype=torch.float64):
     y = torch.tanh(h @ W[8].T + B[8]).squeeze(1)
     (y * up).sum().backward()
     return z.grad.detach().numpy(), y.detach().numpy()
+
+
+def decoder_vjp_latent_lowp(latent, xyz, dLdy, params=None, lowp=torch.bfloat16):
+    """The arithmetic of the tensor-core backward kernel (fused_decoder_kernel<., BWD>), emulated on the CPU:
+    grad[256] = sum_m dLdy[m] d sdf_m / d latent with
+
+    * the forward of ``decoder_forward_lowp`` (ReLU masks = pre-activation > 0);
+    * g_m = (dLdy[m] 2^-e)(1 - y_m^2) in fp32, 2^e the power of two just above max |dLdy| (undone at the end:
+      the deltas then sit in the same range whatever the caller's loss scale); delta7 = lowp(g_m w8[n]) where
+      h7's pre-activation is positive;
+    * delta_{l-1} = lowp(mask_{l-1} * (delta_l @ lowp(W_l))) with fp32 accumulation (the skip layer hands only
+      its 253 hidden columns down);
+    * the two column sums the latent sees, sum_m delta4 and sum_m delta0, are taken over the UNROUNDED fp32
+      values, and contracted with the fp32 latent columns of W4 and W0.
+    Returns (grad, sdf) as numpy arrays."""
+    params = decoder_weights() if params is None else params
+    f32 = torch.float32
+    W = [_as_t(w, f32) for w, _ in params]
+    B = [_as_t(b, f32) for _, b in params]
+    z = _as_t(latent, f32).reshape(DEC_LATENT)
+    x = _as_t(xyz, f32).reshape(-1, 3)
+    up = _as_t(dLdy, f32).reshape(-1)
+    L, S = DEC_LATENT, DEC_SKIP_OUT
+    rnd = lambda t: _round_to(t, lowp)
+    Wq = {i: rnd(W[i]) for i in (1, 2, 3, 5, 6, 7)}
+    W4h, W4x = rnd(W[4][:, :S]), rnd(W[4][:, S + L:S + L + 3])
+    with torch.no_grad():
+        pre = [x @ W[0][:, L:L + 3].T + (B[0] + W[0][:, :L] @ z)]
+        h = rnd(torch.relu(pre[0]))
+        for li in (1, 2, 3):
+            pre.append(h @ Wq[li].T + B[li])
+            h = rnd(torch.relu(pre[-1]))
+        pre.append(h @ W4h.T + rnd(x) @ W4x.T + (B[4] + W[4][:, S:S + L] @ z))
+        h = rnd(torch.relu(pre[-1]))
+        for li in (5, 6):
+            pre.append(h @ Wq[li].T + B[li])
+            h = rnd(torch.relu(pre[-1]))
+        pre.append(h @ Wq[7].T + B[7])
+        y = torch.tanh(torch.relu(pre[7]) @ W[8].T + B[8]).squeeze(1)
+        mask = [(p > 0).to(f32) for p in pre]
+        amax = float(up.abs().max()) if up.numel() else 0.0     # the kernel's power-of-two scaling of the upstream gradient
+        ex = int(np.clip(np.frexp(np.float32(amax))[1], -100, 100)) if 0.0 < amax <= 3.0e38 else 0
+        g = (up * float(2.0 ** -ex)) * (1.0 - y * y)
+        d = rnd(g[:, None] * W[8][0][None, :]) * mask[7]
+        d = rnd((d @ Wq[7]) * mask[6])
+        d = rnd((d @ Wq[6]) * mask[5])
+        d4 = (d @ Wq[5]) * mask[4]
+        d = rnd((rnd(d4) @ W4h) * mask[3])
+        d = rnd((d @ Wq[3]) * mask[2])
+        d = rnd((d @ Wq[2]) * mask[1])
+        d0 = (d @ Wq[1]) * mask[0]
+        grad = (d0.sum(0) @ W[0][:, :L] + d4.sum(0) @ W[4][:, S:S + L]) * float(2.0 ** ex)
+    return grad.numpy(), y.numpy()

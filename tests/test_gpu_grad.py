@@ -63,3 +63,80 @@ def test_fit_latent_recovers_a_shape(cuda_decoder):
           f"target shape has {frac_in:.2f} of the samples inside")
     assert 0.05 < frac_in < 0.6              # a real surface, not a saturated field
     assert err < 0.25 * base
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_tensor_core_vjp_matches_the_lowp_oracle(cuda_decoder, precision):
+    """The forward + backward instance of the fused kernel against oracle.decoder_vjp_latent_lowp (same operand
+    roundings, fp32 accumulation in another order).
+
+    Tolerances.  Row by row (one-hot upstream gradients, rows in both CTAs of a pair, in a ragged second tile) the bf16
+    results agree to fp32 rounding - median relative error < 1e-5 (measured 1e-6) - unless one of the row's ~4000
+    activations happens to round the other way (then that row is off by a fraction of a percent; every row must keep
+    cosine > 0.999).  In fp16 such one-ulp differences are ~8x more frequent and ~8x smaller (test_gpu_decoder.py:
+    the forward values themselves differ by up to 5e-4 in bulk), and the factor 1 - sdf^2 carries them into every
+    row's gradient: median < 2e-3 (measured 4-5e-4).  Over a
+    batch those rare one-ulp differences and the ReLU-mask flips they cause downstream add up chaotically, the same
+    way in bf16 (fewer, larger) and fp16 (more, smaller): measured 1-2 % of |grad|_max with random-sign upstream
+    gradients, 10x closer than the distance to the fp64 autograd gradient; gated at 3 % with cosine > 0.9995.  With a
+    coherent upstream gradient (M = 5000, all 1/M) it is 3e-4 and the cosine to the fp64 autograd gradient is
+    > 0.9995.  The forward values are exactly Decoder(latent, xyz)'s at that precision."""
+    lowp = torch.bfloat16 if precision == "bf16" else torch.float16
+    rs = np.random.RandomState(21)
+    z = oracle.default_latent(2)
+    xyz = (rs.rand(300, 3) * 2 - 1).astype(np.float32)
+    rel = []
+    for r in (0, 31, 37, 127, 128, 200, 255, 261, 299):
+        up = np.zeros(300, np.float32)
+        up[r] = 0.37
+        g, _ = cuda_decoder.latent_vjp(z, xyz, up, precision=precision)
+        g = g.cpu().numpy().astype(np.float64)
+        g_ref, _ = oracle.decoder_vjp_latent_lowp(z, xyz, up, lowp=lowp)
+        rel.append(np.abs(g - g_ref).max() / np.abs(g_ref).max())
+        assert float(g @ g_ref / (np.linalg.norm(g) * np.linalg.norm(g_ref))) > 0.999
+    print(f"{precision} one-hot rows: relative errors {' '.join(f'{v:.1e}' for v in rel)}")
+    assert np.median(rel) < (1e-5 if precision == "bf16" else 2e-3)
+    for M in (1, 255, 256, 257, 5000, 40000):       # ragged tiles, one tile, more tiles than CTA pairs
+        xyz = (rs.rand(M, 3) * 2 - 1).astype(np.float32)
+        up = (rs.standard_normal(M) if M != 5000 else np.full(M, 1.0 / M)).astype(np.float32)
+        g, y = cuda_decoder.latent_vjp(z, xyz, up, precision=precision)
+        y_fwd = cuda_decoder(z, xyz, precision=precision)
+        assert torch.equal(y, y_fwd)                # the same tile arithmetic, bit for bit
+        g = g.cpu().numpy().astype(np.float64)
+        g_ref, _ = oracle.decoder_vjp_latent_lowp(z, xyz, up, lowp=lowp)
+        scale = np.abs(g_ref).max()
+        err = np.abs(g - g_ref).max()
+        cos = float(g @ g_ref / (np.linalg.norm(g) * np.linalg.norm(g_ref)))
+        g64, _ = oracle.decoder_vjp_latent(z, xyz, up)
+        cos64 = float(g @ g64 / (np.linalg.norm(g) * np.linalg.norm(g64)))
+        print(f"{precision} M={M}: max|grad - lowp oracle| = {err:.3e} (|grad|_max {scale:.3e}), cosine {cos:.7f}; "
+              f"vs fp64 autograd: max {np.abs(g - g64).max():.3e}, cosine {cos64:.7f}")
+        assert err < 3e-2 * scale and cos > 0.9995
+        if M == 5000:
+            assert err < 2e-3 * scale and cos64 > 0.9995
+    # exact properties: deterministic; doubling the upstream gradient doubles every delta exactly (power of two)
+    g1, _ = cuda_decoder.latent_vjp(z, xyz, up, precision=precision)
+    g2, _ = cuda_decoder.latent_vjp(z, xyz, up, precision=precision)
+    assert torch.equal(g1, g2)
+    g4, _ = cuda_decoder.latent_vjp(z, xyz, 4.0 * up, precision=precision)
+    assert torch.equal(g4, 4.0 * g1)
+    g0, _ = cuda_decoder.latent_vjp(z, xyz[:0], up[:0], precision=precision)
+    assert float(g0.abs().max()) == 0.0
+    # a forward decode afterwards is unaffected by the backward instance having run on the same context
+    assert torch.equal(cuda_decoder(z, xyz, precision=precision), y_fwd)
+
+
+def test_fit_latent_on_the_tensor_pipe(cuda_decoder):
+    """Latent fitting with bf16 forward/backward passes reaches the same held-out error class as the fp32 path."""
+    rs = np.random.RandomState(5)
+    z_true = oracle.default_latent(7)
+    xyz = (rs.rand(20000, 3) * 2 - 1).astype(np.float32)
+    tgt = cuda_decoder(z_true, xyz, precision="fp32")
+    base = float((torch.clamp(cuda_decoder(np.zeros(256, np.float32), xyz, precision="fp32"), -0.1, 0.1)
+                  - torch.clamp(tgt, -0.1, 0.1)).abs().mean())
+    z_fit, loss = cuda_decoder.fit_latent(xyz, tgt, steps=200, lr=1e-2, reg=0.0, precision="bf16")
+    test_xyz = (rs.rand(5000, 3) * 2 - 1).astype(np.float32)
+    err = float((torch.clamp(cuda_decoder(z_fit, test_xyz, precision="fp32"), -0.1, 0.1)
+                 - torch.clamp(cuda_decoder(z_true, test_xyz, precision="fp32"), -0.1, 0.1)).abs().mean())
+    print(f"fit_latent(bf16): clamped-L1 {base:.5f} (zero latent) -> {loss:.5f} (train) / {err:.5f} (held-out, fp32 decode)")
+    assert err < 0.3 * base

@@ -54,6 +54,15 @@ rows.append(("config 3 on ONE GPU: 64 latents x 128^3 bf16", ms, q / ms / 1e3, q
 sdf, signs, _ = dec.decode_grid_bits(z, 256, mask=False)
 ms = timed(lambda: pkg.extract_surface(sdf, 256, 0, sign_words=signs))
 rows.append(("marching cubes 256^3 (count + scan + generate)", ms, 255 ** 3 / ms / 1e3, 0.0))
+# latent gradient (row N4): fp32 FFMA path vs the forward + backward instance of the fused kernel
+# (executed tensor flops per point: 6 forward + 6 backward 512 x 512 products)
+for n_pts, prec in ((1 << 18, "fp32"), (1 << 20, "bf16"), (1 << 24, "bf16"), (1 << 24, "fp16")):
+    pts = torch.rand((n_pts, 3), device=dev) * 2 - 1
+    up = torch.randn(n_pts, device=dev) / n_pts
+    ms = timed(lambda: dec.latent_vjp(z, pts, up, precision=prec))
+    rows.append((f"latent_vjp {n_pts / 1e6:.2f}M points {prec} (forward + backward)", ms, n_pts / ms / 1e3,
+                 0.0 if prec == "fp32" else n_pts * 2 * FLOP_Q / ms / 1e9))
+    del pts, up
 print(f"{'workload':58s} {'ms':>10s} {'M units/s':>12s} {'TFLOP/s':>9s}")
 for name, ms, rate, tf in rows:
     print(f"{name:58s} {ms:10.3f} {rate:12.1f} {tf:9.1f}")
