@@ -174,7 +174,7 @@ struct sdfb_decoder {
   // backward workspace (lazy): stored activations of one chunk, two delta buffers, column-sum partials
   float* bw_act[8] = {}; float *bw_d0 = nullptr, *bw_d1 = nullptr, *bw_y = nullptr, *bw_partial = nullptr;
   long long bw_rows = 0, bw_blocks = 0;
-  uint32_t* bw_masks = nullptr;   // tensor-core backward: ReLU-mask scratch [num_sms][6][16][128]
+  uint32_t* bw_masks = nullptr;   // tensor-core backward: ReLU-mask scratch [num_sms][6 + 2][16][128]
   float* bw_colsum = nullptr;     //                       column sums [num_sms * 4][1024]
   unsigned int* bw_amax = nullptr;   //                    bits of max |dLdy|
   // fp32 workspace (lazy)
@@ -618,7 +618,7 @@ int sdfb_decoder_vjp_latent_tc(sdfb_decoder* d, const float* latent_dev, const f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (M == 0) { CU_TRY(cudaMemsetAsync(grad_latent_dev, 0, kLatent * sizeof(float), st)); return SDFB_OK; }
   if (d->bw_masks == nullptr) {
-    CU_TRY(cudaMalloc(&d->bw_masks, static_cast<size_t>(d->num_sms) * 6 * 16 * kTileM * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&d->bw_masks, static_cast<size_t>(d->num_sms) * 8 * 16 * kTileM * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&d->bw_colsum, static_cast<size_t>(d->num_sms) * 4 * 1024 * sizeof(float)));
     CU_TRY(cudaMalloc(&d->bw_amax, sizeof(unsigned int)));
   }
@@ -637,6 +637,7 @@ int sdfb_decoder_vjp_latent_tc(sdfb_decoder* d, const float* latent_dev, const f
   p.dump_pass = -1;
   p.timeout_ns = d->timeout_ns;
   p.debug_flags = d->debug_flags;
+  p.prof = d->prof;
   p.dLdy = dLdy_dev;
   p.dLdy_amax = d->bw_amax;
   p.mask_scratch = d->bw_masks;

@@ -34,7 +34,8 @@
 // BWD = true (oracle: oracle/decoder.py decoder_vjp_latent_lowp): the same
 // tile then runs BACKWARDS through the same machinery - 13 more passes against the transposed weight
 // blocks (kernels.h) - to produce what the latent's gradient needs:
-//   g = dLdy (1 - sdf^2);  delta7 = g w8 where h7 > 0 (epilogue, like the first layer);
+//   delta7' = w8 where h7 > 0 (epilogue, like the first layer; written half by half behind the last forward
+//   pass);  g = dLdy (1 - sdf^2) is applied per row to the accumulator of the first backward layer;
 //   delta_{l-1} = mask_{l-1} * (delta_l W_l): the accumulator is masked instead of biased + rectified and
 //   written back in place as the next A operand.  The ReLU masks of layers 1-6 are one 32-bit word per
 //   (thread, 32 columns) parked in an L2-resident scratch (48 KiB per CTA, written and read by the same
@@ -118,6 +119,12 @@ __device__ __forceinline__ Query load_query(const DecodeParams& p, long long m) 
   return q;
 }
 
+// ReLU masks (BWD kernels) are built most-significant-bit first, two instructions per value: column i of a
+// 32-column group ends up in bit 31 - i.  0 - f is negative exactly when f > 0 (+0 and -0 both give +0).
+__device__ __forceinline__ uint32_t push_positive(uint32_t bits, float f) {
+  return __funnelshift_l(__float_as_uint(__fsub_rn(0.f, f)), bits, 1);
+}
+
 struct Epi {
   uint32_t bars;          // shared address of the barrier array
   uint32_t tmem_row;      // TMEM address of this warp's lane quadrant, column 0
@@ -171,14 +178,12 @@ __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict_
       }
       packed[2 * j] = pack_relu<FP16>(f0, f1);
       packed[2 * j + 1] = pack_relu<FP16>(f2, f3);
-      if constexpr (MASK)
-        bits |= (f0 > 0.f ? 1u : 0u) << (4 * j) | (f1 > 0.f ? 1u : 0u) << (4 * j + 1) |
-                (f2 > 0.f ? 1u : 0u) << (4 * j + 2) | (f3 > 0.f ? 1u : 0u) << (4 * j + 3);
+      if constexpr (MASK) bits = push_positive(push_positive(push_positive(push_positive(bits, f0), f1), f2), f3);
       if constexpr (L3) {
         if (j == 7 && cc == 3 && e.set == 1) {   // features 252 | x, y | z  (x, y, z unrectified)
           packed[14] = pack_plain<FP16>(fmaxf(f0, 0.f), q.x);
           packed[15] = pack_plain<FP16>(q.y, q.z);
-          if constexpr (MASK) bits &= 0x1FFFFFFFu;   // columns 253-255 are not features: nothing flows back
+          if constexpr (MASK) bits &= ~7u;   // columns 253-255 (the last three pushed) are not features: nothing flows back
         }
       }
     }
@@ -243,9 +248,7 @@ __device__ __forceinline__ bool epi_head_pass(Epi& e, const float* __restrict__ 
       dot = fmaf(fmaxf(f1, 0.f), h.y, dot);
       dot = fmaf(fmaxf(f2, 0.f), h.z, dot);
       dot = fmaf(fmaxf(f3, 0.f), h.w, dot);
-      if constexpr (MASK)
-        bits |= (f0 > 0.f ? 1u : 0u) << (4 * j) | (f1 > 0.f ? 1u : 0u) << (4 * j + 1) |
-                (f2 > 0.f ? 1u : 0u) << (4 * j + 2) | (f3 > 0.f ? 1u : 0u) << (4 * j + 3);
+      if constexpr (MASK) bits = push_positive(push_positive(push_positive(push_positive(bits, f0), f1), f2), f3);
     }
     if constexpr (MASK) hm[g] = bits;
   }
@@ -269,52 +272,53 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-// delta7 = g * w8 where h7's pre-activation was positive: built by the thread that holds the masks (head
-// passes), i.e. set s writes chunks 4b + 2s, 4b + 2s + 1 of its row.  Like the first layer, every chunk
-// must have been released by the last forward pass first.
+// The operand of the first backward layer, half b: w8 where h7's pre-activation was positive.  The per-query factor
+// g = dLdy (1 - sdf^2) commutes with the product and is applied to the accumulator of passes 13 / 14 instead, so
+// this half can be written as soon as its head pass is done - while the other head pass is still on the tensor
+// core - by the thread that holds the masks: set s writes chunks 4b + 2s, 4b + 2s + 1 of its row.  Like the
+// first layer, every chunk must have been released by the last forward pass first.  (wphase: flipped by the caller
+// once both halves are written.)
 template <bool FP16>
-__device__ __forceinline__ bool epi_delta7(Epi& e, const float* __restrict__ shead, float gs, const uint32_t (&hm)[2][4],
-                                           const Watchdog& wd) {
+__device__ __forceinline__ bool epi_delta7_half(Epi& e, const float* __restrict__ shead, const uint32_t (&hm)[4], int b,
+                                                const Watchdog& wd) {
 #pragma unroll
-  for (int b = 0; b < 2; ++b) {
+  for (int g = 0; g < 4; ++g) {
+    const int c = 4 * b + 2 * e.set + (g >> 1);
+    if ((g & 1) == 0) {
+      if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
+    }
+    const int col = 256 * b + 128 * e.set + 32 * g;
+    const uint32_t m = hm[g];
+    uint32_t packed[16];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int c = 4 * b + 2 * e.set + (g >> 1);
-      if ((g & 1) == 0) {
-        if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
-      }
-      const int col = 256 * b + 128 * e.set + 32 * g;
-      const uint32_t m = hm[b][g];
-      uint32_t packed[16];
+    for (int j = 0; j < 8; ++j) {
+      const float4 h = *reinterpret_cast<const float4*>(shead + col + 4 * j);
+      const float v0 = (m >> (31 - 4 * j)) & 1u ? h.x : 0.f, v1 = (m >> (30 - 4 * j)) & 1u ? h.y : 0.f;
+      const float v2 = (m >> (29 - 4 * j)) & 1u ? h.z : 0.f, v3 = (m >> (28 - 4 * j)) & 1u ? h.w : 0.f;
+      packed[2 * j] = pack_plain<FP16>(v0, v1);
+      packed[2 * j + 1] = pack_plain<FP16>(v2, v3);
+    }
+    const uint32_t base = e.a_row_addr + c * kAChunkBytes;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 h = *reinterpret_cast<const float4*>(shead + col + 4 * j);
-        const float v0 = (m >> (4 * j)) & 1u ? gs * h.x : 0.f, v1 = (m >> (4 * j + 1)) & 1u ? gs * h.y : 0.f;
-        const float v2 = (m >> (4 * j + 2)) & 1u ? gs * h.z : 0.f, v3 = (m >> (4 * j + 3)) & 1u ? gs * h.w : 0.f;
-        packed[2 * j] = pack_plain<FP16>(v0, v1);
-        packed[2 * j + 1] = pack_plain<FP16>(v2, v3);
-      }
-      const uint32_t base = e.a_row_addr + c * kAChunkBytes;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        st_shared_v4(base + (((4 * (g & 1) + u) ^ e.row7) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
-                     packed[4 * u + 3]);
-      if (g & 1) {
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c), 2);   // 4 warps x 2 = the 8 expected per CTA
-      }
+    for (int u = 0; u < 4; ++u)
+      st_shared_v4(base + (((4 * (g & 1) + u) ^ e.row7) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
+                   packed[4 * u + 3]);
+    if (g & 1) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c), 2);   // 4 warps x 2 = the 8 expected per CTA
     }
   }
-  e.wphase ^= 0xFFu;
   return true;
 }
 
 // Backward hidden pass: delta = mask * accumulator, rounded and written in place as the next A operand
 // (same thread <-> column mapping as the forward pass that stored the mask words at `mrow`).
 // `cs` != nullptr: also the column sums of the unrounded values (delta4), one column per lane and chunk.
+// `row_scale` != nullptr (passes 13 / 14): the accumulator is first multiplied by the row's g (see epi_delta7_half).
 template <bool FP16, bool WAIT_FREE>
-__device__ __forceinline__ bool epi_bwd_pass(Epi& e, const uint32_t* mrow, int c0, int b, const Watchdog& wd, float* cs) {
+__device__ __forceinline__ bool epi_bwd_pass(Epi& e, const uint32_t* mrow, int c0, int b, const Watchdog& wd, float* cs,
+                                             const float* row_scale = nullptr) {
   uint32_t mw[4];
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) mw[cc] = mrow[(2 * cc + e.set) * kTileM];
@@ -338,7 +342,12 @@ __device__ __forceinline__ bool epi_bwd_pass(Epi& e, const uint32_t* mrow, int c
     const uint32_t(&vc)[32] = v[cc & 1];
     float f[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = (mw[cc] >> i) & 1u ? __uint_as_float(vc[i]) : 0.f;
+    for (int i = 0; i < 32; ++i) f[i] = (mw[cc] >> (31 - i)) & 1u ? __uint_as_float(vc[i]) : 0.f;
+    if (row_scale != nullptr) {
+      const float g = *row_scale;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] *= g;
+    }
     uint32_t packed[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) packed[k] = pack_plain<FP16>(f[2 * k], f[2 * k + 1]);
@@ -360,10 +369,15 @@ __device__ __forceinline__ bool epi_bwd_pass(Epi& e, const uint32_t* mrow, int c
   return true;
 }
 
-// delta0 is only ever summed over the queries: mask (recomputed from the coordinates with the first
-// layer's own expression) and column sums, nothing written back.  `l0`: consts->l0 + 256 * half.
-__device__ __forceinline__ bool epi_bwd_l0_pass(Epi& e, const float4* __restrict__ l0, Query q, int b, const Watchdog& wd,
-                                                float* cs) {
+// delta0 is only ever summed over the queries: mask (the first layer's ballot words, see epi_layer0) and column
+// sums, nothing written back.  `m0`: this tile's mask block + 8 * half * 128 + row.
+__device__ __forceinline__ bool epi_bwd_l0_pass(Epi& e, const uint32_t* m0, int b, const Watchdog& wd, float* cs) {
+  uint32_t me[4], mo[4];
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    me[cc] = m0[(2 * cc) * kTileM] >> (16 * e.set);       // this thread's 32 columns are lanes 16 set .. 16 set + 15
+    mo[cc] = m0[(2 * cc + 1) * kTileM] >> (16 * e.set);
+  }
   if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
   e.acc_phase ^= 1u << b;
   __syncwarp();
@@ -382,14 +396,9 @@ __device__ __forceinline__ bool epi_bwd_l0_pass(Epi& e, const float4* __restrict
       if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAccEmpty + b), 1);
     }
     const uint32_t(&vc)[32] = v[cc & 1];
-    const float4* w = l0 + cc * 64 + e.set * 32;
     float f[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float4 wi = __ldg(w + i);
-      const float pre = fmaf(q.z, wi.z, fmaf(q.y, wi.y, fmaf(q.x, wi.x, wi.w)));
-      f[i] = pre > 0.f ? __uint_as_float(vc[i]) : 0.f;
-    }
+    for (int i = 0; i < 32; ++i) f[i] = (((i & 1) ? mo[cc] : me[cc]) >> (i >> 1)) & 1u ? __uint_as_float(vc[i]) : 0.f;
     cs[cc] += warp_colsum32(f, e.lane);
   }
   return true;
@@ -402,9 +411,12 @@ __device__ __forceinline__ bool epi_bwd_l0_pass(Epi& e, const float4* __restrict
 // rows sit in shared memory.
 struct L0Weights { float4 a, b; };
 
-template <bool FP16>
+// `m0` (BWD kernels): where the ReLU mask of h0 goes - per chunk c two ballot words per row, m0[(2 c + par) * 128 + row],
+// bit l of word `par` = (feature 64 c + 2 l + par is positive); lane r - r0 keeps row r's words and stores them.
+template <bool FP16, bool MASK = false>
 __device__ __forceinline__ bool epi_layer0(Epi& e, int warp, const L0Weights (&wl)[4],
-                                           const float4* __restrict__ sxyz, uint32_t smem_a, const Watchdog& wd) {
+                                           const float4* __restrict__ sxyz, uint32_t smem_a, const Watchdog& wd,
+                                           uint32_t* m0 = nullptr) {
   const uint32_t unit = e.lane >> 2;
   const int r0 = (warp >> 1) * 32;
 #pragma unroll
@@ -413,6 +425,7 @@ __device__ __forceinline__ bool epi_layer0(Epi& e, int warp, const L0Weights (&w
     if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
     const uint32_t chunk = smem_a + c * kAChunkBytes + ((e.lane & 3) << 2);
     const float4 wa = wl[i].a, wb = wl[i].b;
+    uint32_t keep_e = 0, keep_o = 0;
 #pragma unroll 8
     for (int r = r0; r < r0 + 32; ++r) {
       const float4 q = sxyz[r];
@@ -420,6 +433,14 @@ __device__ __forceinline__ bool epi_layer0(Epi& e, int warp, const L0Weights (&w
       const float f1 = fmaf(q.z, wb.z, fmaf(q.y, wb.y, fmaf(q.x, wb.x, wb.w)));
       const uint32_t v = pack_relu<FP16>(f0, f1);
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(chunk + r * 128 + ((unit ^ (r & 7)) << 4)), "r"(v) : "memory");
+      if constexpr (MASK) {
+        const uint32_t be = __ballot_sync(0xffffffffu, f0 > 0.f), bo = __ballot_sync(0xffffffffu, f1 > 0.f);
+        if (e.lane == r - r0) { keep_e = be; keep_o = bo; }
+      }
+    }
+    if constexpr (MASK) {
+      m0[(2 * c) * kTileM + r0 + e.lane] = keep_e;
+      m0[(2 * c + 1) * kTileM + r0 + e.lane] = keep_o;
     }
     fence_proxy_async_smem();
     __syncwarp();
@@ -576,12 +597,17 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
     e.wphase = 0;
     e.acc_phase = 0;
     L0Weights wl[4];                                      // layer-0 features of this lane, per step
+    auto load_l0_weights = [&](L0Weights (&w)[4]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int n0 = (2 * i + (warp & 1)) * 64 + 2 * lane;
-      wl[i].a = cs->l0[n0];
-      wl[i].b = cs->l0[n0 + 1];
-    }
+      for (int i = 0; i < 4; ++i) {
+        const int n0 = (2 * i + (warp & 1)) * 64 + 2 * lane;
+        w[i].a = cs->l0[n0];
+        w[i].b = cs->l0[n0 + 1];
+      }
+    };
+    if constexpr (!BWD) load_l0_weights(wl);              // BWD: reloaded per tile (registers are scarcer there)
+    // BWD: h0's ReLU masks, double-buffered by tile parity (the next tile's first layer runs before this tile's last pass)
+    uint32_t* const m0_base = BWD ? p.mask_scratch + static_cast<size_t>(blockIdx.x) * (8 * 16 * kTileM) + 6 * 16 * kTileM : nullptr;
     const float head_b = cs->head_b[0];
     const long long tile_stride = npairs * 2 * kTileM;
     long long row_base = pidx * 2 * kTileM + rank * kTileM;   // first query of this CTA's half tile
@@ -594,7 +620,12 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
         sxyz[row] = make_float4(q0.x, q0.y, q0.z, 0.f);
       }
       named_bar_sync(1, kEpiThreads);
-      if (!epi_layer0<FP16>(e, warp, wl, sxyz, smem0 + oA, wd)) goto done;
+      if constexpr (BWD) {
+        load_l0_weights(wl);
+        if (!epi_layer0<FP16, true>(e, warp, wl, sxyz, smem0 + oA, wd, m0_base)) goto done;
+      } else {
+        if (!epi_layer0<FP16>(e, warp, wl, sxyz, smem0 + oA, wd)) goto done;
+      }
       float4 qv = sxyz[row];
       Query q{qv.x, qv.y, qv.z};
       if constexpr (!BWD) {
@@ -649,9 +680,8 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
       }
       } else {
         // ============ forward + backward (latent gradient) ============
-        uint32_t* mbase = p.mask_scratch + static_cast<size_t>(blockIdx.x) * (6 * 16 * kTileM) + row;
+        uint32_t* mbase = p.mask_scratch + static_cast<size_t>(blockIdx.x) * (8 * 16 * kTileM) + row;
         const float up_scale = ldexpf(1.f, -vjp_scale_exponent(__uint_as_float(__ldg(p.dLdy_amax))));
-        const float4* l0 = cs->l0;
         for (long long it = 0; it < my_tiles; ++it, row_base += tile_stride) {
 #pragma unroll 1
           for (int ps = 0; ps < 11; ++ps, ++gpass) {
@@ -671,11 +701,16 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
             if (!ok) goto done;
           }
           float dot = 0.f;
-          uint32_t hm[2][4];
-          if (!epi_head_pass<true>(e, sbias + 6 * kHid, shead, gpass & 1u, wd, dot, nullptr, hm[0])) goto done;
-          ++gpass;
-          if (!epi_head_pass<true>(e, sbias + 6 * kHid + 256, shead + 256, gpass & 1u, wd, dot, nullptr, hm[1])) goto done;
-          ++gpass;
+          {
+            uint32_t hm[4];
+            if (!epi_head_pass<true>(e, sbias + 6 * kHid, shead, gpass & 1u, wd, dot, nullptr, hm)) goto done;
+            ++gpass;
+            if (!epi_delta7_half<FP16>(e, shead, hm, 0, wd)) goto done;      // behind pass 12's reads of h6, chunk by chunk
+            if (!epi_head_pass<true>(e, sbias + 6 * kHid + 256, shead + 256, gpass & 1u, wd, dot, nullptr, hm)) goto done;
+            ++gpass;
+            if (!epi_delta7_half<FP16>(e, shead, hm, 1, wd)) goto done;
+            e.wphase ^= 0xFFu;
+          }
           if (e.set == 1) sdot[row] = dot;
           named_bar_sync(2, kEpiThreads);
           if (e.set == 0) {
@@ -690,7 +725,6 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
           }
           named_bar_sync(2, kEpiThreads);
           const float gs = sdot[row];
-          if (!epi_delta7<FP16>(e, shead, gs, hm, wd)) goto done;
 #pragma unroll 1
           for (int ps = 13; ps < kPassesBwd; ++ps, ++gpass) {
             const uint32_t b = gpass & 1u;
@@ -702,11 +736,15 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
                   sxyz[row] = make_float4(qn.x, qn.y, qn.z, 0.f);
                 }
                 named_bar_sync(1, kEpiThreads);
-                if (!epi_layer0<FP16>(e, warp, wl, sxyz, smem0 + oA, wd)) goto done;
+                {
+                  L0Weights wn[4];
+                  load_l0_weights(wn);
+                  if (!epi_layer0<FP16, true>(e, warp, wn, sxyz, smem0 + oA, wd, m0_base + ((it + 1) & 1) * (16 * kTileM))) goto done;
+                }
                 qv = sxyz[row];
               }
               float t[4] = {0.f, 0.f, 0.f, 0.f};
-              ok = epi_bwd_l0_pass(e, l0 + (ps - 24) * 256, q, b, wd, t);
+              ok = epi_bwd_l0_pass(e, m0_base + (it & 1) * (16 * kTileM) + (ps - 24) * (8 * kTileM) + row, b, wd, t);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 if (ps == 24) cs0[0][i] += t[i]; else cs0[1][i] += t[i];
@@ -719,10 +757,11 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
               const uint32_t* mrow = mbase + ((layer - 1) * 16 + half * 8) * kTileM;
               float t[4] = {0.f, 0.f, 0.f, 0.f};
               float* tp = layer == 4 ? t : nullptr;
+              const float* rs = layer == 6 ? &gs : nullptr;
               if (half == 0 && layer != 3)
-                ok = epi_bwd_pass<FP16, true>(e, mrow, 0, b, wd, tp);
+                ok = epi_bwd_pass<FP16, true>(e, mrow, 0, b, wd, tp, rs);
               else
-                ok = epi_bwd_pass<FP16, false>(e, mrow, half * 4, b, wd, tp);
+                ok = epi_bwd_pass<FP16, false>(e, mrow, half * 4, b, wd, tp, rs);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 if (half == 0) cs4[0][i] += t[i]; else cs4[1][i] += t[i];

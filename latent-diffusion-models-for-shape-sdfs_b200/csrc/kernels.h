@@ -77,7 +77,7 @@ struct DecodeParams {
   // forward + backward kernel only (dLdy != nullptr selects it; `out` is then optional, `signs` unused)
   const float* dLdy;           // [M] upstream gradient d loss / d sdf
   const unsigned int* dLdy_amax;   // bits of max |dLdy| (launch_abs_max): the kernel works on dLdy * 2^-vjp_scale_exponent
-  uint32_t* mask_scratch;      // [grid][6 layers][16 words][128 rows]: ReLU masks of the tile in flight
+  uint32_t* mask_scratch;      // [grid][6 layers + 2][16 words][128 rows]: ReLU masks of the tile in flight (layers 1-6; h0's, two tiles deep)
   float* colsum;               // [grid * 4][1024]: per-warp-quadrant column sums of delta0 (512) | delta4 (512)
 };
 

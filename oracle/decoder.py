@@ -155,8 +155,9 @@ def decoder_vjp_latent_lowp(latent, xyz, dLdy, params=None, lowp=torch.bfloat16)
 
     * the forward of ``decoder_forward_lowp`` (ReLU masks = pre-activation > 0);
     * g_m = (dLdy[m] 2^-e)(1 - y_m^2) in fp32, 2^e the power of two just above max |dLdy| (undone at the end:
-      the deltas then sit in the same range whatever the caller's loss scale); delta7 = lowp(g_m w8[n]) where
-      h7's pre-activation is positive;
+      the deltas then sit in the same range whatever the caller's loss scale); the first backward operand is
+      lowp(w8[n]) where h7's pre-activation is positive, and g_m multiplies the fp32 result of that product
+      (it commutes with it), i.e. delta6 = lowp(g_m mask6 * ((mask7 * lowp(w8)) @ lowp(W7)));
     * delta_{l-1} = lowp(mask_{l-1} * (delta_l @ lowp(W_l))) with fp32 accumulation (the skip layer hands only
       its 253 hidden columns down);
     * the two column sums the latent sees, sum_m delta4 and sum_m delta0, are taken over the UNROUNDED fp32
@@ -190,8 +191,8 @@ def decoder_vjp_latent_lowp(latent, xyz, dLdy, params=None, lowp=torch.bfloat16)
         amax = float(up.abs().max()) if up.numel() else 0.0     # the kernel's power-of-two scaling of the upstream gradient
         ex = int(np.clip(np.frexp(np.float32(amax))[1], -100, 100)) if 0.0 < amax <= 3.0e38 else 0
         g = (up * float(2.0 ** -ex)) * (1.0 - y * y)
-        d = rnd(g[:, None] * W[8][0][None, :]) * mask[7]
-        d = rnd((d @ Wq[7]) * mask[6])
+        d = rnd(W[8][0])[None, :] * mask[7]
+        d = rnd(g[:, None] * ((d @ Wq[7]) * mask[6]))
         d = rnd((d @ Wq[6]) * mask[5])
         d4 = (d @ Wq[5]) * mask[4]
         d = rnd((rnd(d4) @ W4h) * mask[3])
