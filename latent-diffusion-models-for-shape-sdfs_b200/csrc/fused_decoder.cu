@@ -119,6 +119,12 @@ __device__ __forceinline__ Query load_query(const DecodeParams& p, long long m) 
   return q;
 }
 
+// A compile-time bool usable where a runtime bool is accepted (see epi_hidden_pass).
+template <bool V>
+struct Flag {
+  __device__ __forceinline__ constexpr operator bool() const { return V; }
+};
+
 // ReLU masks (BWD kernels) are built most-significant-bit first, two instructions per value: column i of a
 // 32-column group ends up in bit 31 - i.  0 - f is negative exactly when f > 0 (+0 and -0 both give +0).
 __device__ __forceinline__ uint32_t push_positive(uint32_t bits, float f) {
@@ -143,9 +149,13 @@ struct Epi {
 // the query coordinates into layer 4.
 // `mrow` (BWD kernels only): where this thread parks the ReLU mask of its 32 columns of chunk cc: word
 // (2 cc + set) * 128 of the (layer, half) block, already offset by the row.
-template <bool FP16, bool L3, bool WAIT_FREE, bool MASK = false>
+// `l3` / `wait_free` are Flag<true> / Flag<false> in the forward kernel (folded at compile time, three
+// instances) and plain bools in the BWD kernel (ONE instance: that kernel's code must stay close to the
+// instruction cache's size - the first version, 240 KB of SASS, spent 17 % of its issue slots on no_inst stalls).
+template <bool FP16, bool MASK, typename L3T, typename WFT>
 __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict__ sbias, Query q, int c0, int b,
-                                                const Watchdog& wd, float* dump_row, uint32_t* mrow = nullptr) {
+                                                const Watchdog& wd, float* dump_row, L3T l3, WFT wait_free,
+                                                uint32_t* mrow = nullptr) {
   if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
   e.acc_phase ^= 1u << b;
   __syncwarp();
@@ -179,7 +189,7 @@ __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict_
       packed[2 * j] = pack_relu<FP16>(f0, f1);
       packed[2 * j + 1] = pack_relu<FP16>(f2, f3);
       if constexpr (MASK) bits = push_positive(push_positive(push_positive(push_positive(bits, f0), f1), f2), f3);
-      if constexpr (L3) {
+      if (l3) {
         if (j == 7 && cc == 3 && e.set == 1) {   // features 252 | x, y | z  (x, y, z unrectified)
           packed[14] = pack_plain<FP16>(fmaxf(f0, 0.f), q.x);
           packed[15] = pack_plain<FP16>(q.y, q.z);
@@ -192,7 +202,7 @@ __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict_
     // Chunks written by a layer's LAST pass were read for the last time by that very pass, whose
     // completion acc_full already reported: only a first-half pass must wait for the other half's
     // MMAs to release the chunk.  (The phase bits are advanced by schedule, not by waiting.)
-    if (WAIT_FREE) {
+    if (wait_free) {
       if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
     }
     const uint32_t base = e.a_row_addr + c * kAChunkBytes;
@@ -312,16 +322,14 @@ __device__ __forceinline__ bool epi_delta7_half(Epi& e, const float* __restrict_
   return true;
 }
 
-// Backward hidden pass: delta = mask * accumulator, rounded and written in place as the next A operand
-// (same thread <-> column mapping as the forward pass that stored the mask words at `mrow`).
-// `cs` != nullptr: also the column sums of the unrounded values (delta4), one column per lane and chunk.
-// `row_scale` != nullptr (passes 13 / 14): the accumulator is first multiplied by the row's g (see epi_delta7_half).
-template <bool FP16, bool WAIT_FREE>
-__device__ __forceinline__ bool epi_bwd_pass(Epi& e, const uint32_t* mrow, int c0, int b, const Watchdog& wd, float* cs,
-                                             const float* row_scale = nullptr) {
-  uint32_t mw[4];
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) mw[cc] = mrow[(2 * cc + e.set) * kTileM];
+// Backward pass epilogue (ONE instance, runtime flags): delta = mask * accumulator [* row_scale], then
+//   write_back: rounded and written in place as the next A operand (chunks c0 .. c0 + 3; `wait_free` as in the
+//               forward pass); same thread <-> column mapping as the forward pass that built the mask words;
+//   cs != nullptr: the column sums of the unrounded values are added to cs[0..3] (one column per lane and chunk).
+// `mw`: the mask words of this thread's four 32-column groups (column i in bit 31 - i).
+template <bool FP16>
+__device__ __forceinline__ bool epi_bwd_pass(Epi& e, const uint32_t (&mw)[4], int c0, int b, const Watchdog& wd, float* cs,
+                                             const float* row_scale, bool wait_free, bool write_back) {
   if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
   e.acc_phase ^= 1u << b;
   __syncwarp();
@@ -348,60 +356,40 @@ __device__ __forceinline__ bool epi_bwd_pass(Epi& e, const uint32_t* mrow, int c
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] *= g;
     }
-    uint32_t packed[16];
+    if (write_back) {
+      uint32_t packed[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) packed[k] = pack_plain<FP16>(f[2 * k], f[2 * k + 1]);
-    const int c = c0 + cc;
-    if (WAIT_FREE) {
-      if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
+      for (int k = 0; k < 16; ++k) packed[k] = pack_plain<FP16>(f[2 * k], f[2 * k + 1]);
+      const int c = c0 + cc;
+      if (wait_free) {
+        if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
+      }
+      const uint32_t base = e.a_row_addr + c * kAChunkBytes;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        st_shared_v4(base + (((4 * e.set + u) ^ e.row7) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
+                     packed[4 * u + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c), 1);
     }
-    const uint32_t base = e.a_row_addr + c * kAChunkBytes;
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      st_shared_v4(base + (((4 * e.set + u) ^ e.row7) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
-                   packed[4 * u + 3]);
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c), 1);
     if (cs != nullptr) cs[cc] += warp_colsum32(f, e.lane);
   }
-  e.wphase ^= 0xFu << c0;
+  if (write_back) e.wphase ^= 0xFu << c0;
   return true;
 }
 
-// delta0 is only ever summed over the queries: mask (the first layer's ballot words, see epi_layer0) and column
-// sums, nothing written back.  `m0`: this tile's mask block + 8 * half * 128 + row.
-__device__ __forceinline__ bool epi_bwd_l0_pass(Epi& e, const uint32_t* m0, int b, const Watchdog& wd, float* cs) {
-  uint32_t me[4], mo[4];
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    me[cc] = m0[(2 * cc) * kTileM] >> (16 * e.set);       // this thread's 32 columns are lanes 16 set .. 16 set + 15
-    mo[cc] = m0[(2 * cc + 1) * kTileM] >> (16 * e.set);
-  }
-  if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
-  e.acc_phase ^= 1u << b;
-  __syncwarp();
-  tc_fence_after();
-  const uint32_t tbase = e.tmem_row + b * 256 + e.set * 32;
-  uint32_t v[2][32];
-  tmem_ld32(tbase, v[0]);
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    tmem_ld_wait();
-    if (cc < 3) {
-      tmem_ld32(tbase + (cc + 1) * 64, v[(cc + 1) & 1]);
-    } else {
-      tc_fence_before();
-      __syncwarp();
-      if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAccEmpty + b), 1);
-    }
-    const uint32_t(&vc)[32] = v[cc & 1];
-    float f[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = (((i & 1) ? mo[cc] : me[cc]) >> (i >> 1)) & 1u ? __uint_as_float(vc[i]) : 0.f;
-    cs[cc] += warp_colsum32(f, e.lane);
-  }
-  return true;
+// h0's masks arrive as ballot words (epi_layer0): even features in E, odd ones in O, this thread's 32 columns in bits
+// 16 set .. 16 set + 15 of each.  Interleave them into the MSB-first word the backward pass expects.
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+  x &= 0xFFFFu;
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  return (x | (x << 1)) & 0x55555555u;
+}
+__device__ __forceinline__ uint32_t l0_mask_word(uint32_t even, uint32_t odd, int set) {
+  return __brev(spread16(even >> (16 * set)) | (spread16(odd >> (16 * set)) << 1));
 }
 
 // First layer of a tile, column-mapped.  Chunks of the activation buffer are released in pairs
@@ -615,20 +603,17 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
     float cs0[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // BWD: column sums of delta0 / delta4 (lane = column)
     float cs4[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     if (my_tiles > 0) {
+      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+      Query q{0.f, 0.f, 0.f};
+      if constexpr (!BWD) {
       if (e.set == 0) {
         const Query q0 = load_query(p, row_base + row);
         sxyz[row] = make_float4(q0.x, q0.y, q0.z, 0.f);
       }
       named_bar_sync(1, kEpiThreads);
-      if constexpr (BWD) {
-        load_l0_weights(wl);
-        if (!epi_layer0<FP16, true>(e, warp, wl, sxyz, smem0 + oA, wd, m0_base)) goto done;
-      } else {
-        if (!epi_layer0<FP16>(e, warp, wl, sxyz, smem0 + oA, wd)) goto done;
-      }
-      float4 qv = sxyz[row];
-      Query q{qv.x, qv.y, qv.z};
-      if constexpr (!BWD) {
+      if (!epi_layer0<FP16>(e, warp, wl, sxyz, smem0 + oA, wd)) goto done;
+      qv = sxyz[row];
+      q = Query{qv.x, qv.y, qv.z};
       for (long long it = 0; it < my_tiles; ++it, row_base += tile_stride) {
         const bool dump_tile = p.dump != nullptr && row_base == 0;
 #pragma unroll 1
@@ -641,11 +626,11 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
           float* dump_row = (dump_tile && ps == p.dump_pass) ? p.dump + row * 256 : nullptr;
           bool ok;
           if (layer == 3)
-            ok = epi_hidden_pass<FP16, true, false>(e, bias, q, 0, gpass & 1u, wd, dump_row);
+            ok = epi_hidden_pass<FP16, false>(e, bias, q, 0, gpass & 1u, wd, dump_row, Flag<true>{}, Flag<false>{});
           else if (half == 0)
-            ok = epi_hidden_pass<FP16, false, true>(e, bias, q, 0, gpass & 1u, wd, dump_row);
+            ok = epi_hidden_pass<FP16, false>(e, bias, q, 0, gpass & 1u, wd, dump_row, Flag<false>{}, Flag<true>{});
           else
-            ok = epi_hidden_pass<FP16, false, false>(e, bias, q, 4, gpass & 1u, wd, dump_row);
+            ok = epi_hidden_pass<FP16, false>(e, bias, q, 4, gpass & 1u, wd, dump_row, Flag<false>{}, Flag<false>{});
           if (!ok) goto done;
         }
         float dot = 0.f;
@@ -680,95 +665,91 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
       }
       } else {
         // ============ forward + backward (latent gradient) ============
+        // One call site per epilogue function (code size, see epi_hidden_pass).  Iteration -1 only computes the
+        // first layer of the first tile; iteration `it` ends with the first layer of tile it + 1, placed before
+        // its own last pass exactly like the forward kernel's.
         uint32_t* mbase = p.mask_scratch + static_cast<size_t>(blockIdx.x) * (8 * 16 * kTileM) + row;
         const float up_scale = ldexpf(1.f, -vjp_scale_exponent(__uint_as_float(__ldg(p.dLdy_amax))));
-        for (long long it = 0; it < my_tiles; ++it, row_base += tile_stride) {
 #pragma unroll 1
-          for (int ps = 0; ps < 11; ++ps, ++gpass) {
-            int layer, half;
-            if (ps < 4) { layer = 1 + (ps >> 1); half = ps & 1; }
-            else if (ps == 4) { layer = 3; half = 0; }
-            else { layer = 4 + ((ps - 5) >> 1); half = (ps - 5) & 1; }
-            const float* bias = sbias + (layer - 1) * kHid + half * 256;
-            uint32_t* mrow = mbase + ((layer - 1) * 16 + half * 8) * kTileM;
-            bool ok;
-            if (layer == 3)
-              ok = epi_hidden_pass<FP16, true, false, true>(e, bias, q, 0, gpass & 1u, wd, nullptr, mrow);
-            else if (half == 0)
-              ok = epi_hidden_pass<FP16, false, true, true>(e, bias, q, 0, gpass & 1u, wd, nullptr, mrow);
-            else
-              ok = epi_hidden_pass<FP16, false, false, true>(e, bias, q, 4, gpass & 1u, wd, nullptr, mrow);
-            if (!ok) goto done;
-          }
-          float dot = 0.f;
-          {
-            uint32_t hm[4];
-            if (!epi_head_pass<true>(e, sbias + 6 * kHid, shead, gpass & 1u, wd, dot, nullptr, hm)) goto done;
-            ++gpass;
-            if (!epi_delta7_half<FP16>(e, shead, hm, 0, wd)) goto done;      // behind pass 12's reads of h6, chunk by chunk
-            if (!epi_head_pass<true>(e, sbias + 6 * kHid + 256, shead + 256, gpass & 1u, wd, dot, nullptr, hm)) goto done;
-            ++gpass;
-            if (!epi_delta7_half<FP16>(e, shead, hm, 1, wd)) goto done;
-            e.wphase ^= 0xFFu;
-          }
-          if (e.set == 1) sdot[row] = dot;
-          named_bar_sync(2, kEpiThreads);
-          if (e.set == 0) {
-            const long long m = row_base + row;
-            const float v = tanhf((dot + sdot[row]) + head_b);
-            float gsv = 0.f;
-            if (m < p.M) {
-              if (p.out != nullptr) p.out[m] = v;
-              gsv = (__ldg(p.dLdy + m) * up_scale) * (1.f - v * v);
+        for (long long it = -1; it < my_tiles; ++it) {
+          if (it >= 0) {
+#pragma unroll 1
+            for (int ps = 0; ps < 11; ++ps, ++gpass) {
+              int layer, half;
+              if (ps < 4) { layer = 1 + (ps >> 1); half = ps & 1; }
+              else if (ps == 4) { layer = 3; half = 0; }
+              else { layer = 4 + ((ps - 5) >> 1); half = (ps - 5) & 1; }
+              const float* bias = sbias + (layer - 1) * kHid + half * 256;
+              uint32_t* mrow = mbase + ((layer - 1) * 16 + half * 8) * kTileM;
+              if (!epi_hidden_pass<FP16, true>(e, bias, q, half * 4, gpass & 1u, wd, nullptr, layer == 3,
+                                               half == 0 && layer != 3, mrow))
+                goto done;
             }
-            sdot[row] = gsv;                                     // rows past M carry no gradient
+            float dot = 0.f;
+#pragma unroll 1
+            for (int hb = 0; hb < 2; ++hb, ++gpass) {   // head halves; each leaves its half of the first backward operand behind
+              uint32_t hm[4];
+              if (!epi_head_pass<true>(e, sbias + 6 * kHid + 256 * hb, shead + 256 * hb, gpass & 1u, wd, dot, nullptr, hm)) goto done;
+              if (!epi_delta7_half<FP16>(e, shead, hm, hb, wd)) goto done;
+            }
+            e.wphase ^= 0xFFu;
+            if (e.set == 1) sdot[row] = dot;
+            named_bar_sync(2, kEpiThreads);
+            if (e.set == 0) {
+              const long long m = row_base + row;
+              const float v = tanhf((dot + sdot[row]) + head_b);
+              float gsv = 0.f;
+              if (m < p.M) {
+                if (p.out != nullptr) p.out[m] = v;
+                gsv = (__ldg(p.dLdy + m) * up_scale) * (1.f - v * v);
+              }
+              sdot[row] = gsv;                                     // rows past M carry no gradient
+            }
+            named_bar_sync(2, kEpiThreads);
           }
-          named_bar_sync(2, kEpiThreads);
           const float gs = sdot[row];
 #pragma unroll 1
-          for (int ps = 13; ps < kPassesBwd; ++ps, ++gpass) {
-            const uint32_t b = gpass & 1u;
-            bool ok;
-            if (ps >= 24) {
-              if (ps == 25 && it + 1 < my_tiles) {   // first layer of the next tile, behind the last readers of delta1
-                if (e.set == 0) {
-                  const Query qn = load_query(p, row_base + tile_stride + row);
-                  sxyz[row] = make_float4(qn.x, qn.y, qn.z, 0.f);
-                }
-                named_bar_sync(1, kEpiThreads);
-                {
-                  L0Weights wn[4];
-                  load_l0_weights(wn);
-                  if (!epi_layer0<FP16, true>(e, warp, wn, sxyz, smem0 + oA, wd, m0_base + ((it + 1) & 1) * (16 * kTileM))) goto done;
-                }
-                qv = sxyz[row];
+          for (int ps = 13; ps < kPassesBwd; ++ps) {
+            if (ps == 25 && it + 1 < my_tiles) {   // first layer of the next tile, behind the last readers of delta1
+              const long long next_base = it < 0 ? row_base : row_base + tile_stride;
+              if (e.set == 0) {
+                const Query qn = load_query(p, next_base + row);
+                sxyz[row] = make_float4(qn.x, qn.y, qn.z, 0.f);
               }
-              float t[4] = {0.f, 0.f, 0.f, 0.f};
-              ok = epi_bwd_l0_pass(e, m0_base + (it & 1) * (16 * kTileM) + (ps - 24) * (8 * kTileM) + row, b, wd, t);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (ps == 24) cs0[0][i] += t[i]; else cs0[1][i] += t[i];
-              }
-            } else {
-              int layer, half;
-              if (ps < 19) { layer = 6 - ((ps - 13) >> 1); half = (ps - 13) & 1; }
-              else if (ps == 19) { layer = 3; half = 0; }
-              else { layer = 2 - ((ps - 20) >> 1); half = (ps - 20) & 1; }
-              const uint32_t* mrow = mbase + ((layer - 1) * 16 + half * 8) * kTileM;
-              float t[4] = {0.f, 0.f, 0.f, 0.f};
-              float* tp = layer == 4 ? t : nullptr;
-              const float* rs = layer == 6 ? &gs : nullptr;
-              if (half == 0 && layer != 3)
-                ok = epi_bwd_pass<FP16, true>(e, mrow, 0, b, wd, tp, rs);
-              else
-                ok = epi_bwd_pass<FP16, false>(e, mrow, half * 4, b, wd, tp, rs);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (half == 0) cs4[0][i] += t[i]; else cs4[1][i] += t[i];
-              }
+              named_bar_sync(1, kEpiThreads);
+              load_l0_weights(wl);
+              if (!epi_layer0<FP16, true>(e, warp, wl, sxyz, smem0 + oA, wd, m0_base + ((it + 1) & 1) * (16 * kTileM))) goto done;
+              qv = sxyz[row];
             }
-            if (!ok) goto done;
+            if (it < 0) continue;
+            const uint32_t b = gpass & 1u;
+            int layer, half;                       // the layer whose delta this pass produces
+            if (ps < 19) { layer = 6 - ((ps - 13) >> 1); half = (ps - 13) & 1; }
+            else if (ps == 19) { layer = 3; half = 0; }
+            else { layer = 2 - ((ps - 20) >> 1); half = (ps - 20) & 1; }
+            uint32_t mw[4];
+            if (layer > 0) {
+              const uint32_t* mrow = mbase + ((layer - 1) * 16 + half * 8) * kTileM;
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) mw[cc] = mrow[(2 * cc + e.set) * kTileM];
+            } else {
+              const uint32_t* m0 = m0_base + (it & 1) * (16 * kTileM) + half * (8 * kTileM) + row;
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) mw[cc] = l0_mask_word(m0[(2 * cc) * kTileM], m0[(2 * cc + 1) * kTileM], e.set);
+            }
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool sums = layer == 4 || layer == 0;
+            if (!epi_bwd_pass<FP16>(e, mw, half * 4, b, wd, sums ? t : nullptr, layer == 6 ? &gs : nullptr,
+                                    half == 0 && layer != 3, layer != 0))
+              goto done;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (layer == 4) { if (half == 0) cs4[0][i] += t[i]; else cs4[1][i] += t[i]; }
+              if (layer == 0) { if (half == 0) cs0[0][i] += t[i]; else cs0[1][i] += t[i]; }
+            }
+            ++gpass;
           }
+          if (it >= 0) row_base += tile_stride;
           q = Query{qv.x, qv.y, qv.z};
         }
       }
