@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--no-config5", action="store_true", help="skip the 512^3 z-slab-sharded case that runs when N > 1")
     ap.add_argument("--no-config4", action="store_true", help="skip the sample-then-decode leg (configs[3])")
     ap.add_argument("--no-ddpm", action="store_true", help="skip the latent-DDPM leg (second half of the metric)")
+    ap.add_argument("--no-vjp", action="store_true", help="skip the latent-gradient leg (SURVEY 8f row N4)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -391,6 +392,43 @@ def main():
             cfg4 = {"error": repr(exc)}
             print(f"bench.py: optional leg failed: {exc!r}", file=sys.stderr)
 
+    # ---- latent gradient (auto-decoder fitting) through the forward + backward instance of the fused
+    # kernel, next to the fp32 path on a sample of the same points
+    vjp = None
+    if not args.no_vjp:
+        try:
+            n_v = 1 << 22
+            gv = torch.Generator(device=dev).manual_seed(7 + rank)
+            pts = torch.rand((n_v, 3), generator=gv, device=dev) * 2 - 1
+            up = torch.randn(n_v, generator=gv, device=dev) / n_v
+            zv = torch.from_numpy(pkg.synthetic.latent(rank)).to(dev)
+            dec.latent_vjp(zv, pts, up, precision=args.precision)
+            barrier()
+            ms_v = []
+            for _ in range(3):
+                dec.latent_vjp(zv, pts, up, precision=args.precision)
+                ms_v.append(dec.last_kernel_ms())
+            n32 = 1 << 17
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dec.latent_vjp(zv, pts[:n32], up[:n32], precision="fp32")
+            a.record()
+            dec.latent_vjp(zv, pts[:n32], up[:n32], precision="fp32")
+            b.record()
+            b.synchronize()
+            t_v = torch.tensor([statistics.median(ms_v)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_v, op=dist.ReduceOp.MAX)
+            kv = float(t_v.item())
+            vjp = {"workload": f"per GPU: latent_vjp over {n_v} random points, precision {args.precision} (one launch of "
+                               "fused_decoder_kernel<., BWD>: forward + 13 backward passes per tile)",
+                   "kernel_ms": kv, "points_per_s": world * n_v / (kv * 1e-3),
+                   "achieved_tflops_per_gpu": n_v * 2 * FLOP_TENSOR_PER_QUERY / (kv * 1e-3) / 1e12,
+                   "fp32_path_points_per_s": n32 / (a.elapsed_time(b) * 1e-3)}
+            del pts, up
+        except Exception as exc:                     # an optional leg must never cost the headline line
+            vjp = {"error": repr(exc)}
+            print(f"bench.py: optional leg failed: {exc!r}", file=sys.stderr)
+
     if rank == 0:
         peaks = read_peaks()
         k_ms = statistics.mean(kernel_ms)
@@ -427,6 +465,10 @@ def main():
             line["config5_512cubed_sharded"] = cfg5
         if cfg4 is not None:
             line["config4_sample_then_decode"] = cfg4
+        if vjp is not None:
+            if "achieved_tflops_per_gpu" in vjp:
+                vjp["frac_of_burst_peak"] = vjp["achieved_tflops_per_gpu"] / peaks["burst"]
+            line["latent_gradient"] = vjp
         if ddpm_line is not None:
             if "achieved_tflops" in ddpm_line:
                 ddpm_line["frac_of_burst_peak"] = ddpm_line["achieved_tflops"] / peaks["burst"]
