@@ -106,6 +106,14 @@ int sdfb_decoder_vjp_latent_tc(sdfb_decoder* dec, const float* latent_dev, const
                                const float* dLdy_dev, float* grad_latent_dev, float* sdf_dev, int precision,
                                void* stream);
 
+/* One step's worth of auto-decoder latent fitting (DeepSDF's inference-time reconstruction) in ONE launch of the
+ * same instance: loss_dev[0] = mean_m |clamp(sdf_m) - clamp(target_dev[m])|, clamping to [-clamp_dist, clamp_dist],
+ * and grad_latent_dev[256] = d loss / d latent; the upstream gradient is formed inside the kernel.
+ * precision SDFB_PREC_BF16 or SDFB_PREC_FP16; sdf_dev optional. */
+int sdfb_decoder_fit_loss_grad(sdfb_decoder* dec, const float* latent_dev, const float* xyz_dev, int64_t M,
+                               const float* target_dev, float clamp_dist, float* grad_latent_dev,
+                               float* loss_dev, float* sdf_dev, int precision, void* stream);
+
 /* Host-buffer forms (what a plugin caller with CPU arrays uses): stage through
  * pinned memory owned by the context, run, copy back, synchronise. */
 int sdfb_decode_grid_host(sdfb_decoder* dec, const float* latent_host, int res, int z0, int z1,

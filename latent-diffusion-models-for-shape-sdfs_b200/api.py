@@ -191,6 +191,26 @@ class Decoder:
                                                        _stream_ptr(self.device.index)))
         return grad, sdf
 
+    def fit_loss_grad(self, latent, xyz, sdf_target, clamp: float = 0.1, precision: str = "bf16", return_sdf: bool = False):
+        """(loss [1], grad [256]) of loss = mean |clamp(sdf(latent, xyz)) - clamp(sdf_target)| w.r.t. the latent, in ONE
+        launch of the forward + backward instance of the fused kernel (the upstream gradient is formed in the kernel).
+        Nothing is synchronised: both results stay on the device."""
+        prec = PRECISIONS[precision]
+        lat = _as_dev_f32(latent, self.device, (LATENT,))
+        pts = _as_dev_f32(xyz, self.device)
+        tgt = _as_dev_f32(sdf_target, self.device)
+        if pts.ndim != 2 or pts.shape[1] != 3 or tgt.shape != (pts.shape[0],):
+            raise ValueError("expected xyz [M,3] and sdf_target [M]")
+        M = pts.shape[0]
+        grad = torch.empty(LATENT, dtype=torch.float32, device=self.device)
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        sdf = torch.empty(M, dtype=torch.float32, device=self.device) if return_sdf else None
+        check(self._lib.sdfb_decoder_fit_loss_grad(self._h, lat.data_ptr(), pts.data_ptr() if M else None, M,
+                                                   tgt.data_ptr() if M else None, float(clamp), grad.data_ptr(),
+                                                   loss.data_ptr(), sdf.data_ptr() if (sdf is not None and M) else None, prec,
+                                                   _stream_ptr(self.device.index)))
+        return (loss, grad, sdf) if return_sdf else (loss, grad)
+
     def fit_latent(self, xyz, sdf_target, steps: int = 300, lr: float = 5e-3, clamp: float = 0.1, reg: float = 1e-4,
                    init=None, precision: str = "fp32"):
         """Auto-decoder inference (DeepSDF's reconstruction step): Adam on the latent so that the decoded
@@ -203,6 +223,18 @@ class Decoder:
         m = torch.zeros_like(z)
         v = torch.zeros_like(z)
         M = pts.shape[0]
+        if precision != "fp32":              # one launch per step (loss + gradient), nothing synchronised until the end
+            loss_t = None
+            for it in range(1, steps + 1):
+                loss_t, g = self.fit_loss_grad(z, pts, tgt, clamp=clamp, precision=precision)
+                g = g + 2 * reg * z
+                m = 0.9 * m + 0.1 * g
+                v = 0.999 * v + 0.001 * g * g
+                z_new = z - lr * (m / (1 - 0.9 ** it)) / ((v / (1 - 0.999 ** it)).sqrt() + 1e-8)
+                loss_z = z                    # the loss reported belongs to the latent it was evaluated at
+                z = z_new
+            loss = float(loss_t[0] + reg * (loss_z * loss_z).sum()) if loss_t is not None else float("nan")
+            return z, loss
         ones = torch.ones(M, device=self.device)
         loss = float("nan")
         for it in range(1, steps + 1):

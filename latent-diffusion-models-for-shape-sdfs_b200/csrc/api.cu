@@ -177,6 +177,7 @@ struct sdfb_decoder {
   uint32_t* bw_masks = nullptr;   // tensor-core backward: ReLU-mask scratch [num_sms][6 + 2][16][128]
   float* bw_colsum = nullptr;     //                       column sums [num_sms * 4][1024]
   unsigned int* bw_amax = nullptr;   //                    bits of max |dLdy|
+  float* bw_loss = nullptr;          //                    loss mode: per-warp sums [num_sms * 4]
   // fp32 workspace (lazy)
   long long ws_rows = 0;
   float *h0 = nullptr, *h1 = nullptr, *s = nullptr, *x = nullptr;
@@ -456,7 +457,7 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
   cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x); cudaFree(d->prof); cudaFree(d->signs); cudaFree(d->rowmask);
   for (float* a : d->bw_act) cudaFree(a);
   cudaFree(d->bw_d0); cudaFree(d->bw_d1); cudaFree(d->bw_y); cudaFree(d->bw_partial);
-  cudaFree(d->bw_masks); cudaFree(d->bw_colsum); cudaFree(d->bw_amax);
+  cudaFree(d->bw_masks); cudaFree(d->bw_colsum); cudaFree(d->bw_amax); cudaFree(d->bw_loss);
   if (d->pin) cudaFreeHost(d->pin);
   cudaFree(d->dstage);
   if (d->ev0) cudaEventDestroy(d->ev0);
@@ -608,21 +609,26 @@ int sdfb_decoder_vjp_latent(sdfb_decoder* d, const float* latent_dev, const floa
 // The same gradient on the tensor pipe: ONE launch of the forward + backward instance of the fused kernel (every
 // tile is decoded, then run backwards through the transposed weight blocks while it is still in shared memory),
 // then the small contraction of the two column sums with the fp32 latent columns of W0 and W4.
-int sdfb_decoder_vjp_latent_tc(sdfb_decoder* d, const float* latent_dev, const float* xyz_dev, int64_t M, const float* dLdy_dev,
-                               float* grad_latent_dev, float* sdf_dev, int precision, void* stream) {
-  if (!d || !latent_dev || !grad_latent_dev || (M > 0 && (!xyz_dev || !dLdy_dev))) return fail(SDFB_E_INVALID, "null argument");
-  if (M < 0) return fail(SDFB_E_INVALID, "negative point count");
+// `target_dev` != nullptr: loss mode - the kernel forms the upstream gradient of mean |clamp(sdf) - clamp(target)| itself.
+namespace {
+int vjp_tc(sdfb_decoder* d, const float* latent_dev, const float* xyz_dev, int64_t M, const float* dLdy_dev,
+           const float* target_dev, float clamp, float* grad_latent_dev, float* loss_dev, float* sdf_dev, int precision,
+           cudaStream_t st) {
   if (precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16)
     return fail(SDFB_E_INVALID, "the tensor-core gradient runs in bf16 or fp16 (precision %d); fp32: sdfb_decoder_vjp_latent", precision);
-  DeviceGuard g(d->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (M == 0) { CU_TRY(cudaMemsetAsync(grad_latent_dev, 0, kLatent * sizeof(float), st)); return SDFB_OK; }
+  if (M == 0) {
+    CU_TRY(cudaMemsetAsync(grad_latent_dev, 0, kLatent * sizeof(float), st));
+    if (loss_dev != nullptr) CU_TRY(cudaMemsetAsync(loss_dev, 0, sizeof(float), st));
+    return SDFB_OK;
+  }
   if (d->bw_masks == nullptr) {
     CU_TRY(cudaMalloc(&d->bw_masks, static_cast<size_t>(d->num_sms) * 8 * 16 * kTileM * sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&d->bw_colsum, static_cast<size_t>(d->num_sms) * 4 * 1024 * sizeof(float)));
     CU_TRY(cudaMalloc(&d->bw_amax, sizeof(unsigned int)));
+    CU_TRY(cudaMalloc(&d->bw_loss, static_cast<size_t>(d->num_sms) * 4 * sizeof(float)));
   }
-  CU_TRY(launch_abs_max(dLdy_dev, M, d->bw_amax, st));
+  const bool loss_mode = target_dev != nullptr;
+  if (!loss_mode) CU_TRY(launch_abs_max(dLdy_dev, M, d->bw_amax, st));
   const bool fp16 = precision == SDFB_PREC_FP16;
   const float* P = d->params;
   const LayerOff* o = d->off;
@@ -638,8 +644,12 @@ int sdfb_decoder_vjp_latent_tc(sdfb_decoder* d, const float* latent_dev, const f
   p.timeout_ns = d->timeout_ns;
   p.debug_flags = d->debug_flags;
   p.prof = d->prof;
+  p.bwd = 1;
   p.dLdy = dLdy_dev;
   p.dLdy_amax = d->bw_amax;
+  p.target = target_dev;
+  p.clamp = clamp;
+  p.loss_partial = loss_mode ? d->bw_loss : nullptr;
   p.mask_scratch = d->bw_masks;
   p.colsum = d->bw_colsum;
   CU_TRY(cudaEventRecord(d->ev0, st));
@@ -649,8 +659,33 @@ int sdfb_decoder_vjp_latent_tc(sdfb_decoder* d, const float* latent_dev, const f
   const long long tiles = (M + 2 * kTileM - 1) / (2 * kTileM);
   const long long pairs = tiles < d->num_sms / 2 ? tiles : d->num_sms / 2;
   CU_TRY(launch_vjp_finish(d->bw_colsum, static_cast<int>(2 * pairs * 4), P + o[0].w, P + o[4].w, grad_latent_dev, st,
-                           d->bw_amax));
+                           loss_mode ? nullptr : d->bw_amax, loss_mode ? d->bw_loss : nullptr,
+                           loss_mode ? 1.f / static_cast<float>(M) : 1.f, loss_mode ? loss_dev : nullptr));
   return SDFB_OK;
+}
+}  // namespace
+
+int sdfb_decoder_vjp_latent_tc(sdfb_decoder* d, const float* latent_dev, const float* xyz_dev, int64_t M, const float* dLdy_dev,
+                               float* grad_latent_dev, float* sdf_dev, int precision, void* stream) {
+  if (!d || !latent_dev || !grad_latent_dev || (M > 0 && (!xyz_dev || !dLdy_dev))) return fail(SDFB_E_INVALID, "null argument");
+  if (M < 0) return fail(SDFB_E_INVALID, "negative point count");
+  DeviceGuard g(d->device);
+  return vjp_tc(d, latent_dev, xyz_dev, M, dLdy_dev, nullptr, 0.f, grad_latent_dev, nullptr, sdf_dev, precision,
+                static_cast<cudaStream_t>(stream));
+}
+
+// One step's worth of auto-decoder fitting in one launch: loss = mean_m |clamp(sdf_m) - clamp(target_m)| (clamp to
+// [-clamp_dist, clamp_dist]) and its gradient w.r.t. the latent, the upstream gradient formed inside the kernel.
+int sdfb_decoder_fit_loss_grad(sdfb_decoder* d, const float* latent_dev, const float* xyz_dev, int64_t M, const float* target_dev,
+                               float clamp_dist, float* grad_latent_dev, float* loss_dev, float* sdf_dev, int precision,
+                               void* stream) {
+  if (!d || !latent_dev || !grad_latent_dev || !loss_dev || (M > 0 && (!xyz_dev || !target_dev)))
+    return fail(SDFB_E_INVALID, "null argument");
+  if (M < 0) return fail(SDFB_E_INVALID, "negative point count");
+  if (!(clamp_dist > 0.f)) return fail(SDFB_E_INVALID, "clamp distance must be positive");
+  DeviceGuard g(d->device);
+  return vjp_tc(d, latent_dev, xyz_dev, M, nullptr, target_dev, clamp_dist, grad_latent_dev, loss_dev, sdf_dev, precision,
+                static_cast<cudaStream_t>(stream));
 }
 
 int sdfb_decode_grid_host(sdfb_decoder* d, const float* latent_host, int res, int z0, int z1, float* sdf_host,

@@ -164,7 +164,8 @@ __global__ void abs_max_kernel(const float* __restrict__ v, long long M, unsigne
 // max |dLdy| (vjp_scale_exponent): undo it here, exactly.
 __global__ void vjp_finish_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ W0,
                                   const float* __restrict__ W4, float* __restrict__ grad,
-                                  const unsigned int* __restrict__ amax_bits) {
+                                  const unsigned int* __restrict__ amax_bits, const float* __restrict__ loss_partial,
+                                  float inv_m, float* __restrict__ loss_out) {
   __shared__ float s[1024];
   for (int c = threadIdx.x; c < 1024; c += blockDim.x) {
     float a = 0.f;
@@ -178,7 +179,12 @@ __global__ void vjp_finish_kernel(const float* __restrict__ partial, int nblk, c
     for (int n = 0; n < 512; ++n) g = fmaf(s[n], W0[n * 259 + k], g);
     for (int n = 0; n < 512; ++n) g = fmaf(s[512 + n], W4[n * 512 + 253 + k], g);
     if (amax_bits != nullptr) g = ldexpf(g, vjp_scale_exponent(__uint_as_float(*amax_bits)));
-    grad[k] = g;
+    grad[k] = g * inv_m;
+  }
+  if (loss_out != nullptr && threadIdx.x == 0) {   // loss mode: mean of the per-warp sums, fixed order
+    float l = 0.f;
+    for (int b = 0; b < nblk; ++b) l += loss_partial[b];
+    loss_out[0] = l * inv_m;
   }
 }
 
@@ -379,8 +385,9 @@ cudaError_t launch_colsum_f32(const float* D, long long M, float* partial, int h
 }
 
 cudaError_t launch_vjp_finish(const float* partial, int nblk, const float* W0, const float* W4, float* grad,
-                              cudaStream_t stream, const unsigned int* amax_bits) {
-  vjp_finish_kernel<<<1, 256, 0, stream>>>(partial, nblk, W0, W4, grad, amax_bits);
+                              cudaStream_t stream, const unsigned int* amax_bits, const float* loss_partial, float inv_m,
+                              float* loss_out) {
+  vjp_finish_kernel<<<1, 256, 0, stream>>>(partial, nblk, W0, W4, grad, amax_bits, loss_partial, inv_m, loss_out);
   return cudaGetLastError();
 }
 

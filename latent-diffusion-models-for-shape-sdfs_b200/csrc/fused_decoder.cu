@@ -602,6 +602,7 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
     uint32_t gpass = 0;
     float cs0[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // BWD: column sums of delta0 / delta4 (lane = column)
     float cs4[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float loss_acc_total = 0.f;
     if (my_tiles > 0) {
       float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
       Query q{0.f, 0.f, 0.f};
@@ -669,7 +670,8 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
         // first layer of the first tile; iteration `it` ends with the first layer of tile it + 1, placed before
         // its own last pass exactly like the forward kernel's.
         uint32_t* mbase = p.mask_scratch + static_cast<size_t>(blockIdx.x) * (8 * 16 * kTileM) + row;
-        const float up_scale = ldexpf(1.f, -vjp_scale_exponent(__uint_as_float(__ldg(p.dLdy_amax))));
+        const float up_scale = p.target != nullptr ? 1.f : ldexpf(1.f, -vjp_scale_exponent(__uint_as_float(__ldg(p.dLdy_amax))));
+        float loss_acc = 0.f;                        // loss mode: this thread's share of sum |clamp(sdf) - clamp(target)|
 #pragma unroll 1
         for (long long it = -1; it < my_tiles; ++it) {
           if (it >= 0) {
@@ -701,7 +703,16 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
               float gsv = 0.f;
               if (m < p.M) {
                 if (p.out != nullptr) p.out[m] = v;
-                gsv = (__ldg(p.dLdy + m) * up_scale) * (1.f - v * v);
+                float up;
+                if (p.target != nullptr) {           // clamped-L1 fitting loss, formed here (see kernels.h)
+                  const float c = p.clamp;
+                  const float diff = fminf(fmaxf(v, -c), c) - fminf(fmaxf(__ldg(p.target + m), -c), c);
+                  loss_acc += fabsf(diff);
+                  up = (v > -c && v < c) ? (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) : 0.f;
+                } else {
+                  up = __ldg(p.dLdy + m) * up_scale;
+                }
+                gsv = up * (1.f - v * v);
               }
               sdot[row] = gsv;                                     // rows past M carry no gradient
             }
@@ -752,6 +763,14 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
           if (it >= 0) row_base += tile_stride;
           q = Query{qv.x, qv.y, qv.z};
         }
+        loss_acc_total = loss_acc;
+      }
+    }
+    if constexpr (BWD) {
+      if (p.loss_partial != nullptr && e.set == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) loss_acc_total += __shfl_xor_sync(0xffffffffu, loss_acc_total, o);
+        if (lane == 0) p.loss_partial[blockIdx.x * 4 + (warp & 3)] = loss_acc_total;
       }
     }
     if constexpr (BWD) {   // this warp's share of the column sums: [CTA][quadrant][delta0 512 | delta4 512]
@@ -839,8 +858,9 @@ cudaError_t launch_fused_decoder(const DecodeParams& p, const void* tmap, bool f
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const CUtensorMap* tm = static_cast<const CUtensorMap*>(tmap);
-  if (p.dLdy != nullptr) {   // forward + backward: needs the mask scratch and the column-sum rows of every CTA
-    if (p.mask_scratch == nullptr || p.colsum == nullptr || p.dLdy_amax == nullptr) return cudaErrorInvalidValue;
+  if (p.bwd) {   // forward + backward: needs the mask scratch and the column-sum rows of every CTA
+    if (p.mask_scratch == nullptr || p.colsum == nullptr) return cudaErrorInvalidValue;
+    if (p.target != nullptr ? p.loss_partial == nullptr : (p.dLdy == nullptr || p.dLdy_amax == nullptr)) return cudaErrorInvalidValue;
     if (fp16) return cudaLaunchKernelEx(&cfg, fused_decoder_kernel<true, true>, p, *tm);
     return cudaLaunchKernelEx(&cfg, fused_decoder_kernel<false, true>, p, *tm);
   }

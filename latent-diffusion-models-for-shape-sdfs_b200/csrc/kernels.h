@@ -77,6 +77,13 @@ struct DecodeParams {
   // forward + backward kernel only (dLdy != nullptr selects it; `out` is then optional, `signs` unused)
   const float* dLdy;           // [M] upstream gradient d loss / d sdf
   const unsigned int* dLdy_amax;   // bits of max |dLdy| (launch_abs_max): the kernel works on dLdy * 2^-vjp_scale_exponent
+  // loss mode (target != nullptr, dLdy unused): the kernel forms the upstream gradient of the clamped-L1 fitting loss
+  // itself, dLdy[m] = sign(clamp(sdf_m) - clamp(target_m)) [|sdf_m| < clamp] (the 1 / M is applied by the finish
+  // kernel), and adds up sum_m |clamp(sdf_m) - clamp(target_m)| per warp
+  const float* target;         // [M]
+  float clamp;
+  float* loss_partial;         // [grid * 4]
+  int bwd;                     // 1 selects the forward + backward instance
   uint32_t* mask_scratch;      // [grid][6 layers + 2][16 words][128 rows]: ReLU masks of the tile in flight (layers 1-6; h0's, two tiles deep)
   float* colsum;               // [grid * 4][1024]: per-warp-quadrant column sums of delta0 (512) | delta4 (512)
 };
@@ -179,7 +186,8 @@ cudaError_t launch_head_bwd_f32(const float* dLdy, const float* y, const float* 
                                 cudaStream_t stream);
 cudaError_t launch_colsum_f32(const float* D, long long M, float* partial, int half, cudaStream_t stream);
 cudaError_t launch_vjp_finish(const float* partial, int nblk, const float* W0, const float* W4, float* grad,
-                              cudaStream_t stream, const unsigned int* amax_bits = nullptr);
+                              cudaStream_t stream, const unsigned int* amax_bits = nullptr,
+                              const float* loss_partial = nullptr, float inv_m = 1.f, float* loss_out = nullptr);
 // out[0] = bits of max |v[i]| (0 for an empty or all-zero v)
 cudaError_t launch_abs_max(const float* v, long long M, unsigned int* out, cudaStream_t stream);
 // Tensor-core backward: the upstream gradient is scaled by 2^-e, e = vjp_scale_exponent(max |dLdy|), so that the

@@ -201,3 +201,16 @@ def decoder_vjp_latent_lowp(latent, xyz, dLdy, params=None, lowp=torch.bfloat16)
         d0 = (d @ Wq[1]) * mask[0]
         grad = (d0.sum(0) @ W[0][:, :L] + d4.sum(0) @ W[4][:, S:S + L]) * float(2.0 ** ex)
     return grad.numpy(), y.numpy()
+
+
+def fit_loss_grad_lowp(latent, xyz, sdf_target, clamp: float = 0.1, params=None, lowp=torch.bfloat16):
+    """(loss, grad[256]) of the auto-decoder fitting loss mean_m |clamp(sdf_m) - clamp(target_m)| w.r.t. the latent, with
+    the tensor-core kernel's arithmetic (decoder_forward_lowp / decoder_vjp_latent_lowp); the oracle of
+    sdfb_decoder_fit_loss_grad.  sign(0) = 0 and the clamp's gradient is 1 strictly inside (-clamp, clamp)."""
+    y = decoder_forward_lowp(latent, xyz, params=params, lowp=lowp)
+    t = np.clip(np.asarray(sdf_target, dtype=np.float32).reshape(-1), -clamp, clamp)
+    diff = np.clip(y, -clamp, clamp) - t
+    M = max(y.shape[0], 1)
+    up = (np.sign(diff) * ((y > -clamp) & (y < clamp))).astype(np.float32) / np.float32(M)
+    grad, _ = decoder_vjp_latent_lowp(latent, xyz, up, params=params, lowp=lowp)
+    return float(np.abs(diff).astype(np.float64).sum() / M), grad
