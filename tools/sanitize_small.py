@@ -19,6 +19,20 @@ for prec in ("bf16", "fp16", "fp32"):
     torch.cuda.synchronize()
     print(prec, float(sdf.sum()), int(mask.sum()), float(out.sum()))
 h, m = dec.decode_grid_host(z, 24, 3, 11, mask=True)
+pts = torch.rand((777, 3), device="cuda") * 2 - 1            # latent gradient: fp32 path, backward instance, loss mode
+up = torch.randn(777, device="cuda")
+for prec in ("fp32", "bf16", "fp16"):
+    g, y = dec.latent_vjp(z, pts, up, precision=prec)
+    torch.cuda.synchronize()
+    print("vjp", prec, float(g.sum()), float(y.sum()))
+    if prec != "fp32":
+        loss, g = dec.fit_loss_grad(z, pts, torch.zeros(777, device="cuda"), precision=prec)
+        torch.cuda.synchronize()
+        print("fit", prec, float(loss), float(g.sum()))
+sdf, signs, mw = dec.decode_grid_bits(z, 24, mask=True)
+tri = dec.extract_surface(z, 24)
+tri_s = dec.extract_surface_sparse(z, 33, block=4)
+print("surface", tuple(tri.shape), tuple(tri_s.shape))
 ddpm = pkg.LatentDDPM(pkg.synthetic.ddpm_params(), device="cuda:0")
 rs = np.random.RandomState(0)
 x_T = rs.standard_normal((37, 256)).astype(np.float32)
