@@ -114,6 +114,12 @@ int sdfb_decoder_fit_loss_grad(sdfb_decoder* dec, const float* latent_dev, const
                                const float* target_dev, float clamp_dist, float* grad_latent_dev,
                                float* loss_dev, float* sdf_dev, int precision, void* stream);
 
+/* The same for a batch of shapes (reconstructing a test set): latents_dev [batch][256], xyz_dev
+ * [batch][points_per_shape][3], target_dev [batch][points_per_shape] -> grad_latents_dev [batch][256], loss_dev [batch]. */
+int sdfb_decoder_fit_loss_grad_batch(sdfb_decoder* dec, const float* latents_dev, const float* xyz_dev, int batch,
+                                     int64_t points_per_shape, const float* target_dev, float clamp_dist,
+                                     float* grad_latents_dev, float* loss_dev, int precision, void* stream);
+
 /* Host-buffer forms (what a plugin caller with CPU arrays uses): stage through
  * pinned memory owned by the context, run, copy back, synchronise. */
 int sdfb_decode_grid_host(sdfb_decoder* dec, const float* latent_host, int res, int z0, int z1,

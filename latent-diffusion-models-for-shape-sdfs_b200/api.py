@@ -252,6 +252,37 @@ class Decoder:
         del ones
         return z, loss
 
+    def fit_latents_batch(self, xyz, sdf_target, steps: int = 300, lr: float = 5e-3, clamp: float = 0.1, reg: float = 1e-4,
+                          init=None, precision: str = "bf16"):
+        """``fit_latent`` for a batch of shapes at once (reconstructing a test set): xyz [B,M,3], sdf_target [B,M] ->
+        (latents [B,256], last losses [B]).  Per Adam step: one forward + backward launch per shape, back to back on the
+        stream, and one set of [B,256] torch ops; nothing is synchronised until the end.  Tensor-pipe precisions only."""
+        prec = PRECISIONS[precision]
+        if prec == PRECISIONS["fp32"]:
+            raise ValueError("fit_latents_batch runs on the tensor pipe: precision 'bf16' or 'fp16'")
+        pts = _as_dev_f32(xyz, self.device)
+        if pts.ndim != 3 or pts.shape[2] != 3:
+            raise ValueError("expected xyz [B,M,3]")
+        B, M = pts.shape[0], pts.shape[1]
+        tgt = torch.clamp(_as_dev_f32(sdf_target, self.device, (B, M)), -clamp, clamp)
+        z = (torch.zeros((B, LATENT), device=self.device) if init is None
+             else _as_dev_f32(init, self.device, (B, LATENT)).clone())
+        m, v = torch.zeros_like(z), torch.zeros_like(z)
+        loss = torch.zeros(B, device=self.device)
+        st = _stream_ptr(self.device.index)
+        for it in range(1, steps + 1):
+            g = torch.empty_like(z)
+            loss = torch.empty(B, dtype=torch.float32, device=self.device)
+            check(self._lib.sdfb_decoder_fit_loss_grad_batch(self._h, z.data_ptr(), pts.data_ptr() if M else None, B, M,
+                                                             tgt.data_ptr() if M else None, float(clamp), g.data_ptr(),
+                                                             loss.data_ptr(), prec, st))
+            loss = loss + reg * (z * z).sum(dim=1)
+            g = g + 2 * reg * z
+            m = 0.9 * m + 0.1 * g
+            v = 0.999 * v + 0.001 * g * g
+            z = z - lr * (m / (1 - 0.9 ** it)) / ((v / (1 - 0.999 ** it)).sqrt() + 1e-8)
+        return z, loss
+
     def extract_surface(self, latent, res: int, precision: str | None = None, indexed: bool = False):
         """decode_grid + marching cubes: triangles [n,3,3] of the zero level set on the res^3 grid
         (the decoder's own sign bit-planes classify the cells); ``indexed=True``: (vertices, faces)."""

@@ -688,6 +688,26 @@ int sdfb_decoder_fit_loss_grad(sdfb_decoder* d, const float* latent_dev, const f
                 static_cast<cudaStream_t>(stream));
 }
 
+// A batch of shapes, each with its own latent and its own points_per_shape samples: one fold + one forward + backward
+// launch + one finish per shape, back to back on the stream (the shapes are independent; nothing is synchronised).
+int sdfb_decoder_fit_loss_grad_batch(sdfb_decoder* d, const float* latents_dev, const float* xyz_dev, int batch,
+                                     int64_t points_per_shape, const float* target_dev, float clamp_dist, float* grad_latents_dev,
+                                     float* loss_dev, int precision, void* stream) {
+  if (!d || (batch > 0 && (!latents_dev || !grad_latents_dev || !loss_dev))) return fail(SDFB_E_INVALID, "null argument");
+  if (batch < 0 || points_per_shape < 0) return fail(SDFB_E_INVALID, "negative batch or point count");
+  if (batch > 0 && points_per_shape > 0 && (!xyz_dev || !target_dev)) return fail(SDFB_E_INVALID, "null argument");
+  if (!(clamp_dist > 0.f)) return fail(SDFB_E_INVALID, "clamp distance must be positive");
+  DeviceGuard g(d->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int b = 0; b < batch; ++b) {
+    const long long o = static_cast<long long>(b) * points_per_shape;
+    int rc = vjp_tc(d, latents_dev + static_cast<long long>(b) * kLatent, xyz_dev + 3 * o, points_per_shape, nullptr, target_dev + o,
+                    clamp_dist, grad_latents_dev + static_cast<long long>(b) * kLatent, loss_dev + b, nullptr, precision, st);
+    if (rc) return rc;
+  }
+  return SDFB_OK;
+}
+
 int sdfb_decode_grid_host(sdfb_decoder* d, const float* latent_host, int res, int z0, int z1, float* sdf_host,
                           uint8_t* mask_host, int precision) {
   if (!d || !latent_host || !sdf_host) return fail(SDFB_E_INVALID, "null argument");

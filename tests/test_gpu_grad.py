@@ -206,3 +206,20 @@ def test_tensor_core_vjp_full_size_properties(cuda_decoder):
     assert torch.equal(full, again)
     loss, g0 = cuda_decoder.fit_loss_grad(z, pts, y, clamp=0.1, precision="bf16")
     assert float(loss) == 0.0 and float(g0.abs().max()) == 0.0
+
+
+def test_fit_latents_batch_equals_single_fits(cuda_decoder):
+    """A batch of shapes fitted in one call takes exactly the trajectory of the shapes fitted one by one (the same
+    launches in the same arithmetic; the Adam update is elementwise): latents bit-identical."""
+    rs = np.random.RandomState(8)
+    B, M, steps = 3, 6000, 25
+    xyz = (rs.rand(B, M, 3) * 2 - 1).astype(np.float32)
+    tgt = np.stack([oracle.decoder_forward(oracle.default_latent(20 + b), xyz[b]) for b in range(B)])
+    zb, lb = cuda_decoder.fit_latents_batch(xyz, tgt, steps=steps, lr=1e-2, reg=1e-4, precision="bf16")
+    assert zb.shape == (B, 256) and lb.shape == (B,)
+    for b in range(B):
+        z1, l1 = cuda_decoder.fit_latent(xyz[b], tgt[b], steps=steps, lr=1e-2, reg=1e-4, precision="bf16")
+        assert torch.equal(zb[b], z1), float((zb[b] - z1).abs().max())
+    first = np.array([float(cuda_decoder.fit_loss_grad(np.zeros(256, np.float32), xyz[b], tgt[b])[0]) for b in range(B)])
+    print(f"fit_latents_batch: losses {first} -> {lb.cpu().numpy()}")
+    assert (lb.cpu().numpy() < first).all()
