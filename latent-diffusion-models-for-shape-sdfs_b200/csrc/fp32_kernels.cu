@@ -160,31 +160,57 @@ __global__ void abs_max_kernel(const float* __restrict__ v, long long M, unsigne
   if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(out, __float_as_uint(a));
 }
 
+// Column sums of the nblk partial rows [nblk][1024], in place into row 0: block b owns columns [32 b, 32 b + 32)
+// (nobody else touches them); 8 row groups per block, combined in a fixed order.
+__global__ void vjp_colsum_reduce_kernel(float* __restrict__ partial, int nblk) {
+  __shared__ float s[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+  float a = 0.f;
+  for (int r = g; r < nblk; r += 8) a += partial[static_cast<long long>(r) * 1024 + c];
+  s[g][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (g == 0) {
+    float t = s[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += s[i][threadIdx.x];
+    partial[c] = t;
+  }
+}
+
+// grad[k] = sum_n cs0[n] W0[n][k] + sum_n cs4[n] W4[n][253 + k] from the reduced column sums (1024 threads: 256
+// outputs x 4 quarters of n, combined in a fixed order).
 // `amax_bits` (tensor-core path): the kernel ran on dLdy * 2^-e with 2^e the power of two just above
 // max |dLdy| (vjp_scale_exponent): undo it here, exactly.
-__global__ void vjp_finish_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ W0,
-                                  const float* __restrict__ W4, float* __restrict__ grad,
-                                  const unsigned int* __restrict__ amax_bits, const float* __restrict__ loss_partial,
-                                  float inv_m, float* __restrict__ loss_out) {
+__global__ void __launch_bounds__(1024) vjp_finish_kernel(const float* __restrict__ reduced, int nblk, const float* __restrict__ W0,
+                                                          const float* __restrict__ W4, float* __restrict__ grad,
+                                                          const unsigned int* __restrict__ amax_bits,
+                                                          const float* __restrict__ loss_partial, float inv_m,
+                                                          float* __restrict__ loss_out) {
   __shared__ float s[1024];
-  for (int c = threadIdx.x; c < 1024; c += blockDim.x) {
-    float a = 0.f;
-    for (int b = 0; b < nblk; ++b) a += partial[static_cast<long long>(b) * 1024 + c];
-    s[c] = a;
-  }
+  __shared__ float part[4][256];
+  s[threadIdx.x] = reduced[threadIdx.x];
   __syncthreads();
-  const int k = threadIdx.x;
-  if (k < 256) {
-    float g = 0.f;
-    for (int n = 0; n < 512; ++n) g = fmaf(s[n], W0[n * 259 + k], g);
-    for (int n = 0; n < 512; ++n) g = fmaf(s[512 + n], W4[n * 512 + 253 + k], g);
+  const int k = threadIdx.x & 255, q = threadIdx.x >> 8;
+  float g = 0.f;
+  if (q < 2) {
+    for (int n = 256 * q; n < 256 * q + 256; ++n) g = fmaf(s[n], W0[n * 259 + k], g);
+  } else {
+    for (int n = 256 * (q - 2); n < 256 * (q - 2) + 256; ++n) g = fmaf(s[512 + n], W4[n * 512 + 253 + k], g);
+  }
+  part[q][k] = g;
+  __syncthreads();
+  if (q == 0) {
+    g = ((part[0][k] + part[1][k]) + part[2][k]) + part[3][k];
     if (amax_bits != nullptr) g = ldexpf(g, vjp_scale_exponent(__uint_as_float(*amax_bits)));
     grad[k] = g * inv_m;
   }
-  if (loss_out != nullptr && threadIdx.x == 0) {   // loss mode: mean of the per-warp sums, fixed order
+  if (loss_out != nullptr && threadIdx.x >= 992) {   // loss mode: mean of the per-warp sums (last warp; fixed order)
+    const int lane = threadIdx.x & 31;
     float l = 0.f;
-    for (int b = 0; b < nblk; ++b) l += loss_partial[b];
-    loss_out[0] = l * inv_m;
+    for (int b = lane; b < nblk; b += 32) l += loss_partial[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (lane == 0) loss_out[0] = l * inv_m;
   }
 }
 
@@ -384,10 +410,11 @@ cudaError_t launch_colsum_f32(const float* D, long long M, float* partial, int h
   return cudaGetLastError();
 }
 
-cudaError_t launch_vjp_finish(const float* partial, int nblk, const float* W0, const float* W4, float* grad,
+cudaError_t launch_vjp_finish(float* partial, int nblk, const float* W0, const float* W4, float* grad,
                               cudaStream_t stream, const unsigned int* amax_bits, const float* loss_partial, float inv_m,
                               float* loss_out) {
-  vjp_finish_kernel<<<1, 256, 0, stream>>>(partial, nblk, W0, W4, grad, amax_bits, loss_partial, inv_m, loss_out);
+  vjp_colsum_reduce_kernel<<<32, 256, 0, stream>>>(partial, nblk);
+  vjp_finish_kernel<<<1, 1024, 0, stream>>>(partial, nblk, W0, W4, grad, amax_bits, loss_partial, inv_m, loss_out);
   return cudaGetLastError();
 }
 

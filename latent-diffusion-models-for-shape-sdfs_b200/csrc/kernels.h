@@ -185,7 +185,8 @@ cudaError_t launch_linear_bwd_f32(const float* A, int lda, const float* W, int l
 cudaError_t launch_head_bwd_f32(const float* dLdy, const float* y, const float* w8, const float* H7, float* D, long long M,
                                 cudaStream_t stream);
 cudaError_t launch_colsum_f32(const float* D, long long M, float* partial, int half, cudaStream_t stream);
-cudaError_t launch_vjp_finish(const float* partial, int nblk, const float* W0, const float* W4, float* grad,
+// (reduces the partial rows in place into row 0 first)
+cudaError_t launch_vjp_finish(float* partial, int nblk, const float* W0, const float* W4, float* grad,
                               cudaStream_t stream, const unsigned int* amax_bits = nullptr,
                               const float* loss_partial = nullptr, float inv_m = 1.f, float* loss_out = nullptr);
 // out[0] = bits of max |v[i]| (0 for an empty or all-zero v)
