@@ -38,12 +38,13 @@
 //   pass);  g = dLdy (1 - sdf^2) is applied per row to the accumulator of the first backward layer;
 //   delta_{l-1} = mask_{l-1} * (delta_l W_l): the accumulator is masked instead of biased + rectified and
 //   written back in place as the next A operand.  The ReLU masks of layers 1-6 are one 32-bit word per
-//   (thread, 32 columns) parked in an L2-resident scratch (48 KiB per CTA, written and read by the same
-//   thread); layer 7's stay in registers, layer 0's are recomputed from the coordinates.
+//   (thread, 32 columns) parked in an L2-resident scratch (64 KiB per CTA, written and read by the same
+//   thread); layer 7's stay in registers; layer 0's are warp ballots of the first-layer epilogue, two tiles deep.
 //   The latent enters through the bias of layers 0 and 4 only, so all it needs are the COLUMN SUMS of
 //   delta0 and delta4 over the queries: a 31-shuffle transpose-reduce per 32 x 32 block leaves lane l
 //   with column l's sum, accumulated in registers over all tiles and written once per warp at the end
 //   (vjp_finish_kernel contracts them with the fp32 latent columns of W0 and W4).
+//   Loss mode (DecodeParams::target): dLdy is formed here from the value just decoded (clamped-L1 fitting loss).
 #include <cuda.h>
 
 #include "kernels.h"

@@ -74,7 +74,7 @@ struct DecodeParams {
   unsigned long long timeout_ns;
   long long* prof;             // optional [grid][3 roles][8]: blocked cycles per wait class (diagnostics)
   unsigned int debug_flags;    // bit0: producer skips the weight copies (timing experiment; results are garbage)
-  // forward + backward kernel only (dLdy != nullptr selects it; `out` is then optional, `signs` unused)
+  // forward + backward kernel only (`bwd` selects it; `out` is then optional, `signs` unused)
   const float* dLdy;           // [M] upstream gradient d loss / d sdf
   const unsigned int* dLdy_amax;   // bits of max |dLdy| (launch_abs_max): the kernel works on dLdy * 2^-vjp_scale_exponent
   // loss mode (target != nullptr, dLdy unused): the kernel forms the upstream gradient of the clamped-L1 fitting loss
