@@ -2,6 +2,7 @@
 
     python -m oracle.make_golden            # rewrite tests/golden/oracle_golden.{npz,json}
     python -m oracle.make_golden --calibrate  # print the head bias that puts 25% of 64^3 inside
+    python -m oracle.make_golden --vjp        # rewrite tests/golden/vjp_golden.npz only (latent-gradient fixtures)
 
 There is no upstream reference to generate vectors from
 (`/root/reference/README.md:1` is a title), so these fixtures pin the oracle to
@@ -20,7 +21,7 @@ import torch
 
 from . import (axis_coords, grid_points, sign_change_mask, decoder_weights, ddpm_weights,
                default_latent, weights_sha256, decode_grid, decoder_forward,
-               decoder_forward_lowp, sample_latents)
+               decoder_forward_lowp, sample_latents, decoder_vjp_latent, decoder_vjp_latent_lowp, fit_loss_grad_lowp)
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 DDPM_NOISE_SEED = 2
@@ -43,12 +44,40 @@ def calibrate():
     print("DEC_HEAD_BIAS =", repr(np.float32(-np.quantile(pre, 0.25))))
 
 
+def vjp_golden_inputs():
+    """Points, upstream gradient and fitting target of the latent-gradient fixtures (RandomState(13))."""
+    rs = np.random.RandomState(13)
+    xyz = (rs.rand(192, 3) * 2 - 1).astype(np.float32)
+    up = ((0.5 + rs.rand(192)) / 192).astype(np.float32)          # coherent (all positive): no cancellation
+    target = decoder_forward(default_latent(7), xyz)
+    return xyz, up, target
+
+
+def make_vjp_golden():
+    """tests/golden/vjp_golden.npz: gradients of the SURVEY 8f row N4 oracles at the default latent (seed 2)."""
+    torch.set_num_threads(8)
+    z = default_latent(2)
+    xyz, up, target = vjp_golden_inputs()
+    arrays = {"xyz": xyz, "up": up, "target": target}
+    arrays["grad_fp64"], arrays["sdf_fp64"] = decoder_vjp_latent(z, xyz, up)
+    for name, lowp in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        arrays[f"grad_{name}"], arrays[f"sdf_{name}"] = decoder_vjp_latent_lowp(z, xyz, up, lowp=lowp)
+        loss, g = fit_loss_grad_lowp(z, xyz, target, clamp=0.1, lowp=lowp)
+        arrays[f"fit_loss_{name}"] = np.float64(loss)
+        arrays[f"fit_grad_{name}"] = g
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "vjp_golden.npz"), **arrays)
+    print({k: (v.shape, str(v.dtype)) for k, v in arrays.items()})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--calibrate", action="store_true")
+    ap.add_argument("--vjp", action="store_true")
     args = ap.parse_args()
     if args.calibrate:
         return calibrate()
+    if args.vjp:
+        return make_vjp_golden()
     torch.set_num_threads(os.cpu_count() or 1)
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     z = default_latent()

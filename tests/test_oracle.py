@@ -193,3 +193,26 @@ def test_latent_gradient_oracles_pin_each_other():
     up2 = (np.sign(diff) * (np.abs(y) < 0.1) / 400).astype(np.float32)
     g2, _ = oracle.decoder_vjp_latent_lowp(z, xyz, up2)
     assert np.array_equal(g, g2)
+
+
+def test_latent_gradient_golden_vectors():
+    """tests/golden/vjp_golden.npz (python -m oracle.make_golden --vjp) pins the gradient oracles: recomputed here they
+    match the committed vectors to CPU-BLAS summation order (fp64: 1e-9; lowp emulations: 2e-3 of |grad|_max - a
+    different sgemm blocking may flip a 16-bit rounding or two)."""
+    import os
+    import torch
+    from oracle.make_golden import GOLDEN_DIR, vjp_golden_inputs
+    gold = dict(np.load(os.path.join(GOLDEN_DIR, "vjp_golden.npz")))
+    xyz, up, target = vjp_golden_inputs()
+    assert np.array_equal(xyz, gold["xyz"]) and np.array_equal(up, gold["up"])
+    np.testing.assert_allclose(target, gold["target"], atol=2e-6, rtol=0)
+    z = oracle.default_latent(2)
+    g64, y64 = oracle.decoder_vjp_latent(z, xyz, up)
+    np.testing.assert_allclose(g64, gold["grad_fp64"], atol=1e-9 * np.abs(gold["grad_fp64"]).max(), rtol=0)
+    for name, lowp in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        g, y = oracle.decoder_vjp_latent_lowp(z, xyz, up, lowp=lowp)
+        scale = np.abs(gold[f"grad_{name}"]).max()
+        assert np.abs(g - gold[f"grad_{name}"]).max() < 2e-3 * scale
+        loss, gf = oracle.fit_loss_grad_lowp(z, xyz, gold["target"], clamp=0.1, lowp=lowp)
+        assert abs(loss - float(gold[f"fit_loss_{name}"])) < 2e-5
+        assert np.abs(gf - gold[f"fit_grad_{name}"]).max() < 2e-2 * np.abs(gold[f"fit_grad_{name}"]).max()
