@@ -102,3 +102,29 @@ def sample_latents_sharded(sampler, n: int, seed: int = 0, steps: int = 1000, pr
     dist.all_gather_into_tensor(full, pad, group=group)
     sizes = [batch_range(n, r, world) for r in range(world)]
     return torch.cat([full[r * per: r * per + (b - a)] for r, (a, b) in enumerate(sizes)])
+
+
+def fit_latents_sharded(decoder, xyz: torch.Tensor, sdf_target: torch.Tensor, group=None, gather: bool = False, **fit_kwargs):
+    """Auto-decoder fitting of a batch of shapes, shapes split across ranks: xyz [B,M,3],
+    sdf_target [B,M]; every rank fits its share with ``decoder.fit_latents_batch``.  Shapes are independent, so there is
+    no communication unless ``gather``.  Returns (i0, latents [i1-i0,256], losses [i1-i0]) or the gathered
+    (latents [B,256], losses [B])."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    B = xyz.shape[0]
+    i0, i1 = batch_range(B, rank, world)
+    if i1 > i0:
+        z, loss = decoder.fit_latents_batch(xyz[i0:i1], sdf_target[i0:i1], **fit_kwargs)
+    else:
+        z = torch.empty((0, 256), dtype=torch.float32, device=decoder.device)
+        loss = torch.empty((0,), dtype=torch.float32, device=decoder.device)
+    if not gather:
+        return i0, z, loss
+    per = -(-B // world)
+    pad = torch.zeros((per, 257), dtype=torch.float32, device=z.device)      # latent | loss
+    pad[: z.shape[0], :256] = z
+    pad[: z.shape[0], 256] = loss
+    full = torch.empty((world * per, 257), dtype=torch.float32, device=z.device)
+    dist.all_gather_into_tensor(full, pad, group=group)
+    sizes = [batch_range(B, r, world) for r in range(world)]
+    out = torch.cat([full[r * per: r * per + (b - a)] for r, (a, b) in enumerate(sizes)])
+    return out[:, :256].contiguous(), out[:, 256].contiguous()

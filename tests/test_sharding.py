@@ -65,6 +65,16 @@ class _OracleSampler:
         return torch.from_numpy(oracle.sample_latents(n, x_T, noise, steps=steps))
 
 
+class _StandInFitter:
+    """Stands in for pkg.Decoder.fit_latents_batch on CPU: a deterministic function of each shape's own samples."""
+    device = torch.device("cpu")
+
+    @staticmethod
+    def fit_latents_batch(xyz, sdf_target, **kw):
+        z = torch.stack([torch.full((256,), float(t.mean())) + x.sum() for x, t in zip(xyz, sdf_target)])
+        return z, sdf_target.abs().mean(dim=1)
+
+
 def _worker(rank, world, port, res, field, out_q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -81,6 +91,14 @@ def _worker(rank, world, port, res, field, out_q):
         full = pkg.sample_latents_sharded(_OracleSampler(), 5, seed=77, steps=3, gather=True)
         x_T, noise = oracle.philox_sampler_inputs(77, 5, 3)
         ok = ok and bool(np.array_equal(full.numpy(), oracle.sample_latents(5, x_T, noise, steps=3)))
+        # sharded fitting of 5 shapes: the gathered latents / losses equal one process fitting all of them
+        g = torch.Generator().manual_seed(3)
+        xyz, tgt = torch.rand((5, 7, 3), generator=g), torch.rand((5, 7), generator=g)
+        zs, ls = pkg.fit_latents_sharded(_StandInFitter(), xyz, tgt, gather=True)
+        z_all, l_all = _StandInFitter.fit_latents_batch(xyz, tgt)
+        ok = ok and bool(torch.equal(zs, z_all)) and bool(torch.equal(ls, l_all))
+        j0, zl, _ = pkg.fit_latents_sharded(_StandInFitter(), xyz, tgt)
+        ok = ok and j0 == i0 and bool(torch.equal(zl, z_all[i0:i1]))
         out_q.put((rank, ok, (i0, i1)))
     finally:
         dist.destroy_process_group()
