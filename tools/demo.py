@@ -2,7 +2,10 @@
 """End-to-end demo of the hot path on one GPU: sample latents with the fused DDPM kernel, decode one of them
 (or the synthetic default latent) on a res^3 grid, extract the zero level set and write it as a Wavefront OBJ.
 
-    python tools/demo.py [--res 128] [--out shape.obj] [--sampled] [--sparse]
+    python tools/demo.py [--res 128] [--out shape.obj] [--sampled] [--sparse] [--fit N]
+
+--fit N closes the loop: N SDF samples of the decoded shape are fitted by a FRESH latent (auto-decoder inference, one
+forward + backward launch of the fused kernel per Adam step) and the refitted shape is what gets meshed.
 
 Weights are seeded random-init (there are no checkpoints: the upstream repository has no code), so the
 default latent gives a blob-like surface and a *sampled* latent usually gives an empty or saturated field."""
@@ -31,6 +34,8 @@ def main():
     ap.add_argument("--out", default="shape.obj")
     ap.add_argument("--sampled", action="store_true", help="decode a latent drawn by the DDPM sampler instead of the synthetic one")
     ap.add_argument("--sparse", action="store_true", help="block-sparse extraction (decode only near the surface)")
+    ap.add_argument("--fit", type=int, default=0, metavar="N", help="refit the shape from N of its own SDF samples (tensor-pipe latent fitting)")
+    ap.add_argument("--fit-steps", type=int, default=400)
     args = ap.parse_args()
     pkg = load_package()
     dec = pkg.Decoder(pkg.synthetic.decoder_params())
@@ -41,6 +46,20 @@ def main():
         print(f"sampled 256 latents in {ddpm.last_kernel_ms():.1f} ms (kernel), {1e3 * (time.perf_counter() - t0):.1f} ms (call)")
     else:
         z = torch.from_numpy(pkg.synthetic.latent(0)).cuda()
+    if args.fit > 0:
+        g = torch.Generator(device="cuda").manual_seed(0)
+        pts = torch.rand((args.fit, 3), generator=g, device="cuda") * 2 - 1
+        tgt = dec(z, pts, precision="fp32")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        z_fit, loss = dec.fit_latent(pts, tgt, steps=args.fit_steps, lr=1e-2, reg=0.0, precision="bf16")
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        held = torch.rand((20000, 3), generator=g, device="cuda") * 2 - 1
+        err = float((torch.clamp(dec(z_fit, held, precision="fp32"), -0.1, 0.1) - torch.clamp(dec(z, held, precision="fp32"), -0.1, 0.1)).abs().mean())
+        print(f"refitted a fresh latent to {args.fit} SDF samples: {args.fit_steps} Adam steps in {1e3 * dt:.1f} ms "
+              f"({1e3 * dt / args.fit_steps:.3f} ms/step), train loss {loss:.5f}, held-out clamped-L1 {err:.5f}")
+        z = z_fit
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     if args.sparse:
