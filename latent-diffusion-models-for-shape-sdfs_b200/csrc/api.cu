@@ -621,12 +621,11 @@ int vjp_tc(sdfb_decoder* d, const float* latent_dev, const float* xyz_dev, int64
     if (loss_dev != nullptr) CU_TRY(cudaMemsetAsync(loss_dev, 0, sizeof(float), st));
     return SDFB_OK;
   }
-  if (d->bw_masks == nullptr) {
-    CU_TRY(cudaMalloc(&d->bw_masks, static_cast<size_t>(d->num_sms) * 8 * 16 * kTileM * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&d->bw_colsum, static_cast<size_t>(d->num_sms) * 4 * 1024 * sizeof(float)));
-    CU_TRY(cudaMalloc(&d->bw_amax, sizeof(unsigned int)));
-    CU_TRY(cudaMalloc(&d->bw_loss, static_cast<size_t>(d->num_sms) * 4 * sizeof(float)));
-  }
+  // workspaces: allocated on first use, kept (each checked on its own: a failed allocation is retried by the next call)
+  if (d->bw_masks == nullptr) CU_TRY(cudaMalloc(&d->bw_masks, static_cast<size_t>(d->num_sms) * 8 * 16 * kTileM * sizeof(uint32_t)));
+  if (d->bw_colsum == nullptr) CU_TRY(cudaMalloc(&d->bw_colsum, static_cast<size_t>(d->num_sms) * 4 * 1024 * sizeof(float)));
+  if (d->bw_amax == nullptr) CU_TRY(cudaMalloc(&d->bw_amax, sizeof(unsigned int)));
+  if (d->bw_loss == nullptr) CU_TRY(cudaMalloc(&d->bw_loss, static_cast<size_t>(d->num_sms) * 4 * sizeof(float)));
   const bool loss_mode = target_dev != nullptr;
   if (!loss_mode) CU_TRY(launch_abs_max(dLdy_dev, M, d->bw_amax, st));
   const bool fp16 = precision == SDFB_PREC_FP16;
