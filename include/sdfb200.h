@@ -18,7 +18,15 @@
  *    unless the name ends in _host.
  *  - a context belongs to one device; calls on one context must be issued
  *    from one thread at a time and on one stream at a time (the per-latent
- *    constant block lives in the context).
+ *    constant block lives in the context).  The *_host calls run on streams
+ *    the context owns; they order themselves after every device-path call
+ *    issued on the context before them, and they return synchronised.
+ *  - asynchronous calls return before their kernels run.  A kernel whose
+ *    watchdog trips (a wait bounded by a wall-clock timeout) leaves invalid
+ *    outputs and records the failure in the context: the NEXT call on that
+ *    context - or sdfb_decoder_check / sdfb_ddpm_check, which synchronise the
+ *    stream first - returns SDFB_E_KERNEL once and clears it.  Results of an
+ *    asynchronous call are valid once a later call or *_check has returned 0.
  *  - no CPU fallback exists: without a CUDA device of compute capability
  *    10.x the create calls fail with SDFB_E_DEVICE.
  */
@@ -53,6 +61,7 @@ extern "C" {
 
 typedef struct sdfb_decoder sdfb_decoder;
 typedef struct sdfb_ddpm sdfb_ddpm;
+typedef struct sdfb_comm sdfb_comm;
 
 int sdfb_version(void);
 const char* sdfb_last_error(void);
@@ -171,6 +180,11 @@ int sdfb_mc_blocks_count(const float* fields_dev, const int32_t* block_ids_dev, 
 int sdfb_mc_blocks_generate(const float* fields_dev, const int32_t* block_ids_dev, int64_t n_blocks, int res, int block,
                             const void* workspace_dev, float* triangles_dev, int64_t* edge_keys_dev, void* stream);
 
+/* Synchronises `stream` and reports (once) a watchdog trip of any launch made on this context. */
+int sdfb_decoder_check(sdfb_decoder* dec, void* stream);
+/* Per-wait timeout of the in-kernel watchdog (default 2 s).  Test hook: a few nanoseconds make the next launch fail. */
+int sdfb_decoder_set_timeout_ns(sdfb_decoder* dec, uint64_t timeout_ns);
+
 /* Debug/diagnostic: pre-activation (accumulator + bias, before ReLU) of
  * tensor-core pass `pass` (0..12) for the first 128 queries of a grid decode,
  * 128 x 256 floats.  Used by the parity tests to localise a failing layer. */
@@ -220,6 +234,38 @@ int sdfb_philox_normal(uint64_t seed, int64_t first_latent, int n, int t0, int t
 /* Elapsed device time (ms) of the last fused (bf16/fp16) sampler launch on this context, CUDA
  * events on the launching stream; blocks until it has finished and reports a tripped watchdog. */
 int sdfb_ddpm_last_kernel_ms(sdfb_ddpm* ddpm, float* ms);
+
+int sdfb_ddpm_check(sdfb_ddpm* ddpm, void* stream);
+int sdfb_ddpm_set_timeout_ns(sdfb_ddpm* ddpm, uint64_t timeout_ns);
+
+/* ---- multi-GPU (SURVEY.md 8b row sdf_allgather_slabs, 8e): one process per GPU of one node -------------------
+ * The path shards with no data-path collective (queries are independent); what is left is assembling the slabs of
+ * BASELINE configs[4] on every rank.  A communicator wraps NCCL (resolved at run time: the libnccl.so.2 already in
+ * the process, else the system's) and, for the overlapped path, a symmetric device buffer mapped into every rank
+ * through CUDA IPC.
+ *   sdfb_comm_unique_id : rank 0 fills a 128-byte id and hands it to the others by any means (MPI, a file, torch.distributed)
+ *   sdfb_comm_create    : collective; ncclCommInitRank under the hood
+ *   sdfb_comm_wrap      : use an existing ncclComm_t instead (not destroyed with the context) */
+int sdfb_comm_unique_id(void* id_out /* 128 bytes */);
+int sdfb_comm_create(const void* id, int world, int rank, int device, sdfb_comm** out);
+int sdfb_comm_wrap(void* nccl_comm, int world, int rank, int device, sdfb_comm** out);
+int sdfb_comm_destroy(sdfb_comm* comm);
+int sdfb_comm_barrier(sdfb_comm* comm, void* stream);
+/* In-place all-gather of equal-sized slabs: rank r's bytes_per_rank bytes sit at full_dev + r * bytes_per_rank
+ * (ncclAllGather with sendbuff inside recvbuff); asynchronous on `stream`. */
+int sdfb_allgather_slabs(sdfb_comm* comm, void* full_dev, size_t bytes_per_rank, void* stream);
+/* BASELINE configs[4] in one call per rank: rank r decodes planes [r per, min((r+1) per, res)), per = ceil(res/world),
+ * in sub-slabs of `sub_planes` planes (0 = automatic) into a symmetric buffer owned by `comm`, and pushes every
+ * finished sub-slab into all peers' copies with the copy engines over NVLink while the next one is being decoded;
+ * a rank barrier opens and closes the call.  On return (in `stream` order) *sdf_full_dev is the whole [res][res][res]
+ * field on every rank.  want_mask: the sign-change mask, packed, as `world` blocks of *mask_words_per_rank words;
+ * block r holds rank r's cell layers [r per, min((r+1) per, res-1)) from bit 0 (cell c of the block -> bit c & 31
+ * of word c >> 5); the halo plane a block needs is decoded locally.  When per * (res-1)^2 is a multiple of 32 the
+ * blocks concatenate to the global packing of sdfb_decode_grid_bits.  The buffers stay valid until the next sharded
+ * decode on this communicator.  First use (and growth) allocates and exchanges the buffer: collective, synchronising. */
+int sdfb_decode_grid_sharded(sdfb_decoder* dec, sdfb_comm* comm, const float* latent_dev, int res, int want_mask,
+                             int sub_planes, int precision, float** sdf_full_dev, uint32_t** mask_bits_dev,
+                             size_t* mask_words_per_rank, void* stream);
 
 /* ---- unit-test hook for the UMMA plumbing -------------------------------- */
 /* D[128][256] (fp32) = A[128][64] * B[256][64]^T with A and B given as

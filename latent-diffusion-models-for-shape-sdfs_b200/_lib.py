@@ -48,6 +48,17 @@ SIGNATURES = {
     "sdfb_mc_blocks_generate": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     "sdfb_decode_debug_pass": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
     "sdfb_decoder_last_kernel_ms": (_i, [_vp, C.POINTER(C.c_float)]),
+    "sdfb_decoder_check": (_i, [_vp, _vp]),
+    "sdfb_decoder_set_timeout_ns": (_i, [_vp, C.c_uint64]),
+    "sdfb_ddpm_check": (_i, [_vp, _vp]),
+    "sdfb_ddpm_set_timeout_ns": (_i, [_vp, C.c_uint64]),
+    "sdfb_comm_unique_id": (_i, [_vp]),
+    "sdfb_comm_create": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "sdfb_comm_wrap": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
+    "sdfb_comm_destroy": (_i, [_vp]),
+    "sdfb_comm_barrier": (_i, [_vp, _vp]),
+    "sdfb_allgather_slabs": (_i, [_vp, _vp, _sz, _vp]),
+    "sdfb_decode_grid_sharded": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_sz), _vp]),
     "sdfb_ddpm_create": (_i, [_vp, _sz, _i, C.POINTER(_vp)]),
     "sdfb_ddpm_destroy": (_i, [_vp]),
     "sdfb_ddpm_sample": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

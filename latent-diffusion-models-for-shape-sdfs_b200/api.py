@@ -15,6 +15,9 @@ from ._lib import PRECISIONS, check
 
 LATENT = 256
 DDPM_STEPS = 1000
+# The DDPM works on latents normalised to unit scale; a decoder latent is a sample times this (the N(0, 1/16^2) code scale
+# of the auto-decoder, oracle/ddpm.py DDPM_LATENT_SCALE).  Unscaled samples (|x| up to 1 per component) saturate the decoder.
+DDPM_LATENT_SCALE = 1.0 / 16.0
 
 
 def _flat_params(params, expect: int) -> np.ndarray:
@@ -137,6 +140,9 @@ class Decoder:
         m = None
         if mask:
             m = torch.empty((max(layers, 0), res - 1, res - 1), dtype=torch.uint8, device=self.device)
+        if z1 == z0:            # an empty slab (tail rank of an uneven split): empty results, nothing launched
+            sdf = buf.view(-1)[:0].view(0, res, res)
+            return (sdf, m) if mask else sdf
         check(self._lib.sdfb_decode_grid(self._h, lat.data_ptr(), res, z0, z1, buf.data_ptr(),
                                          m.data_ptr() if (m is not None and m.numel()) else None, prec,
                                          _stream_ptr(self.device.index)))
@@ -234,6 +240,7 @@ class Decoder:
                 loss_z = z                    # the loss reported belongs to the latent it was evaluated at
                 z = z_new
             loss = float(loss_t[0] + reg * (loss_z * loss_z).sum()) if loss_t is not None else float("nan")
+            self.check()
             return z, loss
         ones = torch.ones(M, device=self.device)
         loss = float("nan")
@@ -283,11 +290,19 @@ class Decoder:
             z = z - lr * (m / (1 - 0.9 ** it)) / ((v / (1 - 0.999 ** it)).sqrt() + 1e-8)
         return z, loss
 
+    def fit_latents_batch_checked(self, *a, **kw):
+        """``fit_latents_batch`` followed by ``check()`` (one synchronisation at the end)."""
+        out = self.fit_latents_batch(*a, **kw)
+        self.check()
+        return out
+
     def extract_surface(self, latent, res: int, precision: str | None = None, indexed: bool = False):
         """decode_grid + marching cubes: triangles [n,3,3] of the zero level set on the res^3 grid
         (the decoder's own sign bit-planes classify the cells); ``indexed=True``: (vertices, faces)."""
         sdf, signs, _ = self.decode_grid_bits(latent, res, mask=False, precision=precision)
-        return extract_surface(sdf, res, 0, sign_words=signs, indexed=indexed)
+        out = extract_surface(sdf, res, 0, sign_words=signs, indexed=indexed)
+        self.check()            # the triangle count already synchronised the stream: this only reads the status word
+        return out
 
     def extract_surface_sparse(self, latent, res: int, block: int = 8, lipschitz: float | None = None,
                                precision: str | None = None, return_stats: bool = False, indexed: bool = False):
@@ -336,6 +351,7 @@ class Decoder:
                 if ntri.value:
                     check(lib.sdfb_mc_blocks_generate(fields.data_ptr(), ids.data_ptr(), n, res, block, ws2.data_ptr(),
                                                       tris.data_ptr(), keys.data_ptr() if indexed else None, st))
+        self.check()                # the counts above already synchronised the stream
         if indexed:
             tris = weld(tris, keys)
         if return_stats:
@@ -392,6 +408,16 @@ class Decoder:
         check(self._lib.sdfb_decode_points_host(self._h, lat.ctypes.data, pts.ctypes.data, pts.shape[0],
                                                 out.ctypes.data, prec))
         return out
+
+    # ---- status ----------------------------------------------------------------------------
+    def check(self) -> None:
+        """Waits for the current stream and raises SdfbError if the in-kernel watchdog of any launch made through this
+        object tripped (its outputs are then invalid).  The device-path calls are asynchronous: they cannot report their
+        own launch, only an earlier one - every call first looks at a host-visible status word the kernels write."""
+        check(self._lib.sdfb_decoder_check(self._h, _stream_ptr(self.device.index)))
+
+    def set_watchdog_timeout_ns(self, ns: int) -> None:
+        check(self._lib.sdfb_decoder_set_timeout_ns(self._h, int(ns)))
 
     # ---- diagnostics -----------------------------------------------------------------------
     def debug_pass(self, latent, res: int, pass_index: int, precision: str | None = None) -> torch.Tensor:
@@ -480,6 +506,13 @@ class LatentDDPM:
             self.last_kernel_ms()       # waits for the persistent kernel and raises if its watchdog tripped
         return x
 
+    def check(self) -> None:
+        """Waits for the current stream; raises SdfbError if the fused sampler's watchdog tripped."""
+        check(self._lib.sdfb_ddpm_check(self._h, _stream_ptr(self.device.index)))
+
+    def set_watchdog_timeout_ns(self, ns: int) -> None:
+        check(self._lib.sdfb_ddpm_set_timeout_ns(self._h, int(ns)))
+
     def last_kernel_ms(self) -> float:
         """Device time of the last fused (bf16/fp16) sampler launch; raises SdfbError on a tripped watchdog."""
         ms = C.c_float()
@@ -507,6 +540,96 @@ class LatentDDPM:
             raise ValueError("expected x_T [n,256] and noise [steps,n,256]")
         check(self._lib.sdfb_ddpm_sample_host(self._h, x.ctypes.data, nz.ctypes.data, n, steps, prec))
         return x
+
+
+class _DevArray:
+    """A device pointer owned by the C library, seen by torch without a copy (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class Comm:
+    """Ranks of one node, one process per GPU: wraps ``sdfb_comm`` - NCCL for the barrier and the
+    in-place slab all-gather, and a symmetric device buffer mapped into every rank through CUDA IPC into which finished
+    sub-slabs are pushed by the copy engines while the decoder kernel keeps all SMs.  Bootstrapped over an initialised
+    ``torch.distributed`` group (only to hand rank 0's NCCL id to the others)."""
+
+    def __init__(self, device="cuda:0", group=None):
+        import torch.distributed as dist
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", _device_index(device))
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        ident = np.zeros(128, np.uint8)
+        if self.rank == 0 and self.world > 1:
+            check(self._lib.sdfb_comm_unique_id(ident.ctypes.data))
+        if self.world > 1:
+            t = torch.from_numpy(ident)
+            if dist.get_backend(group) == "nccl":
+                t = t.to(self.device)
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            dist.broadcast(t, src=src, group=group)
+            ident = t.cpu().numpy().copy()
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self._lib.sdfb_comm_create(ident.ctypes.data, self.world, self.rank, self.device.index, C.byref(handle)))
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sdfb_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def barrier(self) -> None:
+        check(self._lib.sdfb_comm_barrier(self._h, _stream_ptr(self.device.index)))
+
+    def allgather_slabs(self, full: torch.Tensor) -> torch.Tensor:
+        """In-place NCCL all-gather: ``full`` is split into ``world`` equal leading blocks, rank r's is already filled."""
+        if not full.is_contiguous() or full.device != self.device or full.shape[0] % self.world:
+            raise ValueError("full must be a contiguous CUDA tensor whose leading size is a multiple of the world size")
+        per = full.numel() * full.element_size() // self.world
+        check(self._lib.sdfb_allgather_slabs(self._h, full.data_ptr(), per, _stream_ptr(self.device.index)))
+        return full
+
+    def decode_grid_sharded(self, decoder: "Decoder", latent, res: int, mask: bool = False, precision: str | None = None,
+                            sub_planes: int = 0):
+        """BASELINE configs[4]: (sdf [res,res,res], mask_words int32 [world, words_per_rank] or None).  Both are views of
+        the communicator's symmetric buffer: valid until the next sharded decode on it.  See ``sdfb_decode_grid_sharded``
+        (include/sdfb200.h) for the block layout of the packed mask and ``unpack_mask_blocks`` for the uint8 form."""
+        prec = _prec(precision or decoder.precision)
+        lat = _as_dev_f32(latent, self.device, (LATENT,))
+        sdf_p, mask_p, words = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        check(self._lib.sdfb_decode_grid_sharded(decoder._h, self._h, lat.data_ptr(), res, 1 if mask else 0, int(sub_planes), prec,
+                                                 C.byref(sdf_p), C.byref(mask_p), C.byref(words), _stream_ptr(self.device.index)))
+        sdf = torch.as_tensor(_DevArray(sdf_p.value, (res, res, res), "<f4"), device=self.device)
+        mw = None
+        if mask:
+            mw = torch.as_tensor(_DevArray(mask_p.value, (self.world, words.value), "<i4"), device=self.device)
+        return sdf, mw
+
+
+def unpack_mask_blocks(mask_words: torch.Tensor, res: int) -> torch.Tensor:
+    """[world, words_per_rank] packed mask blocks of ``Comm.decode_grid_sharded`` -> uint8 [(res-1)^3] cell mask."""
+    world = mask_words.shape[0]
+    per = -(-res // world)
+    cells = (res - 1) * (res - 1)
+    shifts = torch.arange(32, device=mask_words.device, dtype=torch.int32)
+    out = []
+    for r in range(world):
+        z0 = min(r * per, res)
+        layers = max(min(z0 + per, res - 1) - z0, 0)
+        if layers == 0:
+            continue
+        nw = (layers * cells + 31) // 32
+        bits = ((mask_words[r, :nw].unsqueeze(1) >> shifts) & 1).to(torch.uint8).reshape(-1)[: layers * cells]
+        out.append(bits.view(layers, res - 1, res - 1))
+    return torch.cat(out) if out else torch.empty((0, res - 1, res - 1), dtype=torch.uint8, device=mask_words.device)
 
 
 # ---- functional spellings named in the north star ---------------------------------------------

@@ -13,6 +13,7 @@
 #include <cuda_fp16.h>
 
 #include "../../include/sdfb200.h"
+#include "comm.h"
 #include "kernels.h"
 
 using namespace sdfb;
@@ -28,6 +29,21 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+}  // namespace
+
+namespace sdfb {
+// the same thread-local message for the other translation units of the library (comm.cu)
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+}  // namespace sdfb
+
+namespace {
 
 #define CU_TRY(expr)                                                                         \
   do {                                                                                       \
@@ -169,6 +185,10 @@ struct sdfb_decoder {
   float* bias0f = nullptr;       // fp32 path folded biases
   float* bias4f = nullptr;
   unsigned int* status = nullptr;
+  unsigned int* status_host = nullptr;       // mirror of `status` in mapped pinned host memory (kernels store a trip there too)
+  unsigned int* status_host_dev = nullptr;   // its device-side address
+  cudaEvent_t ev_user = nullptr;             // end of the last device-path call: the *_host calls order their own streams after it
+  bool user_pending = false;
   unsigned int* signs = nullptr; long long sign_words = 0;   // sign bit-planes of the last masked decode (lazy)
   unsigned int* rowmask = nullptr; size_t rowmask_words = 0; // row-aligned packed mask scratch (lazy)
   // backward workspace (lazy): stored activations of one chunk, two delta buffers, column-sum partials
@@ -214,6 +234,8 @@ struct sdfb_ddpm {
   DdpmLane lane[2];                           // workspaces of the (at most two) concurrent launches of a call
   cudaStream_t st_b = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   unsigned int* status = nullptr;
+  unsigned int* status_host = nullptr;       // mirror of `status` in mapped pinned host memory
+  unsigned int* status_host_dev = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   unsigned long long timeout_ns = 4000000000ull;
@@ -285,6 +307,7 @@ int decode_tc(sdfb_decoder* d, const float* z, const float* xyz, int res, long l
   p.q0 = q0;
   p.res = res;
   p.status = d->status;
+  p.status_host = d->status_host_dev;
   p.dump = dump;
   p.dump_pass = dump_pass;
   p.timeout_ns = d->timeout_ns;
@@ -338,8 +361,37 @@ int kernel_status(sdfb_decoder* d) {
   CU_TRY(cudaMemcpy(&s, d->status, sizeof(s), cudaMemcpyDeviceToHost));
   if (s != 0) {
     cudaMemset(d->status, 0, sizeof(unsigned int));
+    if (d->status_host) *reinterpret_cast<volatile unsigned int*>(d->status_host) = 0;
     return fail(SDFB_E_KERNEL, "fused decoder watchdog tripped at wait site 0x%x", s);
   }
+  return SDFB_OK;
+}
+
+// Asynchronous entry points cannot know how their own launch will end, but they can refuse to build on a launch that
+// already failed: a kernel whose watchdog trips also stores the code in mapped host memory, which every entry point
+// looks at first (no synchronisation).  The error is reported once and cleared.
+int pending_status(sdfb_decoder* d) {
+  if (d->status_host == nullptr) return SDFB_OK;
+  const unsigned int s = *reinterpret_cast<volatile unsigned int*>(d->status_host);
+  if (s == 0) return SDFB_OK;
+  *reinterpret_cast<volatile unsigned int*>(d->status_host) = 0;
+  cudaMemset(d->status, 0, sizeof(unsigned int));
+  return fail(SDFB_E_KERNEL, "an earlier launch on this context tripped the kernel watchdog at wait site 0x%x: its outputs are invalid", s);
+}
+
+// End of a device-path call: remember where the caller's stream stands, so that a later *_host call (which runs on the
+// context's own streams and rewrites the per-latent constants) starts after it.
+int mark_user(sdfb_decoder* d, cudaStream_t st) {
+  CU_TRY(cudaEventRecord(d->ev_user, st));
+  d->user_pending = true;
+  return SDFB_OK;
+}
+struct UserMark {          // records the end of a device-path call on every return path
+  sdfb_decoder* d; cudaStream_t st;
+  ~UserMark() { if (cudaEventRecord(d->ev_user, st) == cudaSuccess) d->user_pending = true; }
+};
+int order_after_user(sdfb_decoder* d, cudaStream_t st) {
+  if (d->user_pending) CU_TRY(cudaStreamWaitEvent(st, d->ev_user, 0));
   return SDFB_OK;
 }
 
@@ -432,9 +484,13 @@ int sdfb_decoder_create(const float* params_host, size_t n_floats, int device, s
   CU_TRY_D(cudaMalloc(&d->bias4f, 512 * sizeof(float)));
   CU_TRY_D(cudaMalloc(&d->status, sizeof(unsigned int)));
   CU_TRY_D(cudaMemset(d->status, 0, sizeof(unsigned int)));
+  CU_TRY_D(cudaHostAlloc(reinterpret_cast<void**>(&d->status_host), sizeof(unsigned int), cudaHostAllocMapped));
+  *d->status_host = 0;
+  CU_TRY_D(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d->status_host_dev), d->status_host, 0));
+  CU_TRY_D(cudaEventCreateWithFlags(&d->ev_user, cudaEventDisableTiming));
   if (want_prof) {
-    CU_TRY_D(cudaMalloc(&d->prof, static_cast<size_t>(sms) * 3 * 8 * sizeof(long long)));
-    CU_TRY_D(cudaMemset(d->prof, 0, static_cast<size_t>(sms) * 3 * 8 * sizeof(long long)));
+    CU_TRY_D(cudaMalloc(&d->prof, (static_cast<size_t>(sms) * 24 + 128) * sizeof(long long)));   // + a 4 x 32 event trace
+    CU_TRY_D(cudaMemset(d->prof, 0, (static_cast<size_t>(sms) * 24 + 128) * sizeof(long long)));
   }
   CU_TRY_D(cudaEventCreate(&d->ev0));
   CU_TRY_D(cudaEventCreate(&d->ev1));
@@ -454,6 +510,8 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
   cudaDeviceSynchronize();
   cudaFree(d->params); cudaFree(d->w4s); cudaFree(d->wstream[0]); cudaFree(d->wstream[1]);
   cudaFree(d->consts); cudaFree(d->bias0f); cudaFree(d->bias4f); cudaFree(d->status);
+  if (d->status_host) cudaFreeHost(d->status_host);
+  if (d->ev_user) cudaEventDestroy(d->ev_user);
   cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x); cudaFree(d->prof); cudaFree(d->signs); cudaFree(d->rowmask);
   for (float* a : d->bw_act) cudaFree(a);
   cudaFree(d->bw_d0); cudaFree(d->bw_d1); cudaFree(d->bw_y); cudaFree(d->bw_partial);
@@ -473,10 +531,14 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
 
 int sdfb_decode_grid(sdfb_decoder* d, const float* latent_dev, int res, int z0, int z1, float* sdf_dev,
                      uint8_t* mask_dev, int precision, void* stream) {
-  if (!d || !latent_dev || !sdf_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (!d || !latent_dev) return fail(SDFB_E_INVALID, "null argument");
   if (res < 2 || res > 2048) return fail(SDFB_E_INVALID, "res %d outside [2, 2048]", res);
   if (z0 < 0 || z1 > res || z0 > z1) return fail(SDFB_E_INVALID, "bad plane range [%d, %d) for res %d", z0, z1, res);
+  if (z0 == z1) return SDFB_OK;                      // an empty slab (the tail ranks of an uneven split): nothing to do
+  if (!sdf_dev) return fail(SDFB_E_INVALID, "null argument");
   DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  UserMark um{d, static_cast<cudaStream_t>(stream)};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long plane = static_cast<long long>(res) * res;
   int zend = z1;
@@ -497,10 +559,14 @@ int sdfb_decode_grid(sdfb_decoder* d, const float* latent_dev, int res, int z0, 
 
 int sdfb_decode_grid_bits(sdfb_decoder* d, const float* latent_dev, int res, int z0, int z1, float* sdf_dev,
                           uint32_t* sign_bits_dev, uint32_t* mask_bits_dev, int precision, void* stream) {
-  if (!d || !latent_dev || !sdf_dev || !sign_bits_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (!d || !latent_dev) return fail(SDFB_E_INVALID, "null argument");
   if (res < 2 || res > 2048) return fail(SDFB_E_INVALID, "res %d outside [2, 2048]", res);
   if (z0 < 0 || z1 > res || z0 > z1) return fail(SDFB_E_INVALID, "bad plane range [%d, %d) for res %d", z0, z1, res);
+  if (z0 == z1) return SDFB_OK;                      // an empty slab: nothing to do
+  if (!sdf_dev || !sign_bits_dev) return fail(SDFB_E_INVALID, "null argument");
   DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  UserMark um{d, static_cast<cudaStream_t>(stream)};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long plane = static_cast<long long>(res) * res;
   int zend = z1;
@@ -524,6 +590,8 @@ int sdfb_decode_grid_batch(sdfb_decoder* d, const float* latents_dev, int batch,
   if (!d || (batch > 0 && (!latents_dev || !sdf_dev))) return fail(SDFB_E_INVALID, "null argument");
   if (batch < 0 || res < 2 || res > 2048) return fail(SDFB_E_INVALID, "bad batch or res");
   DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  UserMark um{d, static_cast<cudaStream_t>(stream)};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long M = static_cast<long long>(res) * res * res;
   for (int b = 0; b < batch; ++b) {   // shapes are independent: one fold + one persistent launch each, back to back on the stream
@@ -538,6 +606,8 @@ int sdfb_decode_points(sdfb_decoder* d, const float* latent_dev, const float* xy
   if (!d || !latent_dev || (M > 0 && (!xyz_dev || !sdf_dev))) return fail(SDFB_E_INVALID, "null argument");
   if (M < 0) return fail(SDFB_E_INVALID, "negative point count");
   DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  UserMark um{d, static_cast<cudaStream_t>(stream)};
   return decode_any(d, latent_dev, xyz_dev, 0, 0, M, sdf_dev, precision, static_cast<cudaStream_t>(stream));
 }
 
@@ -548,6 +618,8 @@ int sdfb_decoder_vjp_latent(sdfb_decoder* d, const float* latent_dev, const floa
   if (!d || !latent_dev || !grad_latent_dev || (M > 0 && (!xyz_dev || !dLdy_dev))) return fail(SDFB_E_INVALID, "null argument");
   if (M < 0) return fail(SDFB_E_INVALID, "negative point count");
   DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  UserMark um{d, static_cast<cudaStream_t>(stream)};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (M == 0) { CU_TRY(cudaMemsetAsync(grad_latent_dev, 0, kLatent * sizeof(float), st)); return SDFB_OK; }
   constexpr long long kChunkRows = 8192;
@@ -639,6 +711,7 @@ int vjp_tc(sdfb_decoder* d, const float* latent_dev, const float* xyz_dev, int64
   p.out = sdf_dev;
   p.M = M;
   p.status = d->status;
+  p.status_host = d->status_host_dev;
   p.dump_pass = -1;
   p.timeout_ns = d->timeout_ns;
   p.debug_flags = d->debug_flags;
@@ -669,6 +742,8 @@ int sdfb_decoder_vjp_latent_tc(sdfb_decoder* d, const float* latent_dev, const f
   if (!d || !latent_dev || !grad_latent_dev || (M > 0 && (!xyz_dev || !dLdy_dev))) return fail(SDFB_E_INVALID, "null argument");
   if (M < 0) return fail(SDFB_E_INVALID, "negative point count");
   DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  UserMark um{d, static_cast<cudaStream_t>(stream)};
   return vjp_tc(d, latent_dev, xyz_dev, M, dLdy_dev, nullptr, 0.f, grad_latent_dev, nullptr, sdf_dev, precision,
                 static_cast<cudaStream_t>(stream));
 }
@@ -683,6 +758,8 @@ int sdfb_decoder_fit_loss_grad(sdfb_decoder* d, const float* latent_dev, const f
   if (M < 0) return fail(SDFB_E_INVALID, "negative point count");
   if (!(clamp_dist > 0.f)) return fail(SDFB_E_INVALID, "clamp distance must be positive");
   DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  UserMark um{d, static_cast<cudaStream_t>(stream)};
   return vjp_tc(d, latent_dev, xyz_dev, M, nullptr, target_dev, clamp_dist, grad_latent_dev, loss_dev, sdf_dev, precision,
                 static_cast<cudaStream_t>(stream));
 }
@@ -697,6 +774,8 @@ int sdfb_decoder_fit_loss_grad_batch(sdfb_decoder* d, const float* latents_dev, 
   if (batch > 0 && points_per_shape > 0 && (!xyz_dev || !target_dev)) return fail(SDFB_E_INVALID, "null argument");
   if (!(clamp_dist > 0.f)) return fail(SDFB_E_INVALID, "clamp distance must be positive");
   DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  UserMark um{d, static_cast<cudaStream_t>(stream)};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int b = 0; b < batch; ++b) {
     const long long o = static_cast<long long>(b) * points_per_shape;
@@ -707,11 +786,84 @@ int sdfb_decoder_fit_loss_grad_batch(sdfb_decoder* d, const float* latents_dev, 
   return SDFB_OK;
 }
 
+// BASELINE configs[4] as one call per rank: rank r of `comm` decodes planes
+// [r per, min((r + 1) per, res)), per = ceil(res / world), straight into its block of the symmetric buffer, in
+// sub-slabs; each finished sub-slab is PUSHED into the same place of every peer's copy by the copy engines while the
+// next one is being decoded (comm.cu).  The mask's halo plane is recomputed locally; the packed mask of the rank's
+// cell layers is pushed last.  A barrier at the start keeps a rank from overwriting results a slower rank is still
+// reading from the previous call (everything the caller queued on `stream` before this call is ordered before it), a
+// barrier at the end makes the whole grid valid on every rank in stream order.
+int sdfb_decode_grid_sharded(sdfb_decoder* d, sdfb_comm* c, const float* latent_dev, int res, int want_mask, int sub_planes,
+                             int precision, float** sdf_full_dev, uint32_t** mask_bits_dev, size_t* mask_words_per_rank,
+                             void* stream) {
+  if (!d || !c || !latent_dev || !sdf_full_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 2 || res > 2048) return fail(SDFB_E_INVALID, "res %d outside [2, 2048]", res);
+  if (want_mask && (!mask_bits_dev || !mask_words_per_rank)) return fail(SDFB_E_INVALID, "null argument");
+  if (c->device != d->device) return fail(SDFB_E_INVALID, "decoder on device %d, communicator on device %d", d->device, c->device);
+  DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  UserMark um{d, static_cast<cudaStream_t>(stream)};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long plane = static_cast<long long>(res) * res;
+  const int per = (res + c->world - 1) / c->world;
+  const int z0 = c->rank * per < res ? c->rank * per : res;
+  const int z1 = z0 + per < res ? z0 + per : res;
+  const long long cells_layer = static_cast<long long>(res - 1) * (res - 1);
+  const size_t words = static_cast<size_t>((per * cells_layer + 31) >> 5);
+  const size_t off_mask = (static_cast<size_t>(plane) * res * sizeof(float) + 255) / 256 * 256;
+  const size_t total = off_mask + (want_mask ? words * c->world * sizeof(uint32_t) : 0);
+  int rc = comm_shared_alloc(c, total);            // collective on first use / growth
+  if (rc) return rc;
+  float* full = static_cast<float*>(c->local);
+  uint32_t* mbits = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->local) + off_mask);
+  *sdf_full_dev = full;
+  if (want_mask) { *mask_bits_dev = mbits; *mask_words_per_rank = words; }
+  rc = comm_barrier(c, st);
+  if (rc) return rc;
+  if (z1 > z0) {
+    const bool halo = want_mask && z1 < res;
+    const int planes = z1 - z0 + (halo ? 1 : 0);
+    const int layers = (halo ? z1 : (z1 < res - 1 ? z1 : res - 1)) - z0;
+    long long sub = sub_planes > 0 ? sub_planes : (2097152 + plane - 1) / plane;     // >= 2^21 queries per launch
+    if (sub * 16 < planes) sub = (planes + 15) / 16;
+    if (want_mask) {                               // sign words of a sub-slab must start on a word boundary
+      long long unit = 1;
+      while ((unit * plane) % 32 != 0) unit *= 2;
+      sub = (sub + unit - 1) / unit * unit;
+      rc = ensure_signs(d, (planes * plane + 31) >> 5, st);
+      if (rc == SDFB_OK && planes >= 2) rc = ensure_rowmask(d, mask_rows_words(planes, res, res));
+      if (rc) return rc;
+    }
+    for (long long za = 0; za < z1 - z0; za += sub) {
+      long long zb = za + sub < z1 - z0 ? za + sub : z1 - z0;
+      const long long zpush = zb;
+      if (zb == z1 - z0 && halo) zb += 1;          // the halo plane rides with the last sub-slab (it is not pushed)
+      rc = decode_any(d, latent_dev, nullptr, res, (z0 + za) * plane, (zb - za) * plane, full + (z0 + za) * plane, precision, st,
+                      want_mask ? d->signs + ((za * plane) >> 5) : nullptr);
+      if (rc) return rc;
+      rc = comm_push(c, static_cast<size_t>((z0 + za) * plane) * sizeof(float), static_cast<size_t>((zpush - za) * plane) * sizeof(float), st);
+      if (rc) return rc;
+    }
+    if (want_mask && layers > 0) {
+      uint32_t* mine = mbits + static_cast<size_t>(c->rank) * words;
+      CU_TRY(launch_mask_from_bits(d->signs, planes, res, res, nullptr, mine, d->rowmask, st));
+      rc = comm_push(c, off_mask + static_cast<size_t>(c->rank) * words * sizeof(uint32_t),
+                     static_cast<size_t>((layers * cells_layer + 31) >> 5) * sizeof(uint32_t), st);
+      if (rc) return rc;
+    }
+  }
+  rc = comm_join_pushes(c, st);
+  if (rc) return rc;
+  return comm_barrier(c, st);
+}
+
 int sdfb_decode_grid_host(sdfb_decoder* d, const float* latent_host, int res, int z0, int z1, float* sdf_host,
                           uint8_t* mask_host, int precision) {
   if (!d || !latent_host || !sdf_host) return fail(SDFB_E_INVALID, "null argument");
   if (res < 2 || res > 2048 || z0 < 0 || z1 > res || z0 > z1) return fail(SDFB_E_INVALID, "bad grid arguments");
   DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  if (int orc = order_after_user(d, d->st_compute)) return orc;
   const long long plane = static_cast<long long>(res) * res;
   const bool halo = mask_host != nullptr && z1 < res && z1 > z0;
   const long long n_sdf = (z1 - z0 + (halo ? 1 : 0)) * plane;
@@ -729,10 +881,22 @@ int sdfb_decode_grid_host(sdfb_decoder* d, const float* latent_host, int res, in
   const int planes = z1 - z0 + (halo ? 1 : 0);
   long long per = (2097152 + plane - 1) / plane;                   // >= 2^21 queries per chunk keeps the persistent kernel's tail < 1 %
   if (per * 16 < planes) per = (planes + 15) / 16;
+  // With a mask, every chunk's launch also writes the sign bit-planes of its queries into the context's buffer (32
+  // queries per word): a chunk must then start on a word boundary, i.e. hold a multiple of 32 queries.
+  const bool want_mask = n_mask > 0;
+  if (want_mask) {
+    long long unit = 1;
+    while ((unit * plane) % 32 != 0) unit *= 2;                   // 32 / gcd(plane, 32)
+    per = (per + unit - 1) / unit * unit;
+    rc = ensure_signs(d, (n_sdf + 31) >> 5, d->st_compute);
+    if (rc == SDFB_OK) rc = ensure_rowmask(d, mask_rows_words(planes, res, res));
+    if (rc) return rc;
+  }
   int nchunk = 0;
   for (long long za = 0; za < planes; za += per, ++nchunk) {
     const long long zb = za + per < planes ? za + per : planes;
-    rc = decode_any(d, lat_dev, nullptr, res, (z0 + za) * plane, (zb - za) * plane, sdf_dev + za * plane, precision, d->st_compute);
+    rc = decode_any(d, lat_dev, nullptr, res, (z0 + za) * plane, (zb - za) * plane, sdf_dev + za * plane, precision, d->st_compute,
+                    want_mask ? d->signs + ((za * plane) >> 5) : nullptr);
     if (rc) return rc;
     CU_TRY(cudaEventRecord(d->chunk_ev[nchunk], d->st_compute));
     CU_TRY(cudaStreamWaitEvent(d->st_copy, d->chunk_ev[nchunk], 0));
@@ -741,8 +905,8 @@ int sdfb_decode_grid_host(sdfb_decoder* d, const float* latent_host, int res, in
       CU_TRY(cudaMemcpyAsync(sdf_host + za * plane, sdf_dev + za * plane, (zc - za) * plane * sizeof(float),
                              cudaMemcpyDeviceToHost, d->st_copy));
   }
-  if (n_mask) {
-    CU_TRY(launch_sign_change_mask(sdf_dev, planes, res, res, base + off_mask, d->st_compute));
+  if (n_mask) {   // the same combine of the sign bit-planes as the device path (no second pass over the fp32 field)
+    CU_TRY(launch_mask_from_bits(d->signs, planes, res, res, base + off_mask, nullptr, d->rowmask, d->st_compute));
     CU_TRY(cudaEventRecord(d->chunk_ev[16], d->st_compute));
     CU_TRY(cudaStreamWaitEvent(d->st_copy, d->chunk_ev[16], 0));
     CU_TRY(cudaMemcpyAsync(mask_host, base + off_mask, n_mask, cudaMemcpyDeviceToHost, d->st_copy));
@@ -757,6 +921,8 @@ int sdfb_decode_points_host(sdfb_decoder* d, const float* latent_host, const flo
   if (!d || !latent_host || M < 0 || (M > 0 && (!xyz_host || !sdf_host))) return fail(SDFB_E_INVALID, "bad argument");
   if (M == 0) return SDFB_OK;
   DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  if (int orc = order_after_user(d, d->st_compute)) return orc;
   const size_t off_xyz = 1024, off_sdf = off_xyz + ((M * 12 + 255) / 256) * 256;
   int rc = ensure_stage(&d->pin, &d->pin_bytes, &d->dstage, &d->dstage_bytes, 1024, off_sdf + M * 4);
   if (rc) return rc;
@@ -956,11 +1122,26 @@ int sdfb_decode_debug_pass(sdfb_decoder* d, const float* latent_dev, int res, in
     return fail(SDFB_E_INVALID, "debug pass dump exists for the tensor-core path only");
   if (res < 2 || static_cast<long long>(res) * res * res < kTileM) return fail(SDFB_E_INVALID, "grid too small");
   DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  UserMark um{d, static_cast<cudaStream_t>(stream)};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = ensure_stage(nullptr, nullptr, &d->dstage, &d->dstage_bytes, 0, kTileM * sizeof(float));
   if (rc) return rc;
   return decode_tc(d, latent_dev, nullptr, res, 0, kTileM, static_cast<float*>(d->dstage),
                    precision == SDFB_PREC_FP16, dump_dev, pass, st);
+}
+
+int sdfb_decoder_check(sdfb_decoder* d, void* stream) {
+  if (!d) return fail(SDFB_E_INVALID, "null argument");
+  DeviceGuard g(d->device);
+  CU_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return kernel_status(d);
+}
+
+int sdfb_decoder_set_timeout_ns(sdfb_decoder* d, uint64_t timeout_ns) {
+  if (!d || timeout_ns == 0) return fail(SDFB_E_INVALID, "bad argument");
+  d->timeout_ns = timeout_ns;
+  return SDFB_OK;
 }
 
 int sdfb_decoder_last_kernel_ms(sdfb_decoder* d, float* ms) {
@@ -987,6 +1168,17 @@ int sdfb_decoder_last_kernel_ms(sdfb_decoder* d, float* ms) {
       std::fprintf(stderr, "[sdfb prof] %-8s", role[r]);
       for (int i = 0; i < 8; ++i) std::fprintf(stderr, " %s=%.0f", cls[i], m[i] / n);
       std::fprintf(stderr, " (cycles, mean over %d CTAs; %.2f ms)\n", n, *ms);
+    }
+    // per-pass event trace of CTA 0, tile 5 (fused_decoder.cu SDFB_K1_TRACE; written when the grid covers all SMs)
+    std::vector<long long> tr(128);
+    CU_TRY(cudaMemcpy(tr.data(), d->prof + static_cast<size_t>(d->num_sms) * 24, 128 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (tr[0] != 0) {
+      static const char* kind[4] = {"issue_first", "issue_last", "acc_full_seen", "epi_done"};
+      for (int k = 0; k < 4; ++k) {
+        std::fprintf(stderr, "[sdfb trace] %-13s", kind[k]);
+        for (int ps = 0; ps < 13; ++ps) std::fprintf(stderr, " %lld", tr[32 * k + ps] ? tr[32 * k + ps] - tr[0] : -1);
+        std::fprintf(stderr, "\n");
+      }
     }
   }
   return kernel_status(d);
@@ -1118,9 +1310,12 @@ int sdfb_ddpm_create(const float* params_host, size_t n_floats, int device, sdfb
   }
   CU_TRY_D(cudaMalloc(&d->status, sizeof(unsigned int)));
   CU_TRY_D(cudaMemset(d->status, 0, sizeof(unsigned int)));
-  if (std::getenv("SDFB_PROF") != nullptr) {
-    CU_TRY_D(cudaMalloc(&d->prof, (static_cast<size_t>(148) * 24 + 96) * sizeof(long long)));
-    CU_TRY_D(cudaMemset(d->prof, 0, (static_cast<size_t>(148) * 24 + 96) * sizeof(long long)));
+  CU_TRY_D(cudaHostAlloc(reinterpret_cast<void**>(&d->status_host), sizeof(unsigned int), cudaHostAllocMapped));
+  *d->status_host = 0;
+  CU_TRY_D(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d->status_host_dev), d->status_host, 0));
+  if (std::getenv("SDFB_PROF") != nullptr) {   // [num_sms][3 roles][8] wait classes + a 96-entry event trace
+    CU_TRY_D(cudaMalloc(&d->prof, (static_cast<size_t>(sms) * 24 + 96) * sizeof(long long)));
+    CU_TRY_D(cudaMemset(d->prof, 0, (static_cast<size_t>(sms) * 24 + 96) * sizeof(long long)));
   }
   CU_TRY_D(cudaEventCreate(&d->ev0));
   CU_TRY_D(cudaEventCreate(&d->ev1));
@@ -1141,6 +1336,7 @@ int sdfb_ddpm_destroy(sdfb_ddpm* d) {
   if (d->ev_fork) cudaEventDestroy(d->ev_fork);
   if (d->ev_join) cudaEventDestroy(d->ev_join);
   cudaFree(d->status); cudaFree(d->prof); cudaFree(d->nstage);
+  if (d->status_host) cudaFreeHost(d->status_host);
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
   delete d;
@@ -1221,7 +1417,7 @@ static int ddpm_tc_lane(sdfb_ddpm* d, int lane, float* x, const float* noise, lo
     const int v = std::atoi(e);
     if (v >= 2 && v < p.nstages) p.nstages = v;
   }
-  p.counter = L.counter; p.status = d->status; p.timeout_ns = d->timeout_ns; p.prof = lane == 0 ? d->prof : nullptr;
+  p.counter = L.counter; p.status = d->status; p.status_host = d->status_host_dev; p.timeout_ns = d->timeout_ns; p.prof = lane == 0 ? d->prof : nullptr; p.prof_sms = d->num_sms;
   if (const char* e = std::getenv("SDFB_DDPM_FLAGS")) p.flags = static_cast<unsigned int>(std::strtoul(e, nullptr, 0));
   DdpmMaps maps;
   {
@@ -1249,7 +1445,7 @@ static int ddpm_tc_lane(sdfb_ddpm* d, int lane, float* x, const float* noise, lo
   }
   CU_TRY(launch_ddpm_split(x, n, n_pad, L.act, fp16, st));
   CU_TRY(cudaMemsetAsync(L.counter, 0, static_cast<size_t>(m_pairs) * sizeof(unsigned int), st));
-  if (p.prof) CU_TRY(cudaMemsetAsync(d->prof, 0, (static_cast<size_t>(148) * 24 + 96) * sizeof(long long), st));
+  if (p.prof) CU_TRY(cudaMemsetAsync(d->prof, 0, (static_cast<size_t>(d->num_sms) * 24 + 96) * sizeof(long long), st));
   if (time_it) CU_TRY(cudaEventRecord(d->ev0, st));
   CU_TRY(launch_ddpm_sample(p, maps, fp16, d->num_sms, st));
   return SDFB_OK;
@@ -1307,8 +1503,32 @@ static int ddpm_status(sdfb_ddpm* d) {
   CU_TRY(cudaMemcpy(&s, d->status, sizeof(s), cudaMemcpyDeviceToHost));
   if (s != 0) {
     cudaMemset(d->status, 0, sizeof(unsigned int));
+    if (d->status_host) *reinterpret_cast<volatile unsigned int*>(d->status_host) = 0;
     return fail(SDFB_E_KERNEL, "fused DDPM kernel watchdog tripped at wait site 0x%x", s);
   }
+  return SDFB_OK;
+}
+
+// see pending_status(sdfb_decoder*)
+static int ddpm_pending_status(sdfb_ddpm* d) {
+  if (d->status_host == nullptr) return SDFB_OK;
+  const unsigned int s = *reinterpret_cast<volatile unsigned int*>(d->status_host);
+  if (s == 0) return SDFB_OK;
+  *reinterpret_cast<volatile unsigned int*>(d->status_host) = 0;
+  cudaMemset(d->status, 0, sizeof(unsigned int));
+  return fail(SDFB_E_KERNEL, "an earlier launch on this context tripped the fused DDPM kernel's watchdog at wait site 0x%x: its outputs are invalid", s);
+}
+
+int sdfb_ddpm_check(sdfb_ddpm* d, void* stream) {
+  if (!d) return fail(SDFB_E_INVALID, "null argument");
+  DeviceGuard g(d->device);
+  CU_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return ddpm_status(d);
+}
+
+int sdfb_ddpm_set_timeout_ns(sdfb_ddpm* d, uint64_t timeout_ns) {
+  if (!d || timeout_ns == 0) return fail(SDFB_E_INVALID, "bad argument");
+  d->timeout_ns = timeout_ns;
   return SDFB_OK;
 }
 
@@ -1339,7 +1559,7 @@ int sdfb_ddpm_last_kernel_ms(sdfb_ddpm* d, float* ms) {
     }
     // event trace of CTA 0, step 5 (ddpm_step.cu SDFB_TRACE): cycles relative to layer 0's first MMA
     std::vector<long long> tr(96);
-    CU_TRY(cudaMemcpy(tr.data(), d->prof + 148 * 24, 96 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(tr.data(), d->prof + static_cast<size_t>(d->num_sms) * 24, 96 * sizeof(long long), cudaMemcpyDeviceToHost));
     static const char* ev[13] = {"mma_start", "mma_issued", "epi_acc_full", "epi_chunk0_ready", "epi_stores_issued",
                                  "epi_stores_done", "epi_arrived", "prod_at_barrier", "prod_barrier_done", "prod_A_issued",
                                  "L4_tmem_read", "L4_unit0_computed", "L4_unit0_stored"};
@@ -1359,6 +1579,7 @@ int sdfb_ddpm_denoise(sdfb_ddpm* d, const float* x_dev, int t, int n, float* eps
   if (precision != SDFB_PREC_FP32 && precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16)
     return fail(SDFB_E_INVALID, "unknown precision %d", precision);
   DeviceGuard g(d->device);
+  if (int prc = ddpm_pending_status(d)) return prc;
   if (precision != SDFB_PREC_FP32)
     return ddpm_tc(d, const_cast<float*>(x_dev), nullptr, n, 1, t, eps_dev, precision == SDFB_PREC_FP16,
                    static_cast<cudaStream_t>(stream));
@@ -1375,6 +1596,7 @@ int sdfb_ddpm_sample(sdfb_ddpm* d, float* x_dev, const float* noise_dev, int n, 
   if (precision != SDFB_PREC_FP32 && precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16)
     return fail(SDFB_E_INVALID, "unknown precision %d", precision);
   DeviceGuard g(d->device);
+  if (int prc = ddpm_pending_status(d)) return prc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision != SDFB_PREC_FP32)
     return ddpm_tc(d, x_dev, noise_dev, n, steps, steps - 1, nullptr, precision == SDFB_PREC_FP16, st);
@@ -1407,6 +1629,7 @@ int sdfb_ddpm_sample_philox(sdfb_ddpm* d, float* x_dev, uint64_t seed, int64_t f
   if (precision != SDFB_PREC_FP32 && precision != SDFB_PREC_BF16 && precision != SDFB_PREC_FP16)
     return fail(SDFB_E_INVALID, "unknown precision %d", precision);
   DeviceGuard g(d->device);
+  if (int prc = ddpm_pending_status(d)) return prc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (gen_xT) CU_TRY(launch_philox_normal(seed, f0, n, steps, steps + 1, x_dev, st));  // x_T = row t = steps of the stream
   if (precision != SDFB_PREC_FP32)
@@ -1424,6 +1647,7 @@ int sdfb_ddpm_sample_philox_host(sdfb_ddpm* d, float* x_host, uint64_t seed, int
   if (!d || !x_host) return fail(SDFB_E_INVALID, "null argument");
   if (n <= 0 || steps < 1 || steps > kDdpmT) return fail(SDFB_E_INVALID, "bad n or steps");
   DeviceGuard g(d->device);
+  if (int prc = ddpm_pending_status(d)) return prc;
   const size_t cnt = static_cast<size_t>(n) * kDdpmLatent;
   int rc = ensure_stage(nullptr, nullptr, &d->dstage, &d->dstage_bytes, 0, cnt * sizeof(float));
   if (rc) return rc;
@@ -1441,6 +1665,7 @@ int sdfb_ddpm_sample_host(sdfb_ddpm* d, float* x_host, const float* noise_host, 
   if (n <= 0 || steps < 1 || steps > kDdpmT) return fail(SDFB_E_INVALID, "bad n or steps");
   if (steps > 1 && !noise_host) return fail(SDFB_E_INVALID, "noise stream required");
   DeviceGuard g(d->device);
+  if (int prc = ddpm_pending_status(d)) return prc;
   const size_t cnt = static_cast<size_t>(n) * kDdpmLatent;
   const size_t need = (1 + static_cast<size_t>(steps)) * cnt * sizeof(float);
   int rc = ensure_stage(nullptr, nullptr, &d->dstage, &d->dstage_bytes, 0, need);

@@ -63,11 +63,11 @@ enum : uint32_t { kErrFull = 0x110, kErrEmpty = 0x120, kErrAccFull = 0x130, kErr
                   kErrFullFirst = 0x160, kErrXn = 0x170, kErrOwn = 0x180 };
 
 // Diagnostics: with profiling on, CTA 0 stamps clock64() at key events of every layer of step 5 (and
-// of layer 0 of step 6, row 5) into the tail of the profile buffer ([148 * 24 + row * 16 + event]).
+// of layer 0 of step 6, row 5) into the tail of the profile buffer ([prof_sms * 24 + row * 16 + event]).
 #define SDFB_TRACE(ev)                                                                              \
   do {                                                                                              \
     if (p.prof != nullptr && blockIdx.x == 0 && (s == 5 || (s == 6 && l == 0)))                     \
-      p.prof[148 * 24 + (s == 6 ? 5 : l) * 16 + (ev)] = clock64();                                  \
+      p.prof[static_cast<size_t>(p.prof_sms) * 24 + (s == 6 ? 5 : l) * 16 + (ev)] = clock64();            \
   } while (0)
 
 struct Geo {
@@ -152,7 +152,7 @@ __device__ __forceinline__ bool grid_wait(const DdpmParams& p, const unsigned in
       if (*reinterpret_cast<volatile unsigned int*>(p.status) != 0) { *wd.abort_flag = kErrGrid; return false; }
       if (global_timer_ns() - t0 > wd.timeout_ns) {
         *wd.abort_flag = kErrGrid;
-        atomicCAS(wd.status, 0u, static_cast<unsigned int>(kErrGrid));
+        wd_trip(wd, static_cast<unsigned int>(kErrGrid));
         return false;
       }
     }
@@ -273,7 +273,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
   long long waited[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  Watchdog wd{misc + 1, p.status, p.timeout_ns, p.prof != nullptr ? waited : nullptr};
+  Watchdog wd{misc + 1, p.status, p.timeout_ns, p.prof != nullptr ? waited : nullptr, p.status_host};
   const long long t_start = clock64();
 
   if (warp == 8) {
@@ -731,14 +731,15 @@ cudaError_t launch_philox_normal(unsigned long long seed, unsigned int first_lat
   return cudaGetLastError();
 }
 
-int ddpm_max_clusters8(int bn_h, int nstages, bool fp16) {
+// How many clusters of `csize` CTAs of the sampler kernel can be resident at once (0 if the query fails).
+static int ddpm_max_clusters(int csize, int bn_h, int nstages, bool fp16) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(8 * 18);
+  cfg.gridDim = dim3(csize * 18);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes_for(bn_h, nstages);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 8;
+  attr[0].val.clusterDim.x = csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -749,6 +750,8 @@ int ddpm_max_clusters8(int bn_h, int nstages, bool fp16) {
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
+
+int ddpm_max_clusters8(int bn_h, int nstages, bool fp16) { return ddpm_max_clusters(8, bn_h, nstages, fp16); }
 
 cudaError_t launch_ddpm_split(const float* x, int n, int n_pad, uint16_t* act, bool fp16, cudaStream_t stream) {
   const long long total = static_cast<long long>(n_pad) * 32;
@@ -768,18 +771,24 @@ cudaError_t launch_ddpm_sample(const DdpmParams& p, const DdpmMaps& maps, bool f
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes_for(p.bn_h, p.nstages);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cluster8 ? 8 : 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeCooperative;           // every CTA must be resident: they wait on one another
-  attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  // SDFB_DDPM_NO_COOP=1 (profiling only): drop the co-residency guarantee - ncu cannot launch a cooperative
-  // cluster kernel; on an otherwise idle GPU the grid (<= 1 CTA per SM) is resident anyway.
-  // (In cluster8 mode nothing waits across clusters, and the hardware co-schedules a cluster's CTAs: no guarantee needed.)
-  cfg.numAttrs = (p.cluster8 || std::getenv("SDFB_DDPM_NO_COOP") != nullptr) ? 1 : 2;
+  cfg.numAttrs = 1;
+  // Every CTA must be resident: pair tiles of one latent group wait on one another.  The grid never exceeds one CTA
+  // per SM and is checked against the occupancy calculator here, instead of asking for a cooperative launch (which
+  // profilers cannot replay together with clusters): on a GPU this process shares with nothing else the whole grid is
+  // then co-resident, and if something else does hold SMs the in-kernel watchdog turns the wait into SDFB_E_KERNEL.
+  // (In cluster8 mode nothing waits across clusters, and the hardware co-schedules a cluster's CTAs.)
+  if (!p.cluster8) {
+    static int max_pairs_cache[2][3][8] = {};     // [fp16][bn_h / 128][nstages]
+    int& cached = max_pairs_cache[fp16 ? 1 : 0][p.bn_h >> 7][p.nstages & 7];
+    if (cached == 0) cached = ddpm_max_clusters(2, p.bn_h, p.nstages, fp16);
+    if (pairs > cached) return cudaErrorCooperativeLaunchTooLarge;
+  }
   const CUtensorMap* a = reinterpret_cast<const CUtensorMap*>(maps.act);
   const CUtensorMap* wh = reinterpret_cast<const CUtensorMap*>(maps.wh);
   const CUtensorMap* wo = reinterpret_cast<const CUtensorMap*>(maps.wo);

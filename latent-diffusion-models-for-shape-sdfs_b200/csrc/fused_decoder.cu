@@ -99,6 +99,15 @@ __device__ __forceinline__ bool pass_first(int p) { return ((BWD ? kFirstBwd : k
 template <bool BWD>
 __device__ __forceinline__ bool pass_last(int p) { return ((BWD ? kLastBwd : kLastFwd) >> p) & 1u; }
 
+// Diagnostics (SDFB_PROF): CTA 0 stamps clock64() at per-pass events of its tile number 5 into the tail of the profile
+// buffer, [prof_tail + 32 * kind + pass]: kind 0 = issuer about to issue the pass' first MMA, 1 = issuer has issued its last
+// MMA, 2 = epilogue warp 0 sees the accumulator full, 3 = epilogue warp 0 has written its last chunk of the pass.
+#define SDFB_K1_TRACE(kind, pass)                                                                        \
+  do {                                                                                                   \
+    if (p.prof != nullptr && blockIdx.x == 0 && it == 5 && (threadIdx.x & 31) == 0)                      \
+      p.prof[static_cast<size_t>(gridDim.x) * 24 + 32 * (kind) + (pass)] = clock64();                    \
+  } while (0)
+
 struct Query { float x, y, z; };
 
 __device__ __forceinline__ Query load_query(const DecodeParams& p, long long m) {
@@ -141,6 +150,7 @@ struct Epi {
   uint32_t acc_phase;     // bit b: parity of the next acc_full[b] wait
   int set;                // 0/1: which of the two warp sets (splits chunks / head columns)
   int lane;
+  long long* trace;       // diagnostics: where to stamp "accumulator full seen" of the next pass (nullptr: off)
 };
 
 // Hidden pass.  The two warp sets work on the SAME chunk at the same time (set s converts
@@ -159,6 +169,7 @@ __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict_
                                                 uint32_t* mrow = nullptr) {
   if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
   e.acc_phase ^= 1u << b;
+  if (e.trace != nullptr && e.lane == 0) *e.trace = clock64();
   __syncwarp();
   tc_fence_after();
   const uint32_t tbase = e.tmem_row + b * 256 + e.set * 32;
@@ -227,6 +238,7 @@ __device__ __forceinline__ bool epi_head_pass(Epi& e, const float* __restrict__ 
                                               uint32_t* hm = nullptr) {
   if (!mbar_wait(e.bars + 8 * (kBarAccFull + b), (e.acc_phase >> b) & 1u, wd, kErrAccFull, b)) return false;
   e.acc_phase ^= 1u << b;
+  if (e.trace != nullptr && e.lane == 0) *e.trace = clock64();
   __syncwarp();
   tc_fence_after();
   const uint32_t tbase = e.tmem_row + b * 256 + e.set * 128;
@@ -499,13 +511,14 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
   long long waited[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  Watchdog wd{misc + 1, p.status, p.timeout_ns, p.prof != nullptr ? waited : nullptr};
+  Watchdog wd{misc + 1, p.status, p.timeout_ns, p.prof != nullptr ? waited : nullptr, p.status_host};
   const long long t_start = clock64();
 
   if (warp == 8) {
     // ===================== producer: this CTA's half of every weight block =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      if (p.debug_flags & 2u) goto done;   // test hook: no weights ever arrive, so the consumers' waits must time out
       for (long long it = 0; it < my_tiles; ++it) {
 #pragma unroll 1
         for (int blk = 0; blk < kNumBlocks; ++blk) {
@@ -542,6 +555,7 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
           const uint32_t d_tmem = tmem_base + b * 256;
           if (!mbar_wait(bars + 8 * (kBarAccEmpty + b), ((ephase >> b) & 1u) ^ 1u, wd, kErrAccEmpty, b)) goto done;
           ephase ^= 1u << b;
+          SDFB_K1_TRACE(0, ps);
 #pragma unroll 1
           for (int k = 0; k < nk; ++k) {
             if (first) {
@@ -570,6 +584,7 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
             prev_stage = stage;
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
+          SDFB_K1_TRACE(1, ps);
         }
       }
     }
@@ -585,6 +600,7 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
     e.row7 = row & 7u;
     e.wphase = 0;
     e.acc_phase = 0;
+    e.trace = nullptr;
     L0Weights wl[4];                                      // layer-0 features of this lane, per step
     auto load_l0_weights = [&](L0Weights (&w)[4]) {
 #pragma unroll
@@ -626,6 +642,7 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
           else { layer = 4 + ((ps - 5) >> 1); half = (ps - 5) & 1; }
           const float* bias = sbias + (layer - 1) * kHid + half * 256;
           float* dump_row = (dump_tile && ps == p.dump_pass) ? p.dump + row * 256 : nullptr;
+          e.trace = (p.prof != nullptr && blockIdx.x == 0 && it == 5 && warp == 0) ? p.prof + static_cast<size_t>(gridDim.x) * 24 + 64 + ps : nullptr;
           bool ok;
           if (layer == 3)
             ok = epi_hidden_pass<FP16, false>(e, bias, q, 0, gpass & 1u, wd, dump_row, Flag<true>{}, Flag<false>{});
@@ -634,9 +651,11 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
           else
             ok = epi_hidden_pass<FP16, false>(e, bias, q, 4, gpass & 1u, wd, dump_row, Flag<false>{}, Flag<false>{});
           if (!ok) goto done;
+          if (warp == 0) SDFB_K1_TRACE(3, ps);
         }
         float dot = 0.f;
         float* dump_row = (dump_tile && p.dump_pass == 11) ? p.dump + row * 256 : nullptr;
+        if (e.trace != nullptr) e.trace = p.prof + static_cast<size_t>(gridDim.x) * 24 + 64 + 11;
         if (!epi_head_pass(e, sbias + 6 * kHid, shead, gpass & 1u, wd, dot, dump_row)) goto done;
         ++gpass;
         // first layer of the next tile, written behind the last readers of this tile's h6
@@ -650,7 +669,9 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
           qv = sxyz[row];
         }
         dump_row = (dump_tile && p.dump_pass == 12) ? p.dump + row * 256 : nullptr;
+        if (e.trace != nullptr) e.trace = p.prof + static_cast<size_t>(gridDim.x) * 24 + 64 + 12;
         if (!epi_head_pass(e, sbias + 6 * kHid + 256, shead + 256, gpass & 1u, wd, dot, dump_row)) goto done;
+        e.trace = nullptr;
         ++gpass;
         if (e.set == 1) sdot[row] = dot;
         named_bar_sync(2, kEpiThreads);

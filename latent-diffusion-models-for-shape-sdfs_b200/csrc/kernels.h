@@ -69,11 +69,13 @@ struct DecodeParams {
   long long q0;                // grid mode: global index of query 0 (= z0*res*res)
   int res;
   unsigned int* status;        // watchdog status word (0 = ok)
+  unsigned int* status_host;   // its mirror in mapped pinned host memory (optional)
   float* dump;                 // debug: 128x256 pre-activations of pass `dump_pass`, tile 0
   int dump_pass;
   unsigned long long timeout_ns;
   long long* prof;             // optional [grid][3 roles][8]: blocked cycles per wait class (diagnostics)
   unsigned int debug_flags;    // bit0: producer skips the weight copies (timing experiment; results are garbage)
+                               // bit1: producer exits at once (test hook: every consumer wait runs into the watchdog)
   // forward + backward kernel only (`bwd` selects it; `out` is then optional, `signs` unused)
   const float* dLdy;           // [M] upstream gradient d loss / d sdf
   const unsigned int* dLdy_amax;   // bits of max |dLdy| (launch_abs_max): the kernel works on dLdy * 2^-vjp_scale_exponent
@@ -144,8 +146,10 @@ struct DdpmParams {
   unsigned int flags;      // experiments: bit0 no consumer-side proxy fence, bit1 relaxed (not release) barrier arrival
   unsigned int* counter;   // [pair_m_tiles] barrier counters, one per group of pair tiles that share 256 latents (zeroed before the launch)
   unsigned int* status;
+  unsigned int* status_host;   // mirror of `status` in mapped pinned host memory (optional)
   unsigned long long timeout_ns;
-  long long* prof;         // optional diagnostics: [148][3 roles][8] blocked cycles per wait class + an event trace
+  long long* prof;         // optional diagnostics: [prof_sms][3 roles][8] blocked cycles per wait class + an event trace
+  int prof_sms;            // SM count the profile buffer was sized for
 };
 
 // the five tensor maps of a launch (128 B each, 64-byte aligned)

@@ -95,7 +95,18 @@ struct Watchdog {
   unsigned int* status;            // global word: first failure code wins
   uint64_t timeout_ns;
   long long* wait_cycles;          // optional per-thread [8] accumulator of blocked cycles per site class
+  unsigned int* status_host;       // optional mirror of `status` in mapped pinned host memory: the host sees a trip at its
+                                   // next call on the context without synchronising (plain store; any failing site's code will do)
 };
+
+// Records the first failure code in the context's status word and mirrors it to the host.
+__device__ __forceinline__ void wd_trip(const Watchdog& wd, uint32_t code) {
+  atomicCAS(wd.status, 0u, code);
+  if (wd.status_host != nullptr) {
+    *reinterpret_cast<volatile unsigned int*>(wd.status_host) = code;
+    __threadfence_system();
+  }
+}
 
 // Bounded wait.  `site` (a multiple of 16) + `idx` identify the wait site in the status word;
 // site >> 4 is the class under which blocked cycles are accumulated when profiling.
@@ -117,7 +128,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, const W
       if (*wd.abort_flag) return false;
       if (global_timer_ns() - t0 > wd.timeout_ns) {
         *wd.abort_flag = site + idx;
-        atomicCAS(wd.status, 0u, site + idx);
+        wd_trip(wd, site + idx);
         return false;
       }
     }
@@ -319,7 +330,7 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity,
       if (*wd.abort_flag) return false;
       if (global_timer_ns() - t0 > wd.timeout_ns) {
         *wd.abort_flag = site + idx;
-        atomicCAS(wd.status, 0u, site + idx);
+        wd_trip(wd, site + idx);
         return false;
       }
     }

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint16_t* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
-  Watchdog wd{misc + 1, status, 200000000ull, nullptr};
+  Watchdog wd{misc + 1, status, 200000000ull, nullptr, nullptr};
   if (threadIdx.x == 0) {
     constexpr uint32_t idesc = umma_idesc(128, 256, FP16 ? 0 : 1);
     const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sb);

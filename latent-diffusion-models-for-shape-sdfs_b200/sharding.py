@@ -37,14 +37,30 @@ def gather_slabs(local: torch.Tensor, res_planes: int, per: int, group=None) -> 
     return full[:res_planes]
 
 
-def decode_grid_sharded(decoder, latent, res: int, mask: bool = False, precision=None, group=None,
-                        gather: bool = True):
+def decode_grid_sharded(decoder, latent, res: int, mask=False, precision=None, group=None,
+                        gather: bool = True, comm=None):
     """Config 5: every rank decodes its z-slab (plus, for the mask, the halo plane above it,
-    recomputed locally - no halo exchange), then the slabs are all-gathered.
+    recomputed locally - no halo exchange), then the slabs are assembled on every rank.
 
     Returns (sdf, mask_or_None); full [res,res,res] / [(res-1)^3] tensors if ``gather`` else the
-    rank's own slab."""
+    rank's own slab.
+
+    ``comm`` (a ``Comm``): the overlapped path - one C call (``sdfb_decode_grid_sharded``) that pushes every finished
+    sub-slab into all peers' copies of a symmetric buffer with the copy engines while the next one is being decoded; the
+    results are views of that buffer, valid until the next sharded decode.  ``mask="bits"`` then returns the packed mask
+    blocks [world, words_per_rank] as they travelled (``unpack_mask_blocks`` gives the uint8 form ``mask=True`` returns).
+    Without ``comm``: decode, then ``torch.distributed`` all-gathers (NCCL on the box, gloo in the CPU tests)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if comm is not None and gather:
+        sdf_full, words = comm.decode_grid_sharded(decoder, latent, res, mask=bool(mask), precision=precision)
+        if not mask:
+            return sdf_full, None
+        if mask == "bits":
+            return sdf_full, words
+        from .api import unpack_mask_blocks
+        return sdf_full, unpack_mask_blocks(words, res)
+    if mask == "bits":
+        raise ValueError('mask="bits" needs the overlapped path (pass comm=)')
     z0, z1 = slab_range(res, rank, world)
     per = -(-res // world)
     even = res % world == 0
@@ -85,8 +101,11 @@ def decode_batch_sharded(decoder, latents: torch.Tensor, res: int, precision=Non
 
 def sample_latents_sharded(sampler, n: int, seed: int = 0, steps: int = 1000, precision=None, group=None, gather: bool = False):
     """Config 4's sampling phase: the batch of n latents is split across ranks; every rank samples its share with
-    the in-kernel noise addressed by GLOBAL latent index, so the union equals what one rank sampling all n would
-    draw.  No communication unless ``gather``.  Returns (i0, x [i1-i0, 256]) or the gathered [n, 256]."""
+    the in-kernel noise addressed by GLOBAL latent index, so every rank draws exactly the noise a single call over the
+    whole batch would.  The samples themselves equal the whole-batch ones up to fp32 summation order: the fused kernel
+    picks its tile width from the per-call latent count, and a different width sums a layer's products in a different
+    order (bit-equal when the widths coincide, e.g. with SDFB_DDPM_BN set; the fp32 path is always bit-equal).
+    No communication unless ``gather``.  Returns (i0, x [i1-i0, 256]) or the gathered [n, 256]."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     i0, i1 = batch_range(n, rank, world)
     if i1 > i0:

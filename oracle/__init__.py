@@ -19,6 +19,6 @@ from .weights import (DEC_LATENT, DEC_HIDDEN, DEC_SKIP_OUT, DEC_LAYER_DIMS,
 from .grid import axis_coords, grid_points, sign_change_mask
 from .decoder import decoder_forward, decode_grid, decoder_forward_lowp, decoder_vjp_latent, decoder_vjp_latent_lowp, fit_loss_grad_lowp
 from .ddpm import (ddpm_schedule, time_embedding, denoiser_forward,
-                   ddpm_step, sample_latents, denoiser_forward_lowp)
+                   ddpm_step, sample_latents, denoiser_forward_lowp, DDPM_LATENT_SCALE, to_decoder_latent)
 from .philox import philox4x32_10, philox_normal_rows, philox_sampler_inputs
 from .marching import marching_cubes, mesh_is_closed

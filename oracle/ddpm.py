@@ -16,6 +16,16 @@ import torch
 
 from .weights import DDPM_T, DDPM_LATENT, DDPM_TEMB, ddpm_weights
 
+# The DDPM works on latents normalised to unit scale (x0 is clipped to [-1, 1]); a decoder latent is a sample times this
+# factor - the N(0, 1/16^2) scale of the auto-decoder's codes (oracle/weights.py default_latent).  Decoding an unscaled
+# sample saturates the field (tanh -> +1 everywhere, no surface), which would make config 4's geometric checks vacuous.
+DDPM_LATENT_SCALE = 1.0 / 16.0
+
+
+def to_decoder_latent(x0):
+    """x0 [n,256] (DDPM space) -> decoder latents [n,256]."""
+    return (np.asarray(x0, dtype=np.float32) * np.float32(DDPM_LATENT_SCALE)).astype(np.float32)
+
 
 @lru_cache(maxsize=None)
 def ddpm_schedule(T: int = DDPM_T):

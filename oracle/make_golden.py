@@ -3,6 +3,8 @@
     python -m oracle.make_golden            # rewrite tests/golden/oracle_golden.{npz,json}
     python -m oracle.make_golden --calibrate  # print the head bias that puts 25% of 64^3 inside
     python -m oracle.make_golden --vjp        # rewrite tests/golden/vjp_golden.npz only (latent-gradient fixtures)
+    python -m oracle.make_golden --c-abi      # rewrite tests/golden/c_abi_decode32.bin (fp32 32^3 field for tests/c/gpu_decode.c)
+    python -m oracle.make_golden --ddpm-rows  # rewrite tests/golden/ddpm_rows_golden.npz (64 rows of a seeded 4096-latent run)
 
 There is no upstream reference to generate vectors from
 (`/root/reference/README.md:1` is a title), so these fixtures pin the oracle to
@@ -69,15 +71,56 @@ def make_vjp_golden():
     print({k: (v.shape, str(v.dtype)) for k, v in arrays.items()})
 
 
+DDPM_ROWS_SEED = 77
+DDPM_ROWS_N = 4096
+DDPM_ROWS_BLOCKS = (0, 1000, 2555, 4080)     # four blocks of 16 consecutive latents of the 4096-latent batch
+
+
+def ddpm_rows_inputs(steps: int = 1000):
+    """(rows [64], x_T [64,256], noise [steps,64,256]): what the seeded sampler (seed DDPM_ROWS_SEED) draws for 64 of
+    the 4096 latents of BASELINE configs[3] - the counters address latents by their global index, so the oracle can
+    follow any subset of a batch (a latent's trajectory does not depend on the rest of the batch)."""
+    from .philox import philox_normal_rows
+    rows = np.concatenate([np.arange(b, b + 16) for b in DDPM_ROWS_BLOCKS])
+    x_T = np.concatenate([philox_normal_rows(DDPM_ROWS_SEED, 16, steps, steps + 1, first_latent=b)[0] for b in DDPM_ROWS_BLOCKS])
+    noise = np.concatenate([philox_normal_rows(DDPM_ROWS_SEED, 16, 0, steps, first_latent=b) for b in DDPM_ROWS_BLOCKS], axis=1)
+    return rows, x_T, noise
+
+
+def make_ddpm_rows_golden():
+    torch.set_num_threads(os.cpu_count() or 1)
+    rows, x_T, noise = ddpm_rows_inputs()
+    arrays = {"rows": rows.astype(np.int64)}
+    arrays["x0_fp32"] = sample_latents(len(rows), x_T, noise)
+    arrays["x0_bf16"] = sample_latents(len(rows), x_T, noise, lowp=torch.bfloat16)
+    arrays["x0_fp16"] = sample_latents(len(rows), x_T, noise, lowp=torch.float16)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "ddpm_rows_golden.npz"), **arrays)
+    print({k: (v.shape, str(v.dtype)) for k, v in arrays.items()},
+          "bf16 vs fp32", float(np.abs(arrays["x0_bf16"] - arrays["x0_fp32"]).max()))
+
+
+def make_c_abi_golden():
+    torch.set_num_threads(os.cpu_count() or 1)
+    sdf = decode_grid(default_latent(), 32).astype(np.float32)
+    sdf.tofile(os.path.join(GOLDEN_DIR, "c_abi_decode32.bin"))
+    print("c_abi_decode32.bin", sdf.shape, float(sdf.min()), float(sdf.max()), int((sdf < 0).sum()), "inside")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--calibrate", action="store_true")
     ap.add_argument("--vjp", action="store_true")
+    ap.add_argument("--c-abi", action="store_true")
+    ap.add_argument("--ddpm-rows", action="store_true")
     args = ap.parse_args()
     if args.calibrate:
         return calibrate()
     if args.vjp:
         return make_vjp_golden()
+    if args.c_abi:
+        return make_c_abi_golden()
+    if args.ddpm_rows:
+        return make_ddpm_rows_golden()
     torch.set_num_threads(os.cpu_count() or 1)
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     z = default_latent()

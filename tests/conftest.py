@@ -26,6 +26,11 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_rows():
+    return dict(np.load(os.path.join(GOLDEN_DIR, "ddpm_rows_golden.npz")))
+
+
+@pytest.fixture(scope="session")
 def pkg():
     """The product package (hyphenated directory name -> importlib)."""
     import importlib

@@ -4,8 +4,8 @@
         --master-port 29511 tests/multigpu_check.py [res]
 
 Config 5 (one latent, res^3 grid, z-slab per rank, fused mask with locally recomputed halo plane,
-in-place NCCL all-gather) and config 3 (a batch of latents split across ranks) are compared bit for bit
-with what ONE GPU computes on its own.  Prints one JSON line on rank 0; exit code 0 = pass.
+in-place NCCL all-gather; and the overlapped peer-memory path of sdfb_decode_grid_sharded, even and uneven splits) and
+config 3 (a batch of latents split across ranks) are compared bit for bit with what ONE GPU computes on its own.  Prints one JSON line on rank 0; exit code 0 = pass.
 Launched by tests/test_gpu_multirank.py when >= 2 GPUs are visible."""
 import json
 import os
@@ -46,6 +46,35 @@ def main():
     ok_sdf = bool(torch.equal(sdf, ref_sdf))
     ok_mask = bool(torch.equal(mask, ref_mask))
 
+    # the overlapped path: ONE C call per rank (sdfb_decode_grid_sharded) - sub-slabs pushed into every peer's copy of a
+    # symmetric buffer by the copy engines while the next one is decoded, the mask travelling packed
+    comm = pkg.Comm(dev)
+    for _ in range(2):
+        sdf2, words = comm.decode_grid_sharded(dec, z, res, mask=True)
+    dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    sdf2, words = comm.decode_grid_sharded(dec, z, res, mask=True)
+    e1.record(); e1.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ok_push = bool(torch.equal(sdf2, ref_sdf)) and bool(torch.equal(pkg.unpack_mask_blocks(words, res), ref_mask))
+    # uneven splits, including ranks whose slab is empty (res 33 over 8 ranks: per = 5, rank 7 gets [33, 33))
+    for r2 in (33, 50):
+        s3, w3 = comm.decode_grid_sharded(dec, z, r2, mask=True)
+        rs3, rm3 = dec.decode_grid(z, r2, mask=True)
+        ok_push = ok_push and bool(torch.equal(s3, rs3)) and bool(torch.equal(pkg.unpack_mask_blocks(w3, r2), rm3))
+        s4, _ = pkg.decode_grid_sharded(dec, z, r2, mask=True)       # torch.distributed path on the same uneven split
+        ok_push = ok_push and bool(torch.equal(s4, rs3))
+    # the C-ABI in-place all-gather (sdfb_allgather_slabs) on an even split
+    full = torch.zeros((8 * world, 1024), dtype=torch.float32, device=dev)
+    full[8 * rank: 8 * rank + 8] = float(rank + 1)
+    comm.allgather_slabs(full)
+    comm.barrier()
+    torch.cuda.synchronize()
+    want = torch.arange(1, world + 1, device=dev, dtype=torch.float32).repeat_interleave(8)[:, None].expand(-1, 1024)
+    ok_push = ok_push and bool(torch.equal(full, want))
+    dec.check()
+
     # config 3: a batch of latents split across ranks, no communication
     B, bres = 2 * world + 1, 32
     lat = torch.stack([torch.from_numpy(oracle.default_latent(i)) for i in range(B)]).to(dev)
@@ -62,10 +91,11 @@ def main():
 
     counts = torch.tensor([part.shape[0]], device=dev)
     dist.all_reduce(counts)
-    ok = torch.tensor([int(ok_sdf and ok_mask and ok_batch and int(counts.item()) == B)], device=dev)
+    ok = torch.tensor([int(ok_sdf and ok_mask and ok_batch and ok_push and int(counts.item()) == B)], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"world": world, "res": res, "sdf_equal": ok_sdf, "mask_equal": ok_mask, "batch_equal": ok_batch, "sharded_sampling_equal": ok_sample,
+                          "push_path_equal": ok_push, "push_path_ms": float(ms2.item()),
                           "all_ranks_ok": bool(ok.item()), "sharded_decode_mask_gather_ms": float(ms.item()),
                           "queries_per_s": res ** 3 / (float(ms.item()) * 1e-3)}))
     dist.barrier()

@@ -7,8 +7,10 @@ Tolerances (BASELINE.json north_star):
     only in fp32 summation order, which is invisible (~1e-6) except where it pushes an
     activation across a 16-bit rounding boundary; such a flip moves the output by about one
     16-bit ulp of a hidden unit (bf16: rare and ~2e-3; fp16: ~8x more frequent, ~8x smaller).
-    Hence two bounds: the 90th percentile within 2e-5 (bf16) / 5e-4 (fp16), and max-abs
-    within 8e-3 (bf16) / 1.5e-3 (fp16);
+    Hence bounds on the whole distribution of the difference, each about 3x what a B200 run measured
+    (bf16: p90 1.9e-6, p99 1.4e-3, p99.9 2.4e-3, max 2.7e-3; fp16: p90 2.1e-4, p99 4.2e-4, p99.9 4.9e-4,
+    max 5.1e-4 - the tail is the rounding flips, not a bias): a bug that moves a few percent of the
+    points by a few 1e-3 fails the p99 bound;
   * vs the fp32 oracle: fp16 operands meet the north star's 2e-3; bf16's distance is reported
     and bounded at 2e-2 (2e-3 is unattainable with bf16 operands on a non-degenerate field);
   * >= 99.9% sign agreement where |sdf| > 2e-3.
@@ -24,6 +26,8 @@ pytestmark = pytest.mark.gpu
 TOL_FP32 = 1e-5
 TOL_LOWP = {"bf16": 8e-3, "fp16": 1.5e-3}    # max-abs vs the operand-rounding-emulating oracle
 TOL_LOWP_BULK = {"bf16": 2e-5, "fp16": 5e-4}  # 90th percentile of the same difference
+TOL_LOWP_P99 = {"bf16": 4.2e-3, "fp16": 1.3e-3}    # 99th percentile (measured 1.4e-3 / 4.2e-4)
+TOL_LOWP_P999 = {"bf16": 7e-3, "fp16": 1.5e-3}     # 99.9th percentile (measured 2.4e-3 / 4.9e-4)
 
 
 def check_lowp(got, want, prec, what=""):
@@ -34,6 +38,8 @@ def check_lowp(got, want, prec, what=""):
     if d.size:
         assert d.max() < TOL_LOWP[prec], d.max()
         assert q[1] < TOL_LOWP_BULK[prec], q[1]
+        assert q[2] < TOL_LOWP_P99[prec], q[2]
+        assert q[3] < TOL_LOWP_P999[prec], q[3]
 LOWP_T = {"bf16": torch.bfloat16, "fp16": torch.float16}
 
 
