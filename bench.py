@@ -621,6 +621,31 @@ def main():
             vjp = {"error": repr(exc)}
             print(f"bench.py: optional leg failed: {exc!r}", file=sys.stderr)
 
+    # ---- surface extraction at 512^3 on ONE GPU - dense decode + marching cubes against the two-level
+    # sparse decode (every node at most once) feeding the same dense marching-cubes kernels; identical triangle soups
+    sparse = None
+    if world == 1 and not args.no_vjp:
+        try:
+            zs_ = torch.from_numpy(pkg.synthetic.latent(0)).to(dev)
+            dec.extract_surface_sparse(zs_, RES5)
+            torch.cuda.synchronize()
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            tri_s, st_s = dec.extract_surface_sparse(zs_, RES5, return_stats=True)
+            b.record()
+            tri_d = dec.extract_surface(zs_, RES5)
+            c.record()
+            c.synchronize()
+            sparse = {"workload": "extract_surface_sparse(z, 512) vs extract_surface(z, 512) on one GPU (decode + marching cubes)",
+                      "sparse_ms": a.elapsed_time(b), "dense_ms": b.elapsed_time(c), "triangles": int(tri_s.shape[0]),
+                      "identical_triangle_soup": bool(tri_s.shape == tri_d.shape and torch.equal(tri_s, tri_d)),
+                      "queries": st_s["queries"], "dense_queries": st_s["dense_queries"],
+                      "fewer_queries_x": st_s["dense_queries"] / max(st_s["queries"], 1)}
+            del tri_s, tri_d
+        except Exception as exc:                     # an optional leg must never cost the headline line
+            sparse = {"error": repr(exc)}
+            print(f"bench.py: optional leg failed: {exc!r}", file=sys.stderr)
+
     # ---- SURVEY 8f row N4, second half: training steps (decoder weight gradients; DDPM training step), when built
     train = None
     if not args.no_train and hasattr(pkg, "bench_training_legs"):
@@ -682,6 +707,8 @@ def main():
             line["latent_gradient"] = vjp
         if train is not None:
             line["training"] = train
+        if sparse is not None:
+            line["sparse_extraction"] = sparse
         if ddpm_line is not None:
             line["ddpm"] = ddpm_line
         if cpu_base is not None:

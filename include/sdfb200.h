@@ -185,6 +185,21 @@ int sdfb_decoder_check(sdfb_decoder* dec, void* stream);
 /* Per-wait timeout of the in-kernel watchdog (default 2 s).  Test hook: a few nanoseconds make the next launch fail. */
 int sdfb_decoder_set_timeout_ns(sdfb_decoder* dec, uint64_t timeout_ns);
 
+/* Hierarchical sparse decode: decodes only where the surface can be and leaves what the dense
+ * marching-cubes calls above consume - sdf_dense_dev [res^3] valid at every node of every cell the surface crosses
+ * (elsewhere untouched), and sign_bits_dev, the COMPLETE sign bit-planes of the grid (ceil(res^3 / 32) + 1 words).
+ * Two levels: corners of 8^3-cell blocks, kept if they differ in sign or come within L 8h sqrt(3)/2 of zero; inside the
+ * kept blocks the lattice of 2^3-cell sub-blocks, same test with 2h; then the remaining nodes of the kept sub-blocks.
+ * Every node is decoded at most once (node bitmaps compacted into query lists).  A node never decoded lies only in
+ * discarded (sub-)blocks and inherits their constant sign.  lipschitz > 0: the bound L (field units per unit length);
+ * 0: estimated - the largest difference quotient on the level-1 lattice times safety1 (e.g. 2), and the largest one
+ * seen on either lattice times safety2 (e.g. 1.25) for level 2.  With a valid bound the marching-cubes output equals
+ * the dense extraction's bit for bit, order included.  Synchronises `stream` (three counts are read back).
+ * stats_host (optional, int64[8]): level-1 corners, kept blocks, level-2 lattice nodes, kept sub-blocks, remaining
+ * nodes, total queries, and the two difference quotients x 1e6.  res <= 1024. */
+int sdfb_decode_sparse_field(sdfb_decoder* dec, const float* latent_dev, int res, float lipschitz, float safety1, float safety2,
+                             float* sdf_dense_dev, uint32_t* sign_bits_dev, int precision, int64_t* stats_host, void* stream);
+
 /* Debug/diagnostic: pre-activation (accumulator + bias, before ReLU) of
  * tensor-core pass `pass` (0..12) for the first 128 queries of a grid decode,
  * 128 x 256 floats.  Used by the parity tests to localise a failing layer. */

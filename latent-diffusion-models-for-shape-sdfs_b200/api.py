@@ -304,14 +304,46 @@ class Decoder:
         self.check()            # the triangle count already synchronised the stream: this only reads the status word
         return out
 
+    def decode_sparse_field(self, latent, res: int, lipschitz: float | None = None, safety: tuple = (2.0, 1.25),
+                            precision: str | None = None):
+        """(sdf [res,res,res] float32, sign_words int32, stats): the two-level sparse decode of ``sdfb_decode_sparse_field`` -
+        ``sdf`` is valid at every node of every cell the surface crosses (uninitialised elsewhere), ``sign_words`` are the
+        complete sign bit-planes of the grid; together they are what ``extract_surface(sdf, sign_words=...)`` needs."""
+        prec = _prec(precision or self.precision)
+        lat = _as_dev_f32(latent, self.device, (LATENT,))
+        sdf = torch.empty((res, res, res), dtype=torch.float32, device=self.device)
+        signs = torch.empty(((res ** 3 + 31) // 32 + 1,), dtype=torch.int32, device=self.device)
+        stats = (C.c_int64 * 8)()
+        check(self._lib.sdfb_decode_sparse_field(self._h, lat.data_ptr(), res, C.c_float(0.0 if lipschitz is None else float(lipschitz)),
+                                                 C.c_float(float(safety[0])), C.c_float(float(safety[1])), sdf.data_ptr(), signs.data_ptr(),
+                                                 prec, stats, _stream_ptr(self.device.index)))
+        keys = ("corner_queries", "blocks_kept", "lattice_queries", "sub_blocks_kept", "fill_queries", "queries")
+        st = {k: int(stats[i]) for i, k in enumerate(keys)}
+        st.update(dense_queries=res ** 3, lipschitz_level1=stats[6] * 1e-6, lipschitz_level2=stats[7] * 1e-6)
+        return sdf, signs, st
+
     def extract_surface_sparse(self, latent, res: int, block: int = 8, lipschitz: float | None = None,
-                               precision: str | None = None, return_stats: bool = False, indexed: bool = False):
-        """The zero level set on the res^3 grid WITHOUT decoding the whole grid: decode the corners of
+                               precision: str | None = None, return_stats: bool = False, indexed: bool = False,
+                               method: str = "hier"):
+        """The zero level set on the res^3 grid WITHOUT decoding the whole grid.
+
+        ``method="hier"`` (default): two-level refinement (``decode_sparse_field``), every node decoded at most once, then
+        the DENSE marching-cubes kernels over the complete sign bit-planes - with a valid Lipschitz bound the triangle soup
+        equals ``extract_surface``'s bit for bit, order included.
+
+        ``method="blocks"`` (round 1): decode the corners of
         `block`^3-cell blocks, keep the blocks whose corners straddle zero or come within
         tau = L * block * h * sqrt(3) / 2 of it (h = 2 / (res - 1)), decode only their nodes and run marching
         cubes on them.  With a valid Lipschitz bound L the triangles are those of the dense extraction, bit for
         bit (the order differs).  ``lipschitz=None`` estimates L from the block-corner values (largest difference
         quotient along block edges, times 2)."""
+        if method == "hier":
+            sdf, signs, st = self.decode_sparse_field(latent, res, lipschitz=lipschitz, precision=precision)
+            out = extract_surface(sdf, res, 0, sign_words=signs, indexed=indexed)
+            self.check()
+            return (out, st) if return_stats else out
+        if method != "blocks":
+            raise ValueError("method must be 'hier' or 'blocks'")
         lib = self._lib
         nb = (res - 1 + block - 1) // block
         st = _stream_ptr(self.device.index)

@@ -8,8 +8,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libsdfb200.so")
-SOURCES = ("api.cu", "fused_decoder.cu", "tc_common.cu", "fp32_kernels.cu", "umma_rate.cu", "ddpm_step.cu", "marching.cu", "comm.cu")
+LIB = os.environ.get("SDFB_LIB") or os.path.join(HERE, "libsdfb200.so")     # SDFB_LIB: an experimental build beside the product one
+SOURCES = ("api.cu", "fused_decoder.cu", "tc_common.cu", "fp32_kernels.cu", "umma_rate.cu", "ddpm_step.cu", "marching.cu", "comm.cu", "sparse.cu")
 HEADERS = ("kernels.h", "ptx.cuh", "philox.cuh", "mc_tables.h", "comm.h", os.path.join("..", "..", "include", "sdfb200.h"))
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-cudart", "static")
@@ -35,7 +35,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB + ".tmp", *srcs]
+    extra = os.environ.get("SDFB_NVCC_EXTRA", "").split()      # e.g. -DSDFB_K1_EXPERIMENTS for the timing experiments
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB + ".tmp", *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -198,6 +198,14 @@ struct sdfb_decoder {
   float* bw_colsum = nullptr;     //                       column sums [num_sms * 4][1024]
   unsigned int* bw_amax = nullptr;   //                    bits of max |dLdy|
   float* bw_loss = nullptr;          //                    loss mode: per-warp sums [num_sms * 4]
+  // hierarchical sparse decode workspace (lazy): node bitmaps, scan tiles, query lists, level-1 lattice
+  struct SparseWs {
+    unsigned int *need1 = nullptr, *need2 = nullptr, *keep = nullptr, *tiles = nullptr, *idx = nullptr, *lip = nullptr;
+    unsigned long long* kept = nullptr;
+    float *xyz = nullptr, *vals = nullptr, *cs = nullptr;
+    int* ids = nullptr;
+    long long words = 0, idx_cap = 0, corners = 0, blocks = 0;
+  } sp;
   // fp32 workspace (lazy)
   long long ws_rows = 0;
   float *h0 = nullptr, *h1 = nullptr, *s = nullptr, *x = nullptr;
@@ -381,11 +389,6 @@ int pending_status(sdfb_decoder* d) {
 
 // End of a device-path call: remember where the caller's stream stands, so that a later *_host call (which runs on the
 // context's own streams and rewrites the per-latent constants) starts after it.
-int mark_user(sdfb_decoder* d, cudaStream_t st) {
-  CU_TRY(cudaEventRecord(d->ev_user, st));
-  d->user_pending = true;
-  return SDFB_OK;
-}
 struct UserMark {          // records the end of a device-path call on every return path
   sdfb_decoder* d; cudaStream_t st;
   ~UserMark() { if (cudaEventRecord(d->ev_user, st) == cudaSuccess) d->user_pending = true; }
@@ -513,6 +516,8 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
   if (d->status_host) cudaFreeHost(d->status_host);
   if (d->ev_user) cudaEventDestroy(d->ev_user);
   cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x); cudaFree(d->prof); cudaFree(d->signs); cudaFree(d->rowmask);
+  cudaFree(d->sp.need1); cudaFree(d->sp.need2); cudaFree(d->sp.keep); cudaFree(d->sp.tiles); cudaFree(d->sp.idx); cudaFree(d->sp.lip);
+  cudaFree(d->sp.kept); cudaFree(d->sp.xyz); cudaFree(d->sp.vals); cudaFree(d->sp.cs); cudaFree(d->sp.ids);
   for (float* a : d->bw_act) cudaFree(a);
   cudaFree(d->bw_d0); cudaFree(d->bw_d1); cudaFree(d->bw_y); cudaFree(d->bw_partial);
   cudaFree(d->bw_masks); cudaFree(d->bw_colsum); cudaFree(d->bw_amax); cudaFree(d->bw_loss);
@@ -1112,6 +1117,143 @@ int sdfb_mc_blocks_generate(const float* fields_dev, const int32_t* block_ids_de
   const int nb = (res - 1 + block - 1) / block;
   return mc_generate_impl(fields_dev, mc_block_geom(res, block, nb, block_ids_dev, n_blocks), workspace_dev, triangles_dev,
                           reinterpret_cast<long long*>(edge_keys_dev), static_cast<cudaStream_t>(stream));
+}
+
+// ---- hierarchical sparse decode (sparse.cu): decode only where the surface can be, hand the dense MC kernels a field that
+// is valid around the surface and the complete sign bit-planes ----
+namespace {
+int sparse_reserve_queries(sdfb_decoder* d, long long n) {
+  if (d->sp.idx_cap >= n) return SDFB_OK;
+  cudaFree(d->sp.idx); cudaFree(d->sp.xyz); cudaFree(d->sp.vals);
+  d->sp.idx = nullptr; d->sp.xyz = nullptr; d->sp.vals = nullptr; d->sp.idx_cap = 0;
+  const long long cap = n + n / 8 + 1024;
+  CU_TRY(cudaMalloc(&d->sp.idx, cap * sizeof(unsigned int)));
+  CU_TRY(cudaMalloc(&d->sp.xyz, cap * 3 * sizeof(float)));
+  CU_TRY(cudaMalloc(&d->sp.vals, cap * sizeof(float)));
+  d->sp.idx_cap = cap;
+  return SDFB_OK;
+}
+// bitmap -> ascending index list in d->sp.idx (synchronises the stream to learn the count)
+int sparse_compact(sdfb_decoder* d, const unsigned int* bits, long long words, long long* n_out, cudaStream_t st) {
+  const long long tiles = bitmap_scan_tiles(words);
+  CU_TRY(launch_bitmap_count(bits, words, d->sp.tiles, st));
+  unsigned int total = 0;
+  CU_TRY(cudaMemcpyAsync(&total, d->sp.tiles + tiles, sizeof(total), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  *n_out = total;
+  int rc = sparse_reserve_queries(d, total);
+  if (rc) return rc;
+  if (total) CU_TRY(launch_bitmap_emit(bits, words, d->sp.tiles, d->sp.idx, st));
+  return SDFB_OK;
+}
+// decode the listed nodes (d->sp.idx[0 .. n)) and scatter the values into the dense field
+int sparse_decode_nodes(sdfb_decoder* d, const float* latent_dev, int res, long long n, float* dense, int precision, cudaStream_t st) {
+  if (n == 0) return SDFB_OK;
+  CU_TRY(launch_node_points(res, d->sp.idx, n, d->sp.xyz, st));
+  int rc = decode_any(d, latent_dev, d->sp.xyz, 0, 0, n, d->sp.vals, precision, st);
+  if (rc) return rc;
+  CU_TRY(launch_scatter(d->sp.idx, d->sp.vals, n, dense, st));
+  return SDFB_OK;
+}
+}  // namespace
+
+int sdfb_decode_sparse_field(sdfb_decoder* d, const float* latent_dev, int res, float lipschitz, float safety1, float safety2,
+                             float* sdf_dense_dev, uint32_t* sign_bits_dev, int precision, int64_t* stats_host, void* stream) {
+  if (!d || !latent_dev || !sdf_dense_dev || !sign_bits_dev) return fail(SDFB_E_INVALID, "null argument");
+  if (res < 3 || res > 1024) return fail(SDFB_E_INVALID, "res %d outside [3, 1024] (node indices are 32-bit)", res);
+  if (!(lipschitz >= 0.f) || !(safety1 >= 1.f) || !(safety2 >= 1.f)) return fail(SDFB_E_INVALID, "bad lipschitz bound or safety factor");
+  DeviceGuard g(d->device);
+  if (int prc = pending_status(d)) return prc;
+  UserMark um{d, static_cast<cudaStream_t>(stream)};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  constexpr int B1 = 8, B2 = 2;
+  const int nb1 = (res - 1 + B1 - 1) / B1;
+  const long long nodes = static_cast<long long>(res) * res * res, words = (nodes + 31) >> 5;
+  const long long corners = static_cast<long long>(nb1 + 1) * (nb1 + 1) * (nb1 + 1), blocks = static_cast<long long>(nb1) * nb1 * nb1;
+  const float h = 2.f / static_cast<float>(res - 1);
+  auto& sp = d->sp;
+  if (sp.words < words) {
+    cudaFree(sp.need1); cudaFree(sp.need2); cudaFree(sp.tiles); sp.need1 = sp.need2 = sp.tiles = nullptr; sp.words = 0;
+    CU_TRY(cudaMalloc(&sp.need1, words * sizeof(unsigned int)));
+    CU_TRY(cudaMalloc(&sp.need2, words * sizeof(unsigned int)));
+    CU_TRY(cudaMalloc(&sp.tiles, (bitmap_scan_tiles(words) + 1) * sizeof(unsigned int)));
+    sp.words = words;
+  }
+  if (sp.corners < corners) {
+    cudaFree(sp.cs); cudaFree(sp.keep); cudaFree(sp.ids); sp.cs = nullptr; sp.keep = nullptr; sp.ids = nullptr; sp.corners = 0;
+    CU_TRY(cudaMalloc(&sp.cs, corners * sizeof(float)));
+    CU_TRY(cudaMalloc(&sp.keep, ((blocks + 31) / 32 + 1) * sizeof(unsigned int)));
+    CU_TRY(cudaMalloc(&sp.ids, blocks * sizeof(int)));
+    sp.corners = corners;
+  }
+  if (sp.lip == nullptr) CU_TRY(cudaMalloc(&sp.lip, 4 * sizeof(unsigned int)));
+  if (sp.kept == nullptr) CU_TRY(cudaMalloc(&sp.kept, sizeof(unsigned long long)));
+  CU_TRY(cudaMemsetAsync(sp.need1, 0, words * sizeof(unsigned int), st));
+  CU_TRY(cudaMemsetAsync(sp.need2, 0, words * sizeof(unsigned int), st));
+  CU_TRY(cudaMemsetAsync(sp.keep, 0, ((blocks + 31) / 32 + 1) * sizeof(unsigned int), st));
+  CU_TRY(cudaMemsetAsync(sp.lip, 0, 4 * sizeof(unsigned int), st));
+  CU_TRY(cudaMemsetAsync(sp.kept, 0, sizeof(unsigned long long), st));
+  // level 1: the (nb1 + 1)^3 block corners
+  int rc = sparse_reserve_queries(d, corners);
+  if (rc) return rc;
+  CU_TRY(launch_corner_nodes(res, B1, nb1, sp.idx, st));
+  CU_TRY(launch_node_points(res, sp.idx, corners, sp.xyz, st));
+  rc = decode_any(d, latent_dev, sp.xyz, 0, 0, corners, sp.cs, precision, st);
+  if (rc) return rc;
+  CU_TRY(launch_scatter(sp.idx, sp.cs, corners, sdf_dense_dev, st));
+  float lip1_node;                                     // Lipschitz bound in field units per node spacing
+  float raw1 = 0.f;
+  if (lipschitz > 0.f) {
+    lip1_node = lipschitz * h;
+  } else {
+    CU_TRY(launch_corner_lipschitz(sp.cs, res, B1, nb1, sp.lip, st));
+    unsigned int bits = 0;
+    CU_TRY(cudaMemcpyAsync(&bits, sp.lip, sizeof(bits), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    std::memcpy(&raw1, &bits, sizeof(raw1));
+    lip1_node = safety1 * raw1;
+  }
+  const float tau1 = lip1_node * B1 * 0.8660254f;
+  CU_TRY(launch_select_blocks_bits(sp.cs, nb1, tau1, sp.keep, st));
+  // kept block ids: the same compaction as for nodes (ascending ids), into sp.idx, then copied to sp.ids
+  long long nA = 0;
+  rc = sparse_compact(d, sp.keep, (blocks + 31) / 32, &nA, st);
+  if (rc) return rc;
+  if (nA) CU_TRY(cudaMemcpyAsync(sp.ids, sp.idx, nA * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  // level 2: the sub-block lattice inside the kept blocks, every node once
+  long long n1 = 0, n2 = 0;
+  unsigned long long kept_sub = 0;
+  float raw2 = 0.f;
+  if (nA) {
+    CU_TRY(launch_mark_sub_corners(res, B1, B2, nb1, sp.ids, nA, sp.need1, st));
+    rc = sparse_compact(d, sp.need1, words, &n1, st);
+    if (rc) return rc;
+    rc = sparse_decode_nodes(d, latent_dev, res, n1, sdf_dense_dev, precision, st);
+    if (rc) return rc;
+    // the finer lattice sees the field's steepest slopes better than the coarse one: L2 = safety2 * max(raw1, raw2)
+    // (sp.lip[0] = level-1 quotient, sp.lip[1] = level-2 quotient; the selection kernel takes the larger)
+    if (!(lipschitz > 0.f)) CU_TRY(launch_sub_lipschitz(res, B1, B2, nb1, sp.ids, nA, sdf_dense_dev, sp.lip + 1, st));
+    CU_TRY(launch_select_sub_blocks(res, B1, B2, nb1, sp.ids, nA, sdf_dense_dev, sp.lip, lipschitz > 0.f ? lipschitz * h : 0.f,
+                                    safety2, sp.need2, sp.kept, st));
+    CU_TRY(launch_andnot(sp.need2, sp.need1, words, st));
+    rc = sparse_compact(d, sp.need2, words, &n2, st);
+    if (rc) return rc;
+    rc = sparse_decode_nodes(d, latent_dev, res, n2, sdf_dense_dev, precision, st);
+    if (rc) return rc;
+  }
+  CU_TRY(launch_fill_signs(res, B1, B2, nb1, sdf_dense_dev, sp.need1, sp.need2, sp.cs, sign_bits_dev, st));
+  if (stats_host != nullptr) {
+    unsigned int bits2 = 0;
+    CU_TRY(cudaMemcpyAsync(&kept_sub, sp.kept, sizeof(kept_sub), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(&bits2, sp.lip + 1, sizeof(bits2), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    std::memcpy(&raw2, &bits2, sizeof(raw2));
+    stats_host[0] = corners; stats_host[1] = nA; stats_host[2] = n1; stats_host[3] = static_cast<int64_t>(kept_sub); stats_host[4] = n2;
+    stats_host[5] = corners + n1 + n2;                                       // queries decoded in total
+    stats_host[6] = static_cast<int64_t>(1e6f * raw1 / h);                   // level-1 difference quotient, field units per unit length, x 1e6
+    stats_host[7] = static_cast<int64_t>(1e6f * raw2 / h);                   // level-2
+  }
+  return SDFB_OK;
 }
 
 int sdfb_decode_debug_pass(sdfb_decoder* d, const float* latent_dev, int res, int pass, float* dump_dev,

@@ -9,6 +9,7 @@
 //     device-to-device over NVLink / NVSwitch) while its SMs keep decoding the next sub-slab - the persistent decoder
 //     kernel occupies every SM, so a collective that needs SMs of its own (an NCCL kernel) cannot overlap with it.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -111,6 +112,7 @@ namespace sdfb {
 
 int comm_barrier(sdfb_comm* c, cudaStream_t st) {
   if (c->world == 1) return SDFB_OK;
+  if (const char* e = std::getenv("SDFB_PUSH_OFF")) if (e[0] == '2') return SDFB_OK;   // diagnostics only
   NcclApi* a = nccl_api();
   if (!a) return set_error(SDFB_E_CUDA, "NCCL is not available (libnccl.so.2 could not be loaded)");
   const int rc = a->all_reduce(c->token, c->token + 1, 1, kNcclInt32, kNcclSum, c->nccl, st);
@@ -161,6 +163,7 @@ int comm_shared_alloc(sdfb_comm* c, size_t bytes) {
 
 int comm_push(sdfb_comm* c, size_t offset, size_t bytes, cudaStream_t after) {
   if (c->world == 1 || bytes == 0) return SDFB_OK;
+  if (std::getenv("SDFB_PUSH_OFF") != nullptr) return SDFB_OK;      // diagnostics (tools/prof_sharded.py): peers get nothing
   if (offset + bytes > c->bytes) return set_error(SDFB_E_INVALID, "push outside the symmetric buffer");
   CU_TRY(cudaEventRecord(c->ev_ready, after));
   for (cudaStream_t s : c->st_push) CU_TRY(cudaStreamWaitEvent(s, c->ev_ready, 0));

@@ -151,6 +151,7 @@ struct Epi {
   int set;                // 0/1: which of the two warp sets (splits chunks / head columns)
   int lane;
   long long* trace;       // diagnostics: where to stamp "accumulator full seen" of the next pass (nullptr: off)
+  uint32_t dbg;           // DecodeParams::debug_flags (timing experiments under SDFB_K1_EXPERIMENTS: bit2 / bit3, see kernels.h)
 };
 
 // Hidden pass.  The two warp sets work on the SAME chunk at the same time (set s converts
@@ -189,6 +190,16 @@ __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict_
     const int col = cc * 64 + e.set * 32;
     uint32_t packed[16];
     uint32_t bits = 0;
+#ifdef SDFB_K1_EXPERIMENTS
+    if (e.dbg & 4u) {      // timing experiment: no conversion, no stores - only the barrier protocol (results are garbage)
+      if (wait_free) {
+        if (!mbar_wait(e.bars + 8 * (kBarAFree + c0 + cc), ((e.wphase >> (c0 + cc)) & 1u) ^ 1u, wd, kErrAFree, c0 + cc)) return false;
+      }
+      __syncwarp();
+      if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c0 + cc), 1);
+      continue;
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 t = *reinterpret_cast<const float4*>(sbias + col + 4 * j);
@@ -218,11 +229,18 @@ __device__ __forceinline__ bool epi_hidden_pass(Epi& e, const float* __restrict_
       if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
     }
     const uint32_t base = e.a_row_addr + c * kAChunkBytes;
+#ifdef SDFB_K1_EXPERIMENTS
+    if (e.dbg & 8u) {      // (bit3, timing experiment: conversion but no stores / proxy fence)
+      asm volatile("" ::"r"(packed[0] ^ packed[5] ^ packed[10] ^ packed[15]));
+    } else
+#endif
+    {
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      st_shared_v4(base + (((4 * e.set + u) ^ e.row7) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
-                   packed[4 * u + 3]);
-    fence_proxy_async_smem();
+      for (int u = 0; u < 4; ++u)
+        st_shared_v4(base + (((4 * e.set + u) ^ e.row7) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
+                     packed[4 * u + 3]);
+      fence_proxy_async_smem();
+    }
     __syncwarp();
     if (e.lane == 0) arrive_on_leader(e.bars + 8 * (kBarAReady + c), 1);
   }
@@ -601,6 +619,7 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
     e.wphase = 0;
     e.acc_phase = 0;
     e.trace = nullptr;
+    e.dbg = p.debug_flags;
     L0Weights wl[4];                                      // layer-0 features of this lane, per step
     auto load_l0_weights = [&](L0Weights (&w)[4]) {
 #pragma unroll

@@ -76,6 +76,8 @@ struct DecodeParams {
   long long* prof;             // optional [grid][3 roles][8]: blocked cycles per wait class (diagnostics)
   unsigned int debug_flags;    // bit0: producer skips the weight copies (timing experiment; results are garbage)
                                // bit1: producer exits at once (test hook: every consumer wait runs into the watchdog)
+                               // bit2: hidden-pass epilogues only run the barrier protocol; bit3: they convert but do not store
+                               //       (timing experiments, results are garbage)
   // forward + backward kernel only (`bwd` selects it; `out` is then optional, `signs` unused)
   const float* dLdy;           // [M] upstream gradient d loss / d sdf
   const unsigned int* dLdy_amax;   // bits of max |dLdy| (launch_abs_max): the kernel works on dLdy * 2^-vjp_scale_exponent
@@ -255,6 +257,27 @@ size_t block_select_temp_bytes(long long nblocks);
 cudaError_t launch_block_select(const float* corner_sdf, int nb, float tau, unsigned char* flags, int* ids_all, int* ids_out,
                                 int* count_dev, void* temp, size_t temp_bytes, cudaStream_t stream);
 cudaError_t launch_block_points(int res, int B, int nb, const int* blocks, long long nblk, float* xyz, cudaStream_t stream);
+
+// ---- hierarchical sparse decode (sparse.cu) -----------------------------------------------------------------------
+cudaError_t launch_corner_nodes(int res, int B, int nb, unsigned int* idx, cudaStream_t st);
+cudaError_t launch_node_points(int res, const unsigned int* idx, long long n, float* xyz, cudaStream_t st);
+cudaError_t launch_scatter(const unsigned int* idx, const float* vals, long long n, float* dense, cudaStream_t st);
+cudaError_t launch_corner_lipschitz(const float* cs, int res, int B, int nb, unsigned int* out_bits, cudaStream_t st);
+cudaError_t launch_select_blocks_bits(const float* cs, int nb, float tau, unsigned int* keep, cudaStream_t st);
+cudaError_t launch_mark_sub_corners(int res, int B1, int B2, int nb1, const int* blocks, long long nblk, unsigned int* need,
+                                    cudaStream_t st);
+cudaError_t launch_sub_lipschitz(int res, int B1, int B2, int nb1, const int* blocks, long long nblk, const float* dense,
+                                 unsigned int* out_bits, cudaStream_t st);
+cudaError_t launch_select_sub_blocks(int res, int B1, int B2, int nb1, const int* blocks, long long nblk, const float* dense,
+                                     const unsigned int* lip_bits, float lip_given_per_node, float safety, unsigned int* need,
+                                     unsigned long long* kept, cudaStream_t st);
+cudaError_t launch_andnot(unsigned int* a, const unsigned int* b, long long words, cudaStream_t st);
+long long bitmap_scan_tiles(long long words);
+cudaError_t launch_bitmap_count(const unsigned int* bits, long long words, unsigned int* tile_sums, cudaStream_t st);
+cudaError_t launch_bitmap_emit(const unsigned int* bits, long long words, const unsigned int* tile_offsets, unsigned int* out,
+                               cudaStream_t st);
+cudaError_t launch_fill_signs(int res, int B1, int B2, int nb1, const float* dense, const unsigned int* need1,
+                              const unsigned int* need2, const float* cs, unsigned int* signs, cudaStream_t st);
 
 // A1: node coordinate, one correctly rounded divide of two exact integers.
 __host__ __device__ inline float axis_coord_num(int i, int res) { return static_cast<float>(2 * i - (res - 1)); }

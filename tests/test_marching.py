@@ -106,9 +106,9 @@ def test_sparse_extraction_equals_dense(cuda_decoder, res, block):
     dense = cuda_decoder.extract_surface(z, res).cpu().numpy()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    cuda_decoder.extract_surface_sparse(z, res, block=block)
+    cuda_decoder.extract_surface_sparse(z, res, block=block, method="blocks")
     a.record()
-    sparse, st = cuda_decoder.extract_surface_sparse(z, res, block=block, return_stats=True)
+    sparse, st = cuda_decoder.extract_surface_sparse(z, res, block=block, return_stats=True, method="blocks")
     b.record()
     b.synchronize()
     print(f"res {res} block {block}: {st['blocks']}/{st['blocks_total']} blocks, {st['queries']} of {st['dense_queries']} queries "
@@ -117,6 +117,42 @@ def test_sparse_extraction_equals_dense(cuda_decoder, res, block):
     assert np.array_equal(_sorted_tris(sparse.cpu().numpy()), _sorted_tris(dense))
     if res >= 256:        # the criterion is exact (Lipschitz band), hence conservative: the saving grows with the resolution
         assert st["queries"] < st["dense_queries"] * (0.5 if res >= 512 else 0.75)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res,seed,scale", [(64, 0, 1.0), (97, 1, 1.0), (130, 2, 1.0), (256, 0, 1.0), (256, 3, 1.5), (255, 5, 0.5), (512, 0, 1.0)])
+def test_hierarchical_sparse_extraction_equals_dense(cuda_decoder, res, seed, scale):
+    """The two-level sparse decode (corners of 8^3 blocks -> lattice of 2^3 sub-blocks -> remaining nodes, every node once)
+    followed by the DENSE marching-cubes kernels gives the dense extraction's triangle soup bit for bit, ORDER INCLUDED, and
+    the complete sign bit-planes it builds (decoded signs + inherited signs of the discarded regions) equal the dense ones.
+    Different latents and latent scales vary the shapes; odd sizes make every level ragged at the upper faces."""
+    z = oracle.default_latent(seed) * np.float32(scale)
+    sdf_d, signs_d, _ = cuda_decoder.decode_grid_bits(z, res, mask=False)
+    dense = cuda_decoder.extract_surface(z, res)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cuda_decoder.extract_surface_sparse(z, res)
+    a.record()
+    sparse, st = cuda_decoder.extract_surface_sparse(z, res, return_stats=True)
+    b.record()
+    b.synchronize()
+    print(f"res {res} latent {seed} x{scale}: {st['queries']} of {st['dense_queries']} queries ({st['dense_queries'] / max(st['queries'], 1):.1f}x fewer: "
+          f"{st['corner_queries']} corners, {st['blocks_kept']} blocks -> {st['lattice_queries']} lattice nodes, {st['sub_blocks_kept']} sub-blocks -> "
+          f"{st['fill_queries']} more), {sparse.shape[0]} triangles in {a.elapsed_time(b):.2f} ms, L1 {st['lipschitz_level1']:.2f} L2 {st['lipschitz_level2']:.2f}")
+    assert sparse.shape == dense.shape and torch.equal(sparse, dense)
+    assert dense.shape[0] > 1000                                                 # a real surface (not a saturated field)
+    sdf_s, signs_s, _ = cuda_decoder.decode_sparse_field(z, res)
+    nw = (res ** 3 + 31) // 32
+    assert torch.equal(signs_s[:nw], signs_d[:nw])                               # every node's sign, decoded or inherited
+    act = cuda_decoder.decode_grid(z, res, mask=True)[1].bool()                  # cells the surface crosses: all 8 corners were decoded
+    for dz in (0, 1):
+        for dy in (0, 1):
+            for dx in (0, 1):
+                va = sdf_s[dz:res - 1 + dz, dy:res - 1 + dy, dx:res - 1 + dx][act]
+                vb = sdf_d[dz:res - 1 + dz, dy:res - 1 + dy, dx:res - 1 + dx][act]
+                assert torch.equal(va, vb)
+    if res >= 256 and scale == 1.0:
+        assert st["queries"] < st["dense_queries"] * (0.2 if res >= 512 else 0.4)
 
 
 @pytest.mark.gpu
@@ -136,6 +172,8 @@ def test_indexed_mesh_welding(pkg, cuda_decoder):
     assert verts.shape[0] - n_edges + fa.shape[0] == 2                       # a sphere
     z = oracle.default_latent()
     v1, f1 = cuda_decoder.extract_surface(z, 97, indexed=True)
-    v2, f2 = cuda_decoder.extract_surface_sparse(z, 97, block=8, indexed=True)
+    v2, f2 = cuda_decoder.extract_surface_sparse(z, 97, block=8, indexed=True, method="blocks")
+    v3, f3 = cuda_decoder.extract_surface_sparse(z, 97, indexed=True)         # two-level path: same soup, same order
+    assert torch.equal(v1, v3) and torch.equal(f1, f3)
     assert v1.shape == v2.shape and torch.equal(v1, v2)                      # unique() sorts by edge key: identical vertex arrays
     assert f1.shape == f2.shape
