@@ -62,6 +62,8 @@ extern "C" {
 typedef struct sdfb_decoder sdfb_decoder;
 typedef struct sdfb_ddpm sdfb_ddpm;
 typedef struct sdfb_comm sdfb_comm;
+typedef struct sdfb_ddpm_trainer sdfb_ddpm_trainer;
+typedef struct sdfb_decoder_trainer sdfb_decoder_trainer;
 
 int sdfb_version(void);
 const char* sdfb_last_error(void);
@@ -281,6 +283,43 @@ int sdfb_allgather_slabs(sdfb_comm* comm, void* full_dev, size_t bytes_per_rank,
 int sdfb_decode_grid_sharded(sdfb_decoder* dec, sdfb_comm* comm, const float* latent_dev, int res, int want_mask,
                              int sub_planes, int precision, float** sdf_full_dev, uint32_t** mask_bits_dev,
                              size_t* mask_words_per_rank, void* stream);
+
+/* ---- training (second half) ---------------------------------------------------------------
+ * The inference kernels keep activations on chip; a training step needs every layer's activations and deltas for
+ * the weight gradients, so it runs layer by layer on a general tensor-core product (csrc/gemm_tc.cu: 16-bit
+ * operands through TMA, fp32 accumulation in TMEM; the weight gradient dW = delta^T h contracts over the batch
+ * rows of two row-major arrays, i.e. with MN-major operand descriptors), activations and deltas kept in 16 bits,
+ * master weights, Adam moments and all reductions in fp32.
+ *
+ * DDPM denoiser training step: x_t = sqrt(abar_t) x0 + sqrt(1 - abar_t) eps per row (t_dev [n] in [0, 1000)),
+ * loss = mean (eps_hat(x_t, t) - eps)^2, gradients of all weights and biases, Adam with bias correction (apply != 0;
+ * apply == 0 only evaluates).  loss_dev [1]; grads_dev (optional): the gradient in the parameter blob's layout.
+ * A trainer owns its copy of the parameters; sdfb_ddpm_trainer_get_params downloads them (synchronising), e.g. to
+ * build a sampler from them with sdfb_ddpm_create.  precision: SDFB_PREC_BF16 or SDFB_PREC_FP16. */
+int sdfb_ddpm_trainer_create(const float* params_host, size_t n_floats, int device, int precision, sdfb_ddpm_trainer** out);
+int sdfb_ddpm_trainer_destroy(sdfb_ddpm_trainer* trainer);
+int sdfb_ddpm_trainer_step(sdfb_ddpm_trainer* trainer, const float* x0_dev, const int32_t* t_dev, const float* eps_dev, int n,
+                           float lr, float beta1, float beta2, float adam_eps, int apply, float* loss_dev, float* grads_dev,
+                           void* stream);
+int sdfb_ddpm_trainer_get_params(sdfb_ddpm_trainer* trainer, float* params_host);
+/* Auto-decoder training step (DeepSDF): a batch of shapes, latents_dev [batch][256], xyz_dev [batch][points_per_shape][3],
+ * target_dev [batch][points_per_shape]; loss = mean over all points of |clamp(sdf) - clamp(target)| (clamp to
+ * [-clamp_dist, clamp_dist]); gradients of all nine layers' weights and biases (dW_l = delta_l^T a_l on the tensor pipe,
+ * the head in fp32) and Adam on them (apply != 0).  The products run on the dense inputs [z | xyz] and [h3 | z | xyz] as
+ * the oracle does (the latents differ per row, so nothing is folded).  grads_dev (optional): the gradient in the
+ * decoder blob's layout; sdf_dev (optional, [batch * points_per_shape]): the forward values.  The latents' own gradient
+ * is what sdfb_decoder_fit_loss_grad_batch returns.  At most 2^21 points per step (17 KiB of workspace per point). */
+int sdfb_decoder_trainer_create(const float* params_host, size_t n_floats, int device, int precision, sdfb_decoder_trainer** out);
+int sdfb_decoder_trainer_destroy(sdfb_decoder_trainer* trainer);
+int sdfb_decoder_trainer_step(sdfb_decoder_trainer* trainer, const float* latents_dev, const float* xyz_dev, const float* target_dev,
+                              int batch, int64_t points_per_shape, float clamp_dist, float lr, float beta1, float beta2,
+                              float adam_eps, int apply, float* loss_dev, float* grads_dev, float* sdf_dev, void* stream);
+int sdfb_decoder_trainer_get_params(sdfb_decoder_trainer* trainer, float* params_host);
+/* Unit-test hook of the general product: out_dev [ksplit][M][N] fp32 partial sums of a . b^T (tn = 0: a [M][K], b [N][K])
+ * or a^T . b (tn = 1: a [K][M], b [K][N]); row-major 16-bit inputs, leading dimensions in elements (multiples of 8);
+ * bn = output tile width (64, 128, 256; N % bn == 0); tn: M % 64 == 0.  Runs on the current device; synchronises. */
+int sdfb_gemm_selftest(const uint16_t* a_dev, int lda, const uint16_t* b_dev, int ldb, int M, int N, int K, int tn, int ksplit,
+                       int bn, int precision, float* out_dev, void* stream);
 
 /* ---- unit-test hook for the UMMA plumbing -------------------------------- */
 /* D[128][256] (fp32) = A[128][64] * B[256][64]^T with A and B given as

@@ -69,6 +69,16 @@ SIGNATURES = {
     "sdfb_ddpm_sample_philox": (_i, [_vp, _vp, C.c_uint64, _i64, _i, _i, _i, _i, _vp]),
     "sdfb_ddpm_sample_philox_host": (_i, [_vp, _vp, C.c_uint64, _i64, _i, _i, _i, _i]),
     "sdfb_philox_normal": (_i, [C.c_uint64, _i64, _i, _i, _i, _vp, _vp]),
+    "sdfb_ddpm_trainer_create": (_i, [_vp, _sz, _i, _i, C.POINTER(_vp)]),
+    "sdfb_ddpm_trainer_destroy": (_i, [_vp]),
+    "sdfb_ddpm_trainer_step": (_i, [_vp, _vp, _vp, _vp, _i, C.c_float, C.c_float, C.c_float, C.c_float, _i, _vp, _vp, _vp]),
+    "sdfb_ddpm_trainer_get_params": (_i, [_vp, _vp]),
+    "sdfb_decoder_trainer_create": (_i, [_vp, _sz, _i, _i, C.POINTER(_vp)]),
+    "sdfb_decoder_trainer_destroy": (_i, [_vp]),
+    "sdfb_decoder_trainer_step": (_i, [_vp, _vp, _vp, _vp, _i, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i, _vp, _vp,
+                                       _vp, _vp]),
+    "sdfb_decoder_trainer_get_params": (_i, [_vp, _vp]),
+    "sdfb_gemm_selftest": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sdfb_umma_selftest": (_i, [_vp, _vp, _vp, _i, _vp]),
     "sdfb_umma_rate": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]),
 }

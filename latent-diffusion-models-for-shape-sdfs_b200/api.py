@@ -574,6 +574,121 @@ class LatentDDPM:
         return x
 
 
+class DDPMTrainer:
+    """Training of the latent DDPM's denoiser: one ``step`` = noising, forward, loss, backward
+    through all five layers and Adam, on the tensor pipe (``sdfb_ddpm_trainer_step``).  The trainer owns its copy of the
+    parameters; ``params()`` downloads them, ``sampler()`` builds a ``LatentDDPM`` from them."""
+
+    def __init__(self, params, device="cuda:0", precision: str = "bf16"):
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", _device_index(device))
+        self.precision = precision
+        if precision not in ("bf16", "fp16"):
+            raise ValueError("the training step runs on the tensor pipe: precision 'bf16' or 'fp16'")
+        flat = _flat_params(params, _lib.DDPM_PARAM_FLOATS)
+        handle = C.c_void_p()
+        check(self._lib.sdfb_ddpm_trainer_create(flat.ctypes.data, flat.size, self.device.index, _prec(precision), C.byref(handle)))
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sdfb_ddpm_trainer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, x0, t, eps, lr: float = 1e-4, betas=(0.9, 0.999), adam_eps: float = 1e-8, apply: bool = True,
+             return_grads: bool = False):
+        """x0 [n,256] clean latents, t [n] int32 in [0, 1000), eps [n,256] noise -> loss [1] (device tensor; nothing is
+        synchronised) and, with ``return_grads``, the gradient in the parameter blob's layout.  ``apply=False`` only evaluates."""
+        x = _as_dev_f32(x0, self.device)
+        e = _as_dev_f32(eps, self.device)
+        tt = torch.as_tensor(np.asarray(t) if not isinstance(t, torch.Tensor) else t).to(device=self.device, dtype=torch.int32).contiguous()
+        n = x.shape[0]
+        if x.shape != (n, LATENT) or e.shape != (n, LATENT) or tt.shape != (n,):
+            raise ValueError("expected x0 [n,256], t [n], eps [n,256]")
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        grads = torch.empty(_lib.DDPM_PARAM_FLOATS, dtype=torch.float32, device=self.device) if return_grads else None
+        check(self._lib.sdfb_ddpm_trainer_step(self._h, x.data_ptr(), tt.data_ptr(), e.data_ptr(), n, float(lr), float(betas[0]),
+                                               float(betas[1]), float(adam_eps), 1 if apply else 0, loss.data_ptr(),
+                                               grads.data_ptr() if grads is not None else None, _stream_ptr(self.device.index)))
+        return (loss, grads) if return_grads else loss
+
+    def params(self) -> np.ndarray:
+        out = np.empty(_lib.DDPM_PARAM_FLOATS, np.float32)
+        check(self._lib.sdfb_ddpm_trainer_get_params(self._h, out.ctypes.data))
+        return out
+
+    def sampler(self, precision: str | None = None) -> "LatentDDPM":
+        return LatentDDPM(self.params(), device=self.device, precision=precision or self.precision)
+
+
+class DecoderTrainer:
+    """Auto-decoder training: one ``step`` = forward over a batch of shapes' SDF samples,
+    clamped-L1 loss, gradients of every decoder weight and bias (weight gradients as tensor-core products contracting over
+    the sample index) and Adam (``sdfb_decoder_trainer_step``).  The latents' gradient comes from
+    ``Decoder.fit_loss_grad`` / ``fit_latents_batch``.  ``params()`` downloads the weights, ``decoder()`` builds a
+    ``Decoder`` from them."""
+
+    def __init__(self, params, device="cuda:0", precision: str = "bf16"):
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", _device_index(device))
+        self.precision = precision
+        if precision not in ("bf16", "fp16"):
+            raise ValueError("the training step runs on the tensor pipe: precision 'bf16' or 'fp16'")
+        flat = _flat_params(params, _lib.DECODER_PARAM_FLOATS)
+        handle = C.c_void_p()
+        check(self._lib.sdfb_decoder_trainer_create(flat.ctypes.data, flat.size, self.device.index, _prec(precision), C.byref(handle)))
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sdfb_decoder_trainer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, latents, xyz, sdf_target, clamp: float = 0.1, lr: float = 1e-4, betas=(0.9, 0.999), adam_eps: float = 1e-8,
+             apply: bool = True, return_grads: bool = False, return_sdf: bool = False):
+        """latents [B,256], xyz [B,P,3], sdf_target [B,P] -> loss [1] (device tensor, nothing synchronised), optionally the
+        gradient (decoder blob layout) and the forward values [B,P]."""
+        lat = _as_dev_f32(latents, self.device)
+        pts = _as_dev_f32(xyz, self.device)
+        tgt = _as_dev_f32(sdf_target, self.device)
+        if lat.ndim != 2 or lat.shape[1] != LATENT or pts.ndim != 3 or pts.shape[0] != lat.shape[0] or pts.shape[2] != 3 or tgt.shape != pts.shape[:2]:
+            raise ValueError("expected latents [B,256], xyz [B,P,3], sdf_target [B,P]")
+        B, P = pts.shape[0], pts.shape[1]
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        grads = torch.empty(_lib.DECODER_PARAM_FLOATS, dtype=torch.float32, device=self.device) if return_grads else None
+        sdf = torch.empty((B, P), dtype=torch.float32, device=self.device) if return_sdf else None
+        check(self._lib.sdfb_decoder_trainer_step(self._h, lat.data_ptr(), pts.data_ptr(), tgt.data_ptr(), B, P, float(clamp), float(lr),
+                                                  float(betas[0]), float(betas[1]), float(adam_eps), 1 if apply else 0, loss.data_ptr(),
+                                                  grads.data_ptr() if grads is not None else None,
+                                                  sdf.data_ptr() if sdf is not None else None, _stream_ptr(self.device.index)))
+        out = (loss,)
+        if return_grads:
+            out += (grads,)
+        if return_sdf:
+            out += (sdf,)
+        return out if len(out) > 1 else loss
+
+    def params(self) -> np.ndarray:
+        out = np.empty(_lib.DECODER_PARAM_FLOATS, np.float32)
+        check(self._lib.sdfb_decoder_trainer_get_params(self._h, out.ctypes.data))
+        return out
+
+    def decoder(self, precision: str | None = None) -> "Decoder":
+        return Decoder(self.params(), device=self.device, precision=precision or self.precision)
+
+
 class _DevArray:
     """A device pointer owned by the C library, seen by torch without a copy (``__cuda_array_interface__``)."""
 

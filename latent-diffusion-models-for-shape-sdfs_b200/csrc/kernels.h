@@ -176,6 +176,64 @@ int ddpm_max_clusters8(int bn_h, int nstages, bool fp16);
 cudaError_t launch_philox_normal(unsigned long long seed, unsigned int first_latent, int n, int t0, int t1, float* out,
                                  cudaStream_t stream);
 
+// ---- general tensor-core product for the training steps (gemm_tc.cu) ---------------------------------------------
+enum : int { kGemmEpiF32 = 0, kGemmEpiBiasReluLowp = 1, kGemmEpiMaskLowp = 2 };
+struct GemmParams {
+  int M, N, K;                 // output C[M][N]; contraction length K
+  int bn;                      // output tile width: 64, 128 or 256 (N % bn == 0)
+  int ksplit;                  // K is cut into `ksplit` ranges; range s accumulates into out_f32 + s * split_stride
+  int epi;                     // kGemmEpi*: what happens to alpha * acc (+ bias) before it is stored
+  float alpha;
+  const float* bias;           // [N] or nullptr
+  const uint16_t* mask_h;      // kGemmEpiMaskLowp: forward activations [M][ldh], the value is kept where they are > 0
+  int ldh;
+  float* out_f32;              // optional fp32 output [M][ldo_f32] (kGemmEpiBiasReluLowp: the pre-activation unless f32_post_relu)
+  int ldo_f32;
+  long long split_stride;      // elements between the partial outputs of consecutive k-ranges
+  int f32_post_relu;
+  uint16_t* out_lowp;          // optional 16-bit output [M][ldo_lowp] (rectified for kGemmEpiBiasReluLowp)
+  int ldo_lowp;
+  unsigned int* status;        // watchdog status word + host mirror
+  unsigned int* status_host;
+  unsigned long long timeout_ns;
+};
+cudaError_t gemm_tc_init();
+cudaError_t launch_gemm_tc(const GemmParams& p, const uint16_t* a, int lda, const uint16_t* b, int ldb, bool tn, bool fp16,
+                           int num_sms, cudaStream_t stream);
+
+// ---- training helpers (train_kernels.cu) ------------------------------------------------------------------------------
+// x_t = sa[t] x0 + sb[t] eps per row -> in0 [n][512] 16-bit = [x_t | temb(t_row)] (temb table [1000][256] fp32)
+cudaError_t launch_ddpm_train_prep(const float* x0, const float* eps, const int* t, const float* coef_ab /* [1000][2] */,
+                                   const float* temb, int n, uint16_t* in0, bool fp16, cudaStream_t st);
+// residual d = eps_hat - eps -> 16-bit [n][256]; loss_partial[block] = sum d^2 (fixed order)
+cudaError_t launch_ddpm_train_residual(const float* eps_hat, const float* eps, int n, uint16_t* d_lowp, float* loss_partial,
+                                       int* nblocks, bool fp16, cudaStream_t st);
+// out[j] = scale * sum_m D[m][j], D 16-bit [M][ld] (deterministic: row slabs in parallel, partial sums added in slab order, fp32);
+// scratch: kColsumSlabs * N floats
+constexpr int kColsumSlabs = 128;
+cudaError_t launch_colsum_lowp(const uint16_t* D, long long M, int ld, int N, float scale, float* out, float* scratch, bool fp16,
+                               cudaStream_t st);
+// fused Adam over one parameter tensor: g = scale * sum_{s < nparts} grad[s * part_stride + i]; updates master fp32 weights and
+// moments in place and refreshes the 16-bit copies W [rows][ldw] and W^T [cols][ldwt] (either may be null; rows x cols = the
+// tensor's shape, cols = 1 for a bias with both copies null).  grad_out (optional): receives g.
+struct AdamParams { float lr, beta1, beta2, eps, bias_corr1, bias_corr2; };
+cudaError_t launch_adam_update(float* w, float* m, float* v, const float* grad, int nparts, long long part_stride, int ld_grad,
+                               float scale, int rows, int cols, const AdamParams& a, uint16_t* w_lowp, int ldw, uint16_t* wt_lowp,
+                               int ldwt, float* grad_out, bool fp16, bool apply, cudaStream_t st);
+cudaError_t launch_sum_loss(const float* partial, int n, float scale, float* loss_out, cudaStream_t st);
+// fp32 [rows][cols] (leading dimension ld) -> 16-bit copy [rows][ldw] and transposed copy [cols][ldwt] (either may be null)
+cudaError_t launch_lowp_copies(const float* w, int ld, int rows, int cols, uint16_t* w_lowp, int ldw, uint16_t* wt_lowp, int ldwt,
+                               bool fp16, cudaStream_t st);
+
+// decoder training: input rows [z_shape | xyz | 0] into columns [col0, col0 + ncols) of a 16-bit matrix; head forward + loss terms +
+// delta7; head gradients (out[0..511] = dW8, out[512] = db8)
+cudaError_t launch_dec_train_input(const float* latents, const float* xyz, long long M, long long per_shape, int ld, int col0, int ncols,
+                                   uint16_t* out, bool fp16, cudaStream_t st);
+cudaError_t launch_dec_train_head(const uint16_t* a8, const float* w8, const float* b8, const float* target, float clamp, long long M,
+                                  float* y, float* d8, uint16_t* delta7, float* loss_partial, int* nblocks, bool fp16, cudaStream_t st);
+cudaError_t launch_dec_train_head_grad(const uint16_t* a8, const float* d8, long long M, float scale, float* out, float* scratch, bool fp16,
+                                       cudaStream_t st);
+
 // ---- fp32 SIMT kernels (fp32_kernels.cu) -----------------------------------
 // C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); row-major, leading dims in elements.
 cudaError_t launch_linear_f32(const float* A, int lda, const float* W, int ldw, const float* bias,

@@ -1,0 +1,357 @@
+// Small HBM-bound kernels around the tensor-core products of the training steps (oracle:
+// oracle/train.py; no upstream source exists, /root/reference/README.md:1): noising + input assembly, residual and loss,
+// deterministic column sums (bias gradients), fused Adam with refresh of the 16-bit weight copies.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "kernels.h"
+
+namespace sdfb {
+
+namespace {
+
+template <bool FP16>
+__device__ __forceinline__ uint16_t to_lowp_bits(float f) {
+  if constexpr (FP16) return __half_as_ushort(__float2half_rn(f));
+  else return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+template <bool FP16>
+__device__ __forceinline__ float from_lowp_bits(uint16_t b) {
+  if constexpr (FP16) return __half2float(__ushort_as_half(b));
+  else return __uint_as_float(static_cast<uint32_t>(b) << 16);
+}
+
+// one thread per (row, column): columns [0, 256) = x_t, [256, 512) = temb(t_row)
+template <bool FP16>
+__global__ void ddpm_train_prep_kernel(const float* __restrict__ x0, const float* __restrict__ eps, const int* __restrict__ t,
+                                       const float* __restrict__ coef_ab, const float* __restrict__ temb, int n,
+                                       uint16_t* __restrict__ in0) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(n) * 512) return;
+  const long long r = i >> 9;
+  const int c = static_cast<int>(i & 511);
+  const int tr = t[r];
+  float v;
+  if (c < 256) {
+    const float a = coef_ab[2 * tr], b = coef_ab[2 * tr + 1];
+    v = __fadd_rn(__fmul_rn(a, x0[r * 256 + c]), __fmul_rn(b, eps[r * 256 + c]));
+  } else {
+    v = temb[tr * 256 + (c - 256)];
+  }
+  in0[i] = to_lowp_bits<FP16>(v);
+}
+
+constexpr int kResBlock = 256, kResPerThread = 16;
+
+template <bool FP16>
+__global__ void __launch_bounds__(kResBlock) ddpm_train_residual_kernel(const float* __restrict__ eps_hat, const float* __restrict__ eps,
+                                                                        long long count, uint16_t* __restrict__ d_lowp,
+                                                                        float* __restrict__ loss_partial) {
+  __shared__ float warp_sums[kResBlock / 32];
+  const long long base = static_cast<long long>(blockIdx.x) * kResBlock * kResPerThread;
+  float s = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < kResPerThread; ++k) {
+    const long long i = base + static_cast<long long>(k) * kResBlock + threadIdx.x;
+    if (i < count) {
+      const float d = __fsub_rn(eps_hat[i], eps[i]);
+      d_lowp[i] = to_lowp_bits<FP16>(d);
+      s = fmaf(d, d, s);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < kResBlock / 32; ++i) tot += warp_sums[i];
+    loss_partial[blockIdx.x] = tot;
+  }
+}
+
+__global__ void sum_loss_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ out) {
+  // one warp, fixed order: lane l adds entries l, l + 32, ...; then a shuffle tree
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) s += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+
+// column sums of a 16-bit matrix: block = 32 columns x 8 row-slices; rows in order inside a slice, slices added in order
+// (blockIdx.y = row slab of `slab_rows` rows: partial sums [slab][N], added up in slab order by colsum_finish_kernel)
+template <bool FP16>
+__global__ void __launch_bounds__(256) colsum_lowp_kernel(const uint16_t* __restrict__ D, long long M, int ld, int N, long long slab_rows,
+                                                          float* __restrict__ partial) {
+  __shared__ float part[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int slice = threadIdx.x >> 5;
+  const long long s0 = blockIdx.y * slab_rows, s1 = s0 + slab_rows < M ? s0 + slab_rows : M;
+  const long long per = (s1 - s0 + 7) / 8;
+  const long long r0 = s0 + slice * per, r1 = r0 + per < s1 ? r0 + per : s1;
+  float s = 0.f;
+  if (col < N)
+    for (long long r = r0; r < r1; ++r) s += from_lowp_bits<FP16>(D[r * ld + col]);
+  part[slice][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (slice == 0 && col < N) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += part[k][threadIdx.x];
+    partial[static_cast<long long>(blockIdx.y) * N + col] = tot;
+  }
+}
+
+__global__ void colsum_finish_kernel(const float* __restrict__ partial, int slabs, int N, float scale, float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  float tot = 0.f;
+  for (int k = 0; k < slabs; ++k) tot += partial[static_cast<long long>(k) * N + col];
+  out[col] = tot * scale;
+}
+
+// Adam on a [rows][cols] tensor; tile of 32 x 32 per block (a transposed 16-bit copy is written coalesced through smem)
+template <bool FP16>
+__global__ void __launch_bounds__(256) adam_update_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                                                          const float* __restrict__ grad, int nparts, long long part_stride, int ld_grad,
+                                                          float scale, int rows, int cols, AdamParams a, uint16_t* __restrict__ w_lowp,
+                                                          int ldw, uint16_t* __restrict__ wt_lowp, int ldwt, float* __restrict__ grad_out,
+                                                          int apply) {
+  __shared__ uint16_t tile[32][34];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    uint16_t lw = 0;
+    if (r < rows && c < cols) {
+      const long long i = static_cast<long long>(r) * cols + c;
+      float g = 0.f;
+      for (int s = 0; s < nparts; ++s) g += grad[s * part_stride + static_cast<long long>(r) * ld_grad + c];
+      g *= scale;
+      if (grad_out != nullptr) grad_out[i] = g;
+      float wi = w[i];
+      if (apply) {
+        const float mi = a.beta1 * m[i] + (1.f - a.beta1) * g;
+        const float vi = a.beta2 * v[i] + (1.f - a.beta2) * g * g;
+        m[i] = mi;
+        v[i] = vi;
+        wi = wi - a.lr * (mi / a.bias_corr1) / (sqrtf(vi / a.bias_corr2) + a.eps);
+        w[i] = wi;
+      }
+      lw = to_lowp_bits<FP16>(wi);
+      if (w_lowp != nullptr) w_lowp[static_cast<long long>(r) * ldw + c] = lw;
+    }
+    tile[ty + 8 * k][tx] = lw;
+  }
+  if (wt_lowp == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k, r = r0 + tx;         // transposed: row index of W^T = column of W
+    if (r < rows && c < cols) wt_lowp[static_cast<long long>(c) * ldwt + r] = tile[tx][ty + 8 * k];
+  }
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(256) lowp_copies_kernel(const float* __restrict__ w, int ld, int rows, int cols,
+                                                          uint16_t* __restrict__ w_lowp, int ldw, uint16_t* __restrict__ wt_lowp, int ldwt) {
+  __shared__ uint16_t tile[32][34];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    uint16_t lw = 0;
+    if (r < rows && c < cols) {
+      lw = to_lowp_bits<FP16>(w[static_cast<long long>(r) * ld + c]);
+      if (w_lowp != nullptr) w_lowp[static_cast<long long>(r) * ldw + c] = lw;
+    }
+    tile[ty + 8 * k][tx] = lw;
+  }
+  if (wt_lowp == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k, r = r0 + tx;
+    if (r < rows && c < cols) wt_lowp[static_cast<long long>(c) * ldwt + r] = tile[tx][ty + 8 * k];
+  }
+}
+
+// ---- decoder training helpers ------------------------------------------------------------------------------------------
+// decoder input rows [M][ld] 16-bit: columns [0, 256) = the row's shape latent, 256..258 = xyz, the rest zero
+template <bool FP16>
+__global__ void dec_train_input_kernel(const float* __restrict__ latents, const float* __restrict__ xyz, long long M,
+                                       long long per_shape, int ld, int col0, int ncols, uint16_t* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M * ncols) return;
+  const long long r = i / ncols;
+  const int c = static_cast<int>(i - r * ncols);
+  float v = 0.f;
+  if (c < 256) v = latents[(r / per_shape) * 256 + c];
+  else if (c < 259) v = xyz[r * 3 + (c - 256)];
+  out[r * ld + col0 + c] = to_lowp_bits<FP16>(v);
+}
+
+// head forward + loss + first delta: y = tanh(a8 . w8 + b8) (fp32 dot over the 16-bit activations), clamped-L1 loss terms,
+// d8 = sign(clamp(y) - clamp(target)) [|y| < clamp] (1 - y^2)  (the 1 / M is applied later), delta7 = d8 w8 [a8 > 0] -> 16-bit.
+// One warp per row.
+template <bool FP16>
+__global__ void __launch_bounds__(256) dec_train_head_kernel(const uint16_t* __restrict__ a8, const float* __restrict__ w8,
+                                                             const float* __restrict__ b8, const float* __restrict__ target, float clamp,
+                                                             long long M, float* __restrict__ y_out, float* __restrict__ d8_out,
+                                                             uint16_t* __restrict__ delta7, float* __restrict__ loss_partial) {
+  __shared__ float wsum[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + warp;
+  float lterm = 0.f;
+  if (r < M) {
+    float h[16];
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      h[k] = from_lowp_bits<FP16>(a8[r * 512 + lane + 32 * k]);
+      dot = fmaf(h[k], w8[lane + 32 * k], dot);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float y = tanhf(dot + b8[0]);
+    const float c = clamp;
+    const float diff = fminf(fmaxf(y, -c), c) - fminf(fmaxf(target[r], -c), c);
+    const float up = (y > -c && y < c) ? (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) : 0.f;
+    const float d8 = up * (1.f - y * y);
+    if (lane == 0) { y_out[r] = y; d8_out[r] = d8; lterm = fabsf(diff); }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      delta7[r * 512 + lane + 32 * k] = to_lowp_bits<FP16>(h[k] > 0.f ? d8 * w8[lane + 32 * k] : 0.f);
+  }
+  if (lane == 0) wsum[warp] = lterm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += wsum[i];
+    loss_partial[blockIdx.x] = s;
+  }
+}
+
+// dW8[k] = scale sum_m d8[m] a8[m][k]; db8 = scale sum_m d8[m]   (same slicing as colsum_lowp_kernel; column 512 = the bias)
+template <bool FP16>
+__global__ void __launch_bounds__(256) dec_train_head_grad_kernel(const uint16_t* __restrict__ a8, const float* __restrict__ d8, long long M,
+                                                                  long long slab_rows, float* __restrict__ partial /* [slabs][513] */) {
+  __shared__ float part[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int slice = threadIdx.x >> 5;
+  const long long s0 = blockIdx.y * slab_rows, s1 = s0 + slab_rows < M ? s0 + slab_rows : M;
+  const long long per = (s1 - s0 + 7) / 8;
+  const long long r0 = s0 + slice * per, r1 = r0 + per < s1 ? r0 + per : s1;
+  float s = 0.f;
+  if (col < 512) {
+    for (long long r = r0; r < r1; ++r) s = fmaf(d8[r], from_lowp_bits<FP16>(a8[r * 512 + col]), s);
+  } else if (col == 512) {
+    for (long long r = r0; r < r1; ++r) s += d8[r];
+  }
+  part[slice][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (slice == 0 && col <= 512) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += part[k][threadIdx.x];
+    partial[static_cast<long long>(blockIdx.y) * 513 + col] = tot;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_ddpm_train_prep(const float* x0, const float* eps, const int* t, const float* coef_ab, const float* temb, int n,
+                                   uint16_t* in0, bool fp16, cudaStream_t st) {
+  const long long total = static_cast<long long>(n) * 512;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (fp16) ddpm_train_prep_kernel<true><<<blocks, 256, 0, st>>>(x0, eps, t, coef_ab, temb, n, in0);
+  else ddpm_train_prep_kernel<false><<<blocks, 256, 0, st>>>(x0, eps, t, coef_ab, temb, n, in0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ddpm_train_residual(const float* eps_hat, const float* eps, int n, uint16_t* d_lowp, float* loss_partial,
+                                       int* nblocks, bool fp16, cudaStream_t st) {
+  const long long count = static_cast<long long>(n) * 256;
+  const int blocks = static_cast<int>((count + kResBlock * kResPerThread - 1) / (kResBlock * kResPerThread));
+  *nblocks = blocks;
+  if (fp16) ddpm_train_residual_kernel<true><<<blocks, kResBlock, 0, st>>>(eps_hat, eps, count, d_lowp, loss_partial);
+  else ddpm_train_residual_kernel<false><<<blocks, kResBlock, 0, st>>>(eps_hat, eps, count, d_lowp, loss_partial);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sum_loss(const float* partial, int n, float scale, float* loss_out, cudaStream_t st) {
+  sum_loss_kernel<<<1, 32, 0, st>>>(partial, n, scale, loss_out);
+  return cudaGetLastError();
+}
+
+// `scratch`: kColsumSlabs x N floats
+cudaError_t launch_colsum_lowp(const uint16_t* D, long long M, int ld, int N, float scale, float* out, float* scratch, bool fp16,
+                               cudaStream_t st) {
+  const long long slab_rows = M <= 4096 ? (M > 0 ? M : 1) : (M + kColsumSlabs - 1) / kColsumSlabs;
+  const int slabs = static_cast<int>((M + slab_rows - 1) / slab_rows);
+  const dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>(slabs > 0 ? slabs : 1));
+  if (fp16) colsum_lowp_kernel<true><<<grid, 256, 0, st>>>(D, M, ld, N, slab_rows, scratch);
+  else colsum_lowp_kernel<false><<<grid, 256, 0, st>>>(D, M, ld, N, slab_rows, scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  colsum_finish_kernel<<<(N + 255) / 256, 256, 0, st>>>(scratch, slabs > 0 ? slabs : 1, N, scale, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adam_update(float* w, float* m, float* v, const float* grad, int nparts, long long part_stride, int ld_grad,
+                               float scale, int rows, int cols, const AdamParams& a, uint16_t* w_lowp, int ldw, uint16_t* wt_lowp,
+                               int ldwt, float* grad_out, bool fp16, bool apply, cudaStream_t st) {
+  const dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
+  if (fp16)
+    adam_update_kernel<true><<<grid, 256, 0, st>>>(w, m, v, grad, nparts, part_stride, ld_grad, scale, rows, cols, a, w_lowp, ldw,
+                                                    wt_lowp, ldwt, grad_out, apply ? 1 : 0);
+  else
+    adam_update_kernel<false><<<grid, 256, 0, st>>>(w, m, v, grad, nparts, part_stride, ld_grad, scale, rows, cols, a, w_lowp, ldw,
+                                                     wt_lowp, ldwt, grad_out, apply ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lowp_copies(const float* w, int ld, int rows, int cols, uint16_t* w_lowp, int ldw, uint16_t* wt_lowp, int ldwt,
+                               bool fp16, cudaStream_t st) {
+  const dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
+  if (fp16) lowp_copies_kernel<true><<<grid, 256, 0, st>>>(w, ld, rows, cols, w_lowp, ldw, wt_lowp, ldwt);
+  else lowp_copies_kernel<false><<<grid, 256, 0, st>>>(w, ld, rows, cols, w_lowp, ldw, wt_lowp, ldwt);
+  return cudaGetLastError();
+}
+
+}  // namespace sdfb
+
+namespace sdfb {
+cudaError_t launch_dec_train_input(const float* latents, const float* xyz, long long M, long long per_shape, int ld, int col0, int ncols,
+                                   uint16_t* out, bool fp16, cudaStream_t st) {
+  const long long total = M * ncols;
+  if (total <= 0) return cudaSuccess;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (fp16) dec_train_input_kernel<true><<<blocks, 256, 0, st>>>(latents, xyz, M, per_shape, ld, col0, ncols, out);
+  else dec_train_input_kernel<false><<<blocks, 256, 0, st>>>(latents, xyz, M, per_shape, ld, col0, ncols, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_dec_train_head(const uint16_t* a8, const float* w8, const float* b8, const float* target, float clamp, long long M,
+                                  float* y, float* d8, uint16_t* delta7, float* loss_partial, int* nblocks, bool fp16, cudaStream_t st) {
+  const int blocks = static_cast<int>((M + 7) / 8);
+  *nblocks = blocks;
+  if (fp16) dec_train_head_kernel<true><<<blocks, 256, 0, st>>>(a8, w8, b8, target, clamp, M, y, d8, delta7, loss_partial);
+  else dec_train_head_kernel<false><<<blocks, 256, 0, st>>>(a8, w8, b8, target, clamp, M, y, d8, delta7, loss_partial);
+  return cudaGetLastError();
+}
+cudaError_t launch_dec_train_head_grad(const uint16_t* a8, const float* d8, long long M, float scale, float* out, float* scratch, bool fp16,
+                                       cudaStream_t st) {
+  const long long slab_rows = M <= 4096 ? (M > 0 ? M : 1) : (M + kColsumSlabs - 1) / kColsumSlabs;
+  const int slabs = static_cast<int>((M + slab_rows - 1) / slab_rows);
+  const dim3 grid(17, static_cast<unsigned>(slabs > 0 ? slabs : 1));
+  if (fp16) dec_train_head_grad_kernel<true><<<grid, 256, 0, st>>>(a8, d8, M, slab_rows, scratch);
+  else dec_train_head_grad_kernel<false><<<grid, 256, 0, st>>>(a8, d8, M, slab_rows, scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  colsum_finish_kernel<<<3, 256, 0, st>>>(scratch, slabs > 0 ? slabs : 1, 513, scale, out);
+  return cudaGetLastError();
+}
+}  // namespace sdfb

@@ -22,3 +22,5 @@ from .ddpm import (ddpm_schedule, time_embedding, denoiser_forward,
                    ddpm_step, sample_latents, denoiser_forward_lowp, DDPM_LATENT_SCALE, to_decoder_latent)
 from .philox import philox4x32_10, philox_normal_rows, philox_sampler_inputs
 from .marching import marching_cubes, mesh_is_closed
+from .train import (ddpm_train_grads, ddpm_train_grads_lowp, adam_step, flatten_grads, ddpm_noised_input,
+                    decoder_train_grads, decoder_train_grads_lowp)

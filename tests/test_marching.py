@@ -49,6 +49,59 @@ def test_oracle_sphere_area_orientation_and_watertightness():
     assert oracle.marching_cubes(np.ones((4, 4, 4), np.float32)).shape == (0, 3, 3)
 
 
+def _mesh_volume(tris):
+    """Signed volume enclosed by an oriented closed triangle soup (divergence theorem), float64."""
+    t = tris.astype(np.float64)
+    return float(np.einsum("ij,ij->i", t[:, 0], np.cross(t[:, 1], t[:, 2])).sum() / 6.0)
+
+
+def _euler_characteristic(tris):
+    v = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 3)
+    _, idx = np.unique(v.view(np.uint32).reshape(-1, 3), axis=0, return_inverse=True)
+    f = idx.reshape(-1, 3)
+    f = f[(f[:, 0] != f[:, 1]) & (f[:, 1] != f[:, 2]) & (f[:, 0] != f[:, 2])]
+    e = np.unique(np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1), axis=0)
+    return int(np.unique(f).size - e.shape[0] + f.shape[0])
+
+
+def test_tables_against_analytic_shapes():
+    """A check of the generated case tables that does not go through the generator's own reasoning: meshes of shapes with
+    known volume, area and genus.  A wrong or mis-oriented table entry changes the enclosed volume (divergence theorem over
+    the oriented soup), the Euler characteristic or the watertightness of at least one of them; the offsets and radii are
+    irrational-ish so that the cells see many different sign configurations, ambiguous faces included (the two tori touch
+    cells diagonally)."""
+    res = 56
+    a = oracle.axis_coords(res)
+    zz, yy, xx = np.meshgrid(a, a, a, indexing="ij")
+    # ellipsoid x^2/a^2 + y^2/b^2 + z^2/c^2 = 1 as the level set of a smooth function (not a distance, which is fine)
+    ea, eb, ec = 0.71, 0.52, 0.43
+    f = (np.sqrt(((xx - 0.031) / ea) ** 2 + ((yy + 0.017) / eb) ** 2 + ((zz - 0.023) / ec) ** 2) - 1.0).astype(np.float32)
+    t = oracle.marching_cubes(f)
+    assert oracle.mesh_is_closed(t) and _euler_characteristic(t) == 2
+    assert abs(_mesh_volume(t) / (4.0 / 3.0 * np.pi * ea * eb * ec) - 1) < 1e-2
+    # torus (genus 1): R = 0.55, r = 0.21, axis z, centre offset
+    R, r = 0.55, 0.21
+    q = np.sqrt((xx - 0.013) ** 2 + (yy + 0.029) ** 2) - R
+    g = (np.sqrt(q ** 2 + (zz - 0.041) ** 2) - r).astype(np.float32)
+    t = oracle.marching_cubes(g)
+    assert oracle.mesh_is_closed(t) and _euler_characteristic(t) == 0
+    assert abs(_mesh_volume(t) / (2 * np.pi ** 2 * R * r * r) - 1) < 1e-2
+    area = np.linalg.norm(np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]), axis=1).sum() / 2
+    assert abs(area / (4 * np.pi ** 2 * R * r) - 1) < 1e-2
+    # the complement: an inside-out field (everything inside except a ball) bounded by a positive shell; volume = box - ball
+    h = -_sphere(res, 0.5)
+    h[0], h[-1], h[:, 0], h[:, -1], h[:, :, 0], h[:, :, -1] = 1, 1, 1, 1, 1, 1
+    t = oracle.marching_cubes(h)
+    assert oracle.mesh_is_closed(t) and _euler_characteristic(t) == 4            # two spheres' worth: the shell and the cavity
+    box = (a[-2] - a[1] + (a[1] - a[0])) ** 3                                   # roughly the shell's extent; only the sign matters here
+    assert 0 < _mesh_volume(t) < box
+    # two unions of shapes -> components add up
+    u = np.minimum(_sphere(res, 0.3, (-0.45, -0.4, -0.42)), _sphere(res, 0.33, (0.43, 0.41, 0.4)))
+    t = oracle.marching_cubes(u)
+    assert oracle.mesh_is_closed(t) and _euler_characteristic(t) == 4
+    assert abs(_mesh_volume(t) / (4.0 / 3.0 * np.pi * (0.3 ** 3 + 0.33 ** 3)) - 1) < 2e-2
+
+
 @pytest.mark.gpu
 def test_cuda_marching_cubes_bit_exact(pkg, cuda_decoder):
     rs = np.random.RandomState(3)
