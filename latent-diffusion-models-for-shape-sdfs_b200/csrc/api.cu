@@ -1532,10 +1532,11 @@ static int ddpm_tc_lane(sdfb_ddpm* d, int lane, float* x, const float* noise, lo
   // tile width of the hidden layers: 256 if that still gives about one pair tile per CTA pair
   const int max_pairs = d->num_sms / 2;
   int bn_h = (m_pairs * (kDdpmHid / 256) * 4 >= max_pairs * 3) ? 256 : 128;
+  if (m_pairs * (kDdpmHid / 64) <= max_pairs) bn_h = 64;      // small batches (n <= 1024): 16 narrow tiles per latent group
   if (bn_force) bn_h = bn_force;
   if (const char* e = std::getenv("SDFB_DDPM_BN")) {
     const int v = std::atoi(e);
-    if (v == 128 || v == 256) bn_h = v;
+    if (v == 64 || v == 128 || v == 256) bn_h = v;
   }
   DdpmParams p{};
   p.tb0 = d->tb0; p.bias = d->bias_dev; p.coef = d->coef_dev;
@@ -1543,7 +1544,7 @@ static int ddpm_tc_lane(sdfb_ddpm* d, int lane, float* x, const float* noise, lo
   p.philox = philox ? 1 : 0; p.seed = seed; p.first_latent = first_latent;
   p.n = n; p.pair_m_tiles = m_pairs; p.steps = steps; p.t_first = t_first;
   p.bn_h = bn_h;
-  p.nstages = bn_h == 256 ? 5 : 6;   // 5 x 32 KiB or 6 x 24 KiB of operand ring + 64 KiB of epilogue staging
+  p.nstages = bn_h == 256 ? 5 : (bn_h == 128 ? 6 : 8);   // 5 x 32 KiB, 6 x 24 KiB or 8 x 20 KiB of operand ring + 64 KiB of epilogue staging
   // the four pair tiles of a latent group as ONE cluster of 8 CTAs (cluster-scope group barrier) when every pair has
   // exactly one tile per layer and that many clusters can be resident
   if (bn_h == 256 && m_pairs * 4 <= max_pairs) {

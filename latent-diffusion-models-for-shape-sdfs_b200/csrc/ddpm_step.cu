@@ -308,7 +308,10 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             if (need_sync) {
               // weights first (they do not depend on the previous layer), then the group barrier, then A
               const int rest = g.nk - o.n;
-              const int pre = rest < static_cast<int>(nst) ? rest : static_cast<int>(nst);
+              // (an odd number of own chunks: the issuer releases the last own stage only together with the first streamed one
+              // - it commits per PAIR of chunks - so the prefetch must not wrap around onto that stage)
+              const int room = static_cast<int>(nst) - (o.n & 1);
+              const int pre = rest < room ? rest : room;
               uint32_t st = stage, ph = phase;
               for (int k = 0; k < pre; ++k) {
                 if (!mbar_wait(bars + 8 * (kBarEmpty + st), ph ^ 1u, wd, kErrEmpty, st)) goto done;
@@ -480,7 +483,46 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
           __syncwarp();
           tc_fence_after();
           if (threadIdx.x == 0) SDFB_TRACE(2);
-          if (l < 4) {
+          if (l < 4 && g.bn == 64) {
+            // hidden layer, 64-wide tile (small batches: more, narrower tiles keep more SMs busy): ONE chunk, the two warp
+            // sets convert its two 32-column halves; set 0 publishes it once both halves are written
+            uint32_t v[32];
+            tmem_ld32(tbase + set * 32, v);
+            const uint32_t srow = stg + slot0 * kChunk + row * 128u;
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive_on_leader(bars + 8 * (kBarAccEmpty + b), 1, lrank);
+            const float4* b4 = reinterpret_cast<const float4*>(sb + 32 * set);
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 bb = b4[e];
+              pk[2 * e] = pack_relu<FP16>(__uint_as_float(v[4 * e]) + bb.x, __uint_as_float(v[4 * e + 1]) + bb.y);
+              pk[2 * e + 1] = pack_relu<FP16>(__uint_as_float(v[4 * e + 2]) + bb.z, __uint_as_float(v[4 * e + 3]) + bb.w);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              st_shared_v4(srow + (((4 * set + u) ^ row7) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            fence_proxy_async_smem();
+            named_bar_sync(1, kEpiThreads);
+            if (set == 0 && lane == 0) arrive_on_leader(bars + 8 * (kBarOwn + slot0), 1, lrank);   // 4 warps x 2 CTAs = the 8 expected
+            if (threadIdx.x == 0) {
+              SDFB_TRACE(3);
+              tma_store_2d(&tm_act, g.o_col0 + j * 64, g_row, stg + slot0 * kChunk);
+              bulk_commit_group();
+              SDFB_TRACE(4);
+              bulk_wait_group0();
+              SDFB_TRACE(5);
+              if (p.flags & 2u) {
+                red_relaxed_gpu_add(p.counter + pm, 2u);
+              } else {
+                fence_proxy_async_global();
+                red_release_gpu_add(p.counter + pm, 2u);                         // both warp sets' worth
+              }
+              SDFB_TRACE(6);
+            }
+          } else if (l < 4) {
             // hidden layer: + bias, ReLU, round to 16 bits -> swizzled operand image in the staging
             // buffer -> one TMA store per 64-feature chunk (set s owns chunks c = s, s + 2, ...)
             const int nch = g.bn >> 6;
@@ -698,7 +740,8 @@ uint32_t smem_bytes_for(int bn_h, int nstages) {
 }  // namespace
 
 cudaError_t ddpm_step_init() {
-  const int max_smem = static_cast<int>(smem_bytes_for(256, 5));   // 5 x 32 KiB ring + 64 KiB staging: the largest configuration
+  const uint32_t m1 = smem_bytes_for(256, 5), m2 = smem_bytes_for(128, 6), m3 = smem_bytes_for(64, 8);
+  const int max_smem = static_cast<int>(m1 > m2 ? (m1 > m3 ? m1 : m3) : (m2 > m3 ? m2 : m3));   // ring + 64 KiB staging, largest configuration
   cudaError_t e = cudaFuncSetAttribute(ddpm_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(ddpm_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);

@@ -430,31 +430,59 @@ __device__ __forceinline__ uint32_t l0_mask_word(uint32_t even, uint32_t odd, in
 // rows sit in shared memory.
 struct L0Weights { float4 a, b; };
 
+// Packed fp32 FMA (FFMA2): two independent IEEE fused multiply-adds per instruction, each lane bit-identical to fmaf.
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long dup2(float v) {
+  const unsigned long long u = __float_as_uint(v);
+  return u | (u << 32);
+}
+
 // `m0` (BWD kernels): where the ReLU mask of h0 goes - per chunk c two ballot words per row, m0[(2 c + par) * 128 + row],
 // bit l of word `par` = (feature 64 c + 2 l + par is positive); lane r - r0 keeps row r's words and stores them.
+// The coordinates sit in shared memory as three arrays sx / sy / sz [128] (so that one 64-bit load brings a coordinate of
+// two consecutive rows): every packed FMA works on rows (r, r + 1) of one feature.  Same operations in the same order as
+// the scalar chain fmaf(z, wz, fmaf(y, wy, fmaf(x, wx, b))) -> identical bits.  (The first layer sits on the critical path at
+// every tile boundary - the next tile cannot start before its chunks exist, and they can only be written once the last
+// layer of the current tile has released them - so its instruction count matters: profiles/r2_k1_pass_trace_experiments.txt.)
 template <bool FP16, bool MASK = false>
 __device__ __forceinline__ bool epi_layer0(Epi& e, int warp, const L0Weights (&wl)[4],
-                                           const float4* __restrict__ sxyz, uint32_t smem_a, const Watchdog& wd,
+                                           const float* __restrict__ sxyz, uint32_t smem_a, const Watchdog& wd,
                                            uint32_t* m0 = nullptr) {
   const uint32_t unit = e.lane >> 2;
   const int r0 = (warp >> 1) * 32;
+  const float* sx = sxyz;
+  const float* sy = sxyz + kTileM;
+  const float* sz = sxyz + 2 * kTileM;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = 2 * i + (warp & 1);
     if (!mbar_wait(e.bars + 8 * (kBarAFree + c), ((e.wphase >> c) & 1u) ^ 1u, wd, kErrAFree, c)) return false;
     const uint32_t chunk = smem_a + c * kAChunkBytes + ((e.lane & 3) << 2);
     const float4 wa = wl[i].a, wb = wl[i].b;
+    const unsigned long long wax = dup2(wa.x), way = dup2(wa.y), waz = dup2(wa.z), waw = dup2(wa.w);
+    const unsigned long long wbx = dup2(wb.x), wby = dup2(wb.y), wbz = dup2(wb.z), wbw = dup2(wb.w);
     uint32_t keep_e = 0, keep_o = 0;
-#pragma unroll 8
-    for (int r = r0; r < r0 + 32; ++r) {
-      const float4 q = sxyz[r];
-      const float f0 = fmaf(q.z, wa.z, fmaf(q.y, wa.y, fmaf(q.x, wa.x, wa.w)));
-      const float f1 = fmaf(q.z, wb.z, fmaf(q.y, wb.y, fmaf(q.x, wb.x, wb.w)));
-      const uint32_t v = pack_relu<FP16>(f0, f1);
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(chunk + r * 128 + ((unit ^ (r & 7)) << 4)), "r"(v) : "memory");
+#pragma unroll 4
+    for (int r = r0; r < r0 + 32; r += 2) {
+      const unsigned long long qx = *reinterpret_cast<const unsigned long long*>(sx + r);
+      const unsigned long long qy = *reinterpret_cast<const unsigned long long*>(sy + r);
+      const unsigned long long qz = *reinterpret_cast<const unsigned long long*>(sz + r);
+      const unsigned long long ta = ffma2(qz, waz, ffma2(qy, way, ffma2(qx, wax, waw)));     // feature 2 l    of rows r, r + 1
+      const unsigned long long tb = ffma2(qz, wbz, ffma2(qy, wby, ffma2(qx, wbx, wbw)));     // feature 2 l + 1
+      const float f0a = __uint_as_float(static_cast<uint32_t>(ta)), f0b = __uint_as_float(static_cast<uint32_t>(ta >> 32));
+      const float f1a = __uint_as_float(static_cast<uint32_t>(tb)), f1b = __uint_as_float(static_cast<uint32_t>(tb >> 32));
+      const uint32_t va = pack_relu<FP16>(f0a, f1a), vb = pack_relu<FP16>(f0b, f1b);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(chunk + r * 128 + ((unit ^ (r & 7)) << 4)), "r"(va) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(chunk + (r + 1) * 128 + ((unit ^ ((r + 1) & 7)) << 4)), "r"(vb) : "memory");
       if constexpr (MASK) {
-        const uint32_t be = __ballot_sync(0xffffffffu, f0 > 0.f), bo = __ballot_sync(0xffffffffu, f1 > 0.f);
-        if (e.lane == r - r0) { keep_e = be; keep_o = bo; }
+        const uint32_t bea = __ballot_sync(0xffffffffu, f0a > 0.f), boa = __ballot_sync(0xffffffffu, f1a > 0.f);
+        const uint32_t beb = __ballot_sync(0xffffffffu, f0b > 0.f), bob = __ballot_sync(0xffffffffu, f1b > 0.f);
+        if (e.lane == r - r0) { keep_e = bea; keep_o = boa; }
+        if (e.lane == r + 1 - r0) { keep_e = beb; keep_o = bob; }
       }
     }
     if constexpr (MASK) {
@@ -485,7 +513,7 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
   volatile uint32_t* misc = reinterpret_cast<volatile uint32_t*>(gen + oMisc);   // [0] tmem base, [1] abort
   float* sbias = reinterpret_cast<float*>(gen + oBias);
   float* shead = reinterpret_cast<float*>(gen + oHead);
-  float4* sxyz = reinterpret_cast<float4*>(gen + oXyz);
+  float* sxyz = reinterpret_cast<float*>(gen + oXyz);        // sx [128] | sy [128] | sz [128]
   float* sdot = reinterpret_cast<float*>(gen + oDot);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -645,11 +673,11 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
       if constexpr (!BWD) {
       if (e.set == 0) {
         const Query q0 = load_query(p, row_base + row);
-        sxyz[row] = make_float4(q0.x, q0.y, q0.z, 0.f);
+        sxyz[row] = q0.x; sxyz[kTileM + row] = q0.y; sxyz[2 * kTileM + row] = q0.z;
       }
       named_bar_sync(1, kEpiThreads);
       if (!epi_layer0<FP16>(e, warp, wl, sxyz, smem0 + oA, wd)) goto done;
-      qv = sxyz[row];
+      qv = make_float4(sxyz[row], sxyz[kTileM + row], sxyz[2 * kTileM + row], 0.f);
       q = Query{qv.x, qv.y, qv.z};
       for (long long it = 0; it < my_tiles; ++it, row_base += tile_stride) {
         const bool dump_tile = p.dump != nullptr && row_base == 0;
@@ -681,11 +709,11 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
         if (it + 1 < my_tiles) {
           if (e.set == 0) {
             const Query qn = load_query(p, row_base + tile_stride + row);
-            sxyz[row] = make_float4(qn.x, qn.y, qn.z, 0.f);
+            sxyz[row] = qn.x; sxyz[kTileM + row] = qn.y; sxyz[2 * kTileM + row] = qn.z;
           }
           named_bar_sync(1, kEpiThreads);
           if (!epi_layer0<FP16>(e, warp, wl, sxyz, smem0 + oA, wd)) goto done;
-          qv = sxyz[row];
+          qv = make_float4(sxyz[row], sxyz[kTileM + row], sxyz[2 * kTileM + row], 0.f);
         }
         dump_row = (dump_tile && p.dump_pass == 12) ? p.dump + row * 256 : nullptr;
         if (e.trace != nullptr) e.trace = p.prof + static_cast<size_t>(gridDim.x) * 24 + 64 + 12;
@@ -766,12 +794,12 @@ fused_decoder_kernel(const DecodeParams p, const __grid_constant__ CUtensorMap t
               const long long next_base = it < 0 ? row_base : row_base + tile_stride;
               if (e.set == 0) {
                 const Query qn = load_query(p, next_base + row);
-                sxyz[row] = make_float4(qn.x, qn.y, qn.z, 0.f);
+                sxyz[row] = qn.x; sxyz[kTileM + row] = qn.y; sxyz[2 * kTileM + row] = qn.z;
               }
               named_bar_sync(1, kEpiThreads);
               load_l0_weights(wl);
               if (!epi_layer0<FP16, true>(e, warp, wl, sxyz, smem0 + oA, wd, m0_base + ((it + 1) & 1) * (16 * kTileM))) goto done;
-              qv = sxyz[row];
+              qv = make_float4(sxyz[row], sxyz[kTileM + row], sxyz[2 * kTileM + row], 0.f);
             }
             if (it < 0) continue;
             const uint32_t b = gpass & 1u;

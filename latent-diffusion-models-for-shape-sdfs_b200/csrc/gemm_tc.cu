@@ -12,8 +12,8 @@
 // two accumulators ping-pong so the epilogue of a tile overlaps the products of the next.  Persistent over
 // (tile, k-split) work items.
 //
-//   warps 0-3  epilogue (TMEM lane quadrant = warp): TMEM -> registers -> global, per 32-column group
-//   warp 4     TMA producer          warp 5   MMA issuer + TMEM allocation
+//   warps 0-7  epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2): TMEM -> registers -> global, per 32-column group
+//   warp 8     TMA producer          warp 9   MMA issuer + TMEM allocation
 //
 // Shared-memory operand layouts (what the TMA boxes produce and the descriptors describe):
 //   K-major  (NT): rows = M or N index, 128 B per row = 64 k, 16-byte units XOR (row & 7)            (SBO = 1024 B)
@@ -30,7 +30,8 @@ namespace {
 
 constexpr int kGStages = 4;
 constexpr int kGBM = 128, kGBK = 64;
-constexpr int kGThreads = 192;
+constexpr int kGEpiWarps = 8;
+constexpr int kGThreads = (kGEpiWarps + 2) * 32;
 constexpr uint32_t kGAStage = kGBM * kGBK * 2;                  // 16 KiB
 constexpr uint32_t kGBStageMax = 256 * kGBK * 2;                // 32 KiB
 constexpr uint32_t kGStage = kGAStage + kGBStageMax;            // 48 KiB
@@ -92,11 +93,11 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bars + 8 * (kGBarAccFull + b), 1);
-      mbar_init(bars + 8 * (kGBarAccEmpty + b), 4);
+      mbar_init(bars + 8 * (kGBarAccEmpty + b), kGEpiWarps);
     }
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == kGEpiWarps + 1) {
     tmem_alloc<1>(smem_u32(const_cast<uint32_t*>(misc)), 512);
     tmem_relinquish<1>();
   }
@@ -106,7 +107,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
   const uint32_t tmem_base = misc[0];
   Watchdog wd{misc + 1, p.status, p.timeout_ns, nullptr, p.status_host};
 
-  if (warp == 4) {
+  if (warp == kGEpiWarps) {
     // ===================== producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -135,7 +136,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kGEpiWarps + 1) {
     // ===================== MMA issuer (whole warp runs the loop, tcgen05 under elect) =====================
     const uint32_t idesc = umma_idesc(kGBM, BN, FP16 ? 0 : 1) | (TN ? ((1u << 15) | (1u << 16)) : 0u);
     uint32_t stage = 0, phase = 0, ephase = 0, item = 0;
@@ -171,7 +172,8 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
   } else {
     // ===================== epilogue warps =====================
     uint32_t acc_phase = 0, item = 0;
-    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int quad = warp & 3, chalf = warp >> 2;                  // TMEM lane quadrant; which half of the tile's columns
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     for (long long w = blockIdx.x; w < items; w += gridDim.x, ++item) {
       const int split = static_cast<int>(w % p.ksplit);
       const long long t = w / p.ksplit;
@@ -181,9 +183,10 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
       acc_phase ^= 1u << b;
       __syncwarp();
       tc_fence_after();
-      const long long row = static_cast<long long>(tm) * kGBM + warp * 32 + lane;
+      const long long row = static_cast<long long>(tm) * kGBM + quad * 32 + lane;
       const bool row_ok = row < p.M;
-      for (int c = 0; c < BN; c += 32) {
+      const int cbeg = BN >= 64 ? chalf * (BN / 2) : (chalf == 0 ? 0 : BN), cend = BN >= 64 ? cbeg + BN / 2 : BN;
+      for (int c = cbeg; c < cend; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_row + b * 256 + c, v);
         tmem_ld_wait();
@@ -244,7 +247,7 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
 done:
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kGEpiWarps + 1) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, 512);

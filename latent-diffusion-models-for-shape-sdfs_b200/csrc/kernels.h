@@ -125,7 +125,7 @@ constexpr int kDdpmW0Rows = 4 * 1024;
 constexpr int kDdpmWHidRows = 16 * 1024;
 constexpr int kDdpmW4Rows = 16 * 256;
 constexpr int kDdpmWRows = kDdpmW0Rows + 3 * kDdpmWHidRows + kDdpmW4Rows;   // 57,344 rows of 128 B = 7 MiB
-constexpr int kDdpmMaxStages = 6;
+constexpr int kDdpmMaxStages = 8;
 constexpr int kDdpmActCols = 512 + 1024 + 1024;
 constexpr int kDdpmOutTile = 64;          // output-layer tile width (fixed)
 
@@ -138,7 +138,7 @@ struct DdpmParams {
   int pair_m_tiles;        // ceil(n / 256)
   int steps;               // steps to run: t = t_first, t_first - 1, ...
   int t_first;
-  int bn_h;                // output-tile width of the hidden layers (256 or 128)
+  int bn_h;                // output-tile width of the hidden layers (256, 128 or - small batches - 64)
   int nstages;
   int cluster8;            // 1: clusters of 8 CTAs = the four pair tiles of one latent group (bn_h = 256, one tile per pair and
                            // layer): the group barrier is an mbarrier in every member instead of a counter in L2

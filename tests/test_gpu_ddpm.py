@@ -60,7 +60,7 @@ def _stats(d):
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
-@pytest.mark.parametrize("n,bn", [(37, 0), (300, 256), (300, 128), (2400, 128), (5000, 256)])
+@pytest.mark.parametrize("n,bn", [(37, 0), (300, 256), (300, 128), (300, 64), (1000, 64), (2400, 128), (5000, 256)])
 def test_denoiser_single_step_tensor_core(cuda_ddpm, monkeypatch, prec, n, bn):
     """One denoiser evaluation; ragged n, every tile width, and more pair tiles than CTA pairs: (2400, 128) = two
     tiles per pair with own chunks kept per round, (5000, 256) = two tiles per pair without own chunks."""
@@ -97,7 +97,7 @@ def test_sample_latents_tensor_core_golden(cuda_ddpm, golden, prec):
     assert np.array_equal(xh, x)            # deterministic, and the host entry point is the same path
 
 
-@pytest.mark.parametrize("n,bn,steps", [(300, 256, 12), (2400, 128, 6), (515, 0, 12), (5000, 256, 4)])
+@pytest.mark.parametrize("n,bn,steps", [(300, 256, 12), (2400, 128, 6), (515, 0, 12), (515, 64, 12), (1024, 64, 6), (1500, 64, 4), (5000, 256, 4)])
 def test_sample_latents_tensor_core_short_runs(cuda_ddpm, monkeypatch, n, bn, steps):
     if bn:
         monkeypatch.setenv("SDFB_DDPM_BN", str(bn))
@@ -212,12 +212,15 @@ def test_batch_split_over_two_concurrent_launches(cuda_ddpm, monkeypatch):
     whole = cuda_ddpm.sample_latents(4096, steps=steps, seed=seed, precision="bf16")
     ms = cuda_ddpm.last_kernel_ms()
     a = cuda_ddpm.sample_latents(3840, steps=steps, seed=seed, precision="bf16", first_latent=0)
+    monkeypatch.setenv("SDFB_DDPM_BN", "128")      # (on its own a batch of 256 would pick the 64-wide tiles of small batches)
     b128 = cuda_ddpm.sample_latents(256, steps=steps, seed=seed, precision="bf16", first_latent=3840)
+    monkeypatch.delenv("SDFB_DDPM_BN")
     g = torch.Generator(device="cuda").manual_seed(8)
     x_T = torch.randn((4096, 256), generator=g, device="cuda")
     noise = torch.randn((steps, 4096, 256), generator=g, device="cuda")
     we = cuda_ddpm.sample_latents(4096, x_T=x_T, noise=noise, steps=steps, precision="bf16")      # explicit stream, strided share
     tail_noise = noise[:, 3840:].contiguous()
+    monkeypatch.setenv("SDFB_DDPM_BN", "128")
     be128 = cuda_ddpm.sample_latents(256, x_T=x_T[3840:], noise=tail_noise, steps=steps, precision="bf16")
     monkeypatch.setenv("SDFB_DDPM_BN", "256")
     b256 = cuda_ddpm.sample_latents(256, steps=steps, seed=seed, precision="bf16", first_latent=3840)
