@@ -195,12 +195,16 @@ int sdfb_decoder_set_timeout_ns(sdfb_decoder* dec, uint64_t timeout_ns);
  * Every node is decoded at most once (node bitmaps compacted into query lists).  A node never decoded lies only in
  * discarded (sub-)blocks and inherits their constant sign.  lipschitz > 0: the bound L (field units per unit length);
  * 0: estimated - the largest difference quotient on the level-1 lattice times safety1 (e.g. 2), and the largest one
- * seen on either lattice times safety2 (e.g. 1.25) for level 2.  With a valid bound the marching-cubes output equals
+ * seen on either lattice times safety2 (e.g. 1.25) for level 2.  local_floor in (0, 1]: level 2 uses each 8^3 block's OWN
+ * largest quotient (125 lattice samples per block) instead of the global one, but never less than local_floor times the
+ * global one - a tighter, less conservative band (the field's steepest spot no longer widens the band everywhere);
+ * 0 = global.  With a valid bound the marching-cubes output equals
  * the dense extraction's bit for bit, order included.  Synchronises `stream` (three counts are read back).
  * stats_host (optional, int64[8]): level-1 corners, kept blocks, level-2 lattice nodes, kept sub-blocks, remaining
  * nodes, total queries, and the two difference quotients x 1e6.  res <= 1024. */
 int sdfb_decode_sparse_field(sdfb_decoder* dec, const float* latent_dev, int res, float lipschitz, float safety1, float safety2,
-                             float* sdf_dense_dev, uint32_t* sign_bits_dev, int precision, int64_t* stats_host, void* stream);
+                             float local_floor, float* sdf_dense_dev, uint32_t* sign_bits_dev, int precision, int64_t* stats_host,
+                             void* stream);
 
 /* Debug/diagnostic: pre-activation (accumulator + bias, before ReLU) of
  * tensor-core pass `pass` (0..12) for the first 128 queries of a grid decode,

@@ -305,7 +305,7 @@ class Decoder:
         return out
 
     def decode_sparse_field(self, latent, res: int, lipschitz: float | None = None, safety: tuple = (2.0, 1.25),
-                            precision: str | None = None):
+                            precision: str | None = None, local_floor: float = 0.0):
         """(sdf [res,res,res] float32, sign_words int32, stats): the two-level sparse decode of ``sdfb_decode_sparse_field`` -
         ``sdf`` is valid at every node of every cell the surface crosses (uninitialised elsewhere), ``sign_words`` are the
         complete sign bit-planes of the grid; together they are what ``extract_surface(sdf, sign_words=...)`` needs."""
@@ -315,7 +315,8 @@ class Decoder:
         signs = torch.empty(((res ** 3 + 31) // 32 + 1,), dtype=torch.int32, device=self.device)
         stats = (C.c_int64 * 8)()
         check(self._lib.sdfb_decode_sparse_field(self._h, lat.data_ptr(), res, C.c_float(0.0 if lipschitz is None else float(lipschitz)),
-                                                 C.c_float(float(safety[0])), C.c_float(float(safety[1])), sdf.data_ptr(), signs.data_ptr(),
+                                                 C.c_float(float(safety[0])), C.c_float(float(safety[1])), C.c_float(float(local_floor)),
+                                                 sdf.data_ptr(), signs.data_ptr(),
                                                  prec, stats, _stream_ptr(self.device.index)))
         keys = ("corner_queries", "blocks_kept", "lattice_queries", "sub_blocks_kept", "fill_queries", "queries")
         st = {k: int(stats[i]) for i, k in enumerate(keys)}
@@ -324,12 +325,13 @@ class Decoder:
 
     def extract_surface_sparse(self, latent, res: int, block: int = 8, lipschitz: float | None = None,
                                precision: str | None = None, return_stats: bool = False, indexed: bool = False,
-                               method: str = "hier"):
+                               method: str = "hier", local_floor: float = 0.0):
         """The zero level set on the res^3 grid WITHOUT decoding the whole grid.
 
         ``method="hier"`` (default): two-level refinement (``decode_sparse_field``), every node decoded at most once, then
         the DENSE marching-cubes kernels over the complete sign bit-planes - with a valid Lipschitz bound the triangle soup
-        equals ``extract_surface``'s bit for bit, order included.
+        equals ``extract_surface``'s bit for bit, order included.  ``local_floor`` in (0, 1] lets level 2 use every 8^3 block's
+        own slope estimate (never less than that fraction of the global one): a thinner band, fewer queries, less margin.
 
         ``method="blocks"`` (round 1): decode the corners of
         `block`^3-cell blocks, keep the blocks whose corners straddle zero or come within
@@ -338,7 +340,7 @@ class Decoder:
         bit (the order differs).  ``lipschitz=None`` estimates L from the block-corner values (largest difference
         quotient along block edges, times 2)."""
         if method == "hier":
-            sdf, signs, st = self.decode_sparse_field(latent, res, lipschitz=lipschitz, precision=precision)
+            sdf, signs, st = self.decode_sparse_field(latent, res, lipschitz=lipschitz, precision=precision, local_floor=local_floor)
             out = extract_surface(sdf, res, 0, sign_words=signs, indexed=indexed)
             self.check()
             return (out, st) if return_stats else out

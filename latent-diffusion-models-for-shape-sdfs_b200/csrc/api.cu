@@ -200,7 +200,7 @@ struct sdfb_decoder {
   float* bw_loss = nullptr;          //                    loss mode: per-warp sums [num_sms * 4]
   // hierarchical sparse decode workspace (lazy): node bitmaps, scan tiles, query lists, level-1 lattice
   struct SparseWs {
-    unsigned int *need1 = nullptr, *need2 = nullptr, *keep = nullptr, *tiles = nullptr, *idx = nullptr, *lip = nullptr;
+    unsigned int *need1 = nullptr, *need2 = nullptr, *keep = nullptr, *tiles = nullptr, *idx = nullptr, *lip = nullptr, *qblk = nullptr;
     unsigned long long* kept = nullptr;
     float *xyz = nullptr, *vals = nullptr, *cs = nullptr;
     int* ids = nullptr;
@@ -517,7 +517,7 @@ int sdfb_decoder_destroy(sdfb_decoder* d) {
   if (d->ev_user) cudaEventDestroy(d->ev_user);
   cudaFree(d->h0); cudaFree(d->h1); cudaFree(d->s); cudaFree(d->x); cudaFree(d->prof); cudaFree(d->signs); cudaFree(d->rowmask);
   cudaFree(d->sp.need1); cudaFree(d->sp.need2); cudaFree(d->sp.keep); cudaFree(d->sp.tiles); cudaFree(d->sp.idx); cudaFree(d->sp.lip);
-  cudaFree(d->sp.kept); cudaFree(d->sp.xyz); cudaFree(d->sp.vals); cudaFree(d->sp.cs); cudaFree(d->sp.ids);
+  cudaFree(d->sp.kept); cudaFree(d->sp.xyz); cudaFree(d->sp.vals); cudaFree(d->sp.cs); cudaFree(d->sp.ids); cudaFree(d->sp.qblk);
   for (float* a : d->bw_act) cudaFree(a);
   cudaFree(d->bw_d0); cudaFree(d->bw_d1); cudaFree(d->bw_y); cudaFree(d->bw_partial);
   cudaFree(d->bw_masks); cudaFree(d->bw_colsum); cudaFree(d->bw_amax); cudaFree(d->bw_loss);
@@ -1158,10 +1158,12 @@ int sparse_decode_nodes(sdfb_decoder* d, const float* latent_dev, int res, long 
 }  // namespace
 
 int sdfb_decode_sparse_field(sdfb_decoder* d, const float* latent_dev, int res, float lipschitz, float safety1, float safety2,
-                             float* sdf_dense_dev, uint32_t* sign_bits_dev, int precision, int64_t* stats_host, void* stream) {
+                             float local_floor, float* sdf_dense_dev, uint32_t* sign_bits_dev, int precision, int64_t* stats_host,
+                             void* stream) {
   if (!d || !latent_dev || !sdf_dense_dev || !sign_bits_dev) return fail(SDFB_E_INVALID, "null argument");
   if (res < 3 || res > 1024) return fail(SDFB_E_INVALID, "res %d outside [3, 1024] (node indices are 32-bit)", res);
-  if (!(lipschitz >= 0.f) || !(safety1 >= 1.f) || !(safety2 >= 1.f)) return fail(SDFB_E_INVALID, "bad lipschitz bound or safety factor");
+  if (!(lipschitz >= 0.f) || !(safety1 >= 1.f) || !(safety2 >= 1.f) || !(local_floor >= 0.f) || local_floor > 1.f)
+    return fail(SDFB_E_INVALID, "bad lipschitz bound, safety factor or local floor");
   DeviceGuard g(d->device);
   if (int prc = pending_status(d)) return prc;
   UserMark um{d, static_cast<cudaStream_t>(stream)};
@@ -1180,7 +1182,9 @@ int sdfb_decode_sparse_field(sdfb_decoder* d, const float* latent_dev, int res, 
     sp.words = words;
   }
   if (sp.corners < corners) {
-    cudaFree(sp.cs); cudaFree(sp.keep); cudaFree(sp.ids); sp.cs = nullptr; sp.keep = nullptr; sp.ids = nullptr; sp.corners = 0;
+    cudaFree(sp.cs); cudaFree(sp.keep); cudaFree(sp.ids); cudaFree(sp.qblk); sp.cs = nullptr; sp.keep = nullptr; sp.ids = nullptr; sp.qblk = nullptr;
+    sp.corners = 0;
+    CU_TRY(cudaMalloc(&sp.qblk, blocks * sizeof(unsigned int)));
     CU_TRY(cudaMalloc(&sp.cs, corners * sizeof(float)));
     CU_TRY(cudaMalloc(&sp.keep, ((blocks + 31) / 32 + 1) * sizeof(unsigned int)));
     CU_TRY(cudaMalloc(&sp.ids, blocks * sizeof(int)));
@@ -1232,9 +1236,11 @@ int sdfb_decode_sparse_field(sdfb_decoder* d, const float* latent_dev, int res, 
     if (rc) return rc;
     // the finer lattice sees the field's steepest slopes better than the coarse one: L2 = safety2 * max(raw1, raw2)
     // (sp.lip[0] = level-1 quotient, sp.lip[1] = level-2 quotient; the selection kernel takes the larger)
-    if (!(lipschitz > 0.f)) CU_TRY(launch_sub_lipschitz(res, B1, B2, nb1, sp.ids, nA, sdf_dense_dev, sp.lip + 1, st));
+    const bool local = local_floor > 0.f && !(lipschitz > 0.f);
+    if (local) CU_TRY(cudaMemsetAsync(sp.qblk, 0, nA * sizeof(unsigned int), st));
+    if (!(lipschitz > 0.f)) CU_TRY(launch_sub_lipschitz(res, B1, B2, nb1, sp.ids, nA, sdf_dense_dev, sp.lip + 1, local ? sp.qblk : nullptr, st));
     CU_TRY(launch_select_sub_blocks(res, B1, B2, nb1, sp.ids, nA, sdf_dense_dev, sp.lip, lipschitz > 0.f ? lipschitz * h : 0.f,
-                                    safety2, sp.need2, sp.kept, st));
+                                    safety2, local ? sp.qblk : nullptr, local_floor, sp.need2, sp.kept, st));
     CU_TRY(launch_andnot(sp.need2, sp.need1, words, st));
     rc = sparse_compact(d, sp.need2, words, &n2, st);
     if (rc) return rc;

@@ -325,9 +325,10 @@ cudaError_t launch_select_blocks_bits(const float* cs, int nb, float tau, unsign
 cudaError_t launch_mark_sub_corners(int res, int B1, int B2, int nb1, const int* blocks, long long nblk, unsigned int* need,
                                     cudaStream_t st);
 cudaError_t launch_sub_lipschitz(int res, int B1, int B2, int nb1, const int* blocks, long long nblk, const float* dense,
-                                 unsigned int* out_bits, cudaStream_t st);
+                                 unsigned int* out_bits, unsigned int* per_block, cudaStream_t st);
 cudaError_t launch_select_sub_blocks(int res, int B1, int B2, int nb1, const int* blocks, long long nblk, const float* dense,
-                                     const unsigned int* lip_bits, float lip_given_per_node, float safety, unsigned int* need,
+                                     const unsigned int* lip_bits, float lip_given_per_node, float safety,
+                                     const unsigned int* per_block, float local_floor, unsigned int* need,
                                      unsigned long long* kept, cudaStream_t st);
 cudaError_t launch_andnot(unsigned int* a, const unsigned int* b, long long words, cudaStream_t st);
 long long bitmap_scan_tiles(long long words);

@@ -116,8 +116,9 @@ __global__ void mark_sub_corners_kernel(SubGeom g, const int* __restrict__ block
 }
 
 // level 2, step 2: largest difference quotient along the 12 edges of every candidate sub-block
+// (per_block, optional: the same maximum per level-1 block - the candidates of a block are consecutive)
 __global__ void sub_lipschitz_kernel(SubGeom g, const int* __restrict__ blocks, long long nblk, const float* __restrict__ dense,
-                                     unsigned int* __restrict__ out) {
+                                     unsigned int* __restrict__ out, unsigned int* __restrict__ per_block) {
   const long long per3 = static_cast<long long>(g.per) * g.per * g.per;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   float m = 0.f;
@@ -135,6 +136,7 @@ __global__ void sub_lipschitz_kernel(SubGeom g, const int* __restrict__ blocks, 
       if (!(c & 2)) edge_max(v[c], v[c | 2], ext[1], m);
       if (!(c & 4)) edge_max(v[c], v[c | 4], ext[2], m);
     }
+    if (per_block != nullptr && m > 0.f) atomicMax(per_block + i / per3, __float_as_uint(m));
   }
   publish_max(m, out);
 }
@@ -143,13 +145,21 @@ __global__ void sub_lipschitz_kernel(SubGeom g, const int* __restrict__ blocks, 
 // B2 sqrt(3)/2 with L2' in field units per node) of zero; a kept sub-block marks all its nodes.
 __global__ void select_sub_blocks_kernel(SubGeom g, const int* __restrict__ blocks, long long nblk, const float* __restrict__ dense,
                                          const unsigned int* __restrict__ lip_bits, float lip_given_per_node, float safety,
+                                         const unsigned int* __restrict__ per_block, float local_floor,
                                          unsigned int* __restrict__ need, unsigned long long* __restrict__ kept) {
   const long long per3 = static_cast<long long>(g.per) * g.per * g.per;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= nblk * per3) return;
   int lo[3], ext[3];
   if (!sub_block(g, blocks[i / per3], static_cast<int>(i % per3), lo, ext)) return;
-  const float lip = lip_given_per_node > 0.f ? lip_given_per_node : safety * __uint_as_float(max(lip_bits[0], lip_bits[1]));
+  float lip;
+  if (lip_given_per_node > 0.f) {
+    lip = lip_given_per_node;
+  } else {
+    const float global = __uint_as_float(max(lip_bits[0], lip_bits[1]));
+    // local mode: the block's own largest quotient, but never less than `local_floor` of the global one
+    lip = safety * (per_block != nullptr ? fmaxf(__uint_as_float(per_block[i / per3]), local_floor * global) : global);
+  }
   const float half_diag = 0.5f * sqrtf(static_cast<float>(ext[0] * ext[0] + ext[1] * ext[1] + ext[2] * ext[2]));
   const float tau = lip * half_diag;
   int n_in = 0;
@@ -338,20 +348,22 @@ cudaError_t launch_mark_sub_corners(int res, int B1, int B2, int nb1, const int*
   return cudaGetLastError();
 }
 cudaError_t launch_sub_lipschitz(int res, int B1, int B2, int nb1, const int* blocks, long long nblk, const float* dense,
-                                 unsigned int* out_bits, cudaStream_t st) {
+                                 unsigned int* out_bits, unsigned int* per_block, cudaStream_t st) {
   const SubGeom g{res, B1, B2, nb1, B1 / B2};
   const long long total = nblk * g.per * g.per * g.per;
   if (total <= 0) return cudaSuccess;
-  sub_lipschitz_kernel<<<blocks_for(total), 256, 0, st>>>(g, blocks, nblk, dense, out_bits);
+  sub_lipschitz_kernel<<<blocks_for(total), 256, 0, st>>>(g, blocks, nblk, dense, out_bits, per_block);
   return cudaGetLastError();
 }
 cudaError_t launch_select_sub_blocks(int res, int B1, int B2, int nb1, const int* blocks, long long nblk, const float* dense,
-                                     const unsigned int* lip_bits, float lip_given_per_node, float safety, unsigned int* need,
+                                     const unsigned int* lip_bits, float lip_given_per_node, float safety,
+                                     const unsigned int* per_block, float local_floor, unsigned int* need,
                                      unsigned long long* kept, cudaStream_t st) {
   const SubGeom g{res, B1, B2, nb1, B1 / B2};
   const long long total = nblk * g.per * g.per * g.per;
   if (total <= 0) return cudaSuccess;
-  select_sub_blocks_kernel<<<blocks_for(total), 256, 0, st>>>(g, blocks, nblk, dense, lip_bits, lip_given_per_node, safety, need, kept);
+  select_sub_blocks_kernel<<<blocks_for(total), 256, 0, st>>>(g, blocks, nblk, dense, lip_bits, lip_given_per_node, safety, per_block,
+                                                               local_floor, need, kept);
   return cudaGetLastError();
 }
 cudaError_t launch_select_blocks_bits(const float* cs, int nb, float tau, unsigned int* keep, cudaStream_t st) {

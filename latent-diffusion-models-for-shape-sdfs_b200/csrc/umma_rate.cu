@@ -10,7 +10,12 @@ namespace {
 template <int CG>
 __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int iters, int k_per_commit, int n_acc, int flags, long long* out) {
   // flags bit0: no intermediate waits (commits go to a second, never-waited barrier); bit1: never
-  // restart the accumulation; bit2: two commits per commit point
+  // restart the accumulation; bit2: two commits per commit point;
+  // bit3: TS form - the A operand comes from TMEM (columns 256.., packed 16-bit), N = 128 accumulators (what an
+  //       activations-in-TMEM version of the fused decoder would issue);
+  // bit4 / bit5: no MMAs at all - the four warps run an epilogue-shaped loop `iters` times per chunk of 32 columns
+  //       (TMEM load, bias add, ReLU, round, hand the operand over) with the hand-over through tcgen05.st + wait::st (bit4)
+  //       or through st.shared + fence.proxy.async (bit5); out = cycles per chunk seen by warp 0
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (smem0 - smem_u32(smem_raw));
@@ -39,17 +44,68 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int iters, int k_per_
   if constexpr (CG == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
-  if (threadIdx.x == 0 && rank == 0) {
-    constexpr uint32_t idesc = umma_idesc(128 * CG, 256, 1);
+  if (flags & 8) {
+    // the TMEM operand region is written once (zeros) so the MMAs never read tensor memory nobody has stored to
+    uint32_t z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = 0u;
+    for (int c = 0; c < 16; ++c) tmem_st16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + 256 + c * 16, z);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();
+    tc_fence_after();
+  }
+  if (flags & 48) {
+    // ---- epilogue-shaped loop (see the flags above) ----
+    const int lane = threadIdx.x & 31;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t srow = sa + (warp * 32 + lane) * 128;
+    const uint32_t row7 = (warp * 32 + lane) & 7u;
+    float bias = 0.25f * lane;
+    __syncthreads();
+    const long long t0 = clock64();
+    uint32_t v[32];
+    tmem_ld32(trow, v);
+    for (int it = 0; it < iters; ++it) {
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_relu<false>(__uint_as_float(v[2 * j]) + bias, __uint_as_float(v[2 * j + 1]) + bias);
+      tmem_ld32(trow + ((it + 1) & 7) * 32, v);            // next chunk's accumulator in flight
+      if (flags & 16) {
+        tmem_st16(trow + 256 + (it & 7) * 16, pk);
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          st_shared_v4(srow + ((it & 3) * kAChunkBytes) + ((static_cast<uint32_t>(u) ^ row7) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar + 16);
+    }
+    tmem_ld_wait();
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x / CG] = t1 - t0;    // the host divides by iters * k_per_commit * 4
+  } else if (threadIdx.x == 0 && rank == 0) {
+    const uint32_t idesc = (flags & 8) ? umma_idesc(128 * CG, 128, 1) : umma_idesc(128 * CG, 256, 1);
     uint32_t parity = 0;
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       for (int k = 0; k < k_per_commit; ++k) {
         const uint64_t adesc = umma_desc_sw128(sa + (k & 3) * kAChunkBytes);
         const uint64_t bdesc = umma_desc_sw128(sb + (k & 1) * kBlockBytes);
-        const uint32_t d = tmem_base + ((it % n_acc) * 256);
+        const uint32_t d = tmem_base + ((it % n_acc) * ((flags & 8) ? 128 : 256));
+        if (flags & 8) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_ss<CG>(d, adesc + 2 * j, bdesc + 2 * j, idesc, ((k | j) != 0 || ((flags & 2) && it > 0)) ? 1u : 0u);
+          for (int j = 0; j < 4; ++j)
+            umma_ts<CG>(d, tmem_base + 256 + ((k & 7) * 32) + 8 * j, bdesc + 2 * j, idesc, ((k | j) != 0 || ((flags & 2) && it > 0)) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma_ss<CG>(d, adesc + 2 * j, bdesc + 2 * j, idesc, ((k | j) != 0 || ((flags & 2) && it > 0)) ? 1u : 0u);
+        }
       }
       if (flags & 1) {
         umma_commit<CG>(bar + 8);                       // nobody waits on this one

@@ -49,6 +49,32 @@ def test_oracle_sphere_area_orientation_and_watertightness():
     assert oracle.marching_cubes(np.ones((4, 4, 4), np.float32)).shape == (0, 3, 3)
 
 
+def test_every_case_is_oriented_along_the_trilinear_field():
+    """Per case, independent of how the tables were generated: with corner values -1 (inside) / +1 (outside) and vertices at
+    the edge midpoints, every triangle's normal points along INCREASING trilinear interpolant of the corner values (from
+    inside to outside) - 820 triangles over the 254 non-trivial cases."""
+    corners = mc_tables.CORNERS.astype(np.float64)
+
+    def trilinear(p, vals):
+        x, y, z = p
+        w = [(x if c[0] else 1 - x) * (y if c[1] else 1 - y) * (z if c[2] else 1 - z) for c in mc_tables.CORNERS]
+        return float(np.dot(w, vals))
+
+    total = 0
+    for case in range(1, 255):
+        vals = np.array([-1.0 if (case >> i) & 1 else 1.0 for i in range(8)])
+        for t in range(int(mc_tables.MC_NTRI[case])):
+            es = mc_tables.MC_TRI[case, 3 * t: 3 * t + 3]
+            pts = np.array([(corners[mc_tables.EDGES[e, 0]] + corners[mc_tables.EDGES[e, 1]]) / 2 for e in es])
+            n = np.cross(pts[1] - pts[0], pts[2] - pts[0])
+            assert np.linalg.norm(n) > 1e-9, (case, t)                    # no degenerate triangle in the tables
+            n /= np.linalg.norm(n)
+            c = pts.mean(axis=0)
+            assert trilinear(c + 0.05 * n, vals) > trilinear(c - 0.05 * n, vals), (case, t)
+            total += 1
+    assert total == int(mc_tables.MC_NTRI.sum()) == 820
+
+
 def _mesh_volume(tris):
     """Signed volume enclosed by an oriented closed triangle soup (divergence theorem), float64."""
     t = tris.astype(np.float64)
@@ -206,6 +232,27 @@ def test_hierarchical_sparse_extraction_equals_dense(cuda_decoder, res, seed, sc
                 assert torch.equal(va, vb)
     if res >= 256 and scale == 1.0:
         assert st["queries"] < st["dense_queries"] * (0.2 if res >= 512 else 0.4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res,seed,scale", [(128, 0, 1.0), (256, 0, 1.0), (256, 3, 1.5), (255, 5, 0.5), (512, 0, 1.0), (512, 2, 1.0)])
+def test_hierarchical_sparse_local_slopes_equal_dense(cuda_decoder, res, seed, scale):
+    """local_floor = 0.5: level 2 uses every 8^3 block's own largest difference quotient (x 1.25, never below half the global
+    one) instead of the global maximum - a thinner band.  Still the dense extraction's soup, bit for bit, on every test shape."""
+    z = oracle.default_latent(seed) * np.float32(scale)
+    dense = cuda_decoder.extract_surface(z, res)
+    cuda_decoder.extract_surface_sparse(z, res, local_floor=0.5)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    sparse, st = cuda_decoder.extract_surface_sparse(z, res, local_floor=0.5, return_stats=True)
+    b.record()
+    b.synchronize()
+    _, st_g = cuda_decoder.extract_surface_sparse(z, res, return_stats=True)
+    print(f"res {res} latent {seed} x{scale}: local slopes {st['queries']} queries ({st['dense_queries'] / max(st['queries'], 1):.1f}x fewer) in "
+          f"{a.elapsed_time(b):.2f} ms; global bound {st_g['queries']} queries; {sparse.shape[0]} triangles")
+    assert sparse.shape == dense.shape and torch.equal(sparse, dense)
+    assert st["queries"] <= st_g["queries"]
 
 
 @pytest.mark.gpu
