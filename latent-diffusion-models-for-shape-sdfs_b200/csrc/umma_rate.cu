@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int iters, int k_per_
     uint32_t z[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) z[j] = 0u;
-    for (int c = 0; c < 16; ++c) tmem_st16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + 256 + c * 16, z);
+    for (int c = 0; c < 32; ++c) tmem_st16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 16, z);
     tmem_st_wait();
     tc_fence_before();
     __syncthreads();
@@ -90,18 +90,22 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int iters, int k_per_
     const long long t1 = clock64();
     if (threadIdx.x == 0) out[blockIdx.x / CG] = t1 - t0;    // the host divides by iters * k_per_commit * 4
   } else if (threadIdx.x == 0 && rank == 0) {
-    const uint32_t idesc = (flags & 8) ? umma_idesc(128 * CG, 128, 1) : umma_idesc(128 * CG, 256, 1);
+    // bit6: the TS form with N = 256 (one accumulator); bit7: operand in columns [0, 256), accumulators above it
+    const bool ts = (flags & 8) != 0, ts_wide = (flags & 64) != 0;
+    const bool ss_narrow = (flags & 256) != 0;            // bit8: the SS form with N = 128
+    const uint32_t idesc = ((ts && !ts_wide) || ss_narrow) ? umma_idesc(128 * CG, 128, 1) : umma_idesc(128 * CG, 256, 1);
+    const uint32_t a_t = tmem_base + ((flags & 128) ? 0u : 256u), d_t = tmem_base + ((flags & 128) ? 256u : 0u);
     uint32_t parity = 0;
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       for (int k = 0; k < k_per_commit; ++k) {
         const uint64_t adesc = umma_desc_sw128(sa + (k & 3) * kAChunkBytes);
         const uint64_t bdesc = umma_desc_sw128(sb + (k & 1) * kBlockBytes);
-        const uint32_t d = tmem_base + ((it % n_acc) * ((flags & 8) ? 128 : 256));
-        if (flags & 8) {
+        const uint32_t d = ts ? d_t + (ts_wide ? 0 : (it % n_acc) * 128) : tmem_base + (it % n_acc) * 256;
+        if (ts) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            umma_ts<CG>(d, tmem_base + 256 + ((k & 7) * 32) + 8 * j, bdesc + 2 * j, idesc, ((k | j) != 0 || ((flags & 2) && it > 0)) ? 1u : 0u);
+            umma_ts<CG>(d, a_t + ((k & 7) * 32) + 8 * j, bdesc + 2 * j, idesc, ((k | j) != 0 || ((flags & 2) && it > 0)) ? 1u : 0u);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) umma_ss<CG>(d, adesc + 2 * j, bdesc + 2 * j, idesc, ((k | j) != 0 || ((flags & 2) && it > 0)) ? 1u : 0u);

@@ -25,9 +25,15 @@ if mode == 'epi':
 if mode == 'ts':
     # TMEM-operand probes (DESIGN §3 "Round 2"): the TS form an activations-in-TMEM decoder would issue (N = 128), and the
     # epilogue hand-over cost through tcgen05.st against the shipped st.shared + proxy fence
+    extra = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 64: N = 256; 128: operand below the accumulators
+    grid = int(sys.argv[3]) if len(sys.argv) > 3 else 148
+    n_acc = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+    base = int(sys.argv[5]) if len(sys.argv) > 5 else 8
     for cg in (1, 2):
         for kpc in (4, 8, 16):
-            for flags in (8, 9):
+            for flags in ((base + 1,) if not (extra & 64) else (base, base + 1)):   # N = 128 only without intermediate waits: the
+                # one-outstanding-group protocol of the probe assumes the pipe is slower than the issuing thread
                 v = C.c_double()
-                rc = lib.sdfb_umma_rate(cg, 148, 200, kpc, 2, flags, C.byref(v))
-                print(f"TS form (A in TMEM, N=128) cg={cg} k_per_commit={kpc:2d} nowait={flags&1}: rc={rc} {v.value:7.1f} cycles/MMA", flush=True)
+                print(f"TS form (A in TMEM) base={base} n_acc={n_acc} extra={extra} grid={grid} cg={cg} k_per_commit={kpc:2d} nowait={flags&1}: ", end="", flush=True)
+                rc = lib.sdfb_umma_rate(cg, grid, 200, kpc, n_acc, flags | extra, C.byref(v))
+                print(f"rc={rc} {v.value:7.1f} cycles/MMA", flush=True)
