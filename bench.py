@@ -441,11 +441,13 @@ def main():
         dist.all_reduce(okc, op=dist.ReduceOp.MIN)
         push_path = bool(okc.item())
 
-        def cfg5_step():
+        def cfg5_step(precision=None):
             if push_path:
-                return comm.decode_grid_sharded(dec, z5, RES5, mask=True)
-            sd, mk = pkg.decode_grid_sharded(dec, z5, RES5, mask=True)
-            return sd, mk
+                return comm.decode_grid_sharded(dec, z5, RES5, mask=True, precision=precision)
+            if precision is None:
+                return pkg.decode_grid_sharded(dec, z5, RES5, mask=True)
+            z0_, z1_ = pkg.slab_range(RES5, rank, world)          # fallback in the other precision: this rank's slab only
+            return dec.decode_grid(z5, RES5, z0_, z1_, mask=True, precision=precision)
 
         for _ in range(W):
             s5, m5 = cfg5_step()
@@ -471,6 +473,22 @@ def main():
         active = int(ref_m.sum().item())
         chk = float(s5[::32, ::32, ::32].double().sum().item())
         del ref_s, ref_m
+        # the same step in the other 16-bit operand type (fp16 meets the 2e-3 bound against the fp32 oracle)
+        other5 = "fp16" if args.precision == "bf16" else "bf16"
+        t_other = []
+        for i in range(1 + 4):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            so, mo = cfg5_step(other5)
+            b.record()
+            b.synchronize()
+            if i:
+                t_other.append(a.elapsed_time(b))
+        dec.check()
+        other_ms = max_over_ranks(statistics.mean(t_other))
+        other_chk = float(so[::32, ::32, ::32].double().sum().item()) if push_path else None
+        del so, mo
         # the torch.distributed path of round 1 (decode, then NCCL all-gathers of sdf and uint8 mask), for comparison
         t_nccl = []
         for _ in range(3):
@@ -500,6 +518,8 @@ def main():
                 "path": "sdfb_decode_grid_sharded (copy-engine pushes into CUDA-IPC peer buffers, overlapped)" if push_path
                         else "fallback: decode, then torch.distributed all-gathers (" + why[:120] + ")",
                 "torch_distributed_path_ms": max_over_ranks(statistics.median(t_nccl)),
+                "second_precision": {"dtype": other5, "ms_per_step": other_ms, "steps": len(t_other), "sdf_checksum": other_chk,
+                                     "frac_of_burst_peak_per_gpu": (RES5 ** 3 / world) * FLOP_TENSOR_PER_QUERY / (other_ms * 1e-3) / 1e12 / peaks["burst"]},
                 "e2e_host_slabs_queries_per_s": e2e5, "e2e_d2h_bytes_per_rank": int(slab_host.nbytes + mh.nbytes),
                 "clocks": clk5.summary()}
         del s5, m5
@@ -657,12 +677,22 @@ def main():
             tri_d = dec.extract_surface(zs_, RES5)
             c.record()
             c.synchronize()
+            dec.extract_surface_sparse(zs_, RES5, local_floor=0.5)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            tri_l, st_l = dec.extract_surface_sparse(zs_, RES5, local_floor=0.5, return_stats=True)
+            e1.record()
+            e1.synchronize()
             sparse = {"workload": "extract_surface_sparse(z, 512) vs extract_surface(z, 512) on one GPU (decode + marching cubes)",
                       "sparse_ms": a.elapsed_time(b), "dense_ms": b.elapsed_time(c), "triangles": int(tri_s.shape[0]),
                       "identical_triangle_soup": bool(tri_s.shape == tri_d.shape and torch.equal(tri_s, tri_d)),
                       "queries": st_s["queries"], "dense_queries": st_s["dense_queries"],
-                      "fewer_queries_x": st_s["dense_queries"] / max(st_s["queries"], 1)}
-            del tri_s, tri_d
+                      "fewer_queries_x": st_s["dense_queries"] / max(st_s["queries"], 1),
+                      "local_slopes": {"what": "second level bounded by each block's own measured slope (floor 0.5 x the global bound)",
+                                       "sparse_ms": e0.elapsed_time(e1), "queries": st_l["queries"],
+                                       "fewer_queries_x": st_l["dense_queries"] / max(st_l["queries"], 1),
+                                       "identical_triangle_soup": bool(tri_l.shape == tri_d.shape and torch.equal(tri_l, tri_d))}}
+            del tri_s, tri_d, tri_l
         except Exception as exc:                     # an optional leg must never cost the headline line
             sparse = {"error": repr(exc)}
             print(f"bench.py: optional leg failed: {exc!r}", file=sys.stderr)

@@ -229,7 +229,10 @@ int sdfb_ddpm_destroy(sdfb_ddpm* ddpm);
  * sample_latents(n): x_dev [n][256] holds x_T on entry and x_0 on return.
  * noise_dev [steps][n][256] is the explicit noise stream (noise[t] is consumed
  * at step t, noise[0] is ignored).  Runs t = steps-1 .. 0 of the 1000-step
- * linear-beta schedule with the x0-clipped posterior-mean update. */
+ * linear-beta schedule with the x0-clipped posterior-mean update.
+ * steps < 1000 TRUNCATES that schedule (it is not respaced: the coefficients stay those of the 1000-step
+ * chain), which is what the short parity tests and the profilers want; samples of the trained distribution
+ * need steps = 1000.  1 <= steps <= 1000, anything else is SDFB_E_INVALID. */
 int sdfb_ddpm_sample(sdfb_ddpm* ddpm, float* x_dev, const float* noise_dev, int n, int steps,
                      int precision, void* stream);
 /* one denoiser evaluation eps_hat(x, t) -> eps_dev [n][256] */

@@ -516,7 +516,9 @@ class LatentDDPM:
         the parity tests.  Without ``noise`` the stream is generated in the kernel from ``seed``
         (Philox4x32-10, reproducible on the CPU with oracle/philox.py); ``x_T`` is then optional too.
         ``first_latent`` is the global index of this call's latent 0 in the generator's counters, so shares of
-        one batch sampled by different ranks draw the numbers a single call over the whole batch would."""
+        one batch sampled by different ranks draw the numbers a single call over the whole batch would.
+        ``steps`` < 1000 runs only the last ``steps`` steps of the 1000-step chain (truncated, not respaced): a knob
+        for parity tests and profiling, not a quality/speed trade - samples need the full 1000."""
         prec = _prec(precision or self.precision)
         if n <= 0:
             raise ValueError("n must be positive")
