@@ -340,6 +340,17 @@ int sdfb_umma_selftest(const uint16_t* a_dev, const uint16_t* b_dev, float* d_de
 int sdfb_umma_rate(int cta_group, int grid, int iters, int k_per_commit, int n_acc, int flags,
                    double* cycles_per_mma);
 
+/* Diagnostic: bytes per SM cycle one CTA receives from L2 through the TMA unit (16 KiB pieces of a [rows][cols] 16-bit
+ * tensor of `mib` MiB, 8 pieces in flight), over `grid` CTAs in clusters of `cluster` (grid a multiple of it).
+ * mode 0: every CTA its own boxes (128 rows x 128 bytes, 128B swizzle); 1: the CTAs of a cluster load the same boxes;
+ * 2: each box loaded once and multicast to the cluster; 3: own pieces as one 1-D bulk copy each; 4: as four 4 KiB copies;
+ * 5: CTA pairs (cluster 2), own boxes with the .cta_group::2 form counted on the leader CTA's barrier;
+ * 6: CTA pairs, plain loads counted on each CTA's own barrier, the peer forwards every completed stage to the leader.
+ * issuers: 1, 2 or 4 warps issue in turn; uniform != 0: the issuing warps run their loop warp-uniformly with one elected
+ * lane executing the TMA instructions, 0: only lane 0 runs the loop.  cols: 64 (contiguous boxes) or a multiple of 64.
+ * out[0] = mean bytes/cycle/CTA, out[1] = slowest CTA's, out[2] = aggregate GB/s of the launch (event-timed). */
+int sdfb_tma_ingest_rate(int grid, int cluster, int mode, int issuers, int uniform, int cols, int mib, int iters, double* out3);
+
 #ifdef __cplusplus
 }
 #endif

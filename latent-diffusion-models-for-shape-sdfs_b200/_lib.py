@@ -81,6 +81,7 @@ SIGNATURES = {
     "sdfb_gemm_selftest": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sdfb_umma_selftest": (_i, [_vp, _vp, _vp, _i, _vp]),
     "sdfb_umma_rate": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]),
+    "sdfb_tma_ingest_rate": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]),
 }
 
 _lib = None

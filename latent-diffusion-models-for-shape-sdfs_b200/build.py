@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("SDFB_LIB") or os.path.join(HERE, "libsdfb200.so")     # SDFB_LIB: an experimental build beside the product one
-SOURCES = ("api.cu", "fused_decoder.cu", "tc_common.cu", "fp32_kernels.cu", "umma_rate.cu", "ddpm_step.cu", "marching.cu", "comm.cu", "sparse.cu", "gemm_tc.cu", "train_kernels.cu", "train_api.cu")
+SOURCES = ("api.cu", "fused_decoder.cu", "tc_common.cu", "fp32_kernels.cu", "umma_rate.cu", "tma_ingest.cu", "ddpm_step.cu", "marching.cu", "comm.cu", "sparse.cu", "gemm_tc.cu", "train_kernels.cu", "train_api.cu")
 HEADERS = ("kernels.h", "ptx.cuh", "philox.cuh", "mc_tables.h", "comm.h", os.path.join("..", "..", "include", "sdfb200.h"))
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-cudart", "static")

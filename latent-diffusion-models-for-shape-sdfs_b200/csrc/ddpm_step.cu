@@ -362,7 +362,8 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
       const uint32_t idesc_o = umma_idesc(256, kDdpmOutTile, FP16 ? 0 : 1);
       const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
       const uint32_t nst = static_cast<uint32_t>(p.nstages);
-      uint32_t stage = 0, phase = 0, ephase = 0, gt = 0, prev_stage = 0, own_phase = 0, own_pending = 0;
+      uint32_t stage = 0, phase = 0, ephase = 0, gt = 0, own_phase = 0, own_pending = 0;
+      const bool prof = p.prof != nullptr;
       const int rounds = (p.pair_m_tiles * (kDdpmHid / p.bn_h) + npairs - 1) / npairs;
       const uint32_t stg_lo = ((smem0 + o_stage) & 0x3FFFFu) >> 4;
       for (int s = 0; s < p.steps; ++s) {
@@ -382,35 +383,52 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
             const Own o = own_chunks(p, s, l, tile % ntn, round, rounds);
             if (!mbar_wait(bars + 8 * (kBarAccEmpty + b), ((ephase >> b) & 1u) ^ 1u, wd, kErrAccEmpty, b)) goto done;
             ephase ^= 1u << b;
+            // Two chunks per trip (nk is even; one commit point per pair - see the header comment), each issued as soon as
+            // its own operands are there: this warp's instructions issue ~4 cycles apart, so a trip costs its instruction count
+            // times that, and with 64- or 128-wide tiles that, not the tensor pipe, paced the layer.  Outside profiling runs
+            // a wait is one try_wait.
 #pragma unroll 1
-            for (int k = 0; k < nk; ++k) {
-              uint32_t a_lo;
-              if (k < o.n) {   // own chunk: A from the staging buffer, as soon as both CTAs' epilogues have finished it
+            for (int k = 0; k < nk; k += 2) {
+              const uint32_t s0 = stage, s1 = stage + 1 == nst ? 0u : stage + 1;
+              const uint32_t ph1 = s1 == 0 ? phase ^ 1u : phase;
+              uint32_t a0 = (((smem0 + s0 * stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+              uint32_t a1 = (((smem0 + s1 * stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+              const uint32_t b0 = a0 + (kChunk >> 4), b1 = a1 + (kChunk >> 4);
+              if (k < o.n) {       // own chunks: A from the staging buffer, as soon as both CTAs' epilogues have finished it
                 const uint32_t slot = static_cast<uint32_t>(o.slot0 + k);
-                if (!mbar_wait(bars + 8 * (kBarOwn + slot), (own_phase >> slot) & 1u, wd, kErrOwn, slot)) goto done;
-                a_lo = (stg_lo + slot * (kChunk >> 4)) | (1u << 16);
-              } else {
-                a_lo = (((smem0 + stage * stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-              }
-              if (!mbar_wait(bars + 8 * (kBarFull + stage), phase, wd, k == 0 ? kErrFullFirst : kErrFull, stage)) goto done;
-              tc_fence_after();
-              if (k == 0 && lane == 0) SDFB_TRACE(0);
-              const uint32_t b_lo = ((((smem0 + stage * stage_bytes) & 0x3FFFFu) >> 4) + (kChunk >> 4)) | (1u << 16);
-              const uint64_t adesc = desc_hi | a_lo;
-              const uint64_t bdesc = desc_hi | b_lo;
-              if (elect_one()) {
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) umma_ss<2>(d_tmem, adesc + 2 * jj, bdesc + 2 * jj, idesc, (k | jj) != 0 ? 1u : 0u);
-                if (k & 1) {   // one commit point per pair of chunks
-                  umma_commit<2>(bars + 8 * (kBarEmpty + prev_stage), pmask);
-                  umma_commit<2>(bars + 8 * (kBarEmpty + stage), pmask);
-                  if (k == nk - 1) umma_commit<2>(bars + 8 * (kBarAccFull + b), pmask);
+                const uint32_t ob = bars + 8 * (kBarOwn + slot), op = (own_phase >> slot) & 1u;
+                if (prof || !mbar_try_wait(ob, op)) { if (!mbar_wait(ob, op, wd, kErrOwn, slot)) goto done; }
+                a0 = (stg_lo + slot * (kChunk >> 4)) | (1u << 16);
+                if (k + 1 < o.n) {
+                  const uint32_t ob1 = ob + 8, op1 = (own_phase >> (slot + 1)) & 1u;
+                  if (prof || !mbar_try_wait(ob1, op1)) { if (!mbar_wait(ob1, op1, wd, kErrOwn, slot + 1)) goto done; }
+                  a1 = (stg_lo + (slot + 1) * (kChunk >> 4)) | (1u << 16);
                 }
               }
+              const uint32_t f0 = bars + 8 * (kBarFull + s0), f1 = bars + 8 * (kBarFull + s1);
+              if (prof || !mbar_try_wait(f0, phase)) { if (!mbar_wait(f0, phase, wd, k == 0 ? kErrFullFirst : kErrFull, s0)) goto done; }
+              tc_fence_after();
+              if (k == 0 && lane == 0) SDFB_TRACE(0);
+              if (elect_one()) {
+                const uint64_t ad0 = desc_hi | a0, bd0 = desc_hi | b0;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) umma_ss<2>(d_tmem, ad0 + 2 * jj, bd0 + 2 * jj, idesc, (k | jj) != 0 ? 1u : 0u);
+              }
+              if (prof || !mbar_try_wait(f1, ph1)) { if (!mbar_wait(f1, ph1, wd, kErrFull, s1)) goto done; }
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t ad1 = desc_hi | a1, bd1 = desc_hi | b1;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) umma_ss<2>(d_tmem, ad1 + 2 * jj, bd1 + 2 * jj, idesc, 1u);
+                umma_commit<2>(bars + 8 * (kBarEmpty + s0), pmask);
+                umma_commit<2>(bars + 8 * (kBarEmpty + s1), pmask);
+                if (k + 2 == nk) umma_commit<2>(bars + 8 * (kBarAccFull + b), pmask);
+              }
               __syncwarp();
-              if (k == nk - 1 && lane == 0) SDFB_TRACE(1);
-              prev_stage = stage;
-              if (++stage == nst) { stage = 0; phase ^= 1u; }
+              if (k + 2 == nk && lane == 0) SDFB_TRACE(1);
+              if (s1 == 0) phase ^= 1u;
+              stage = s1 + 1;
+              if (stage == nst) { stage = 0; phase ^= 1u; }
             }
           }
           // The phases the previous layer's epilogues completed are behind us now, whether or not they were waited

@@ -103,6 +103,8 @@ cudaError_t launch_umma_selftest(const uint16_t* a, const uint16_t* b, float* d,
                                  bool fp16, cudaStream_t stream);
 
 // Diagnostic: cycles per back-to-back tcgen05.mma (umma_rate.cu).
+cudaError_t launch_tma_ingest(const void* tensor, int cols, int rows, int grid, int csize, int mode, int issuers, int uniform, int iters,
+                              long long* out_dev, cudaStream_t stream);
 cudaError_t launch_umma_rate(int cg, int grid, int iters, int k_per_commit, int n_acc, int flags, long long* out_dev,
                              cudaStream_t stream);
 
