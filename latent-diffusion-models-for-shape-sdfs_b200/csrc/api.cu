@@ -249,6 +249,7 @@ struct sdfb_ddpm {
   unsigned long long timeout_ns = 4000000000ull;
   long long* prof = nullptr;                  // wait profile buffer (allocated when SDFB_PROF is set)
   int max_clusters8[2] = {-1, -1};            // resident 8-CTA clusters of the sampler kernel (queried once), [bf16, fp16]
+  int max_clusters16[2] = {-1, -1};           // ... and 16-CTA clusters (128-wide tiles)
 };
 
 namespace {
@@ -1596,12 +1597,20 @@ static int ddpm_tc_lane(sdfb_ddpm* d, int lane, float* x, const float* noise, lo
   if (bn_h == 256 && m_pairs * 4 <= max_pairs) {
     if (d->max_clusters8[fp16 ? 1 : 0] < 0) d->max_clusters8[fp16 ? 1 : 0] = ddpm_max_clusters8(256, p.nstages, fp16);
     p.cluster8 = m_pairs <= d->max_clusters8[fp16 ? 1 : 0] ? 1 : 0;
+    p.cluster_ctas = p.cluster8 ? 8 : 0;
+  }
+  // ... and with 128-wide tiles the eight pair tiles of a group as ONE cluster of 16 (non-portable size; few of them fit)
+  if (bn_h == 128 && lane == 0 && eps_out == nullptr && std::getenv("SDFB_DDPM_NO_C16") == nullptr) {
+    if (d->max_clusters16[fp16 ? 1 : 0] < 0) d->max_clusters16[fp16 ? 1 : 0] = ddpm_max_clusters16(128, p.nstages, fp16);
+    p.cluster8 = m_pairs <= d->max_clusters16[fp16 ? 1 : 0] ? 1 : 0;
+    p.cluster_ctas = p.cluster8 ? 16 : 0;
   }
   if (const char* e = std::getenv("SDFB_DDPM_CLUSTER8")) p.cluster8 = (p.cluster8 && std::atoi(e) != 0) ? 1 : 0;
   if (lane != 0) p.cluster8 = 0;     // the second launch runs beside a full house of 8-CTA clusters: plain pairs only
+  if (!p.cluster8) p.cluster_ctas = 0;
   if (d->prof != nullptr)
-    std::fprintf(stderr, "[sdfb ddpm prof] lane %d: n=%d bn_h=%d stages=%d cluster8=%d (resident 8-CTA clusters: %d)\n", lane, n, bn_h,
-                 p.nstages, p.cluster8, d->max_clusters8[fp16 ? 1 : 0]);
+    std::fprintf(stderr, "[sdfb ddpm prof] lane %d: n=%d bn_h=%d stages=%d cluster_ctas=%d (resident 8-CTA clusters: %d, 16-CTA: %d)\n", lane, n, bn_h,
+                 p.nstages, p.cluster_ctas, d->max_clusters8[fp16 ? 1 : 0], d->max_clusters16[fp16 ? 1 : 0]);
   if (const char* e = std::getenv("SDFB_DDPM_STAGES")) {   // diagnostics: a shallower ring (leaves shared memory to a profiler)
     const int v = std::atoi(e);
     if (v >= 2 && v < p.nstages) p.nstages = v;

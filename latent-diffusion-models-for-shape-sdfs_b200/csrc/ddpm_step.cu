@@ -92,6 +92,14 @@ __device__ __forceinline__ Geo layer_geo(const DdpmParams& p, int l) {
   return g;
 }
 
+// First tile of pair `pidx` in layer l (further tiles follow npairs apart).  With 16-CTA clusters (eight pairs of 128-wide
+// hidden tiles per latent group) the last layer has only FOUR 64-wide tiles per group: pairs 0-3 of the cluster take them
+// and pairs 4-7 sit the layer out, so that a group's tiles never leave its cluster.
+__device__ __forceinline__ int first_tile(const DdpmParams& p, int l, int pidx, int T) {
+  if (l == 4 && p.cluster_ctas == 16) return (pidx & 7) < 4 ? (pidx >> 3) * 4 + (pidx & 7) : T;
+  return pidx;
+}
+
 // Own chunks.  With one tile per pair and layer, the k-chunks a pair produced in the previous layer are
 // still in its staging buffer in operand layout: the next layer starts on them at once (weights come
 // through the ring, A straight from staging) while the peers' chunks travel through L2.
@@ -236,7 +244,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
   float* sbias = reinterpret_cast<float*>(smem_raw + o_bar + kBarBytes + 16);                    // 2 x 256 floats: the tile's bias slice
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // The cluster is one CTA pair, or (cluster8 mode) the four pairs that share 256 latents.
+  // The cluster is one CTA pair, or (cluster8 mode) the four - with 128-wide tiles eight - pairs that share 256 latents.
   const uint32_t crank = cluster_ctarank();
   const uint32_t rank = crank & 1u;                    // rank inside the pair
   const uint32_t lrank = crank & ~1u;                  // cluster rank of this pair's leader CTA
@@ -260,7 +268,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
     }
     mbar_init(bars + 8 * kBarXn, 1);
     for (int c = 0; c < 6; ++c) mbar_init(bars + 8 * (kBarOwn + c), kEpiWarps);   // one warp set x 2 CTAs arrive per phase
-    mbar_init(bars + 8 * kBarGroup, 16);                                        // 8 CTAs x 2 warp sets
+    mbar_init(bars + 8 * kBarGroup, p.cluster_ctas == 16 ? 32u : 16u);          // 8 (or 16) CTAs x 2 warp sets
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -290,7 +298,13 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
           const uint32_t target = static_cast<uint32_t>(s) * arr_step + static_cast<uint32_t>(l) * arr_h;
           const int T = p.pair_m_tiles * g.ntn;
           const int rounds = (p.pair_m_tiles * (kDdpmHid / p.bn_h) + npairs - 1) / npairs;
-          for (int tile = pidx, round = 0; tile < T; tile += npairs, ++round) {
+          if (p.cluster_ctas == 16 && l == 4 && first_tile(p, l, pidx, T) >= T) {
+            // sitting the last layer out (see first_tile): the group barrier's phase must still be SEEN, or the next wait
+            // would test a parity two phases away and pass at once
+            if (!mbar_wait_cluster(bars + 8 * kBarGroup, gphase, wd, kErrGrid)) goto done;
+            gphase ^= 1u;
+          }
+          for (int tile = first_tile(p, l, pidx, T), round = 0; tile < T; tile += npairs, ++round) {
             const int pm = tile / g.ntn, j = tile - pm * g.ntn;
             const int a_row = (2 * pm + static_cast<int>(rank)) * 128;
             const int w_row = g.w_row0 + j * g.bn + static_cast<int>(rank) * (g.bn >> 1);
@@ -375,7 +389,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
           // staging slots this pair's epilogue fills in this layer (one barrier phase each per tile)
           uint32_t my_slots = 0;
           int round = 0;
-          for (int tile = pidx; tile < T; tile += npairs, ++gt, ++round) {
+          for (int tile = first_tile(p, l, pidx, T); tile < T; tile += npairs, ++gt, ++round) {
             // staging slots this tile's epilogue fills (one barrier phase each)
             my_slots |= l == 4 ? (p.eps_mode ? 0u : 0xCu) : ((((1u << (p.bn_h >> 6)) - 1u) << (round * (p.bn_h >> 6))) & 0xFu);
             const uint32_t b = gt & 1u;
@@ -457,7 +471,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
                                    : (l < 4 ? p.bias + (l - 1) * kDdpmHid : p.bias + 3 * kDdpmHid);
         const int T = p.pair_m_tiles * g.ntn;
         const int rounds = (p.pair_m_tiles * (kDdpmHid / p.bn_h) + npairs - 1) / npairs;
-        for (int tile = pidx, round = 0; tile < T; tile += npairs, ++gt, ++round) {
+        for (int tile = first_tile(p, l, pidx, T), round = 0; tile < T; tile += npairs, ++gt, ++round) {
           const int pm = tile / g.ntn, j = tile - pm * g.ntn;
           const int g_row = (2 * pm + static_cast<int>(rank)) * 128;             // first latent of this CTA's half tile
           // staging slots of this tile's hidden output: one set per round while they all fit (they are then the
@@ -587,8 +601,7 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
                 // the latent group IS the cluster: one arrival on every member's group barrier instead of a counter in L2
                 fence_proxy_async_global();
                 fence_acq_rel_cluster();
-#pragma unroll
-                for (uint32_t r = 0; r < 8; ++r) mbar_arrive_remote_relaxed(bars + 8 * kBarGroup, r, 1u);
+                for (uint32_t r = 0; r < static_cast<uint32_t>(p.cluster_ctas); ++r) mbar_arrive_remote_relaxed(bars + 8 * kBarGroup, r, 1u);
               } else if (p.flags & 2u) {
                 red_relaxed_gpu_add(p.counter + pm, 1u);
               } else {
@@ -679,8 +692,9 @@ ddpm_sample_kernel(const DdpmParams p, const __grid_constant__ CUtensorMap tm_ac
               if (p.cluster8) {
                 fence_proxy_async_global();
                 fence_acq_rel_cluster();
-#pragma unroll
-                for (uint32_t r = 0; r < 8; ++r) mbar_arrive_remote_relaxed(bars + 8 * kBarGroup, r, 2u);
+                // (four tiles per group: with 16 CTAs each of the eight arriving CTAs stands in for two)
+                for (uint32_t r = 0; r < static_cast<uint32_t>(p.cluster_ctas); ++r)
+                  mbar_arrive_remote_relaxed(bars + 8 * kBarGroup, r, p.cluster_ctas == 16 ? 4u : 2u);
               } else if (p.flags & 2u) {
                 red_relaxed_gpu_add(p.counter + pm, 2u);
               } else {
@@ -762,7 +776,12 @@ cudaError_t ddpm_step_init() {
   const int max_smem = static_cast<int>(m1 > m2 ? (m1 > m3 ? m1 : m3) : (m2 > m3 ? m2 : m3));   // ring + 64 KiB staging, largest configuration
   cudaError_t e = cudaFuncSetAttribute(ddpm_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(ddpm_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  e = cudaFuncSetAttribute(ddpm_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e != cudaSuccess) return e;
+  // clusters of 16 CTAs (one latent group of eight 128-wide pair tiles) are beyond the portable size of 8
+  e = cudaFuncSetAttribute(ddpm_sample_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(ddpm_sample_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
 }
 
 cudaError_t make_tensor_map(void* tmap_out, const void* base, int elem_bytes, int rank, const unsigned long long* dims,
@@ -813,6 +832,7 @@ static int ddpm_max_clusters(int csize, int bn_h, int nstages, bool fp16) {
 }
 
 int ddpm_max_clusters8(int bn_h, int nstages, bool fp16) { return ddpm_max_clusters(8, bn_h, nstages, fp16); }
+int ddpm_max_clusters16(int bn_h, int nstages, bool fp16) { return ddpm_max_clusters(16, bn_h, nstages, fp16); }
 
 cudaError_t launch_ddpm_split(const float* x, int n, int n_pad, uint16_t* act, bool fp16, cudaStream_t stream) {
   const long long total = static_cast<long long>(n_pad) * 32;
@@ -834,7 +854,7 @@ cudaError_t launch_ddpm_sample(const DdpmParams& p, const DdpmMaps& maps, bool f
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = p.cluster8 ? 8 : 2;
+  attr[0].val.clusterDim.x = p.cluster8 ? p.cluster_ctas : 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;

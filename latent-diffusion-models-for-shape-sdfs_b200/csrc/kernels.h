@@ -142,8 +142,9 @@ struct DdpmParams {
   int t_first;
   int bn_h;                // output-tile width of the hidden layers (256, 128 or - small batches - 64)
   int nstages;
-  int cluster8;            // 1: clusters of 8 CTAs = the four pair tiles of one latent group (bn_h = 256, one tile per pair and
-                           // layer): the group barrier is an mbarrier in every member instead of a counter in L2
+  int cluster8;            // 1: a cluster = the pair tiles of one latent group (one tile per pair and layer): the group barrier
+                           // is an mbarrier in every member instead of a counter in L2
+  int cluster_ctas;        // CTAs of such a cluster: 8 (four pairs, bn_h = 256) or 16 (eight pairs, bn_h = 128); 0 without
   int philox;              // 1: noise[t] is generated in the kernel (Philox4x32-10, csrc/philox.cuh) instead of read through tm_nz
   unsigned long long seed;
   unsigned int first_latent;   // global index of latent 0 of this call in the Philox counters (sharded sampling)
@@ -174,6 +175,7 @@ cudaError_t launch_ddpm_split(const float* x, int n, int n_pad, uint16_t* act, b
 cudaError_t launch_ddpm_sample(const DdpmParams& p, const DdpmMaps& maps, bool fp16, int num_sms, cudaStream_t stream);
 // how many 8-CTA clusters of the sampler kernel can be resident at once (0 if the query fails)
 int ddpm_max_clusters8(int bn_h, int nstages, bool fp16);
+int ddpm_max_clusters16(int bn_h, int nstages, bool fp16);
 // Philox normals of steps [t0, t1) for latents [first_latent, first_latent + n) -> out [(t1 - t0)][n][256]
 cudaError_t launch_philox_normal(unsigned long long seed, unsigned int first_latent, int n, int t0, int t1, float* out,
                                  cudaStream_t stream);
