@@ -1,7 +1,7 @@
 """Oracle isosurface extraction: marching cubes over the sign-change cells of an SDF slab.
 
 Reference: none (`/root/reference/README.md:1`); this is SURVEY.md section 8(f) row N1, the consumer
-of the sign-change mask.  Case tables: oracle/mc_tables.py (generated).  Test infrastructure only.
+of the sign-change mask.  Case tables: oracle/mc_tables.py (data written by tools/gen_mc_tables.py).  Test infrastructure only.
 
 Definition (what the CUDA kernels in csrc/marching.cu must reproduce bit for bit):
   * cells in C order (z, y, x), x fastest; a cell's triangles in table order; output = triangle soup

@@ -97,7 +97,8 @@ def test_sample_latents_tensor_core_golden(cuda_ddpm, golden, prec):
     assert np.array_equal(xh, x)            # deterministic, and the host entry point is the same path
 
 
-@pytest.mark.parametrize("n,bn,steps", [(300, 256, 12), (2400, 128, 6), (515, 0, 12), (515, 64, 12), (1024, 64, 6), (1500, 64, 4), (5000, 256, 4)])
+@pytest.mark.parametrize("n,bn,steps", [(300, 256, 12), (2400, 128, 6), (515, 0, 12), (515, 64, 12), (1024, 64, 6), (1500, 64, 4), (5000, 256, 4),
+                                        (1280, 0, 6), (1700, 128, 4), (3000, 0, 4)])      # auto 128 in 16-CTA clusters; 7 of them; auto 256
 def test_sample_latents_tensor_core_short_runs(cuda_ddpm, monkeypatch, n, bn, steps):
     if bn:
         monkeypatch.setenv("SDFB_DDPM_BN", str(bn))
@@ -109,6 +110,22 @@ def test_sample_latents_tensor_core_short_runs(cuda_ddpm, monkeypatch, n, bn, st
     assert mx < 3e-2 and q[1] < 2e-3
     x2 = cuda_ddpm.sample_latents(n, x_T=x_T, noise=noise, steps=steps, precision="bf16").cpu().numpy()
     assert np.array_equal(x, x2)
+
+
+def test_cluster_barrier_and_counter_barrier_agree(cuda_ddpm, monkeypatch):
+    """128-wide tiles: the eight pairs of a latent group as one 16-CTA cluster (group barrier = an mbarrier in every member,
+    pairs 4-7 sit the four-tile last layer out) against plain pairs with a counter in L2: the same bits."""
+    monkeypatch.setenv("SDFB_DDPM_BN", "128")
+    n, steps = 1100, 9
+    x_T, noise = ddpm_golden_inputs(n=n, steps=steps)
+    a = cuda_ddpm.sample_latents(n, x_T=x_T, noise=noise, steps=steps, precision="bf16")
+    monkeypatch.setenv("SDFB_DDPM_NO_C16", "1")
+    b = cuda_ddpm.sample_latents(n, x_T=x_T, noise=noise, steps=steps, precision="bf16")
+    assert torch.equal(a, b)
+    ref = oracle.sample_latents(n, x_T, noise, steps=steps, lowp=torch.bfloat16)
+    msg, q, mx = _stats(a.cpu().numpy() - ref)
+    print(f"bf16 n={n} bn=128 steps={steps}, 16-CTA clusters: |kernel - bf16 oracle| {msg}")
+    assert mx < 3e-2 and q[1] < 2e-3
 
 
 def test_sample_latents_full_batch_properties(cuda_ddpm, monkeypatch):

@@ -6,10 +6,20 @@ import numpy as np
 import pytest
 import torch
 
+import importlib.util
+
 import oracle
 from oracle import mc_tables
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _generator():
+    """tools/gen_mc_tables.py, the product's build tool that writes csrc/mc_tables.h and oracle/mc_tables.npz"""
+    spec = importlib.util.spec_from_file_location("gen_mc_tables", os.path.join(ROOT, "tools", "gen_mc_tables.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def _sphere(res, r=0.6, c=(0.05, -0.1, 0.02)):
@@ -28,8 +38,12 @@ def test_tables_are_consistent_and_header_is_current():
         inside = [(case >> i) & 1 for i in range(8)]
         crossed = {e for e, (a, b) in enumerate(mc_tables.EDGES) if inside[a] != inside[b]}
         assert set(int(e) for e in used) == crossed          # every crossed edge carries a vertex, no other edge does
-    with open(mc_tables.HEADER_PATH) as f:
-        assert f.read() == mc_tables.header_text(), "run `python -m oracle.mc_tables` to regenerate csrc/mc_tables.h"
+    gen = _generator()
+    with open(gen.HEADER_PATH) as f:
+        assert f.read() == gen.header_text(), "run `python tools/gen_mc_tables.py` to regenerate csrc/mc_tables.h"
+    # the oracle's data file holds the generator's numbers too (and the same geometry conventions)
+    assert np.array_equal(mc_tables.MC_NTRI, gen.MC_NTRI) and np.array_equal(mc_tables.MC_TRI, gen.MC_TRI)
+    assert np.array_equal(mc_tables.EDGES, gen.EDGES) and np.array_equal(mc_tables.CORNERS, gen.CORNERS)
 
 
 def test_oracle_sphere_area_orientation_and_watertightness():
