@@ -130,6 +130,13 @@ int sdfb_decoder_fit_loss_grad(sdfb_decoder* dec, const float* latent_dev, const
 int sdfb_decoder_fit_loss_grad_batch(sdfb_decoder* dec, const float* latents_dev, const float* xyz_dev, int batch,
                                      int64_t points_per_shape, const float* target_dev, float clamp_dist,
                                      float* grad_latents_dev, float* loss_dev, int precision, void* stream);
+/* The optimiser step of that fit: Adam on latents_dev [batch][256] with the gradient of the data term in grad_dev and the
+ * regulariser reg |z|^2 added here (g = grad + 2 reg z); m_dev / v_dev [batch][256] are the moments (zero before step 1),
+ * step = 1, 2, ... enters the bias correction.  loss_dev (optional, [batch]) receives += reg |z|^2 of the latents BEFORE the
+ * update, i.e. the full loss at the point the gradient was taken.  One launch; every operation individually rounded
+ * (betas are doubles so that 1 - beta and 1 - beta^step are formed the way the host expression they replace forms them). */
+int sdfb_latent_adam_step(float* latents_dev, float* m_dev, float* v_dev, const float* grad_dev, float* loss_dev, int batch,
+                          float lr, float reg, double beta1, double beta2, float adam_eps, int step, void* stream);
 
 /* Host-buffer forms (what a plugin caller with CPU arrays uses): stage through
  * pinned memory owned by the context, run, copy back, synchronise. */

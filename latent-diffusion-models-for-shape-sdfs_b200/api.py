@@ -229,17 +229,15 @@ class Decoder:
         m = torch.zeros_like(z)
         v = torch.zeros_like(z)
         M = pts.shape[0]
-        if precision != "fp32":              # one launch per step (loss + gradient), nothing synchronised until the end
+        if precision != "fp32":              # two launches per step (loss + gradient, Adam), nothing synchronised until the end
             loss_t = None
+            st = _stream_ptr(self.device.index)
             for it in range(1, steps + 1):
                 loss_t, g = self.fit_loss_grad(z, pts, tgt, clamp=clamp, precision=precision)
-                g = g + 2 * reg * z
-                m = 0.9 * m + 0.1 * g
-                v = 0.999 * v + 0.001 * g * g
-                z_new = z - lr * (m / (1 - 0.9 ** it)) / ((v / (1 - 0.999 ** it)).sqrt() + 1e-8)
-                loss_z = z                    # the loss reported belongs to the latent it was evaluated at
-                z = z_new
-            loss = float(loss_t[0] + reg * (loss_z * loss_z).sum()) if loss_t is not None else float("nan")
+                # the loss reported belongs to the latent it was evaluated at: the kernel adds reg |z|^2 before it moves z
+                check(self._lib.sdfb_latent_adam_step(z.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), loss_t.data_ptr(), 1,
+                                                      float(lr), float(reg), 0.9, 0.999, 1e-8, it, st))
+            loss = float(loss_t[0]) if loss_t is not None else float("nan")
             self.check()
             return z, loss
         ones = torch.ones(M, device=self.device)
@@ -283,11 +281,9 @@ class Decoder:
             check(self._lib.sdfb_decoder_fit_loss_grad_batch(self._h, z.data_ptr(), pts.data_ptr() if M else None, B, M,
                                                              tgt.data_ptr() if M else None, float(clamp), g.data_ptr(),
                                                              loss.data_ptr(), prec, st))
-            loss = loss + reg * (z * z).sum(dim=1)
-            g = g + 2 * reg * z
-            m = 0.9 * m + 0.1 * g
-            v = 0.999 * v + 0.001 * g * g
-            z = z - lr * (m / (1 - 0.9 ** it)) / ((v / (1 - 0.999 ** it)).sqrt() + 1e-8)
+            # loss += reg |z|^2, g += 2 reg z, Adam: one launch (sdfb_latent_adam_step) instead of a dozen elementwise ones
+            check(self._lib.sdfb_latent_adam_step(z.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), loss.data_ptr(), B, float(lr),
+                                                  float(reg), 0.9, 0.999, 1e-8, it, st))
         return z, loss
 
     def fit_latents_batch_checked(self, *a, **kw):

@@ -772,6 +772,16 @@ int sdfb_decoder_fit_loss_grad(sdfb_decoder* d, const float* latent_dev, const f
 
 // A batch of shapes, each with its own latent and its own points_per_shape samples: one fold + one forward + backward
 // launch + one finish per shape, back to back on the stream (the shapes are independent; nothing is synchronised).
+int sdfb_latent_adam_step(float* latents_dev, float* m_dev, float* v_dev, const float* grad_dev, float* loss_dev, int batch,
+                          float lr, float reg, double beta1, double beta2, float adam_eps, int step, void* stream) {
+  if (batch < 0 || step < 1) return fail(SDFB_E_INVALID, "negative batch or step < 1");
+  if (batch > 0 && (!latents_dev || !m_dev || !v_dev || !grad_dev)) return fail(SDFB_E_INVALID, "null argument");
+  if (!(beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1.)) return fail(SDFB_E_INVALID, "betas must be in [0, 1)");
+  CU_TRY(launch_latent_adam(latents_dev, m_dev, v_dev, grad_dev, loss_dev, batch, kLatent, lr, reg, beta1, beta2, adam_eps, step,
+                            static_cast<cudaStream_t>(stream)));
+  return SDFB_OK;
+}
+
 int sdfb_decoder_fit_loss_grad_batch(sdfb_decoder* d, const float* latents_dev, const float* xyz_dev, int batch,
                                      int64_t points_per_shape, const float* target_dev, float clamp_dist, float* grad_latents_dev,
                                      float* loss_dev, int precision, void* stream) {

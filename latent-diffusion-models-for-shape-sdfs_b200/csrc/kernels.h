@@ -224,6 +224,8 @@ struct AdamParams { float lr, beta1, beta2, eps, bias_corr1, bias_corr2; };
 cudaError_t launch_adam_update(float* w, float* m, float* v, const float* grad, int nparts, long long part_stride, int ld_grad,
                                float scale, int rows, int cols, const AdamParams& a, uint16_t* w_lowp, int ldw, uint16_t* wt_lowp,
                                int ldwt, float* grad_out, bool fp16, bool apply, cudaStream_t st);
+cudaError_t launch_latent_adam(float* z, float* m, float* v, const float* grad, float* loss, int batch, int dim, float lr, float reg,
+                               double beta1, double beta2, float eps, int step, cudaStream_t st);
 cudaError_t launch_sum_loss(const float* partial, int n, float scale, float* loss_out, cudaStream_t st);
 // fp32 [rows][cols] (leading dimension ld) -> 16-bit copy [rows][ldw] and transposed copy [cols][ldwt] (either may be null)
 cudaError_t launch_lowp_copies(const float* w, int ld, int rows, int cols, uint16_t* w_lowp, int ldw, uint16_t* wt_lowp, int ldwt,

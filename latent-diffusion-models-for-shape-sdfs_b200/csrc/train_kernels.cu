@@ -354,4 +354,57 @@ cudaError_t launch_dec_train_head_grad(const uint16_t* a8, const float* d8, long
   colsum_finish_kernel<<<3, 256, 0, st>>>(scratch, slabs > 0 ? slabs : 1, 513, scale, out);
   return cudaGetLastError();
 }
+
+// ---- Adam on a batch of latents (auto-decoder fitting): one block per latent ----
+// g = grad + 2 reg z;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g g;  z -= lr (m / c1) / (sqrt(v / c2) + eps);
+// loss[b] += reg |z_b|^2 (the latent the loss was evaluated at, i.e. before the update).  Every operation is rounded on its
+// own, in the order of the fp32 tensor expression in api.py it replaced - including that expression's division of a tensor by
+// a scalar as a multiplication by the scalar's fp32 reciprocal: the moments come out bit-identical to it, the latents within
+// an ulp or two per step (tests/test_gpu_train.py).
+namespace {
+__global__ void __launch_bounds__(256) latent_adam_kernel(float* __restrict__ z, float* __restrict__ m, float* __restrict__ v,
+                                                          const float* __restrict__ grad, float* __restrict__ loss, int dim,
+                                                          float lr, float reg, float b1, float omb1, float b2, float omb2,
+                                                          float c1, float c2, float eps) {
+  __shared__ float red[8];
+  const long long base = static_cast<long long>(blockIdx.x) * dim;
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    const float zi = z[base + i];
+    sq = __fadd_rn(sq, __fmul_rn(zi, zi));
+    const float g = __fadd_rn(grad[base + i], __fmul_rn(__fmul_rn(2.f, reg), zi));
+    const float mi = __fadd_rn(__fmul_rn(b1, m[base + i]), __fmul_rn(omb1, g));
+    const float vi = __fadd_rn(__fmul_rn(b2, v[base + i]), __fmul_rn(__fmul_rn(omb2, g), g));
+    m[base + i] = mi;
+    v[base + i] = vi;
+    const float num = __fmul_rn(lr, __fmul_rn(mi, c1));          // c1, c2: reciprocals of the bias corrections
+    const float den = __fadd_rn(__fsqrt_rn(__fmul_rn(vi, c2)), eps);
+    z[base + i] = __fsub_rn(zi, __fdiv_rn(num, den));
+  }
+  if (loss != nullptr) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) s += red[w];
+      loss[blockIdx.x] = __fadd_rn(loss[blockIdx.x], __fmul_rn(reg, s));
+    }
+  }
+}
+}  // namespace
+
+cudaError_t launch_latent_adam(float* z, float* m, float* v, const float* grad, float* loss, int batch, int dim, float lr, float reg,
+                               double beta1, double beta2, float eps, int step, cudaStream_t st) {
+  if (batch <= 0) return cudaSuccess;
+  // 1 - beta^step in double, rounded once, then its fp32 reciprocal
+  const float c1 = 1.0f / static_cast<float>(1.0 - pow(beta1, step));
+  const float c2 = 1.0f / static_cast<float>(1.0 - pow(beta2, step));
+  const float omb1 = static_cast<float>(1.0 - beta1), omb2 = static_cast<float>(1.0 - beta2);
+  latent_adam_kernel<<<batch, 256, 0, st>>>(z, m, v, grad, loss, dim, lr, reg, static_cast<float>(beta1), omb1, static_cast<float>(beta2), omb2, c1,
+                                            c2, eps);
+  return cudaGetLastError();
+}
+
 }  // namespace sdfb

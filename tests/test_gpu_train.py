@@ -172,3 +172,37 @@ def test_decoder_training_run(pkg):
     assert l0 < 0.8 * losses[0]
     dec.close()
     tr.close()
+
+
+def test_latent_adam_step_is_the_tensor_expression(pkg):
+    """sdfb_latent_adam_step (one launch per fitting step) against the fp32 tensor expression it replaced in
+    Decoder.fit_latent / fit_latents_batch: the same moments bit for bit over several steps, the latents to an ulp or two
+    per step (the library's elementwise division is not the correctly rounded one), the reported loss (a 256-term sum in
+    another order) to rounding."""
+    lib = pkg.load_library()
+    g0 = torch.Generator(device="cuda").manual_seed(3)
+    B, lr, reg = 5, 5e-3, 1e-4
+    z = 0.1 * torch.randn((B, 256), generator=g0, device="cuda")
+    m, v = torch.zeros_like(z), torch.zeros_like(z)
+    z2, m2, v2 = z.clone(), m.clone(), v.clone()
+    for it in range(1, 8):
+        g = torch.randn((B, 256), generator=g0, device="cuda") * (10.0 ** -(it % 4))
+        loss0 = torch.rand(B, generator=g0, device="cuda")
+        # reference: api.py of round 1
+        loss_ref = loss0 + reg * (z * z).sum(dim=1)
+        gg = g + 2 * reg * z
+        m = 0.9 * m + 0.1 * gg
+        v = 0.999 * v + 0.001 * gg * gg
+        z = z - lr * (m / (1 - 0.9 ** it)) / ((v / (1 - 0.999 ** it)).sqrt() + 1e-8)
+        loss = loss0.clone()
+        rc = lib.sdfb_latent_adam_step(z2.data_ptr(), m2.data_ptr(), v2.data_ptr(), g.data_ptr(), loss.data_ptr(), B, lr, reg, 0.9, 0.999,
+                                       1e-8, it, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert torch.equal(m2, m), f"first moments differ at step {it}: {(m2 - m).abs().max().item():.3e}"
+        assert torch.equal(v2, v), f"second moments differ at step {it}: {(v2 - v).abs().max().item():.3e} of {v.abs().max().item():.3e}"
+        assert torch.allclose(z2, z, rtol=0, atol=it * 1e-7), f"latents differ at step {it}: {(z2 - z).abs().max().item():.3e}"
+        z2.copy_(z)                       # keep the two trajectories on the same inputs
+        assert torch.allclose(loss, loss_ref, rtol=1e-6, atol=1e-9)
+    assert lib.sdfb_latent_adam_step(z2.data_ptr(), m2.data_ptr(), v2.data_ptr(), g.data_ptr(), None, B, lr, reg, 0.9, 0.999, 1e-8, 0, None) != 0
+    assert lib.sdfb_latent_adam_step(None, None, None, None, None, 0, lr, reg, 0.9, 0.999, 1e-8, 1, None) == 0       # empty batch
