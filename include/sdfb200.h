@@ -168,6 +168,15 @@ int sdfb_mc_count(const float* sdf_dev, const uint32_t* sign_bits_dev, int nz, i
 int sdfb_mc_generate(const float* sdf_dev, int nz, int ny, int nx, int res, int z0, const void* workspace_dev,
                      float* triangles_dev, int64_t* edge_keys_dev, void* stream);
 
+/* Welding the soup into an indexed mesh: a bitmap over the 3 res^3 grid edges marks the keys that occur, a scan ranks them,
+ * and every triangle corner gets the rank of its key - vertices come out in ascending key order, each once.
+ * count (synchronises): number of distinct vertices; fill: vertices_dev [n_vertices][3] and faces_dev [n_triangles][3] (int64). */
+int sdfb_mc_weld_workspace_bytes(int res, size_t* bytes);
+int sdfb_mc_weld_count(const int64_t* edge_keys_dev, int64_t n_triangles, int res, void* workspace_dev, size_t workspace_bytes,
+                       int64_t* n_vertices_host, void* stream);
+int sdfb_mc_weld_fill(const float* triangles_dev, const int64_t* edge_keys_dev, int64_t n_triangles, int res, const void* workspace_dev,
+                      float* vertices_dev, int64_t* faces_dev, void* stream);
+
 /* ---- sparse extraction: decode only near the surface ---------------------------
  * The res^3 grid is cut into blocks of `block`^3 cells (nb = ceil((res-1)/block) per axis; the last block
  * may be ragged).  1) sdfb_sparse_corner_points: xyz of the (nb+1)^3 block corners -> decode them with

@@ -31,6 +31,9 @@ SIGNATURES = {
     "sdfb_decoder_vjp_latent": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "sdfb_decoder_vjp_latent_tc": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
     "sdfb_decoder_fit_loss_grad": (_i, [_vp, _vp, _vp, _i64, _vp, C.c_float, _vp, _vp, _vp, _i, _vp]),
+    "sdfb_mc_weld_workspace_bytes": (_i, [_i, C.POINTER(C.c_size_t)]),
+    "sdfb_mc_weld_count": (_i, [_vp, _i64, _i, _vp, C.c_size_t, C.POINTER(C.c_int64), _vp]),
+    "sdfb_mc_weld_fill": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
     "sdfb_latent_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.c_float, C.c_float, C.c_double, C.c_double, C.c_float, _i, _vp]),
     "sdfb_decoder_fit_loss_grad_batch": (_i, [_vp, _vp, _vp, _i, _i64, _vp, C.c_float, _vp, _vp, _i, _vp]),
     "sdfb_decode_grid_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i]),

@@ -383,7 +383,7 @@ class Decoder:
                                                       tris.data_ptr(), keys.data_ptr() if indexed else None, st))
         self.check()                # the counts above already synchronised the stream
         if indexed:
-            tris = weld(tris, keys)
+            tris = weld(tris, keys, res)
         if return_stats:
             return tris, {"blocks": n, "blocks_total": nb ** 3, "queries": (nb + 1) ** 3 + n * per, "dense_queries": res ** 3,
                           "tau": tau, "lipschitz": float(lipschitz)}
@@ -800,12 +800,24 @@ def philox_normal(seed: int, n: int, t0: int, t1: int, device="cuda:0", first_la
     return out
 
 
-def weld(tris: torch.Tensor, keys: torch.Tensor):
-    """Triangle soup [n,3,3] + grid-edge keys [n,3] -> indexed mesh (vertices [V,3], faces [n,3] int64)."""
-    uniq, inv = torch.unique(keys.reshape(-1), return_inverse=True)
-    verts = torch.empty((uniq.numel(), 3), dtype=tris.dtype, device=tris.device)
-    verts[inv] = tris.reshape(-1, 3)          # every occurrence of a key carries the same bits
-    return verts, inv.reshape(-1, 3)
+def weld(tris: torch.Tensor, keys: torch.Tensor, res: int):
+    """Triangle soup [n,3,3] + grid-edge keys [n,3] of a res^3 grid -> indexed mesh (vertices [V,3] in ascending key order,
+    faces [n,3] int64).  ``sdfb_mc_weld_count`` / ``_fill``: a bitmap over the grid's edges, ranked by a scan."""
+    lib = _lib.load()
+    n = int(tris.shape[0])
+    t, k = tris.contiguous(), keys.contiguous()
+    with torch.cuda.device(tris.device):
+        nbytes = C.c_size_t()
+        check(lib.sdfb_mc_weld_workspace_bytes(int(res), C.byref(nbytes)))
+        ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=tris.device)
+        nv = C.c_int64()
+        st = _stream_ptr(tris.device.index)
+        check(lib.sdfb_mc_weld_count(k.data_ptr() if n else None, n, int(res), ws.data_ptr(), nbytes.value, C.byref(nv), st))
+        verts = torch.empty((nv.value, 3), dtype=torch.float32, device=tris.device)
+        faces = torch.empty((n, 3), dtype=torch.int64, device=tris.device)
+        if n:
+            check(lib.sdfb_mc_weld_fill(t.data_ptr(), k.data_ptr(), n, int(res), ws.data_ptr(), verts.data_ptr(), faces.data_ptr(), st))
+    return verts, faces
 
 
 def extract_surface(sdf: torch.Tensor, res: int | None = None, z0: int = 0, sign_words: torch.Tensor | None = None,
@@ -836,7 +848,7 @@ def extract_surface(sdf: torch.Tensor, res: int | None = None, z0: int = 0, sign
         if n.value:
             check(lib.sdfb_mc_generate(s.data_ptr(), nz, ny, nx, res, z0, ws.data_ptr(), tris.data_ptr(),
                                        keys.data_ptr() if indexed else None, st))
-    return weld(tris, keys) if indexed else tris
+    return weld(tris, keys, res) if indexed else tris
 
 
 def grid_points(res: int, z0: int = 0, z1: int | None = None, device="cuda:0") -> torch.Tensor:

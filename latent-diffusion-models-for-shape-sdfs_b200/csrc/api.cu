@@ -1054,6 +1054,40 @@ int sdfb_mc_generate(const float* sdf_dev, int nz, int ny, int nx, int res, int 
                           reinterpret_cast<long long*>(edge_keys_dev), static_cast<cudaStream_t>(stream));
 }
 
+// ---- welding the soup into an indexed mesh ----
+int sdfb_mc_weld_workspace_bytes(int res, size_t* bytes) {
+  if (!bytes || res < 2) return fail(SDFB_E_INVALID, "bad argument");
+  *bytes = mc_weld_workspace_bytes(3ll * res * res * res) + 256;
+  return SDFB_OK;
+}
+
+int sdfb_mc_weld_count(const int64_t* edge_keys_dev, int64_t n_triangles, int res, void* workspace_dev, size_t workspace_bytes,
+                       int64_t* n_vertices_host, void* stream) {
+  if (!workspace_dev || !n_vertices_host || res < 2 || n_triangles < 0 || (n_triangles > 0 && !edge_keys_dev))
+    return fail(SDFB_E_INVALID, "bad argument");
+  const long long range = 3ll * res * res * res;
+  if (workspace_bytes < mc_weld_workspace_bytes(range) + 256) return fail(SDFB_E_INVALID, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  int* count_dev = reinterpret_cast<int*>(ws);
+  CU_TRY(launch_mc_weld_count(reinterpret_cast<const long long*>(edge_keys_dev), 3 * n_triangles, range, ws + 256, count_dev, st));
+  int count = 0;
+  CU_TRY(cudaMemcpyAsync(&count, count_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  *n_vertices_host = count;
+  return SDFB_OK;
+}
+
+int sdfb_mc_weld_fill(const float* triangles_dev, const int64_t* edge_keys_dev, int64_t n_triangles, int res, const void* workspace_dev,
+                      float* vertices_dev, int64_t* faces_dev, void* stream) {
+  if (!workspace_dev || res < 2 || n_triangles < 0) return fail(SDFB_E_INVALID, "bad argument");
+  if (n_triangles > 0 && (!triangles_dev || !edge_keys_dev || !vertices_dev || !faces_dev)) return fail(SDFB_E_INVALID, "null argument");
+  CU_TRY(launch_mc_weld_fill(triangles_dev, reinterpret_cast<const long long*>(edge_keys_dev), 3 * n_triangles, 3ll * res * res * res,
+                             static_cast<const uint8_t*>(workspace_dev) + 256, vertices_dev, reinterpret_cast<long long*>(faces_dev),
+                             static_cast<cudaStream_t>(stream)));
+  return SDFB_OK;
+}
+
 // ---- sparse extraction: coarse block corners -> block selection -> nodes of the selected blocks -> marching cubes ----
 int sdfb_sparse_corner_points(int res, int block, float* xyz_dev, void* stream) {
   if (!xyz_dev) return fail(SDFB_E_INVALID, "null argument");

@@ -293,6 +293,11 @@ cudaError_t launch_ddpm_update(float* x, const float* eps, const float* noise, l
                                cudaStream_t stream);
 
 // ---- marching cubes (marching.cu) --------------------------------------------
+size_t mc_weld_workspace_bytes(long long key_range);
+cudaError_t launch_mc_weld_count(const long long* keys, long long n_keys, long long key_range, void* workspace, int* count_dev,
+                                 cudaStream_t stream);
+cudaError_t launch_mc_weld_fill(const float* tris, const long long* keys, long long n_keys, long long key_range, const void* workspace,
+                                float* verts, long long* faces, cudaStream_t stream);
 // A field to extract from: a dense [nz][ny][nx] slab whose first plane is plane z0 of the res^3 grid
 // (blocks == nullptr), or a list of blocks of (B+1)^3 nodes each, block id = (bz * nb + by) * nb + bx,
 // stored back to back (the sparse extractor).
