@@ -26,6 +26,7 @@
 //   warps 0-7  epilogue   (TMEM lane quadrant = warp & 3; the two warp sets split the columns)
 //   warp 8     producer   (TMA; completion counted on the LEADER's barrier)
 //   warp 9     MMA issuer (leader CTA only) + TMEM allocation (both CTAs)
+#include <atomic>
 #include <cstdlib>
 
 #include <cuda.h>
@@ -786,11 +787,16 @@ cudaError_t ddpm_step_init() {
 
 cudaError_t make_tensor_map(void* tmap_out, const void* base, int elem_bytes, int rank, const unsigned long long* dims,
                             const unsigned long long* strides_bytes, const unsigned* box, bool swizzle128) {
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-  if (e != cudaSuccess) return e;
-  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+  // the driver entry point is looked up once (this runs twice per launch of the general product: ~30 times per training step)
+  static std::atomic<void*> cached{nullptr};
+  void* fn = cached.load(std::memory_order_acquire);
+  if (fn == nullptr) {
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    cached.store(fn, std::memory_order_release);
+  }
   cuuint64_t gdim[3], gstride[2];
   cuuint32_t bx[3], estr[3] = {1u, 1u, 1u};
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }

@@ -213,10 +213,10 @@ cudaError_t launch_ddpm_train_prep(const float* x0, const float* eps, const int*
 cudaError_t launch_ddpm_train_residual(const float* eps_hat, const float* eps, int n, uint16_t* d_lowp, float* loss_partial,
                                        int* nblocks, bool fp16, cudaStream_t st);
 // out[j] = scale * sum_m D[m][j], D 16-bit [M][ld] (deterministic: row slabs in parallel, partial sums added in slab order, fp32);
-// scratch: kColsumSlabs * N floats
+// scratch: kColsumSlabs * N floats ([slab][N] partial sums; out = nullptr: left there for the caller, *nslabs_out of them)
 constexpr int kColsumSlabs = 128;
 cudaError_t launch_colsum_lowp(const uint16_t* D, long long M, int ld, int N, float scale, float* out, float* scratch, bool fp16,
-                               cudaStream_t st);
+                               cudaStream_t st, int* nslabs_out = nullptr);
 // fused Adam over one parameter tensor: g = scale * sum_{s < nparts} grad[s * part_stride + i]; updates master fp32 weights and
 // moments in place and refreshes the 16-bit copies W [rows][ldw] and W^T [cols][ldwt] (either may be null; rows x cols = the
 // tensor's shape, cols = 1 for a bias with both copies null).  grad_out (optional): receives g.

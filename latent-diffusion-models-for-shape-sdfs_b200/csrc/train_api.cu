@@ -254,8 +254,9 @@ int sdfb_ddpm_trainer_step(sdfb_ddpm_trainer* t, const float* x0_dev, const int3
                                 t->fin[l], gscale, t->fout[l], t->fin[l], ap, t->w_lowp[l], t->fin[l], t->wt_lowp[l], t->fout[l],
                                 grads_dev ? grads_dev + t->woff[l] : nullptr, t->fp16, apply != 0, st));
     }
-    CU_TRY(launch_colsum_lowp(t->delta[l], n, t->fout[l], t->fout[l], 1.f, t->bias_grad, t->colsum_scratch, t->fp16, st));
-    CU_TRY(launch_adam_update(t->params + t->boff[l], t->adam_m + t->boff[l], t->adam_v + t->boff[l], t->bias_grad, 1, 0, 1, gscale,
+    int nsl = 1;               // db_l: per-slab column sums of delta_l, added up (in slab order) by the Adam kernel itself
+    CU_TRY(launch_colsum_lowp(t->delta[l], n, t->fout[l], t->fout[l], 1.f, nullptr, t->colsum_scratch, t->fp16, st, &nsl));
+    CU_TRY(launch_adam_update(t->params + t->boff[l], t->adam_m + t->boff[l], t->adam_v + t->boff[l], t->colsum_scratch, nsl, t->fout[l], 1, gscale,
                               t->fout[l], 1, ap, nullptr, 0, nullptr, 0, grads_dev ? grads_dev + t->boff[l] : nullptr, t->fp16, apply != 0, st));
   }
   return SDFB_OK;
@@ -461,8 +462,9 @@ int sdfb_decoder_trainer_step(sdfb_decoder_trainer* t, const float* latents_dev,
                                 t->fin_p[l], inv_m, t->fout[l], t->fin[l], ap, t->w_lowp[l], t->fin_p[l], t->wt_lowp[l], t->fout_p[l],
                                 grads_dev ? grads_dev + t->woff[l] : nullptr, t->fp16, apply != 0, st));
     }
-    CU_TRY(launch_colsum_lowp(t->delta[l], M, t->fout_p[l], t->fout[l], 1.f, t->small_grad, t->colsum_scratch, t->fp16, st));
-    CU_TRY(launch_adam_update(t->params + t->boff[l], t->adam_m + t->boff[l], t->adam_v + t->boff[l], t->small_grad, 1, 0, 1, inv_m,
+    int nsl = 1;
+    CU_TRY(launch_colsum_lowp(t->delta[l], M, t->fout_p[l], t->fout[l], 1.f, nullptr, t->colsum_scratch, t->fp16, st, &nsl));
+    CU_TRY(launch_adam_update(t->params + t->boff[l], t->adam_m + t->boff[l], t->adam_v + t->boff[l], t->colsum_scratch, nsl, t->fout[l], 1, inv_m,
                               t->fout[l], 1, ap, nullptr, 0, nullptr, 0, grads_dev ? grads_dev + t->boff[l] : nullptr, t->fp16, apply != 0, st));
   }
   return SDFB_OK;

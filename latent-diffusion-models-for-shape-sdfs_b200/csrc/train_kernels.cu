@@ -289,14 +289,20 @@ cudaError_t launch_sum_loss(const float* partial, int n, float scale, float* los
 
 // `scratch`: kColsumSlabs x N floats
 cudaError_t launch_colsum_lowp(const uint16_t* D, long long M, int ld, int N, float scale, float* out, float* scratch, bool fp16,
-                               cudaStream_t st) {
-  const long long slab_rows = M <= 4096 ? (M > 0 ? M : 1) : (M + kColsumSlabs - 1) / kColsumSlabs;
+                               cudaStream_t st, int* nslabs_out) {
+  // row slabs of at least 64 rows, at most kColsumSlabs of them: a 4096-row batch is 64 slabs x N / 32 blocks (one slab took
+  // 108 us per layer of the DDPM training step: 32 blocks walking 4096 rows each)
+  const long long want = (M + 63) / 64;
+  const long long nsl = want < 1 ? 1 : (want > kColsumSlabs ? kColsumSlabs : want);
+  const long long slab_rows = (M + nsl - 1) / nsl > 0 ? (M + nsl - 1) / nsl : 1;
   const int slabs = static_cast<int>((M + slab_rows - 1) / slab_rows);
   const dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>(slabs > 0 ? slabs : 1));
   if (fp16) colsum_lowp_kernel<true><<<grid, 256, 0, st>>>(D, M, ld, N, slab_rows, scratch);
   else colsum_lowp_kernel<false><<<grid, 256, 0, st>>>(D, M, ld, N, slab_rows, scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (nslabs_out != nullptr) *nslabs_out = slabs > 0 ? slabs : 1;
+  if (out == nullptr) return cudaSuccess;          // the caller adds the slabs up itself (launch_adam_update does, in slab order)
   colsum_finish_kernel<<<(N + 255) / 256, 256, 0, st>>>(scratch, slabs > 0 ? slabs : 1, N, scale, out);
   return cudaGetLastError();
 }
@@ -344,7 +350,11 @@ cudaError_t launch_dec_train_head(const uint16_t* a8, const float* w8, const flo
 }
 cudaError_t launch_dec_train_head_grad(const uint16_t* a8, const float* d8, long long M, float scale, float* out, float* scratch, bool fp16,
                                        cudaStream_t st) {
-  const long long slab_rows = M <= 4096 ? (M > 0 ? M : 1) : (M + kColsumSlabs - 1) / kColsumSlabs;
+  // row slabs of at least 64 rows, at most kColsumSlabs of them: a 4096-row batch is 64 slabs x N / 32 blocks (one slab took
+  // 108 us per layer of the DDPM training step: 32 blocks walking 4096 rows each)
+  const long long want = (M + 63) / 64;
+  const long long nsl = want < 1 ? 1 : (want > kColsumSlabs ? kColsumSlabs : want);
+  const long long slab_rows = (M + nsl - 1) / nsl > 0 ? (M + nsl - 1) / nsl : 1;
   const int slabs = static_cast<int>((M + slab_rows - 1) / slab_rows);
   const dim3 grid(17, static_cast<unsigned>(slabs > 0 ? slabs : 1));
   if (fp16) dec_train_head_grad_kernel<true><<<grid, 256, 0, st>>>(a8, d8, M, slab_rows, scratch);
