@@ -13,7 +13,8 @@
 // (tile, k-split) work items.
 //
 //   warps 0-7  epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2): TMEM -> registers -> global, per 32-column group
-//   warp 8     TMA producer          warp 9   MMA issuer + TMEM allocation
+//   warp 8     TMA producer 0 (arms the stage, A)      warp 9   MMA issuer + TMEM allocation
+//   warps 10, 11  TMA producers 1 and 2 (a half of B each)
 //
 // Shared-memory operand layouts (what the TMA boxes produce and the descriptors describe):
 //   K-major  (NT): rows = M or N index, 128 B per row = 64 k, 16-byte units XOR (row & 7)            (SBO = 1024 B)
@@ -31,7 +32,7 @@ namespace {
 constexpr int kGStages = 4;
 constexpr int kGBM = 128, kGBK = 64;
 constexpr int kGEpiWarps = 8;
-constexpr int kGThreads = (kGEpiWarps + 2) * 32;
+constexpr int kGThreads = (kGEpiWarps + 4) * 32;    // + producer 0, MMA issuer, producers 1 and 2
 constexpr uint32_t kGAStage = kGBM * kGBK * 2;                  // 16 KiB
 constexpr uint32_t kGBStageMax = 256 * kGBK * 2;                // 32 KiB
 constexpr uint32_t kGStage = kGAStage + kGBStageMax;            // 48 KiB
@@ -107,11 +108,20 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
   const uint32_t tmem_base = misc[0];
   Watchdog wd{misc + 1, p.status, p.timeout_ns, nullptr, p.status_host};
 
-  if (warp == kGEpiWarps) {
-    // ===================== producer =====================
+  if (warp == kGEpiWarps || warp >= kGEpiWarps + 2) {
+    // ===================== producers =====================
+    // THREE issuing warps.  The TMA unit works through one thread's boxes one after the other at ~32 bytes per cycle
+    // (tools/tma_ingest.py, profiles/r2_tma_ingest.txt: 32 / 55 / 98 B/cycle/SM with 1 / 2 / 4 issuing warps), and a k-step of
+    // this kernel needs 16 KiB of A + up to 32 KiB of B per 512 tensor cycles = 96 B/cycle: with one producer the product ran
+    // at a third of the tensor rate.  Producer 0 arms the stage and brings A, producers 1 and 2 a half of B each; all three
+    // visit every stage in order, so each waits on the stage's release itself.
+    const int pidx = warp == kGEpiWarps ? 0 : warp - kGEpiWarps - 1;
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const uint32_t tx = kGAStage + static_cast<uint32_t>(BN) * kGBK * 2;
+      // B in units of 64 rows (NT: a box of up to 128 rows = 2 units; TN: one panel = 1 unit); units [u0, u1) are this warp's
+      const int units = BN / 64, half = (units + 1) / 2;
+      const int u0 = pidx == 1 ? 0 : half, u1 = pidx == 1 ? half : units;
       for (long long w = blockIdx.x; w < items; w += gridDim.x) {
         const int split = static_cast<int>(w % p.ksplit);
         const long long t = w / p.ksplit;
@@ -120,17 +130,22 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
         for (int ks = k0; ks < k1; ++ks) {
           if (!mbar_wait(bars + 8 * (kGBarEmpty + stage), phase ^ 1u, wd, kGErrEmpty, stage)) goto done;
           const uint32_t full = bars + 8 * (kGBarFull + stage);
-          mbar_arrive_expect_tx(full, tx);
           const uint32_t sa = smem0 + stage * kGStage, sb = sa + kGAStage;
-          if constexpr (!TN) {
-            tma_load_box(sa, &tm_a, ks * kGBK, tm * kGBM, full);                       // [128 rows][64 k]
-            for (int r = 0; r < BN; r += 128)                                          // box rows <= 256: two boxes of 128
-              tma_load_box(sb + r * 128, &tm_b, ks * kGBK, tn * BN + r, full);
+          if (pidx == 0) {
+            mbar_arrive_expect_tx(full, tx);
+            if constexpr (!TN) {
+              tma_load_box(sa, &tm_a, ks * kGBK, tm * kGBM, full);                     // [128 rows][64 k]
+            } else {
+              for (int pnl = 0; pnl < kGBM / 64; ++pnl)                                // panels of [64 k-rows][64 m]
+                tma_load_box(sa + pnl * 8192, &tm_a, tm * kGBM + pnl * 64, ks * kGBK, full);
+            }
+          } else if constexpr (!TN) {
+            // boxes of 128 rows (one of 64 when the tile is 64 wide): producer 1 takes the first half of them, producer 2 the rest
+            const int nboxes = BN >= 128 ? BN / 128 : 1, bh = (nboxes + 1) / 2;
+            for (int bx = (pidx == 1 ? 0 : bh); bx < (pidx == 1 ? bh : nboxes); ++bx)
+              tma_load_box(sb + bx * 128 * 128, &tm_b, ks * kGBK, tn * BN + bx * 128, full);
           } else {
-            for (int pnl = 0; pnl < kGBM / 64; ++pnl)                                  // panels of [64 k-rows][64 m]
-              tma_load_box(sa + pnl * 8192, &tm_a, tm * kGBM + pnl * 64, ks * kGBK, full);
-            for (int pnl = 0; pnl < BN / 64; ++pnl)
-              tma_load_box(sb + pnl * 8192, &tm_b, tn * BN + pnl * 64, ks * kGBK, full);
+            for (int u = u0; u < u1; ++u) tma_load_box(sb + u * 8192, &tm_b, tn * BN + u * 64, ks * kGBK, full);
           }
           if (++stage == kGStages) { stage = 0; phase ^= 1u; }
         }
@@ -173,6 +188,10 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
     // ===================== epilogue warps =====================
     uint32_t acc_phase = 0, item = 0;
     const int quad = warp & 3, chalf = warp >> 2;                  // TMEM lane quadrant; which half of the tile's columns
+    // 256-bit global accesses need 32-byte alignment: bases and row pitches of everything this epilogue touches
+    const bool wide = (p.out_lowp == nullptr || ((reinterpret_cast<uintptr_t>(p.out_lowp) & 31u) == 0 && (p.ldo_lowp & 15) == 0)) &&
+                      (p.out_f32 == nullptr || ((reinterpret_cast<uintptr_t>(p.out_f32) & 31u) == 0 && (p.ldo_f32 & 7) == 0 && (p.split_stride & 7) == 0)) &&
+                      (p.mask_h == nullptr || ((reinterpret_cast<uintptr_t>(p.mask_h) & 31u) == 0 && (p.ldh & 15) == 0));
     const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     for (long long w = blockIdx.x; w < items; w += gridDim.x, ++item) {
       const int split = static_cast<int>(w % p.ksplit);
@@ -200,28 +219,42 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
           for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + col + i);
         }
         if (p.epi == kGemmEpiMaskLowp && row_ok) {     // delta_in = (delta_out W) where the forward activation was positive
-          const uint4* hp = reinterpret_cast<const uint4*>(p.mask_h + row * p.ldh + col);
+          const uint16_t* hp = p.mask_h + row * p.ldh + col;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint4 hv = __ldg(hp + u);
-            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+          for (int u = 0; u < 2; ++u) {                          // two 32-byte loads (whole sectors) per 32 columns
+            uint32_t hw[8];
+            if (wide) {
+              ld_global_nc_v8(hp + 16 * u, hw);
+            } else {
+              const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(hp) + 2 * u), h1 = __ldg(reinterpret_cast<const uint4*>(hp) + 2 * u + 1);
+              hw[0] = h0.x; hw[1] = h0.y; hw[2] = h0.z; hw[3] = h0.w; hw[4] = h1.x; hw[5] = h1.y; hw[6] = h1.z; hw[7] = h1.w;
+            }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (!(lowp_bits_to_float<FP16>(hw[e] & 0xFFFFu) > 0.f)) f[8 * u + 2 * e] = 0.f;
-              if (!(lowp_bits_to_float<FP16>(hw[e] >> 16) > 0.f)) f[8 * u + 2 * e + 1] = 0.f;
+            for (int e = 0; e < 8; ++e) {
+              if (!(lowp_bits_to_float<FP16>(hw[e] & 0xFFFFu) > 0.f)) f[16 * u + 2 * e] = 0.f;
+              if (!(lowp_bits_to_float<FP16>(hw[e] >> 16) > 0.f)) f[16 * u + 2 * e + 1] = 0.f;
             }
           }
         }
         if (row_ok) {
           if (p.out_f32 != nullptr) {
             float* dst = p.out_f32 + static_cast<long long>(split) * p.split_stride + row * p.ldo_f32 + col;
+            const bool post = p.epi == kGemmEpiBiasReluLowp && p.f32_post_relu;
+            if (wide) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-              if (p.epi == kGemmEpiBiasReluLowp && p.f32_post_relu) {
-                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              for (int i = 0; i < 32; i += 8) {
+                uint32_t o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(post ? fmaxf(f[i + e], 0.f) : f[i + e]);
+                st_global_v8(dst + i, o);
               }
-              *reinterpret_cast<float4*>(dst + i) = o;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                if (post) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4*>(dst + i) = o;
+              }
             }
           }
           if (p.out_lowp != nullptr) {
@@ -233,9 +266,14 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
 #pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = pack_plain<FP16>(f[2 * i], f[2 * i + 1]);
             }
-            uint4* dst = reinterpret_cast<uint4*>(p.out_lowp + row * p.ldo_lowp + col);
+            uint16_t* dst = p.out_lowp + row * p.ldo_lowp + col;
+            if (wide) {          // 2 x 32 bytes: whole sectors (four 16-byte stores per row left every sector half written)
+              st_global_v8(dst, pk);
+              st_global_v8(dst + 16, pk + 8);
+            } else {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) dst[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+              for (int u = 0; u < 4; ++u) reinterpret_cast<uint4*>(dst)[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            }
           }
         }
       }

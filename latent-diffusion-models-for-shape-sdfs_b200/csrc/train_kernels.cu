@@ -79,27 +79,40 @@ __global__ void sum_loss_kernel(const float* __restrict__ partial, int n, float 
   if (threadIdx.x == 0) out[0] = s * scale;
 }
 
-// column sums of a 16-bit matrix: block = 32 columns x 8 row-slices; rows in order inside a slice, slices added in order
-// (blockIdx.y = row slab of `slab_rows` rows: partial sums [slab][N], added up in slab order by colsum_finish_kernel)
+// column sums of a 16-bit matrix: block = 256 columns (32 threads x 8 columns, one 16-byte load per row) x 8 row-slices; rows in
+// order inside a slice, slices added in order (blockIdx.y = row slab of `slab_rows` rows: partial sums [slab][N], added up in
+// slab order by colsum_finish_kernel or by the Adam kernel).  ld must be a multiple of 8 (every caller pads it).
 template <bool FP16>
 __global__ void __launch_bounds__(256) colsum_lowp_kernel(const uint16_t* __restrict__ D, long long M, int ld, int N, long long slab_rows,
                                                           float* __restrict__ partial) {
-  __shared__ float part[8][33];
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int slice = threadIdx.x >> 5;
+  __shared__ float part[8][256 + 8];
+  const int cg = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + cg * 8;
   const long long s0 = blockIdx.y * slab_rows, s1 = s0 + slab_rows < M ? s0 + slab_rows : M;
   const long long per = (s1 - s0 + 7) / 8;
   const long long r0 = s0 + slice * per, r1 = r0 + per < s1 ? r0 + per : s1;
-  float s = 0.f;
-  if (col < N)
-    for (long long r = r0; r < r1; ++r) s += from_lowp_bits<FP16>(D[r * ld + col]);
-  part[slice][threadIdx.x & 31] = s;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < ld) {
+    const uint16_t* src = D + col;
+    for (long long r = r0; r < r1; ++r) {
+      const uint4 q = *reinterpret_cast<const uint4*>(src + r * ld);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s[2 * e] += from_lowp_bits<FP16>(static_cast<uint16_t>(w[e] & 0xFFFFu));
+        s[2 * e + 1] += from_lowp_bits<FP16>(static_cast<uint16_t>(w[e] >> 16));
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[slice][cg * 8 + e] = s[e];
   __syncthreads();
-  if (slice == 0 && col < N) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
     float tot = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) tot += part[k][threadIdx.x];
-    partial[static_cast<long long>(blockIdx.y) * N + col] = tot;
+    partial[static_cast<long long>(blockIdx.y) * N + c] = tot;
   }
 }
 
@@ -182,16 +195,21 @@ __global__ void __launch_bounds__(256) lowp_copies_kernel(const float* __restric
 // ---- decoder training helpers ------------------------------------------------------------------------------------------
 // decoder input rows [M][ld] 16-bit: columns [0, 256) = the row's shape latent, 256..258 = xyz, the rest zero
 template <bool FP16>
-__global__ void dec_train_input_kernel(const float* __restrict__ latents, const float* __restrict__ xyz, long long M,
-                                       long long per_shape, int ld, int col0, int ncols, uint16_t* __restrict__ out) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= M * ncols) return;
-  const long long r = i / ncols;
-  const int c = static_cast<int>(i - r * ncols);
-  float v = 0.f;
-  if (c < 256) v = latents[(r / per_shape) * 256 + c];
-  else if (c < 259) v = xyz[r * 3 + (c - 256)];
-  out[r * ld + col0 + c] = to_lowp_bits<FP16>(v);
+__global__ void __launch_bounds__(256) dec_train_input_kernel(const float* __restrict__ latents, const float* __restrict__ xyz, long long M,
+                                                              long long per_shape, int ld, int col0, int ncols, uint16_t* __restrict__ out) {
+  // eight rows per block, a thread per column (and column + 256): one division per row instead of one per element
+  const long long rb = static_cast<long long>(blockIdx.x) * 8;
+  for (int k = 0; k < 8; ++k) {
+    const long long r = rb + k;
+    if (r >= M) return;
+    const float* z = latents + (r / per_shape) * 256;
+    for (int c = threadIdx.x; c < ncols; c += 256) {
+      float v = 0.f;
+      if (c < 256) v = z[c];
+      else if (c < 259) v = xyz[r * 3 + (c - 256)];
+      out[r * ld + col0 + c] = to_lowp_bits<FP16>(v);
+    }
+  }
 }
 
 // head forward + loss + first delta: y = tanh(a8 . w8 + b8) (fp32 dot over the 16-bit activations), clamped-L1 loss terms,
@@ -296,7 +314,8 @@ cudaError_t launch_colsum_lowp(const uint16_t* D, long long M, int ld, int N, fl
   const long long nsl = want < 1 ? 1 : (want > kColsumSlabs ? kColsumSlabs : want);
   const long long slab_rows = (M + nsl - 1) / nsl > 0 ? (M + nsl - 1) / nsl : 1;
   const int slabs = static_cast<int>((M + slab_rows - 1) / slab_rows);
-  const dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>(slabs > 0 ? slabs : 1));
+  if (ld & 7) return cudaErrorInvalidValue;
+  const dim3 grid(static_cast<unsigned>((N + 255) / 256), static_cast<unsigned>(slabs > 0 ? slabs : 1));
   if (fp16) colsum_lowp_kernel<true><<<grid, 256, 0, st>>>(D, M, ld, N, slab_rows, scratch);
   else colsum_lowp_kernel<false><<<grid, 256, 0, st>>>(D, M, ld, N, slab_rows, scratch);
   cudaError_t e = cudaGetLastError();
@@ -333,9 +352,8 @@ cudaError_t launch_lowp_copies(const float* w, int ld, int rows, int cols, uint1
 namespace sdfb {
 cudaError_t launch_dec_train_input(const float* latents, const float* xyz, long long M, long long per_shape, int ld, int col0, int ncols,
                                    uint16_t* out, bool fp16, cudaStream_t st) {
-  const long long total = M * ncols;
-  if (total <= 0) return cudaSuccess;
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (M <= 0 || ncols <= 0) return cudaSuccess;
+  const unsigned blocks = static_cast<unsigned>((M + 7) / 8);
   if (fp16) dec_train_input_kernel<true><<<blocks, 256, 0, st>>>(latents, xyz, M, per_shape, ld, col0, ncols, out);
   else dec_train_input_kernel<false><<<blocks, 256, 0, st>>>(latents, xyz, M, per_shape, ld, col0, ncols, out);
   return cudaGetLastError();
