@@ -99,6 +99,55 @@ def make_ddpm_rows_golden():
           "bf16 vs fp32", float(np.abs(arrays["x0_bf16"] - arrays["x0_fp32"]).max()))
 
 
+TRAIN_SAMPLE = 4096          # gradient entries kept per fixture (fixed indices, RandomState(5)), plus every tensor's norm
+
+
+def train_golden_inputs():
+    """Inputs of the training-step fixtures (second half): a DDPM batch of 48 latents and an auto-decoder
+    batch of 2 shapes x 96 samples, all from RandomState(21)."""
+    rs = np.random.RandomState(21)
+    x0 = np.clip(rs.standard_normal((48, 256)) * 0.6, -1, 1).astype(np.float32)
+    eps = rs.standard_normal((48, 256)).astype(np.float32)
+    t = rs.randint(0, 1000, 48).astype(np.int32)
+    lat = np.stack([default_latent(i) for i in range(2)])
+    xyz = (rs.rand(2, 96, 3) * 2 - 1).astype(np.float32)
+    tgt = np.stack([decoder_forward(default_latent(7 + i), xyz[i]) for i in range(2)])
+    return (x0, t, eps), (lat, xyz, tgt)
+
+
+def train_sample_indices(n_floats: int):
+    return np.sort(np.random.RandomState(5).choice(n_floats, TRAIN_SAMPLE, replace=False))
+
+
+def make_train_golden():
+    """tests/golden/train_golden.npz: loss, sampled gradient entries and per-tensor gradient norms of the training-step
+    oracles (oracle/train.py: fp64 autograd and the variants that emulate the 16-bit roundings of the tensor-core step)."""
+    from .train import ddpm_train_grads, ddpm_train_grads_lowp, decoder_train_grads, decoder_train_grads_lowp, flatten_grads
+    torch.set_num_threads(os.cpu_count() or 1)
+    (x0, t, eps), (lat, xyz, tgt) = train_golden_inputs()
+    arrays = {}
+
+    def put(prefix, loss, grads):
+        flat = flatten_grads(grads)
+        arrays[prefix + "_loss"] = np.float64(loss)
+        arrays[prefix + "_grad_sample"] = flat[train_sample_indices(flat.size)]
+        arrays[prefix + "_grad_norm"] = np.float64(np.linalg.norm(flat.astype(np.float64)))
+        arrays[prefix + "_tensor_norms"] = np.array([np.linalg.norm(np.asarray(g, dtype=np.float64)) for pair in grads for g in pair])
+
+    l, g = ddpm_train_grads(x0, t, eps)
+    put("ddpm_fp64", l, g)
+    l, g, _ = decoder_train_grads(lat, xyz, tgt)
+    put("dec_fp64", l, g)
+    for name, lowp in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        l, g = ddpm_train_grads_lowp(x0, t, eps, lowp=lowp)
+        put("ddpm_" + name, l, g)
+        l, g, y = decoder_train_grads_lowp(lat, xyz, tgt, lowp=lowp)
+        put("dec_" + name, l, g)
+        arrays["dec_" + name + "_sdf"] = np.asarray(y, dtype=np.float32).ravel()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "train_golden.npz"), **arrays)
+    print({k: (getattr(v, "shape", ()), str(getattr(v, "dtype", type(v)))) for k, v in arrays.items()})
+
+
 def make_c_abi_golden():
     torch.set_num_threads(os.cpu_count() or 1)
     sdf = decode_grid(default_latent(), 32).astype(np.float32)
@@ -112,7 +161,10 @@ def main():
     ap.add_argument("--vjp", action="store_true")
     ap.add_argument("--c-abi", action="store_true")
     ap.add_argument("--ddpm-rows", action="store_true")
+    ap.add_argument("--train", action="store_true")
     args = ap.parse_args()
+    if args.train:
+        return make_train_golden()
     if args.calibrate:
         return calibrate()
     if args.vjp:

@@ -206,3 +206,39 @@ def test_latent_adam_step_is_the_tensor_expression(pkg):
         assert torch.allclose(loss, loss_ref, rtol=1e-6, atol=1e-9)
     assert lib.sdfb_latent_adam_step(z2.data_ptr(), m2.data_ptr(), v2.data_ptr(), g.data_ptr(), None, B, lr, reg, 0.9, 0.999, 1e-8, 0, None) != 0
     assert lib.sdfb_latent_adam_step(None, None, None, None, None, 0, lr, reg, 0.9, 0.999, 1e-8, 1, None) == 0       # empty batch
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_training_steps_against_committed_golden_vectors(pkg, prec):
+    """Both training steps against tests/golden/train_golden.npz (python -m oracle.make_golden --train; the GPU box has no
+    /root/reference and need not recompute the oracle): loss, 4096 sampled gradient entries and every tensor's gradient norm."""
+    import os
+    from oracle.make_golden import train_golden_inputs, train_sample_indices
+    gold = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_golden.npz")))
+    (x0, t, eps), (lat, xyz, tgt) = train_golden_inputs()
+
+    def compare(prefix, loss, g, sizes):
+        smp, ref = g[train_sample_indices(g.size)], gold[prefix + "_grad_sample"]
+        err = np.abs(smp - ref).max() / np.abs(ref).max()
+        cos = float(smp.astype(np.float64) @ ref / np.linalg.norm(smp) / np.linalg.norm(ref))
+        norms, o = [], 0
+        for n in sizes:
+            norms.append(np.linalg.norm(g[o:o + n].astype(np.float64)))
+            o += n
+        nerr = np.abs(np.array(norms) - gold[prefix + "_tensor_norms"]).max() / float(gold[prefix + "_grad_norm"])
+        print(f"{prefix}: loss {loss:.6f} vs {float(gold[prefix + '_loss']):.6f}; sampled entries max err {err:.2e} of max, cosine {cos:.7f}; "
+              f"tensor norms within {nerr:.2e} of |grad|")
+        assert abs(loss - float(gold[prefix + "_loss"])) < 5e-4 * max(1.0, float(gold[prefix + "_loss"]))
+        assert err < 8e-2 and cos > 0.999 and nerr < 1e-2
+
+    dp = oracle.ddpm_weights()
+    tr = pkg.DDPMTrainer(oracle.flatten_params(dp), precision=prec)
+    loss, grads = tr.step(x0, t, eps, apply=False, return_grads=True)
+    compare("ddpm_" + prec, float(loss.item()), grads.cpu().numpy(), [np.asarray(a).size for pair in dp for a in pair])
+    tr.close()
+    wp = oracle.decoder_weights()
+    dt = pkg.DecoderTrainer(oracle.flatten_params(wp), precision=prec)
+    loss, grads, sdf = dt.step(lat, xyz, tgt, apply=False, return_grads=True, return_sdf=True)
+    compare("dec_" + prec, float(loss.item()), grads.cpu().numpy(), [np.asarray(a).size for pair in wp for a in pair])
+    assert np.abs(sdf.cpu().numpy().ravel() - gold["dec_" + prec + "_sdf"]).max() < (8e-3 if prec == "bf16" else 1.5e-3)
+    dt.close()

@@ -216,3 +216,35 @@ def test_latent_gradient_golden_vectors():
         loss, gf = oracle.fit_loss_grad_lowp(z, xyz, gold["target"], clamp=0.1, lowp=lowp)
         assert abs(loss - float(gold[f"fit_loss_{name}"])) < 2e-5
         assert np.abs(gf - gold[f"fit_grad_{name}"]).max() < 2e-2 * np.abs(gold[f"fit_grad_{name}"]).max()
+
+
+def test_training_step_golden_vectors():
+    """tests/golden/train_golden.npz (python -m oracle.make_golden --train) pins the training-step oracles of SURVEY 8f row N4
+    (oracle/train.py): recomputed here, loss, per-tensor gradient norms and 4096 sampled gradient entries match the committed
+    vectors to CPU-BLAS summation order (fp64: 1e-9 relative; the emulations of the 16-bit step: a flipped rounding or ReLU
+    mask may move single entries by a percent of |grad|_max, the norms agree to 1e-3)."""
+    import os
+    import torch
+    from oracle.make_golden import GOLDEN_DIR, train_golden_inputs, train_sample_indices
+    gold = dict(np.load(os.path.join(GOLDEN_DIR, "train_golden.npz")))
+    (x0, t, eps), (lat, xyz, tgt) = train_golden_inputs()
+
+    def check(prefix, loss, grads, tol_entry, tol_norm):
+        flat = oracle.flatten_grads(grads)
+        smp = flat[train_sample_indices(flat.size)]
+        ref = gold[prefix + "_grad_sample"]
+        assert abs(loss - float(gold[prefix + "_loss"])) <= tol_norm * max(1.0, abs(float(gold[prefix + "_loss"])))
+        assert np.abs(smp - ref).max() <= tol_entry * np.abs(ref).max(), prefix
+        norms = np.array([np.linalg.norm(np.asarray(g, dtype=np.float64)) for pair in grads for g in pair])
+        np.testing.assert_allclose(norms, gold[prefix + "_tensor_norms"], rtol=tol_norm, atol=tol_norm * float(gold[prefix + "_grad_norm"]))
+
+    l, g = oracle.ddpm_train_grads(x0, t, eps)
+    check("ddpm_fp64", l, g, 1e-6, 1e-6)           # (the stored samples are fp32)
+    l, g, _ = oracle.decoder_train_grads(lat, xyz, tgt)
+    check("dec_fp64", l, g, 1e-6, 1e-6)
+    for name, lowp in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        l, g = oracle.ddpm_train_grads_lowp(x0, t, eps, lowp=lowp)
+        check("ddpm_" + name, l, g, 5e-2, 2e-3)
+        l, g, y = oracle.decoder_train_grads_lowp(lat, xyz, tgt, lowp=lowp)
+        check("dec_" + name, l, g, 5e-2, 2e-3)
+        assert np.abs(np.asarray(y, np.float32).ravel() - gold["dec_" + name + "_sdf"]).max() < 2e-3
