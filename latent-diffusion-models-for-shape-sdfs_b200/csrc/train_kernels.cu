@@ -197,12 +197,15 @@ __global__ void __launch_bounds__(256) lowp_copies_kernel(const float* __restric
 template <bool FP16>
 __global__ void __launch_bounds__(256) dec_train_input_kernel(const float* __restrict__ latents, const float* __restrict__ xyz, long long M,
                                                               long long per_shape, int ld, int col0, int ncols, uint16_t* __restrict__ out) {
-  // eight rows per block, a thread per column (and column + 256): one division per row instead of one per element
+  // eight rows per block, a thread per column (and column + 256): ONE division per block instead of one per element (the
+  // rows' shape index only steps up inside the block)
   const long long rb = static_cast<long long>(blockIdx.x) * 8;
+  long long shape = rb / per_shape, next = (shape + 1) * per_shape;
   for (int k = 0; k < 8; ++k) {
     const long long r = rb + k;
     if (r >= M) return;
-    const float* z = latents + (r / per_shape) * 256;
+    while (r >= next) { ++shape; next += per_shape; }
+    const float* z = latents + shape * 256;
     for (int c = threadIdx.x; c < ncols; c += 256) {
       float v = 0.f;
       if (c < 256) v = z[c];
