@@ -238,7 +238,7 @@ int sdfb_ddpm_create(const float* params_host, size_t n_floats, int device, sdfb
 int sdfb_ddpm_destroy(sdfb_ddpm* ddpm);
 
 /* precision: SDFB_PREC_FP32 runs the FFMA kernels (one launch per layer and step); BF16 / FP16 run
- * ALL steps in one persistent cooperative tcgen05 kernel (time embedding folded into a per-step
+ * ALL steps in one persistent tcgen05 kernel (all CTAs resident) (time embedding folded into a per-step
  * bias, denoiser MLP and posterior update fused; x stays fp32 and enters layer 0 as an exact
  * two-way 16-bit split).
  *

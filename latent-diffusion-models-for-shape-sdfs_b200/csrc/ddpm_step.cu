@@ -1,5 +1,5 @@
 // K2: fused latent-DDPM sampler for sm_100a (tcgen05 / TMEM / TMA, CTA pairs, one persistent
-// cooperative launch for all steps of a sample_latents call).
+// launch - every CTA resident - for all steps of a sample_latents call).
 //
 // What it computes (oracle: oracle/ddpm.py denoiser_forward_lowp,
 // ddpm_step, sample_latents; no upstream source exists, /root/reference/README.md:1):
