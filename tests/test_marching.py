@@ -291,3 +291,57 @@ def test_indexed_mesh_welding(pkg, cuda_decoder):
     assert torch.equal(v1, v3) and torch.equal(f1, f3)
     assert v1.shape == v2.shape and torch.equal(v1, v2)                      # unique() sorts by edge key: identical vertex arrays
     assert f1.shape == f2.shape
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res,block,thickness_cells", [(96, 8, 1.5), (65, 4, 0.8)])
+def test_block_selection_keeps_a_thin_shell(pkg, res, block, thickness_cells):
+    """A field with a thin feature through the block path of the sparse extractor (corner points -> block selection with the
+    exact Lipschitz threshold -> block nodes -> marching cubes over blocks), fed with an ANALYTIC 1-Lipschitz field instead of
+    the decoder: a spherical shell thinner than a cell or two - two sign changes inside one 8^3 block, none at its corners.
+    The triangle set equals the dense extraction of the same field, and nothing of the shell is lost."""
+    import ctypes as C
+    lib = pkg.load_library()
+    h = 2.0 / (res - 1)
+    half = 0.5 * thickness_cells * h
+
+    def field(p):                                   # |  |x - c| - r  | - half : 1-Lipschitz, negative inside the shell
+        c = torch.tensor([0.03, -0.02, 0.05], device="cuda")
+        return ((p - c).norm(dim=1) - 0.55).abs() - half
+
+    nb = (res - 1 + block - 1) // block
+    corners = torch.empty(((nb + 1) ** 3, 3), dtype=torch.float32, device="cuda")
+    assert lib.sdfb_sparse_corner_points(res, block, corners.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    cs = field(corners).contiguous()
+    assert int((cs < 0).sum()) < cs.numel() // 50                                   # the corner lattice hardly sees the shell
+    tau = 1.0 * block * h * (3.0 ** 0.5) / 2.0                                       # Lipschitz constant 1, exact threshold
+    nbytes = C.c_size_t()
+    assert lib.sdfb_sparse_select_workspace_bytes(res, block, C.byref(nbytes)) == 0
+    ws = torch.empty((nbytes.value,), dtype=torch.uint8, device="cuda")
+    ids = torch.empty((nb ** 3,), dtype=torch.int32, device="cuda")
+    nblk = C.c_int64()
+    assert lib.sdfb_sparse_select_blocks(cs.data_ptr(), res, block, C.c_float(tau), ids.data_ptr(), ws.data_ptr(), nbytes.value,
+                                         C.byref(nblk), None) == 0
+    n, per = nblk.value, (block + 1) ** 3
+    assert 0 < n < nb ** 3
+    pts = torch.empty((n * per, 3), dtype=torch.float32, device="cuda")
+    assert lib.sdfb_sparse_block_points(res, block, ids.data_ptr(), n, pts.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    fields = field(pts).contiguous()
+    assert lib.sdfb_mc_blocks_workspace_bytes(block, n, C.byref(nbytes)) == 0
+    ws2 = torch.empty((nbytes.value,), dtype=torch.uint8, device="cuda")
+    ntri = C.c_int64()
+    assert lib.sdfb_mc_blocks_count(fields.data_ptr(), ids.data_ptr(), n, res, block, ws2.data_ptr(), nbytes.value, C.byref(ntri), None) == 0
+    tris = torch.empty((ntri.value, 3, 3), dtype=torch.float32, device="cuda")
+    assert lib.sdfb_mc_blocks_generate(fields.data_ptr(), ids.data_ptr(), n, res, block, ws2.data_ptr(), tris.data_ptr(), None, None) == 0
+    torch.cuda.synchronize()
+    # dense extraction of the same field on the full grid (the same expression at the same fp32 coordinates)
+    a = torch.from_numpy(oracle.axis_coords(res)).cuda()
+    zz, yy, xx = torch.meshgrid(a, a, a, indexing="ij")
+    dense = field(torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=1)).reshape(res, res, res).contiguous()
+    ref = pkg.extract_surface(dense)
+    key = lambda t: np.unique(t.cpu().numpy().reshape(-1, 9).view(np.uint32), axis=0)
+    print(f"res {res} block {block}: shell of {thickness_cells} cells, {n} of {nb ** 3} blocks kept, {ntri.value} triangles (dense {ref.shape[0]})")
+    assert ref.shape[0] > 1000 and ntri.value == ref.shape[0]
+    assert np.array_equal(key(tris), key(ref))
