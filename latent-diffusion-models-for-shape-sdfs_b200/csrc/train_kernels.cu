@@ -124,8 +124,10 @@ __global__ void colsum_finish_kernel(const float* __restrict__ partial, int slab
   out[col] = tot * scale;
 }
 
-// Adam on a [rows][cols] tensor; tile of 32 x 32 per block (a transposed 16-bit copy is written coalesced through smem)
-template <bool FP16>
+// Adam on a [rows][cols] tensor; tile of 32 x 32 per block (a transposed 16-bit copy is written coalesced through smem).
+// VEC: a thread owns four consecutive columns of one row (128-bit accesses; needs cols, ld_grad, part_stride % 4 == 0 and
+// 16-byte aligned bases - the launcher checks); otherwise one column of four rows.  The arithmetic per element is the same.
+template <bool FP16, bool VEC>
 __global__ void __launch_bounds__(256) adam_update_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
                                                           const float* __restrict__ grad, int nparts, long long part_stride, int ld_grad,
                                                           float scale, int rows, int cols, AdamParams a, uint16_t* __restrict__ w_lowp,
@@ -133,33 +135,68 @@ __global__ void __launch_bounds__(256) adam_update_kernel(float* __restrict__ w,
                                                           int apply) {
   __shared__ uint16_t tile[32][34];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int r = r0 + ty + 8 * k, c = c0 + tx;
-    uint16_t lw = 0;
-    if (r < rows && c < cols) {
-      const long long i = static_cast<long long>(r) * cols + c;
-      float g = 0.f;
-      for (int s = 0; s < nparts; ++s) g += grad[s * part_stride + static_cast<long long>(r) * ld_grad + c];
-      g *= scale;
-      if (grad_out != nullptr) grad_out[i] = g;
-      float wi = w[i];
-      if (apply) {
-        const float mi = a.beta1 * m[i] + (1.f - a.beta1) * g;
-        const float vi = a.beta2 * v[i] + (1.f - a.beta2) * g * g;
-        m[i] = mi;
-        v[i] = vi;
-        wi = wi - a.lr * (mi / a.bias_corr1) / (sqrtf(vi / a.bias_corr2) + a.eps);
-        w[i] = wi;
-      }
-      lw = to_lowp_bits<FP16>(wi);
-      if (w_lowp != nullptr) w_lowp[static_cast<long long>(r) * ldw + c] = lw;
+  auto one = [&](int r, int c, float g, float& wi, float& mi, float& vi) {
+    g *= scale;
+    if (grad_out != nullptr) grad_out[static_cast<long long>(r) * cols + c] = g;
+    if (apply) {
+      mi = a.beta1 * mi + (1.f - a.beta1) * g;
+      vi = a.beta2 * vi + (1.f - a.beta2) * g * g;
+      wi = wi - a.lr * (mi / a.bias_corr1) / (sqrtf(vi / a.bias_corr2) + a.eps);
     }
-    tile[ty + 8 * k][tx] = lw;
+  };
+  if constexpr (VEC) {
+    const int r = r0 + (threadIdx.x >> 3), cq = (threadIdx.x & 7) * 4, c = c0 + cq;
+    uint16_t lw[4] = {0, 0, 0, 0};
+    if (r < rows && c < cols) {                                   // cols % 4 == 0: the four columns exist together
+      const long long i = static_cast<long long>(r) * cols + c;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < nparts; ++s) {
+        const float4 q = *reinterpret_cast<const float4*>(grad + s * part_stride + static_cast<long long>(r) * ld_grad + c);
+        g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+      }
+      float4 wq = *reinterpret_cast<const float4*>(w + i);
+      float4 mq = make_float4(0.f, 0.f, 0.f, 0.f), vq = mq;
+      if (apply) { mq = *reinterpret_cast<const float4*>(m + i); vq = *reinterpret_cast<const float4*>(v + i); }
+      one(r, c, g.x, wq.x, mq.x, vq.x);
+      one(r, c + 1, g.y, wq.y, mq.y, vq.y);
+      one(r, c + 2, g.z, wq.z, mq.z, vq.z);
+      one(r, c + 3, g.w, wq.w, mq.w, vq.w);
+      if (apply) {
+        *reinterpret_cast<float4*>(m + i) = mq;
+        *reinterpret_cast<float4*>(v + i) = vq;
+        *reinterpret_cast<float4*>(w + i) = wq;
+      }
+      lw[0] = to_lowp_bits<FP16>(wq.x); lw[1] = to_lowp_bits<FP16>(wq.y); lw[2] = to_lowp_bits<FP16>(wq.z); lw[3] = to_lowp_bits<FP16>(wq.w);
+      if (w_lowp != nullptr) {
+        uint16_t* d = w_lowp + static_cast<long long>(r) * ldw + c;
+        if ((ldw & 3) == 0) *reinterpret_cast<uint2*>(d) = make_uint2(lw[0] | (static_cast<uint32_t>(lw[1]) << 16), lw[2] | (static_cast<uint32_t>(lw[3]) << 16));
+        else { d[0] = lw[0]; d[1] = lw[1]; d[2] = lw[2]; d[3] = lw[3]; }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tile[threadIdx.x >> 3][cq + e] = lw[e];
+  } else {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + ty + 8 * k, c = c0 + tx;
+      uint16_t lw = 0;
+      if (r < rows && c < cols) {
+        const long long i = static_cast<long long>(r) * cols + c;
+        float g = 0.f;
+        for (int s = 0; s < nparts; ++s) g += grad[s * part_stride + static_cast<long long>(r) * ld_grad + c];
+        float wi = w[i], mi = apply ? m[i] : 0.f, vi = apply ? v[i] : 0.f;
+        one(r, c, g, wi, mi, vi);
+        if (apply) { m[i] = mi; v[i] = vi; w[i] = wi; }
+        lw = to_lowp_bits<FP16>(wi);
+        if (w_lowp != nullptr) w_lowp[static_cast<long long>(r) * ldw + c] = lw;
+      }
+      tile[ty + 8 * k][tx] = lw;
+    }
   }
   if (wt_lowp == nullptr) return;
   __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int c = c0 + ty + 8 * k, r = r0 + tx;         // transposed: row index of W^T = column of W
@@ -333,12 +370,15 @@ cudaError_t launch_adam_update(float* w, float* m, float* v, const float* grad, 
                                float scale, int rows, int cols, const AdamParams& a, uint16_t* w_lowp, int ldw, uint16_t* wt_lowp,
                                int ldwt, float* grad_out, bool fp16, bool apply, cudaStream_t st) {
   const dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>((rows + 31) / 32));
-  if (fp16)
-    adam_update_kernel<true><<<grid, 256, 0, st>>>(w, m, v, grad, nparts, part_stride, ld_grad, scale, rows, cols, a, w_lowp, ldw,
-                                                    wt_lowp, ldwt, grad_out, apply ? 1 : 0);
-  else
-    adam_update_kernel<false><<<grid, 256, 0, st>>>(w, m, v, grad, nparts, part_stride, ld_grad, scale, rows, cols, a, w_lowp, ldw,
-                                                     wt_lowp, ldwt, grad_out, apply ? 1 : 0);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool vec = (cols & 3) == 0 && (ld_grad & 3) == 0 && (part_stride & 3) == 0 && al16(w) && al16(m) && al16(v) && al16(grad) &&
+                   (grad_out == nullptr || al16(grad_out)) && (w_lowp == nullptr || (reinterpret_cast<uintptr_t>(w_lowp) & 7u) == 0);
+#define SDFB_ADAM(F, V)                                                                                                              \
+  adam_update_kernel<F, V><<<grid, 256, 0, st>>>(w, m, v, grad, nparts, part_stride, ld_grad, scale, rows, cols, a, w_lowp, ldw, wt_lowp, \
+                                                 ldwt, grad_out, apply ? 1 : 0)
+  if (fp16) { if (vec) SDFB_ADAM(true, true); else SDFB_ADAM(true, false); }
+  else { if (vec) SDFB_ADAM(false, true); else SDFB_ADAM(false, false); }
+#undef SDFB_ADAM
   return cudaGetLastError();
 }
 
