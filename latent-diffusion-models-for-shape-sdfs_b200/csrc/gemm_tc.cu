@@ -198,14 +198,52 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
       const long long t = w / p.ksplit;
       const int tn = static_cast<int>(t % tiles_n), tm = static_cast<int>(t / tiles_n);
       const uint32_t b = item & 1u;
+      const long long row = static_cast<long long>(tm) * kGBM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int cbeg = BN >= 64 ? chalf * (BN / 2) : (chalf == 0 ? 0 : BN), cend = BN >= 64 ? cbeg + BN / 2 : BN;
+      // ReLU mask of this thread's row (backward-data): the forward activations exist long before the accumulator is full,
+      // so all their loads go out here and their latency hides behind the wait; one bit per column is kept
+      uint32_t mbits[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+      if (p.epi == kGemmEpiMaskLowp && row_ok) {
+        uint32_t hw[4][16];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = cbeg + 32 * ci;
+          if (c < cend) {
+            const uint16_t* hp = p.mask_h + row * p.ldh + tn * BN + c;
+            if (wide) {
+              ld_global_nc_v8(hp, hw[ci]);
+              ld_global_nc_v8(hp + 16, hw[ci] + 8);
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(hp) + u);
+                hw[ci][4 * u] = q.x; hw[ci][4 * u + 1] = q.y; hw[ci][4 * u + 2] = q.z; hw[ci][4 * u + 3] = q.w;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          if (cbeg + 32 * ci < cend) {
+            uint32_t mb = 0;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if (lowp_bits_to_float<FP16>(hw[ci][e] & 0xFFFFu) > 0.f) mb |= 1u << (2 * e);
+              if (lowp_bits_to_float<FP16>(hw[ci][e] >> 16) > 0.f) mb |= 1u << (2 * e + 1);
+            }
+            mbits[ci] = mb;
+          }
+        }
+      }
       if (!mbar_wait(bars + 8 * (kGBarAccFull + b), (acc_phase >> b) & 1u, wd, kGErrAccFull, b)) goto done;
       acc_phase ^= 1u << b;
       __syncwarp();
       tc_fence_after();
-      const long long row = static_cast<long long>(tm) * kGBM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
-      const int cbeg = BN >= 64 ? chalf * (BN / 2) : (chalf == 0 ? 0 : BN), cend = BN >= 64 ? cbeg + BN / 2 : BN;
-      for (int c = cbeg; c < cend; c += 32) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = cbeg + 32 * ci;
+        if (c >= cend) break;
         uint32_t v[32];
         tmem_ld32(tmem_row + b * 256 + c, v);
         tmem_ld_wait();
@@ -218,23 +256,10 @@ gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tm_a, con
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + col + i);
         }
-        if (p.epi == kGemmEpiMaskLowp && row_ok) {     // delta_in = (delta_out W) where the forward activation was positive
-          const uint16_t* hp = p.mask_h + row * p.ldh + col;
+        if (p.epi == kGemmEpiMaskLowp) {     // delta_in = (delta_out W) where the forward activation was positive
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {                          // two 32-byte loads (whole sectors) per 32 columns
-            uint32_t hw[8];
-            if (wide) {
-              ld_global_nc_v8(hp + 16 * u, hw);
-            } else {
-              const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(hp) + 2 * u), h1 = __ldg(reinterpret_cast<const uint4*>(hp) + 2 * u + 1);
-              hw[0] = h0.x; hw[1] = h0.y; hw[2] = h0.z; hw[3] = h0.w; hw[4] = h1.x; hw[5] = h1.y; hw[6] = h1.z; hw[7] = h1.w;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if (!(lowp_bits_to_float<FP16>(hw[e] & 0xFFFFu) > 0.f)) f[16 * u + 2 * e] = 0.f;
-              if (!(lowp_bits_to_float<FP16>(hw[e] >> 16) > 0.f)) f[16 * u + 2 * e + 1] = 0.f;
-            }
-          }
+          for (int i = 0; i < 32; ++i)
+            if (!((mbits[ci] >> i) & 1u)) f[i] = 0.f;
         }
         if (row_ok) {
           if (p.out_f32 != nullptr) {
