@@ -1399,6 +1399,10 @@ int sdfb_umma_rate(int cta_group, int grid, int iters, int k_per_commit, int n_a
   if (!cycles_per_mma || (cta_group != 1 && cta_group != 2) || grid < cta_group || iters < 1 || k_per_commit < 1 ||
       n_acc < 1 || n_acc > 2)
     return fail(SDFB_E_INVALID, "bad argument");
+  // the probe's one-outstanding-group protocol (flags bit0 clear) assumes the tensor pipe is slower than the issuing thread; with
+  // the N = 128 forms (bit3 without bit6, or bit8) it is not, a barrier phase is skipped and the kernel never returns
+  if ((((flags & 8) && !(flags & 64)) || (flags & 256)) && !(flags & 1))
+    return fail(SDFB_E_INVALID, "the N = 128 forms need flags bit0 (no intermediate waits)");
   grid -= grid % cta_group;
   long long* out = nullptr;
   CU_TRY(cudaMalloc(&out, sizeof(long long) * grid));
