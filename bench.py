@@ -431,6 +431,8 @@ def main():
         # ALL ranks fall back to decode + torch.distributed all-gathers (decided collectively, so nobody waits alone)
         comm, why = None, ""
         try:
+            if os.environ.get("SDFB_BENCH_NO_COMM"):          # exercises the fallback below on a box where the peer path works
+                raise RuntimeError("peer-memory path switched off by SDFB_BENCH_NO_COMM")
             comm = pkg.Comm(dev)
             comm.decode_grid_sharded(dec, z5, RES5, mask=True)
             torch.cuda.synchronize()
