@@ -107,3 +107,35 @@ def test_c_program_decodes_through_the_host_entry_point(tmp_path):
     print(run.stdout)
     assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
     assert "gpu_decode ok" in run.stdout
+
+
+def test_round2_entry_points_reject_bad_arguments(pkg):
+    """Error behaviour of the entry points added in round 2: SDFB_E_INVALID (< 0) and a message, never a launch."""
+    import ctypes as C
+    lib = pkg.load_library()
+    z = torch.zeros((2, 256), device="cuda")
+    n = C.c_int64()
+    nbytes = C.c_size_t()
+    # welding: null workspace, grid too small, negative triangle count, workspace too small
+    assert lib.sdfb_mc_weld_workspace_bytes(1, C.byref(nbytes)) < 0
+    assert lib.sdfb_mc_weld_workspace_bytes(16, C.byref(nbytes)) == 0 and nbytes.value > 0
+    ws = torch.empty((nbytes.value,), dtype=torch.uint8, device="cuda")
+    assert lib.sdfb_mc_weld_count(None, 0, 16, None, nbytes.value, C.byref(n), None) < 0
+    assert lib.sdfb_mc_weld_count(None, -1, 16, ws.data_ptr(), nbytes.value, C.byref(n), None) < 0
+    assert lib.sdfb_mc_weld_count(None, 0, 16, ws.data_ptr(), 8, C.byref(n), None) < 0
+    assert lib.sdfb_mc_weld_count(None, 0, 16, ws.data_ptr(), nbytes.value, C.byref(n), None) == 0 and n.value == 0      # empty soup
+    assert lib.sdfb_mc_weld_fill(None, None, 0, 16, ws.data_ptr(), None, None, None) == 0
+    assert lib.sdfb_mc_weld_fill(None, None, 3, 16, ws.data_ptr(), None, None, None) < 0
+    # latent Adam: step 0, betas outside [0, 1), null moments
+    assert lib.sdfb_latent_adam_step(z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), None, 2, 1e-3, 0.0, 0.9, 0.999, 1e-8, 0, None) < 0
+    assert lib.sdfb_latent_adam_step(z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), None, 2, 1e-3, 0.0, 1.0, 0.999, 1e-8, 1, None) < 0
+    assert lib.sdfb_latent_adam_step(z.data_ptr(), None, z.data_ptr(), z.data_ptr(), None, 2, 1e-3, 0.0, 0.9, 0.999, 1e-8, 1, None) < 0
+    # diagnostics: the probes refuse shapes their protocols cannot run
+    out3 = (C.c_double * 3)()
+    assert lib.sdfb_tma_ingest_rate(148, 3, 0, 1, 0, 64, 32, 64, out3) < 0           # cluster size not a power of two
+    assert lib.sdfb_tma_ingest_rate(148, 1, 9, 1, 0, 64, 32, 64, out3) < 0           # unknown mode
+    assert lib.sdfb_tma_ingest_rate(128, 4, 5, 1, 0, 64, 32, 64, out3) < 0           # pair modes need clusters of 2
+    v = C.c_double()
+    assert lib.sdfb_umma_rate(1, 2, 10, 4, 2, 8, C.byref(v)) < 0                     # the N = 128 form with intermediate waits
+    assert b"N = 128" in lib.sdfb_last_error()
+    torch.cuda.synchronize()
