@@ -139,3 +139,31 @@ def test_round2_entry_points_reject_bad_arguments(pkg):
     assert lib.sdfb_umma_rate(1, 2, 10, 4, 2, 8, C.byref(v)) < 0                     # the N = 128 form with intermediate waits
     assert b"N = 128" in lib.sdfb_last_error()
     torch.cuda.synchronize()
+
+
+def test_integration_md_binding_runs_as_written(pkg, cuda_decoder):
+    """The reference-side ctypes binding shown in INTEGRATION.md ("Minimal binding"), executed verbatim from the repo root
+    with the oracle's seeded weights: same results as the package's own wrapper, and the samplers run."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"## Minimal binding.*?```python\n(.*?)```", text, re.S).group(1)
+    ns = {"decoder_layers": oracle.decoder_weights(), "denoiser_layers": oracle.ddpm_weights()}
+    cwd = os.getcwd()
+    os.chdir(root)
+    try:
+        exec(compile(code, "INTEGRATION.md", "exec"), ns)
+        z = oracle.default_latent()
+        sdf, mask = ns["decode_grid"](z, 32)
+        ref_sdf, ref_mask = cuda_decoder.decode_grid(z, 32, mask=True, precision="bf16")
+        assert np.array_equal(sdf, ref_sdf.cpu().numpy()) and np.array_equal(mask, ref_mask.cpu().numpy().reshape(mask.shape))
+        pts = (np.random.RandomState(0).rand(100, 3) * 2 - 1).astype(np.float32)
+        y = ns["Decoder"](z, pts, precision=0)
+        assert np.abs(y - oracle.decoder_forward(z, pts)).max() < 1e-5
+        x = ns["sample_latents"](8, seed=3, steps=6)
+        assert x.shape == (8, 256) and np.isfinite(x).all() and np.abs(x).max() <= 1.0 + 1e-6
+        x_T, noise = np.zeros((4, 256), np.float32), np.zeros((3, 4, 256), np.float32)
+        x2 = ns["sample_latents_explicit"](x_T, noise, precision=0)
+        assert np.abs(x2 - oracle.sample_latents(4, x_T, noise, steps=3)).max() < 1e-4
+    finally:
+        os.chdir(cwd)
