@@ -167,3 +167,37 @@ def test_integration_md_binding_runs_as_written(pkg, cuda_decoder):
         assert np.abs(x2 - oracle.sample_latents(4, x_T, noise, steps=3)).max() < 1e-4
     finally:
         os.chdir(cwd)
+
+
+def test_contexts_release_their_device_memory(pkg):
+    """Create / use / destroy every kind of context a few times: free device memory comes back (no leak per context)."""
+    import gc
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+    def round_trip():
+        dec = pkg.Decoder(pkg.synthetic.decoder_params(), device="cuda:0", precision="bf16")
+        z = torch.from_numpy(pkg.synthetic.latent(0)).cuda()
+        dec.decode_grid(z, 48, mask=True)
+        dec.extract_surface_sparse(z, 65)
+        dd = pkg.LatentDDPM(pkg.synthetic.ddpm_params(), device="cuda:0", precision="bf16")
+        dd.sample_latents(300, steps=3, seed=1)
+        tr = pkg.DDPMTrainer(pkg.synthetic.ddpm_params(), precision="bf16")
+        x0 = torch.zeros((64, 256), device="cuda")
+        tr.step(x0, torch.zeros(64, dtype=torch.int32, device="cuda"), x0)
+        dt = pkg.DecoderTrainer(pkg.synthetic.decoder_params(), precision="bf16")
+        dt.step(z[None], torch.zeros((1, 64, 3), device="cuda"), torch.zeros((1, 64), device="cuda"), lr=1e-6)
+        torch.cuda.synchronize()
+        for c in (dec, dd, tr, dt):
+            c.close()
+        del dec, dd, tr, dt, z, x0
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    round_trip()                                    # first use: lazily created library state stays
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(4):
+        round_trip()
+    free1, _ = torch.cuda.mem_get_info()
+    print(f"free device memory before / after 4 context round trips: {free0 >> 20} / {free1 >> 20} MiB")
+    assert free0 - free1 < (64 << 20)
